@@ -1,0 +1,188 @@
+/*
+ * pyranges_b200.h -- C ABI of the B200-native interval engine (libpyranges_b200.so).
+ *
+ * Drop-in boundary B2 of SURVEY.md section 8(b): these entry points replace the numpy-in/numpy-out
+ * calls pyranges v0 makes into its three native dependencies (ncls, sorted_nearest, pyrle; none of
+ * them is in the reference tree, the cited file:line are the reference's CALL SITES):
+ *
+ *   iv_index_build            <- NCLS(starts, ends, ids)                 pyranges/methods/join.py:12,
+ *                                                                        intersection.py:19,71, coverage.py:20,58
+ *   iv_count_overlaps         <- NCLS.all_overlaps_both + value_counts   pyranges/methods/coverage.py:26-40
+ *                                NCLS.has_overlaps (mode ANY)            pyranges/methods/intersection.py:78
+ *   iv_emit_pairs             <- NCLS.all_overlaps_both                  pyranges/methods/join.py:15,23
+ *                                NCLS.all_overlaps_self                  pyranges/methods/intersection.py:74
+ *                                NCLS.all_containments_both              pyranges/methods/join.py:17, intersection.py:76
+ *                                NCLS.first_overlap_both                 pyranges/methods/join.py:19 (via nearest.py:32)
+ *   iv_coverage_bp            <- NCLS.coverage                           pyranges/methods/coverage.py:64-68
+ *   iv_nearest                <- first_overlap_both + nearest_previous_nonoverlapping +
+ *                                nearest_next_nonoverlapping + nearest_nonoverlapping
+ *                                                                        pyranges/methods/nearest.py:29-53,59,69,113
+ *   iv_cluster                <- sort_values("Start") + annotate_clusters pyranges/methods/cluster.py:11-15,
+ *                                + global id offsets                      pyranges/pyranges_main.py:1210-1223
+ *   iv_merge_count/_emit      <- sort_values("Start") + find_clusters     pyranges/methods/merge.py:12-14
+ *   iv_rle_count/_emit        <- pyrle.methods.coverage                   pyranges/methods/to_rle.py:18
+ *
+ * Where the reference loops over (chromosome, strand) keys in Python and calls the native library
+ * once per key (pyranges/multithreaded.py:182-303, :306-372), every entry point here is BATCHED over
+ * all keys: rows of all keys are concatenated (key-segmented, natsorted key order) and one launch
+ * sequence handles every key.  Groups ("partner frames") are contiguous row ranges of the subject
+ * columns; each query segment names its partner group (or -1 = no partner).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host or the type is a struct below
+ *     (structs live in host memory, their members are device pointers / scalars);
+ *   - all coordinates, labels, counts are int64 (pyranges/methods/init.py:13-16);
+ *   - the caller owns every buffer including the workspace (size from *_workspace_bytes); the library
+ *     never allocates or frees device memory and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: IV_OK or a negative error; iv_last_error_string() describes the last failure of
+ *     the calling thread.
+ *   - intervals are half open [start, end); overlap iff S < e && s < E.  start <= end is required.
+ */
+#ifndef PYRANGES_B200_H
+#define PYRANGES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IV_ABI_VERSION 1
+
+#define IV_OK 0
+#define IV_ERR_INVALID (-1)   /* bad argument */
+#define IV_ERR_CUDA (-2)      /* CUDA runtime error (see iv_last_error_string) */
+#define IV_ERR_WORKSPACE (-3) /* workspace too small */
+#define IV_ERR_RANGE (-4)     /* coordinate span / row count exceeds what the flattened keys can hold */
+
+/* emit / count modes */
+#define IV_MODE_ALL 0     /* every overlapping (query, subject) pair            all_overlaps_both      */
+#define IV_MODE_ANY 1     /* one entry per query with >= 1 hit                   has_overlaps / first   */
+#define IV_MODE_CONTAIN 2 /* pairs with subject.start <= q.start && q.end <= subject.end             */
+
+/* nearest direction per query segment (pyranges/methods/nearest.py:85-90) */
+#define IV_NEAREST_BOTH 0
+#define IV_NEAREST_PREVIOUS 1
+#define IV_NEAREST_NEXT 2
+
+/* index flags */
+#define IV_INDEX_ENDS_PERM 1 /* also keep the row permutation of the end-sorted order (nearest) */
+
+/* Row groups of a set of intervals.  Group g owns rows [row_off[g], row_off[g+1]).
+ * lo[g] <= every start, hi[g] >= every end of the group.  base[] is the flattened-coordinate origin:
+ * base[0] = 0, base[g+1] >= base[g] + (hi[g]-lo[g]) + gap, base[n_groups] = total_span. */
+typedef struct iv_groups {
+    int32_t n_groups;
+    int32_t _pad;
+    const int64_t* row_off; /* [n_groups+1] */
+    const int64_t* lo;      /* [n_groups]   */
+    const int64_t* hi;      /* [n_groups]   */
+    const int64_t* base;    /* [n_groups+1] */
+    int64_t total_span;     /* host copy of base[n_groups] */
+} iv_groups_t;
+
+/* Subject index descriptor, filled by iv_index_build; all arrays live in the caller's workspace. */
+typedef struct iv_index {
+    int64_t n;             /* subjects */
+    int64_t total_span;
+    int32_t shift;         /* bin = flattened coordinate >> shift */
+    int32_t flags;
+    int64_t n_bins;        /* bin tables hold n_bins + 1 entries */
+    const uint64_t* key_s; /* [n] flattened starts, ascending */
+    const uint32_t* row_s; /* [n] subject row of each entry of key_s */
+    const uint64_t* end_s; /* [n] flattened end of the same entries (start order) */
+    const uint64_t* key_e; /* [n] flattened ends, ascending */
+    const uint32_t* row_e; /* [n] subject row of key_e entries (IV_INDEX_ENDS_PERM) or NULL */
+    const uint64_t* max1;  /* [ceil(n/64)]   max end_s per 64 entries   (skip index) */
+    const uint64_t* max2;  /* [ceil(n/4096)] max end_s per 4096 entries (skip index) */
+    const uint32_t* bin_s; /* [n_bins+1] #key_s < (b << shift) */
+    const uint32_t* bin_e; /* [n_bins+1] #key_e < (b << shift) */
+    iv_groups_t groups;
+} iv_index_t;
+
+/* Query rows: key segments in the same concatenated layout. */
+typedef struct iv_queries {
+    int64_t n;
+    const int64_t* start;
+    const int64_t* end;
+    const int64_t* label;     /* NULL -> row number */
+    int32_t n_seg;
+    int32_t _pad;
+    const int64_t* seg_off;   /* [n_seg+1] */
+    const int32_t* seg_group; /* [n_seg] partner group of the subject index, -1 = none */
+    const int32_t* seg_mode;  /* [n_seg] IV_NEAREST_* (iv_nearest only; NULL -> BOTH) */
+    int64_t slack;            /* join(slack=k): start = max(start-k, 0), end += k (multithreaded.py:420-423) */
+} iv_queries_t;
+
+int iv_abi_version(void);
+const char* iv_last_error_string(void);
+int iv_set_device(int device);
+
+/* ---- building blocks (exported for tests and the bench) -------------------------------------- */
+
+size_t iv_sort_workspace_bytes(int64_t n, int32_t value_bytes);
+/* LSD radix sort of 64-bit keys on bits [begin_bit, end_bit), optional 4/8-byte payload, stable.
+ * Sorted data ends up in keys / values. */
+int iv_radix_sort_u64(uint64_t* keys, void* values, int32_t value_bytes, int64_t n, int32_t begin_bit,
+                      int32_t end_bit, void* ws, size_t ws_bytes, void* stream);
+
+/* out_lo[k] = min start, out_hi[k] = max end, out_maxlen[k] = max(end-start) of segment k
+ * (INT64_MAX / INT64_MIN / 0 for an empty segment). */
+int iv_segment_bounds(const int64_t* starts, const int64_t* ends, const int64_t* seg_off, int32_t n_seg,
+                      int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, void* stream);
+
+/* ---- binary operations ------------------------------------------------------------------------ */
+
+size_t iv_index_workspace_bytes(int64_t n, int64_t total_span, int32_t flags);
+int iv_index_build(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups,
+                   int32_t flags, void* ws, size_t ws_bytes, iv_index_t* out, void* stream);
+
+size_t iv_overlap_workspace_bytes(int64_t n_queries);
+/* out_count[i] = number of entries query i emits under `mode`; also leaves the per-tile offsets that
+ * iv_emit_pairs needs in ws and the grand total in *out_total (device). */
+int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mode, int64_t* out_count,
+                      void* ws, size_t ws_bytes, int64_t* out_total, void* stream);
+/* Writes sum(out_count) entries.  out_q gets the query label, out_s the subject row (or
+ * s_label[row]).  Either may be NULL.  In mode ANY out_s receives the FIRST hit: smallest start,
+ * then largest end, then smallest row (the head of the nested-containment-list traversal). */
+int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int32_t mode, const int64_t* counts,
+                  const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label, void* stream);
+/* out_bp[i] = sum over hits of min(e,E)-max(s,S); out_fraction[i] = out_bp / (end-start), NaN -> 0 */
+int iv_coverage_bp(const iv_index_t* index, const iv_queries_t* q, int64_t* out_bp, double* out_fraction,
+                   void* stream);
+/* out_row[i] = subject row of the nearest interval or -1, out_dist[i] = 0 (overlap), gap+1, or -1 */
+int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_t overlap, int64_t* out_row,
+               int64_t* out_dist, void* stream);
+
+/* ---- unary operations ------------------------------------------------------------------------- */
+/* groups->base must leave a gap of max(slack,0)+1 between consecutive groups. `len_bits` = number of
+ * bits of the largest (end-start). */
+
+size_t iv_cluster_workspace_bytes(int64_t n);
+/* out_row[p] = input row at sorted position p (sorted by group, start, end, row);
+ * out_id[p] = 1-based cluster id, global over groups in order;  *out_n_clusters (device). */
+int iv_cluster(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, int64_t slack,
+               int32_t len_bits, int64_t* out_row, int64_t* out_id, int64_t* out_n_clusters, void* ws,
+               size_t ws_bytes, void* stream);
+/* phase 1: sort + scans, *out_n_clusters (device).  phase 2: one row per cluster. */
+int iv_merge_count(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups,
+                   int64_t slack, int32_t len_bits, int64_t* out_n_clusters, void* ws, size_t ws_bytes,
+                   void* stream);
+int iv_merge_emit(int64_t n, int64_t n_clusters, const iv_groups_t* groups, int32_t len_bits, const void* ws,
+                  int64_t* out_start, int64_t* out_end, int64_t* out_count, int32_t* out_group, void* stream);
+
+size_t iv_rle_workspace_bytes(int64_t n, int32_t n_groups);
+/* groups->lo must be 0 (coverage is counted from coordinate 0).  out_run_off [n_groups+1] (device):
+ * runs of group g are [out_run_off[g], out_run_off[g+1]); out_run_off[n_groups] = total runs. */
+int iv_rle_count(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, void* ws,
+                 size_t ws_bytes, int64_t* out_run_off, void* stream);
+/* n_runs = out_run_off[n_groups] read back by the caller; run_off = the array iv_rle_count filled. */
+int iv_rle_emit(int64_t n, const iv_groups_t* groups, const void* ws, int64_t n_runs, const int64_t* run_off,
+                int64_t* out_runs, double* out_values, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRANGES_B200_H */

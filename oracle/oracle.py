@@ -1,0 +1,197 @@
+"""ctypes front-end of the CPU oracle (oracle/iv_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, bench.py (cpu_baseline / --impl reference)
+and __graft_entry__.smoke().  Nothing under pyranges_b200/ may import this module.
+
+The classes/functions mirror the numpy-in / numpy-out API of the three third-party
+libraries the reference calls: ``ncls.NCLS``, ``sorted_nearest.*``
+and ``pyrle.methods.coverage`` so that oracle/shims/* can put them under the *unmodified*
+reference Python layer (only in the authoring container; /root/reference does not travel).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "iv_oracle.c")
+_LIB = os.path.join(_HERE, "libiv_oracle.so")
+_lib = None
+
+_P64 = C.POINTER(C.c_int64)
+_PD = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    """gcc -O3 the C restatement into oracle/libiv_oracle.so (git-ignored, travels with gpurun)."""
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
+        subprocess.check_call(
+            ["gcc", "-O3", "-march=x86-64-v2", "-fPIC", "-shared", "-o", _LIB, _SRC]
+        )
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.ivo_ncls_build.restype = C.c_void_p
+        L.ivo_ncls_build.argtypes = [_P64, _P64, _P64, C.c_int64]
+        L.ivo_ncls_free.argtypes = [C.c_void_p]
+        L.ivo_free.argtypes = [C.c_void_p]
+        for f in (L.ivo_ncls_all_overlaps_both, L.ivo_ncls_first_overlap_both):
+            f.restype = C.c_int64
+            f.argtypes = [C.c_void_p, _P64, _P64, _P64, C.c_int64, C.c_int, C.POINTER(_P64), C.POINTER(_P64)]
+        L.ivo_ncls_count.argtypes = [C.c_void_p, _P64, _P64, C.c_int64, _P64]
+        L.ivo_ncls_coverage.argtypes = [C.c_void_p, _P64, _P64, C.c_int64, _P64]
+        L.ivo_annotate_clusters.argtypes = [_P64, _P64, C.c_int64, C.c_int64, _P64]
+        L.ivo_find_clusters.restype = C.c_int64
+        L.ivo_find_clusters.argtypes = [_P64, _P64, C.c_int64, C.c_int64, _P64, _P64, _P64]
+        L.ivo_nearest_previous.argtypes = [_P64, C.c_int64, _P64, _P64, C.c_int64, _P64, _P64]
+        L.ivo_nearest_next.argtypes = [_P64, C.c_int64, _P64, _P64, C.c_int64, _P64, _P64]
+        L.ivo_nearest_nonoverlapping.argtypes = [_P64, _P64, _P64, _P64, C.c_int64, _P64, _P64]
+        L.ivo_coverage_rle.restype = C.c_int64
+        L.ivo_coverage_rle.argtypes = [_P64, _P64, _PD, C.c_int64, _P64, _PD]
+        L.ivo_brute_count.argtypes = [_P64, _P64, C.c_int64, _P64, _P64, C.c_int64, _P64]
+        _lib = L
+    return _lib
+
+
+def _a64(x):
+    return np.ascontiguousarray(np.asarray(x), dtype=np.int64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_P64)
+
+
+def _take(ptr, n):
+    """copy a malloc'ed int64 buffer of length n into numpy and free it"""
+    if n == 0 or not ptr:
+        out = np.empty(0, dtype=np.int64)
+    else:
+        out = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+    if ptr:
+        lib().ivo_free(C.cast(ptr, C.c_void_p))
+    return out
+
+
+class NCLS:
+    """API twin of ``ncls.NCLS`` (reference call sites: methods/join.py:12, intersection.py:19,71,
+    coverage.py:20,58)."""
+
+    def __init__(self, starts, ends, ids):
+        s, e, i = _a64(starts), _a64(ends), _a64(ids)
+        self._n = len(s)
+        self._h = lib().ivo_ncls_build(_p(s), _p(e), _p(i), len(s))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().ivo_ncls_free(h)
+
+    def _both(self, fn, starts, ends, indexes, mode):
+        s, e, i = _a64(starts), _a64(ends), _a64(indexes)
+        oq, os_ = _P64(), _P64()
+        n = fn(self._h, _p(s), _p(e), _p(i), len(s), mode, C.byref(oq), C.byref(os_))
+        return _take(oq, n), _take(os_, n)
+
+    def all_overlaps_both(self, starts, ends, indexes):
+        return self._both(lib().ivo_ncls_all_overlaps_both, starts, ends, indexes, 0)
+
+    def all_containments_both(self, starts, ends, indexes):
+        return self._both(lib().ivo_ncls_all_overlaps_both, starts, ends, indexes, 1)
+
+    def first_overlap_both(self, starts, ends, indexes):
+        return self._both(lib().ivo_ncls_first_overlap_both, starts, ends, indexes, 0)
+
+    def last_overlap_both(self, starts, ends, indexes):
+        return self._both(lib().ivo_ncls_first_overlap_both, starts, ends, indexes, 1)
+
+    def all_overlaps_self(self, starts, ends, indexes):
+        return self.all_overlaps_both(starts, ends, indexes)[0]
+
+    def count(self, starts, ends):
+        s, e = _a64(starts), _a64(ends)
+        out = np.zeros(len(s), dtype=np.int64)
+        lib().ivo_ncls_count(self._h, _p(s), _p(e), len(s), _p(out))
+        return out
+
+    def has_overlaps(self, starts, ends, indexes):
+        return _a64(indexes)[self.count(starts, ends) > 0]
+
+    def coverage(self, starts, ends, indexes):
+        s, e = _a64(starts), _a64(ends)
+        out = np.zeros(len(s), dtype=np.int64)
+        lib().ivo_ncls_coverage(self._h, _p(s), _p(e), len(s), _p(out))
+        return out
+
+
+def annotate_clusters(starts, ends, slack):
+    s, e = _a64(starts), _a64(ends)
+    out = np.empty(len(s), dtype=np.int64)
+    lib().ivo_annotate_clusters(_p(s), _p(e), len(s), int(slack), _p(out))
+    return out
+
+
+def find_clusters(starts, ends, slack):
+    s, e = _a64(starts), _a64(ends)
+    n = len(s)
+    os_, oe, on = (np.empty(n, dtype=np.int64) for _ in range(3))
+    k = lib().ivo_find_clusters(_p(s), _p(e), n, int(slack), _p(os_), _p(oe), _p(on))
+    return os_[:k].copy(), oe[:k].copy(), on[:k].copy()
+
+
+def nearest_previous_nonoverlapping(l_starts, r_ends, r_indexes):
+    ls, re_, ri = _a64(l_starts), _a64(r_ends), _a64(r_indexes)
+    oi, od = np.empty(len(ls), dtype=np.int64), np.empty(len(ls), dtype=np.int64)
+    lib().ivo_nearest_previous(_p(ls), len(ls), _p(re_), _p(ri), len(re_), _p(oi), _p(od))
+    return oi, od
+
+
+def nearest_next_nonoverlapping(l_ends, r_starts, r_indexes):
+    le, rs, ri = _a64(l_ends), _a64(r_starts), _a64(r_indexes)
+    oi, od = np.empty(len(le), dtype=np.int64), np.empty(len(le), dtype=np.int64)
+    lib().ivo_nearest_next(_p(le), len(le), _p(rs), _p(ri), len(rs), _p(oi), _p(od))
+    return oi, od
+
+
+def nearest_nonoverlapping(prev_idx, prev_dist, next_idx, next_dist):
+    pi, pd_, ni, nd = _a64(prev_idx), _a64(prev_dist), _a64(next_idx), _a64(next_dist)
+    oi, od = np.empty(len(pi), dtype=np.int64), np.empty(len(pi), dtype=np.int64)
+    lib().ivo_nearest_nonoverlapping(_p(pi), _p(pd_), _p(ni), _p(nd), len(pi), _p(oi), _p(od))
+    return oi, od
+
+
+def coverage_rle(starts, ends, weights=None):
+    """-> (runs int64, values float64) of one key; restates pyrle.methods.coverage (to_rle.py:18)."""
+    s, e = _a64(starts), _a64(ends)
+    n = len(s)
+    runs = np.empty(2 * n + 1, dtype=np.int64)
+    vals = np.empty(2 * n + 1, dtype=np.float64)
+    w = None
+    wp = _PD()
+    if weights is not None:
+        w = np.ascontiguousarray(np.asarray(weights), dtype=np.float64)
+        wp = w.ctypes.data_as(_PD)
+    k = lib().ivo_coverage_rle(_p(s), _p(e), wp, n, _p(runs), vals.ctypes.data_as(_PD))
+    return runs[:k].copy(), vals[:k].copy()
+
+
+def brute_count(S, E, qs, qe):
+    S, E, qs, qe = _a64(S), _a64(E), _a64(qs), _a64(qe)
+    out = np.empty(len(qs), dtype=np.int64)
+    lib().ivo_brute_count(_p(S), _p(E), len(S), _p(qs), _p(qe), len(qs), _p(out))
+    return out
+
+
+def brute_pairs(S, E, sid, qs, qe, qid):
+    """numpy brute force of all_overlaps_both -- tiny cases only; canonical (q, s) sorted."""
+    S, E, qs, qe = _a64(S), _a64(E), _a64(qs), _a64(qe)
+    m = (S[None, :] < qe[:, None]) & (qs[:, None] < E[None, :])
+    qi, sj = np.nonzero(m)
+    a, b = _a64(qid)[qi], _a64(sid)[sj]
+    o = np.lexsort([b, a])
+    return a[o], b[o]

@@ -1,0 +1,26 @@
+"""shim of ``sorted_nearest`` over the CPU oracle (test infrastructure).
+
+Only the entry points of the hot path are real; the rest exist so that the
+reference's modules import, and raise when called."""
+from oracle.oracle import (  # noqa: F401
+    annotate_clusters,
+    find_clusters,
+    nearest_next_nonoverlapping,
+    nearest_nonoverlapping,
+    nearest_previous_nonoverlapping,
+)
+
+
+def _out_of_scope(name):
+    def f(*a, **k):
+        raise NotImplementedError("sorted_nearest.%s is outside the oracle's scope" % name)
+
+    f.__name__ = name
+    return f
+
+
+for _n in (
+    "cluster_by merge_by k_nearest_next_nonoverlapping k_nearest_previous_nonoverlapping "
+    "max_disjoint maketiles makewindows get_all_ties get_different_ties"
+).split():
+    globals()[_n] = _out_of_scope(_n)

@@ -1,0 +1,305 @@
+// sort.cu -- stable LSD radix sort of 64-bit keys (+ optional 4/8-byte payload) and the device scans
+// it needs.  Replaces libc qsort inside NCLS construction and pandas sort_values in
+// pyranges/methods/{cluster,merge,nearest}.py and the mergesort of pyrle's event list.
+//
+// Per 8-bit digit: (1) per-tile digit histogram, digit-major; (2) exclusive scan of the 256 x n_tiles
+// table = global scatter offsets; (3) scatter: warp-level multi-split ranks (__match_any_sync), keys
+// staged through shared memory in digit order so that global writes are coalesced runs.
+// No inter-block dependencies (no spin waits), so it cannot hang.
+#include "common.cuh"
+
+namespace iv {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per block
+constexpr int RS_RADIX = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t mask, uint32_t* __restrict__ hist,
+          int64_t ntiles) {
+    __shared__ uint32_t h[RS_RADIX];
+    const int tid = threadIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        int64_t idx = tbase + it * RS_THREADS + tid;
+        bool ok = idx < n;
+        uint32_t d = ok ? (uint32_t)((__ldg(keys + idx) >> shift) & mask) : 0xffffffffu;
+        unsigned m = __match_any_sync(FULL, d);
+        if (ok && (int)(__ffs(m) - 1) == lane_id()) atomicAdd(&h[d], (uint32_t)__popc(m));
+    }
+    __syncthreads();
+    hist[(int64_t)tid * ntiles + blockIdx.x] = h[tid];
+}
+
+template <int VB>
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const void* __restrict__ vin,
+             void* __restrict__ vout, int64_t n, int shift, uint32_t mask,
+             const uint32_t* __restrict__ hist_scanned, int64_t ntiles) {
+    __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
+    __shared__ uint32_t digit_base[RS_RADIX];
+    __shared__ uint32_t gbase[RS_RADIX];
+    __shared__ uint64_t sbuf[RS_TILE];
+    __shared__ uint8_t sdig[RS_TILE];
+    __shared__ uint32_t wsum[RS_WARPS + 1];
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int64_t tile = blockIdx.x;
+    const int64_t tbase = tile * RS_TILE;
+    const int nvalid = (int)((n - tbase) < (int64_t)RS_TILE ? (n - tbase) : (int64_t)RS_TILE);
+
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) ((uint32_t*)warp_cnt)[i] = 0;
+    __syncthreads();
+
+    uint64_t key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        int li = w * (RS_ITEMS * 32) + it * 32 + lane;
+        key[it] = li < nvalid ? __ldg(kin + tbase + li) : ~0ull;
+    }
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        uint32_t d = (uint32_t)((key[it] >> shift) & mask);
+        unsigned m = __match_any_sync(FULL, d);
+        int leader = __ffs(m) - 1;
+        uint32_t c = 0;
+        if (lane == leader) {
+            c = warp_cnt[w][d];
+            warp_cnt[w][d] = c + (uint32_t)__popc(m);
+        }
+        c = __shfl_sync(FULL, c, leader);
+        rank[it] = c + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // thread tid owns digit tid: exclusive scan over warps, then over digits
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            uint32_t c = warp_cnt[ww][tid];
+            warp_cnt[ww][tid] = run;
+            run += c;
+        }
+        uint32_t tot;
+        uint32_t ex = block_excl_sum<uint32_t, RS_THREADS>(run, wsum, tot);
+        digit_base[tid] = ex;
+        gbase[tid] = __ldg(hist_scanned + (int64_t)tid * ntiles + tile) - ex;
+    }
+    __syncthreads();
+    uint32_t pos[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        uint32_t d = (uint32_t)((key[it] >> shift) & mask);
+        pos[it] = digit_base[d] + warp_cnt[w][d] + rank[it];
+        sbuf[pos[it]] = key[it];
+        sdig[pos[it]] = (uint8_t)d;
+    }
+    __syncthreads();
+    for (int k = tid; k < nvalid; k += RS_THREADS) kout[gbase[sdig[k]] + (uint32_t)k] = sbuf[k];
+    if (VB == 8) {
+        __syncthreads();
+        const uint64_t* vi = (const uint64_t*)vin;
+        uint64_t* vo = (uint64_t*)vout;
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            int li = w * (RS_ITEMS * 32) + it * 32 + lane;
+            if (li < nvalid) sbuf[pos[it]] = __ldg(vi + tbase + li);
+        }
+        __syncthreads();
+        for (int k = tid; k < nvalid; k += RS_THREADS) vo[gbase[sdig[k]] + (uint32_t)k] = sbuf[k];
+    } else if (VB == 4) {
+        __syncthreads();
+        const uint32_t* vi = (const uint32_t*)vin;
+        uint32_t* vo = (uint32_t*)vout;
+        uint32_t* sb32 = (uint32_t*)sbuf;
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            int li = w * (RS_ITEMS * 32) + it * 32 + lane;
+            if (li < nvalid) sb32[pos[it]] = __ldg(vi + tbase + li);
+        }
+        __syncthreads();
+        for (int k = tid; k < nvalid; k += RS_THREADS) vo[gbase[sdig[k]] + (uint32_t)k] = sb32[k];
+    }
+}
+
+// ---- device-wide exclusive sum of uint32 (histogram table) ---------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 16;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_u32_tile_sums(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ partials) {
+    __shared__ uint32_t sm[SC_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SC_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int it = 0; it < SC_ITEMS; it++) {
+        int64_t i = base + it * SC_THREADS + threadIdx.x;
+        if (i < n) s += __ldg(in + i);
+    }
+    s = warp_sum(s);
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t x = threadIdx.x < SC_THREADS / 32 ? sm[threadIdx.x] : 0;
+        x = warp_sum(x);
+        if (threadIdx.x == 0) partials[blockIdx.x] = x;
+    }
+}
+
+// single block: in-place exclusive scan of m values
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_small(T* __restrict__ data, int64_t m, T* __restrict__ out_total) {
+    __shared__ T sm[1024 / 32 + 1];
+    T carry = 0;
+    for (int64_t base = 0; base < m; base += 1024 * 4) {
+        T v[4];
+        T tsum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t i = base + (int64_t)threadIdx.x * 4 + j;
+            v[j] = i < m ? data[i] : T(0);
+            tsum += v[j];
+        }
+        T tot;
+        T ex = block_excl_sum<T, 1024>(tsum, sm, tot);
+        T run = carry + ex;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t i = base + (int64_t)threadIdx.x * 4 + j;
+            if (i < m) data[i] = run;
+            run += v[j];
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && out_total) *out_total = carry;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_u32_apply(uint32_t* __restrict__ data, int64_t n, const uint32_t* __restrict__ partials) {
+    __shared__ uint32_t sm[SC_THREADS / 32 + 1];
+    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    uint32_t v[SC_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        int64_t i = base + j;
+        v[j] = i < n ? data[i] : 0;
+        s += v[j];
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_sum<uint32_t, SC_THREADS>(s, sm, tot);
+    uint32_t run = __ldg(partials + blockIdx.x) + ex;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        int64_t i = base + j;
+        if (i < n) data[i] = run;
+        run += v[j];
+    }
+}
+
+size_t scan_u32_large_temp_elems(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, SC_TILE) + 1; }
+
+int scan_exclusive_u32_large(uint32_t* data, int64_t n, uint32_t* temp_partials, cudaStream_t stream) {
+    if (n <= 0) return IV_OK;
+    int64_t nt = cdiv(n, SC_TILE);
+    if (nt == 1) {
+        k_scan_small<uint32_t><<<1, 1024, 0, stream>>>(data, n, nullptr);
+        IV_LAUNCH_CHECK();
+        return IV_OK;
+    }
+    k_u32_tile_sums<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, temp_partials);
+    IV_LAUNCH_CHECK();
+    k_scan_small<uint32_t><<<1, 1024, 0, stream>>>(temp_partials, nt, nullptr);
+    IV_LAUNCH_CHECK();
+    k_u32_apply<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, temp_partials);
+    IV_LAUNCH_CHECK();
+    return IV_OK;
+}
+
+int scan_exclusive_i64_inplace(int64_t* data, int64_t n, int64_t* out_total, cudaStream_t stream) {
+    k_scan_small<int64_t><<<1, 1024, 0, stream>>>(data, n > 0 ? n : 0, out_total);
+    IV_LAUNCH_CHECK();
+    return IV_OK;
+}
+
+// ---- host driver ---------------------------------------------------------------------------------------------
+size_t radix_sort_temp_bytes(int64_t n) {
+    int64_t ntiles = cdiv(n > 0 ? n : 1, RS_TILE);
+    size_t hist = (size_t)ntiles * RS_RADIX;
+    return (hist + scan_u32_large_temp_elems((int64_t)hist)) * sizeof(uint32_t) + 512;
+}
+
+int radix_sort_pingpong(uint64_t* k0, uint64_t* k1, void* v0, void* v1, int value_bytes, int64_t n, int begin_bit,
+                        int end_bit, void* temp, size_t temp_bytes, cudaStream_t stream, int* result_buf) {
+    *result_buf = 0;
+    if (n <= 1 || end_bit <= begin_bit) return IV_OK;
+    IV_REQUIRE(n < ((int64_t)1 << 32) - RS_TILE, IV_ERR_RANGE, "radix sort: n=%lld exceeds 2^32", (long long)n);
+    IV_REQUIRE(value_bytes == 0 || value_bytes == 4 || value_bytes == 8, IV_ERR_INVALID, "radix sort: value_bytes");
+    IV_REQUIRE(temp_bytes >= radix_sort_temp_bytes(n), IV_ERR_WORKSPACE, "radix sort: temp too small");
+    int64_t ntiles = cdiv(n, RS_TILE);
+    uint32_t* hist = (uint32_t*)temp;
+    int64_t nh = ntiles * RS_RADIX;
+    uint32_t* partials = hist + ((nh + 63) & ~(int64_t)63);
+    int cur = 0;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        int bits = end_bit - shift < 8 ? end_bit - shift : 8;
+        uint32_t mask = (1u << bits) - 1u;
+        const uint64_t* kin = cur ? k1 : k0;
+        uint64_t* kout = cur ? k0 : k1;
+        const void* vin = cur ? v1 : v0;
+        void* vout = cur ? v0 : v1;
+        k_rs_hist<<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, n, shift, mask, hist, ntiles);
+        IV_LAUNCH_CHECK();
+        int rc = scan_exclusive_u32_large(hist, nh, partials, stream);
+        if (rc != IV_OK) return rc;
+        if (value_bytes == 0)
+            k_rs_scatter<0><<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, kout, nullptr, nullptr, n, shift, mask, hist, ntiles);
+        else if (value_bytes == 4)
+            k_rs_scatter<4><<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, kout, vin, vout, n, shift, mask, hist, ntiles);
+        else
+            k_rs_scatter<8><<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, kout, vin, vout, n, shift, mask, hist, ntiles);
+        IV_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    *result_buf = cur;
+    return IV_OK;
+}
+
+}  // namespace iv
+
+// ---- exported test entry ----------------------------------------------------------------------------------------
+extern "C" size_t iv_sort_workspace_bytes(int64_t n, int32_t value_bytes) {
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    size_t b = ((nn * 8 + 255) & ~(size_t)255) + ((nn * (size_t)value_bytes + 255) & ~(size_t)255);
+    return b + iv::radix_sort_temp_bytes(n) + 1024;
+}
+
+extern "C" int iv_radix_sort_u64(uint64_t* keys, void* values, int32_t value_bytes, int64_t n, int32_t begin_bit,
+                                 int32_t end_bit, void* ws, size_t ws_bytes, void* stream) {
+    using namespace iv;
+    cudaStream_t st = (cudaStream_t)stream;
+    IV_REQUIRE(n >= 0 && begin_bit >= 0 && end_bit <= 64, IV_ERR_INVALID, "iv_radix_sort_u64: bad arguments");
+    IV_REQUIRE(ws_bytes >= iv_sort_workspace_bytes(n, value_bytes), IV_ERR_WORKSPACE, "iv_radix_sort_u64: workspace");
+    if (n <= 1) return IV_OK;
+    Bump b(ws, ws_bytes);
+    uint64_t* k1 = b.take<uint64_t>((size_t)n);
+    char* v1 = value_bytes ? b.take<char>((size_t)n * value_bytes) : nullptr;
+    void* temp = b.take<char>(radix_sort_temp_bytes(n));
+    int res = 0;
+    int rc = radix_sort_pingpong(keys, k1, values, v1, value_bytes, n, begin_bit, end_bit, temp,
+                                 radix_sort_temp_bytes(n), st, &res);
+    if (rc != IV_OK) return rc;
+    if (res == 1) {
+        IV_CUDA(cudaMemcpyAsync(keys, k1, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        if (value_bytes) IV_CUDA(cudaMemcpyAsync(values, v1, (size_t)n * value_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    return IV_OK;
+}

@@ -1,0 +1,289 @@
+"""Batched interval engine: device-resident, key-segmented int64 columns + the C-ABI kernels.
+
+This is the layer that replaces the reference's per-key calls into ncls / sorted_nearest / pyrle
+(pyranges/methods/join.py:12-23, intersection.py:71-78, coverage.py:20-26,58-64, nearest.py:59-113,
+cluster.py:13, merge.py:14, to_rle.py:18).  Where the reference loops over (chromosome, strand) keys
+and builds one NCLS per key (pyranges/multithreaded.py:221-294), here the rows of all keys sit in one
+concatenated int64 column pair in HBM (natsorted key order) and ONE launch sequence serves every key.
+
+torch is used for device memory and streams only; every computation is a kernel of
+libpyranges_b200.so reached through ctypes (pyranges_b200/_cabi.py).  No CPU fallback exists.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from ._cabi import (IV_INDEX_ENDS_PERM, IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_NEAREST_BOTH,  # noqa: F401
+                    IV_NEAREST_NEXT, IV_NEAREST_PREVIOUS, IvGroups, IvIndex, IvQueries)
+
+I64_MAX = np.iinfo(np.int64).max
+I64_MIN = np.iinfo(np.int64).min
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _use(device):
+    """Make `device` current for this thread in the library's CUDA runtime as well as torch's."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise cabi.CabiError("pyranges_b200 runs on CUDA devices only (got %r); there is no CPU path" % (device,))
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cabi.check(cabi.lib().iv_set_device(idx), "iv_set_device")
+    return torch.device("cuda", idx)
+
+
+def bits_for(v):
+    v = int(v)
+    b = 1
+    while b < 64 and (v >> b):
+        b += 1
+    return b
+
+
+def _bytes(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _to_dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
+
+
+class DeviceIntervals:
+    """Key-segmented interval columns on one GPU.
+
+    start, end : int64 device tensors, rows of all keys concatenated (segment k = rows
+                 [seg_off[k], seg_off[k+1])); mirrors df.Start.values / df.End.values of every
+                 DataFrame of PyRanges.dfs (pyranges/methods/init.py:35-45) laid end to end.
+    lo, hi, maxlen : per-segment min Start / max End / max length, computed once at ingest.
+    """
+
+    def __init__(self, start, end, seg_off, bounds=None):
+        assert start.dtype == torch.int64 and end.dtype == torch.int64 and start.is_cuda and end.is_cuda
+        self.device = _use(start.device)
+        self.start, self.end = start.contiguous(), end.contiguous()
+        self.n = int(start.numel())
+        self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        assert self.seg_off[0] == 0 and self.seg_off[-1] == self.n
+        self.n_seg = len(self.seg_off) - 1
+        self.seg_off_dev = _to_dev(self.seg_off, self.device)
+        if bounds is None:
+            bounds = self._bounds()
+        self.lo, self.hi, self.maxlen = bounds
+
+    @classmethod
+    def from_numpy(cls, starts, ends, seg_off, device="cuda", pinned=False):
+        dev = _use(device)
+        s = torch.from_numpy(np.ascontiguousarray(starts, dtype=np.int64))
+        e = torch.from_numpy(np.ascontiguousarray(ends, dtype=np.int64))
+        return cls(s.to(dev), e.to(dev), seg_off)
+
+    def _bounds(self):
+        k = self.n_seg
+        if k == 0:
+            z = np.zeros(0, np.int64)
+            return z, z.copy(), z.copy()
+        out = torch.empty(3 * k, dtype=torch.int64, device=self.device)
+        cabi.check(cabi.lib().iv_segment_bounds(_ptr(self.start), _ptr(self.end), _ptr(self.seg_off_dev), k,
+                                                C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr() + 8 * k),
+                                                C.c_void_p(out.data_ptr() + 16 * k), _stream()), "iv_segment_bounds")
+        h = out.cpu().numpy()
+        return h[:k].copy(), h[k:2 * k].copy(), h[2 * k:].copy()
+
+
+class Groups:
+    """iv_groups_t: contiguous row groups (partner frames) with their flattened-coordinate origins."""
+
+    def __init__(self, iv, seg_ranges=None, gap=1, zero_lo=False):
+        k = iv.n_seg
+        if seg_ranges is None:
+            seg_ranges = [(i, i + 1) for i in range(k)]
+        a = np.asarray([r[0] for r in seg_ranges], dtype=np.int64)
+        b = np.asarray([r[1] for r in seg_ranges], dtype=np.int64)
+        g = len(seg_ranges)
+        if g:
+            assert a[0] == 0 and b[-1] == k and np.all(a[1:] == b[:-1]), "groups must tile the segments in order"
+        self.n_groups = g
+        self.row_off = np.concatenate([iv.seg_off[a], iv.seg_off[b[-1:]]]) if g else np.zeros(1, np.int64)
+        lo = np.full(g, I64_MAX, np.int64)
+        hi = np.full(g, I64_MIN, np.int64)
+        ml = np.zeros(g, np.int64)
+        if g and k:
+            # per-group reduce of the per-segment bounds (segments of a group are consecutive)
+            lo = np.minimum.reduceat(iv.lo, a)
+            hi = np.maximum.reduceat(iv.hi, a)
+            ml = np.maximum.reduceat(iv.maxlen, a)
+        empty = lo > hi
+        lo = np.where(empty, 0, lo)
+        hi = np.where(empty, 0, hi)
+        if zero_lo:
+            if g and lo.min() < 0:
+                raise ValueError("coverage needs non-negative coordinates")
+            lo = np.zeros(g, np.int64)
+        self.lo, self.hi, self.maxlen = lo, hi, int(ml.max()) if g else 0
+        base = np.zeros(g + 1, np.int64)
+        np.cumsum((hi - lo) + int(gap), out=base[1:])
+        self.base = base
+        self.total_span = int(base[-1])
+        packed = np.concatenate([self.row_off, lo, hi, base]).astype(np.int64)
+        self.dev = _to_dev(packed, iv.device)
+        p = self.dev.data_ptr()
+        self.c = IvGroups(g, 0, p, p + 8 * (g + 1), p + 8 * (2 * g + 1), p + 8 * (3 * g + 1), self.total_span)
+
+
+class Queries:
+    """iv_queries_t over a DeviceIntervals: every segment names its partner group (-1 = none)."""
+
+    def __init__(self, iv, seg_group, seg_mode=None, slack=0, label=None):
+        self.iv = iv
+        sg = np.ascontiguousarray(seg_group, dtype=np.int32)
+        assert len(sg) == iv.n_seg
+        arr = sg if seg_mode is None else np.concatenate([sg, np.ascontiguousarray(seg_mode, dtype=np.int32)])
+        self.dev = _to_dev(arr, iv.device) if len(arr) else torch.zeros(1, dtype=torch.int32, device=iv.device)
+        p = self.dev.data_ptr()
+        self.label = label
+        self.c = IvQueries(iv.n, iv.start.data_ptr(), iv.end.data_ptr(), label.data_ptr() if label is not None else None,
+                           iv.n_seg, 0, iv.seg_off_dev.data_ptr(), p,
+                           (p + 4 * iv.n_seg) if seg_mode is not None else None, int(slack))
+
+
+class SubjectIndex:
+    """Device index over the subject ("other") intervals of ALL groups -- the NCLS replacement
+    (pyranges/methods/join.py:12).  Built by iv_index_build: radix sort of flattened starts and of
+    flattened ends, block-max skip index, direct-address rank tables."""
+
+    def __init__(self, iv, seg_ranges=None, ends_perm=False):
+        self.iv = iv
+        self.groups = Groups(iv, seg_ranges, gap=1)
+        self.flags = IV_INDEX_ENDS_PERM if ends_perm else 0
+        L = cabi.lib()
+        nbytes = L.iv_index_workspace_bytes(iv.n, self.groups.total_span, self.flags)
+        self.ws = _bytes(nbytes, iv.device)
+        self.c = IvIndex()
+        cabi.check(L.iv_index_build(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(self.groups.c), self.flags,
+                                    _ptr(self.ws), self.ws.numel(), C.byref(self.c), _stream()), "iv_index_build")
+
+    # -- counts ------------------------------------------------------------------------------------
+    def count(self, q, mode=IV_MODE_ALL, for_emit=True):
+        """-> (counts int64[nq], ws, total int64[1] device).  NCLS count / has_overlaps /
+        containment count per query (pyranges/methods/coverage.py:26-40, intersection.py:73-78)."""
+        L = cabi.lib()
+        dev = self.iv.device
+        counts = torch.empty(q.iv.n, dtype=torch.int64, device=dev)
+        ws = _bytes(L.iv_overlap_workspace_bytes(q.iv.n), dev) if for_emit else None
+        total = torch.zeros(1, dtype=torch.int64, device=dev) if for_emit else None
+        cabi.check(L.iv_count_overlaps(C.byref(self.c), C.byref(q.c), mode, _ptr(counts), _ptr(ws),
+                                       ws.numel() if ws is not None else 0, _ptr(total), _stream()),
+                   "iv_count_overlaps")
+        return counts, ws, total
+
+    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None):
+        """All (query row | label, subject row | label) pairs in query order: count -> scan -> emit
+        (NCLS.all_overlaps_both / all_containments_both / first_overlap_both, join.py:15-23)."""
+        counts, ws, total = self.count(q, mode, for_emit=True)
+        p = int(total.item())  # the one host sync: output size
+        dev = self.iv.device
+        out_q = torch.empty(p, dtype=torch.int64, device=dev) if want_q else None
+        out_s = torch.empty(p, dtype=torch.int64, device=dev) if want_s else None
+        if p:
+            cabi.check(cabi.lib().iv_emit_pairs(C.byref(self.c), C.byref(q.c), mode, _ptr(counts), _ptr(ws),
+                                                _ptr(out_q), _ptr(out_s), _ptr(s_label), _stream()), "iv_emit_pairs")
+        return counts, out_q, out_s
+
+    def coverage_bp(self, q, want_fraction=True):
+        """NCLS.coverage (pyranges/methods/coverage.py:64-68): covered bp and bp / (End - Start)."""
+        dev = self.iv.device
+        bp = torch.empty(q.iv.n, dtype=torch.int64, device=dev)
+        fr = torch.empty(q.iv.n, dtype=torch.float64, device=dev) if want_fraction else None
+        cabi.check(cabi.lib().iv_coverage_bp(C.byref(self.c), C.byref(q.c), _ptr(bp), _ptr(fr), _stream()),
+                   "iv_coverage_bp")
+        return bp, fr
+
+    def nearest(self, q, overlap=True):
+        """-> (subject row or -1, distance) per query (pyranges/methods/nearest.py:29-53,59,69,113)."""
+        assert self.flags & IV_INDEX_ENDS_PERM, "build the index with ends_perm=True for nearest"
+        dev = self.iv.device
+        row = torch.empty(q.iv.n, dtype=torch.int64, device=dev)
+        dist = torch.empty(q.iv.n, dtype=torch.int64, device=dev)
+        cabi.check(cabi.lib().iv_nearest(C.byref(self.c), C.byref(q.c), 1 if overlap else 0, _ptr(row), _ptr(dist),
+                                         _stream()), "iv_nearest")
+        return row, dist
+
+
+# ---- unary operations -------------------------------------------------------------------------------
+def _cluster_groups(iv, seg_ranges, slack):
+    g = Groups(iv, seg_ranges, gap=max(int(slack), 0) + 1)
+    return g, bits_for(g.maxlen)
+
+
+def cluster(iv, seg_ranges=None, slack=0):
+    """sort_values("Start") + annotate_clusters + global id offsets (pyranges/methods/cluster.py:11-15,
+    pyranges/pyranges_main.py:1210-1223) for all groups at once.
+    -> (row int64[n]: input row at each sorted position, id int64[n]: 1-based global cluster id, n_clusters)."""
+    L = cabi.lib()
+    g, lbits = _cluster_groups(iv, seg_ranges, slack)
+    dev = iv.device
+    ws = _bytes(L.iv_cluster_workspace_bytes(iv.n), dev)
+    row = torch.empty(iv.n, dtype=torch.int64, device=dev)
+    cid = torch.empty(iv.n, dtype=torch.int64, device=dev)
+    nc = torch.zeros(1, dtype=torch.int64, device=dev)
+    cabi.check(L.iv_cluster(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(g.c), int(slack), lbits, _ptr(row), _ptr(cid),
+                            _ptr(nc), _ptr(ws), ws.numel(), _stream()), "iv_cluster")
+    return row, cid, nc
+
+
+def merge(iv, seg_ranges=None, slack=0, want_count=True):
+    """sort_values("Start") + find_clusters (pyranges/methods/merge.py:12-14) for all groups at once.
+    -> (start, end, count | None, group int32) one row per cluster, group-major, Start order."""
+    L = cabi.lib()
+    g, lbits = _cluster_groups(iv, seg_ranges, slack)
+    dev = iv.device
+    ws = _bytes(L.iv_cluster_workspace_bytes(iv.n), dev)
+    nc = torch.zeros(1, dtype=torch.int64, device=dev)
+    cabi.check(L.iv_merge_count(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(g.c), int(slack), lbits, _ptr(nc),
+                                _ptr(ws), ws.numel(), _stream()), "iv_merge_count")
+    m = int(nc.item())
+    st = torch.empty(m, dtype=torch.int64, device=dev)
+    en = torch.empty(m, dtype=torch.int64, device=dev)
+    cnt = torch.empty(m, dtype=torch.int64, device=dev) if want_count else None
+    grp = torch.empty(m, dtype=torch.int32, device=dev)
+    cabi.check(L.iv_merge_emit(iv.n, m, C.byref(g.c), lbits, _ptr(ws), _ptr(st), _ptr(en), _ptr(cnt), _ptr(grp),
+                               _stream()), "iv_merge_emit")
+    return st, en, cnt, grp
+
+
+def coverage_rle(iv, seg_ranges=None):
+    """pyrle.methods.coverage with unit weights (pyranges/methods/to_rle.py:18) for all groups at once.
+    -> (run_off int64[n_groups+1] host, runs int64[R], values float64[R])."""
+    L = cabi.lib()
+    g = Groups(iv, seg_ranges, gap=1, zero_lo=True)
+    dev = iv.device
+    ws = _bytes(L.iv_rle_workspace_bytes(iv.n, g.n_groups), dev)
+    run_off = torch.zeros(g.n_groups + 1, dtype=torch.int64, device=dev)
+    cabi.check(L.iv_rle_count(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(g.c), _ptr(ws), ws.numel(), _ptr(run_off),
+                              _stream()), "iv_rle_count")
+    off_h = run_off.cpu().numpy()
+    r = int(off_h[-1])
+    runs = torch.empty(r, dtype=torch.int64, device=dev)
+    vals = torch.empty(r, dtype=torch.float64, device=dev)
+    cabi.check(L.iv_rle_emit(iv.n, C.byref(g.c), _ptr(ws), r, _ptr(run_off), _ptr(runs), _ptr(vals), _stream()),
+               "iv_rle_emit")
+    return off_h, runs, vals
+
+
+def radix_sort_u64(keys, values=None, begin_bit=0, end_bit=64):
+    """In-place stable LSD radix sort of a uint64 (viewed as int64 tensor) key column (+ optional payload)."""
+    L = cabi.lib()
+    dev = _use(keys.device)
+    vb = 0 if values is None else values.element_size()
+    ws = _bytes(L.iv_sort_workspace_bytes(keys.numel(), vb), dev)
+    cabi.check(L.iv_radix_sort_u64(_ptr(keys), _ptr(values), vb, keys.numel(), begin_bit, end_bit, _ptr(ws), ws.numel(),
+                                   _stream()), "iv_radix_sort_u64")
+    return keys, values

@@ -1,0 +1,242 @@
+"""GPU parity of the C-ABI kernels (through pyranges_b200.engine) against the CPU oracle on seeded inputs.
+Bit-exact: every quantity on this path is int64 (the only float, FractionOverlaps, is one IEEE division)."""
+import numpy as np
+import pytest
+
+from tests.util import canon_pairs, gen_segments, oracle_counts, oracle_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+
+    from pyranges_b200 import engine
+
+    assert torch.cuda.is_available()
+    return engine
+
+
+def _dev(eng, s, e, off):
+    return eng.DeviceIntervals.from_numpy(s, e, off)
+
+
+CASES = [
+    # (seed, n_seg_q, nq, n_seg_s, ns, maxpos, maxlen)
+    (1, 1, 50, 1, 30, 500, 60),
+    (2, 4, 2000, 4, 700, 20000, 300),
+    (3, 6, 5000, 6, 3000, 200000, 2000),
+    (4, 3, 3000, 3, 300, 300, 150),  # deep pile-up: hundreds of hits per query
+    (5, 5, 20000, 5, 9000, 3000000, 500),
+]
+
+
+def _setup(eng, case, empty_every=0):
+    seed, kq, nq, ks, ns, maxpos, maxlen = case
+    qs, qe, qoff = gen_segments(seed, kq, nq, maxpos, maxlen, empty_every=empty_every)
+    ss, se, soff = gen_segments(seed + 100, ks, ns, maxpos, maxlen)
+    seg_group = np.arange(kq, dtype=np.int32) % ks
+    if kq > 2:
+        seg_group[1] = -1  # a query key without partner frame
+    return qs, qe, qoff, ss, se, soff, seg_group
+
+
+def test_radix_sort(eng):
+    import torch
+
+    rng = np.random.default_rng(0)
+    for n, bits in [(1, 64), (1000, 20), (70000, 64), (300001, 37)]:
+        k = rng.integers(0, 2 ** min(bits, 63), n, dtype=np.int64)
+        v8 = np.arange(n, dtype=np.int64)
+        kt, vt = torch.from_numpy(k.copy()).cuda(), torch.from_numpy(v8.copy()).cuda()
+        eng.radix_sort_u64(kt, vt, 0, bits)
+        o = np.argsort(k, kind="stable")
+        assert np.array_equal(kt.cpu().numpy(), k[o])
+        assert np.array_equal(vt.cpu().numpy(), v8[o])
+        v4 = torch.arange(n, dtype=torch.int32).cuda()
+        kt = torch.from_numpy(k.copy()).cuda()
+        eng.radix_sort_u64(kt, v4, 0, bits)
+        assert np.array_equal(v4.cpu().numpy(), o.astype(np.int32))
+        kt = torch.from_numpy(k.copy()).cuda()
+        eng.radix_sort_u64(kt, None, 0, bits)
+        assert np.array_equal(kt.cpu().numpy(), np.sort(k))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("slack", [0, 7])
+def test_count_modes(eng, case, slack):
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, case, empty_every=4)
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg, slack=slack)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff))
+    for mode, name in [(eng.IV_MODE_ALL, "all"), (eng.IV_MODE_ANY, "any"), (eng.IV_MODE_CONTAIN, "contain")]:
+        c, _, total = ix.count(q, mode)
+        want = oracle_counts(qs, qe, qoff, sg, ss, se, soff, name, slack)
+        got = c.cpu().numpy()
+        assert np.array_equal(got, want), name
+        assert int(total.item()) == int(want.sum())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_pairs(eng, case):
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, case)
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff))
+    for mode, name in [(eng.IV_MODE_ALL, "all"), (eng.IV_MODE_CONTAIN, "contain")]:
+        _, a, b = ix.pairs(q, mode)
+        wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, name))
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        assert np.all(np.diff(a) >= 0), "pairs must come out in query order"
+        ga, gb = canon_pairs(a, b)
+        assert np.array_equal(ga, wa) and np.array_equal(gb, wb), name
+    # first_overlap_both: one pair per hit query, subject = head of the nested-list traversal
+    _, a, b = ix.pairs(q, eng.IV_MODE_ANY)
+    wa, wb = oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "first")
+    assert np.array_equal(a.cpu().numpy(), wa) and np.array_equal(b.cpu().numpy(), wb)
+
+
+def test_pairs_labels(eng):
+    import torch
+
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, CASES[1])
+    ql = torch.arange(len(qs), dtype=torch.int64).cuda() * 3 + 5
+    sl = torch.arange(len(ss), dtype=torch.int64).cuda() * 7 + 1
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg, label=ql)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff))
+    _, a, b = ix.pairs(q, eng.IV_MODE_ALL, s_label=sl)
+    wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "all"))
+    ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
+    assert np.array_equal(ga, wa * 3 + 5) and np.array_equal(gb, wb * 7 + 1)
+
+
+@pytest.mark.parametrize("case", CASES[:4])
+def test_coverage_bp(eng, case):
+    from oracle import oracle as orc
+
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, case)
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff))
+    bp, fr = ix.coverage_bp(q)
+    want = np.zeros(len(qs), np.int64)
+    for k in range(len(qoff) - 1):
+        g = sg[k]
+        if g < 0 or soff[g] == soff[g + 1]:
+            continue
+        t = orc.NCLS(ss[soff[g]:soff[g + 1]], se[soff[g]:soff[g + 1]], np.arange(soff[g], soff[g + 1]))
+        sl = slice(qoff[k], qoff[k + 1])
+        want[sl] = t.coverage(qs[sl], qe[sl], np.arange(qoff[k], qoff[k + 1]))
+    assert np.array_equal(bp.cpu().numpy(), want)
+    assert np.array_equal(fr.cpu().numpy(), np.nan_to_num(want / (qe - qs)))
+
+
+def _oracle_nearest(qs, qe, ss, se, mode, overlap):
+    """Composition of the reference's _nearest (pyranges/methods/nearest.py:77-132) over the oracle entry
+    points, for ONE key; returns (distance, candidate-validity helpers)."""
+    from oracle import oracle as orc
+
+    n = len(qs)
+    dist = np.full(n, -1, np.int64)
+    hit = np.zeros(n, bool)
+    if overlap:
+        t = orc.NCLS(ss, se, np.arange(len(ss)))
+        hit = t.count(qs, qe) > 0
+        dist[hit] = 0
+    rest = np.flatnonzero(~hit)
+    o_e = np.argsort(se, kind="stable")
+    o_s = np.argsort(ss, kind="stable")
+    ls = np.argsort(qs[rest], kind="stable")
+    le = np.argsort(qe[rest], kind="stable")
+    pi, pd_ = orc.nearest_previous_nonoverlapping(qs[rest][ls], se[o_e] - 1, o_e)
+    ni, nd = orc.nearest_next_nonoverlapping(qe[rest][le] - 1, ss[o_s], o_s)
+    pi2, pd2, ni2, nd2 = (np.empty(len(rest), np.int64) for _ in range(4))
+    pi2[ls], pd2[ls], ni2[le], nd2[le] = pi, pd_, ni, nd
+    if mode == "previous":
+        ri, rd = pi2, pd2
+    elif mode == "next":
+        ri, rd = ni2, nd2
+    else:
+        ri, rd = orc.nearest_nonoverlapping(pi2, pd2, ni2, nd2)
+    dist[rest] = rd
+    return dist
+
+
+@pytest.mark.parametrize("case", CASES[:4])
+@pytest.mark.parametrize("overlap", [True, False])
+def test_nearest(eng, case, overlap):
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, case)
+    kq = len(qoff) - 1
+    modes = np.asarray([k % 3 for k in range(kq)], np.int32)  # BOTH / PREVIOUS / NEXT per key
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg, seg_mode=modes)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff), ends_perm=True)
+    row, dist = ix.nearest(q, overlap=overlap)
+    row, dist = row.cpu().numpy(), dist.cpu().numpy()
+    names = {0: "both", 1: "previous", 2: "next"}
+    for k in range(kq):
+        sl = slice(qoff[k], qoff[k + 1])
+        g = sg[k]
+        if g < 0 or soff[g] == soff[g + 1]:
+            assert np.all(row[sl] == -1) and np.all(dist[sl] == -1)
+            continue
+        a, b = soff[g], soff[g + 1]
+        want = _oracle_nearest(qs[sl], qe[sl], ss[a:b], se[a:b], names[modes[k]], overlap)
+        assert np.array_equal(dist[sl], want), (k, names[modes[k]])
+        # the chosen subject must realise the distance and lie in the partner group
+        r, d, s, e = row[sl], dist[sl], qs[sl], qe[sl]
+        ok = r >= 0
+        assert np.array_equal(ok, d >= 0)
+        assert np.all((r[ok] >= a) & (r[ok] < b))
+        S, E = ss[r[ok]], se[r[ok]]
+        gap = np.where(E <= s[ok], s[ok] - E + 1, np.where(S >= e[ok], S - e[ok] + 1, 0))
+        assert np.array_equal(gap, d[ok])
+
+
+@pytest.mark.parametrize("seed,n_seg,n,maxpos,maxlen", [(1, 1, 40, 300, 40), (2, 5, 3000, 50000, 300),
+                                                         (3, 7, 20000, 3000000, 2000), (4, 2, 5000, 400, 100)])
+@pytest.mark.parametrize("slack", [0, 10, -5])
+def test_cluster_merge(eng, seed, n_seg, n, maxpos, maxlen, slack):
+    from oracle import oracle as orc
+
+    s, e, off = gen_segments(seed, n_seg, n, maxpos, maxlen, empty_every=3)
+    iv = _dev(eng, s, e, off)
+    row, cid, nc = eng.cluster(iv, slack=slack)
+    row, cid = row.cpu().numpy(), cid.cpu().numpy()
+    ms, me, mc, mg = (t.cpu().numpy() for t in eng.merge(iv, slack=slack))
+    want_row, want_id, W = [], [], []
+    base = 0
+    for k in range(n_seg):
+        a, b = off[k], off[k + 1]
+        if a == b:
+            continue
+        o = np.lexsort([np.arange(a, b), e[a:b], s[a:b]])  # canonical (Start, End, row) order
+        ids = orc.annotate_clusters(s[a:b][o], e[a:b][o], slack)
+        want_row.append(o + a)
+        want_id.append(ids + base)
+        base += ids.max()
+        cs, ce, cn = orc.find_clusters(s[a:b][o], e[a:b][o], slack)
+        W.append((cs, ce, cn, np.full(len(cs), k)))
+    assert np.array_equal(row, np.concatenate(want_row))
+    assert np.array_equal(cid, np.concatenate(want_id))
+    assert int(nc.item()) == base
+    assert np.array_equal(ms, np.concatenate([w[0] for w in W]))
+    assert np.array_equal(me, np.concatenate([w[1] for w in W]))
+    assert np.array_equal(mc, np.concatenate([w[2] for w in W]))
+    assert np.array_equal(mg, np.concatenate([w[3] for w in W]))
+
+
+@pytest.mark.parametrize("seed,n_seg,n,maxpos,maxlen", [(1, 1, 5, 30, 10), (2, 1, 40, 300, 40), (3, 5, 3000, 50000, 300),
+                                                         (4, 7, 20000, 3000000, 2000), (5, 2, 5000, 400, 100)])
+def test_coverage_rle(eng, seed, n_seg, n, maxpos, maxlen):
+    from oracle import oracle as orc
+
+    s, e, off = gen_segments(seed, n_seg, n, maxpos, maxlen, empty_every=3)
+    if seed == 2:
+        s[:3] = 0  # a key whose coverage starts at coordinate 0
+    iv = _dev(eng, s, e, off)
+    run_off, runs, vals = eng.coverage_rle(iv)
+    runs, vals = runs.cpu().numpy(), vals.cpu().numpy()
+    for k in range(n_seg):
+        a, b = off[k], off[k + 1]
+        wr, wv = orc.coverage_rle(s[a:b], e[a:b]) if b > a else (np.zeros(0, np.int64), np.zeros(0))
+        sl = slice(run_off[k], run_off[k + 1])
+        assert np.array_equal(runs[sl], wr), k
+        assert np.array_equal(vals[sl], wv), k
