@@ -15,7 +15,7 @@ $(LIB): $(OBJS)
 	$(NVCC) -shared -o $@ $(OBJS)
 
 oracle/libiv_oracle.so: oracle/iv_oracle.c
-	gcc -O3 -march=x86-64-v2 -fPIC -shared -fopenmp -o $@ $<
+	gcc -O3 -march=x86-64-v2 -fPIC -shared -o $@ $<
 
 clean:
 	rm -rf build $(LIB) oracle/libiv_oracle.so

@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- join overlap pairs/s and count_overlaps queries/s on synthetic hg38-shaped intervals.
+
+Workload (BASELINE.json configs[1]): 10 M reads (100 bp) x 200 k gene/exon annotations, strandedness=None
+(reads are keyed by (chromosome, strand), every key is joined against both strands of its chromosome).
+One "step" = one full join pass: subject index build (the reference rebuilds its NCLS on every call,
+pyranges/methods/join.py:12) -> count -> scan -> emit of all (query row, subject row) int64 pairs.
+
+  python bench.py [--gpus N --steps K --warmup W]             this repo's CUDA path
+  python bench.py --impl reference [...]                       CPU restatement of ncls on the host cores
+
+N > 1 (torchrun): every rank joins its own replicate of the workload (keys shard naturally, no data-path
+collective); ranks exchange only their per-key pair counts (one NCCL all_gather per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--annot", type=int, default=200_000)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def make_workload(args, rank):
+    from pyranges_b200 import synthetic as S
+
+    reads = S.reads(args.reads, seed=1 + 1000 * rank)
+    annot = S.annotations(args.annot, seed=2 + 1000 * rank)
+    seg_group = (np.arange(reads.n_keys) // 2).astype(np.int32)  # strandedness=None: partner = whole chromosome
+    return reads, annot, seg_group
+
+
+# ---------------------------------------------------------------------------------------------------
+def oracle_join(reads, annot, seg_group, frac=1.0, threads=1, budget_s=None):
+    """CPU restatement of the reference path: per chromosome NCLS build + all_overlaps_both of the
+    chromosome's two read keys (first `frac` of each key's rows).  -> (pairs, queries, seconds)"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as orc
+
+    groups = annot.chrom_ranges()
+
+    def one(g):
+        a, b = annot.seg_off[groups[g][0]], annot.seg_off[groups[g][1]]
+        t = orc.NCLS(annot.starts[a:b], annot.ends[a:b], np.arange(a, b, dtype=np.int64))
+        pairs = nq = 0
+        for k in np.flatnonzero(seg_group == g):
+            q0, q1 = reads.seg_off[k], reads.seg_off[k + 1]
+            q1 = q0 + int((q1 - q0) * frac)
+            x, _ = t.all_overlaps_both(reads.starts[q0:q1], reads.ends[q0:q1], np.arange(q0, q1, dtype=np.int64))
+            pairs += len(x)
+            nq += q1 - q0
+        return pairs, nq
+
+    t0 = time.perf_counter()
+    tot_p = tot_q = 0
+    done = 0
+    if threads > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            for p, q in ex.map(one, range(len(groups))):
+                tot_p += p
+                tot_q += q
+        done = len(groups)
+    else:
+        for g in range(len(groups)):
+            p, q = one(g)
+            tot_p += p
+            tot_q += q
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
+    return tot_p, tot_q, time.perf_counter() - t0, done
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path on the host cores (oracle restatement of ncls; the ncls wheel itself
+    is not installable here)."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    orc.build()
+    reads, annot, seg_group = make_workload(args, 0)
+    cores = os.cpu_count() or 1
+    threads = min(cores, len(annot.chrom_ranges()))
+    # calibrate the per-step sample so that the whole run stays within a few minutes
+    p, q, dt, _ = oracle_join(reads, annot, seg_group, frac=0.05, threads=threads)
+    frac = float(min(1.0, 0.05 * 6.0 / max(dt, 1e-3)))  # ~6 s per step at most
+    for _ in range(args.warmup):
+        oracle_join(reads, annot, seg_group, frac=frac, threads=threads)
+    t0 = time.perf_counter()
+    pairs = queries = 0
+    for _ in range(args.steps):
+        p, q, _, _ = oracle_join(reads, annot, seg_group, frac=frac, threads=threads)
+        pairs += p
+        queries += q
+    dt = time.perf_counter() - t0
+    val = pairs / dt
+    sample = "first %.1f%% of the rows of every read key (%d queries/step) x all %d annotations, %d threads over chromosomes" % (
+        100 * frac, queries // max(args.steps, 1), annot.n, threads)
+    line = {
+        "impl": "reference", "metric": "join overlap pairs/s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "count_overlaps_queries_per_s": queries / dt,
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "synthetic hg38-shaped %d reads (100 bp) x %d gene/exon annotations: join (+ count_overlaps), "
+                        "strandedness=None, per GPU" % (args.reads, args.annot),
+            "reads_per_gpu": args.reads, "annotations_per_gpu": args.annot, "keys": 48,
+            "l2": "inputs (%.0f MB of int64 query columns) exceed the 126 MB L2; no flush" % (16 * args.reads / 1e6),
+            "index_build": "inside the timed region", "parallelism": "keys sharded, %d replicate(s)" % n_gpus}
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from pyranges_b200 import _cabi as cabi
+    from pyranges_b200 import engine as E
+    from pyranges_b200 import hostapi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = cabi.lib()
+
+    reads, annot, seg_group = make_workload(args, rank)
+    groups = annot.chrom_ranges()
+    q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off, dev)
+    s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off, dev)
+    s_iv.bounds  # ingest-time metadata (per-key min Start / max End), like the chromosome table
+    nq, ns = reads.n, annot.n
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    gathered = torch.zeros(world * reads.n_keys, dtype=torch.int64, device=dev) if world > 1 else None
+    seg_off_dev = q_iv.seg_off_dev
+
+    def join_step(timers=None):
+        e = [ev() for _ in range(4)] if timers is not None else None
+        if e:
+            e[0].record()
+        ix = E.SubjectIndex(s_iv, groups)
+        q = E.Queries(q_iv, seg_group)
+        if e:
+            e[1].record()
+        counts, ws, total = ix.count(q, E.IV_MODE_ALL)
+        if e:
+            e[2].record()
+        p = int(total.item())
+        out_q = torch.empty(p, dtype=torch.int64, device=dev)
+        out_s = torch.empty(p, dtype=torch.int64, device=dev)
+        import ctypes as C
+        cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), E.IV_MODE_ALL, E._ptr(counts), E._ptr(ws), E._ptr(out_q),
+                                   E._ptr(out_s), None, E._stream()), "iv_emit_pairs")
+        if e:
+            e[3].record()
+            timers.append(e)
+        if world > 1:
+            # per-key pair counts -> every rank can derive the global output offsets (the only collective)
+            key_first = torch.searchsorted(out_q, seg_off_dev)
+            per_key = key_first[1:] - key_first[:-1]
+            dist.all_gather_into_tensor(gathered, per_key)
+        return p, out_q, out_s
+
+    def count_step():
+        ix = E.SubjectIndex(s_iv, groups)
+        q = E.Queries(q_iv, seg_group)
+        c, _, _ = ix.count(q, E.IV_MODE_ALL, for_emit=False)
+        return c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, collect=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = ev(), ev()
+        n0 = L.iv_launch_count()
+        a.record()
+        for _ in range(steps):
+            fn() if collect is None else fn(collect)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        launches = L.iv_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # ---- device-resident join (the headline `value`) ---------------------------------------------
+    p, _, _ = join_step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3)
+    t0 = time.perf_counter()
+    timers = []
+    join_ms, launches = timed(join_step, args.steps, args.warmup, collect=timers)
+    count_ms, _ = timed(count_step, args.steps, args.warmup)
+    t1 = time.perf_counter()
+    clocks = sampler.summary(t0, t1) if sampler else None
+    pairs_all = p
+    if world > 1:
+        t = torch.tensor([p], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        pairs_all = int(t.item())
+    value = pairs_all * args.steps / (join_ms / 1e3)
+    count_qps = nq * world * args.steps / (count_ms / 1e3)
+
+    # per-phase device times (same timed region): index build | count+scan | emit
+    torch.cuda.synchronize()
+    ph = np.asarray([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in timers])
+    ph_ms = ph.mean(axis=0)
+    peak, peak_src = measured_peak_gbs()
+    alg = {"iv_index_build": 24 * ns, "k_count": 16 * nq + 8 * nq, "k_emit": 24 * nq + 16 * p}
+    names = ["iv_index_build", "k_count", "k_emit"]
+    dom = int(np.argmax(ph_ms[1:])) + 1  # dominant single kernel: count or emit
+    ach = alg[names[dom]] / (ph_ms[dom] / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[names[dom]],
+                "phase_ms": {n: float(m) for n, m in zip(names, ph_ms)},
+                "pipeline_algorithmic_bytes": 24 * nq + 24 * ns + 16 * p,
+                "pipeline_achieved": (24 * nq + 24 * ns + 16 * p) / (join_ms / args.steps / 1e3) / 1e9,
+                "pipeline_frac": (24 * nq + 24 * ns + 16 * p) / (join_ms / args.steps / 1e3) / 1e9 / peak}
+
+    # ---- end to end through the host-facing call: pinned host arrays in, host index arrays out ----
+    e2e = None
+    if not args.no_e2e:
+        hq_s, hq_e = torch.from_numpy(reads.starts).pin_memory(), torch.from_numpy(reads.ends).pin_memory()
+        hs_s, hs_e = torch.from_numpy(annot.starts).pin_memory(), torch.from_numpy(annot.ends).pin_memory()
+        cap = int(p * 1.1) + 1024
+        out = (torch.empty(cap, dtype=torch.int64).pin_memory(), torch.empty(cap, dtype=torch.int64).pin_memory())
+        bounds = s_iv.bounds
+
+        def e2e_step():
+            nb = hostapi.NCLSBatch(hs_s, hs_e, annot.seg_off, groups, device=dev, bounds=bounds)
+            a, _ = nb.all_overlaps_both(hq_s, hq_e, reads.seg_off, seg_group, out=out)
+            return a.numel()
+
+        for _ in range(max(1, args.warmup)):
+            e2e_step()
+        barrier()
+        te = time.perf_counter()
+        pe = 0
+        for _ in range(args.steps):
+            pe += e2e_step()
+        barrier()
+        dt = time.perf_counter() - te
+        if world > 1:
+            t = torch.tensor([dt, float(pe)], dtype=torch.float64, device=dev)
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t)
+            dt, pe = float(tm[0].item()), float(t[1].item())
+        e2e = {"value": pe / dt, "unit": "pairs/s", "h2d_bytes_per_step": 16 * nq + 16 * ns,
+               "d2h_bytes_per_step": 16 * p, "ms_per_step": 1e3 * dt / args.steps,
+               "call": "pyranges_b200.hostapi.NCLSBatch(...).all_overlaps_both(...) on pinned host int64 arrays"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        orc.build()
+        cp, cq, cdt, done = oracle_join(reads, annot, seg_group, frac=1.0, threads=1, budget_s=args.cpu_seconds)
+        cpu = {"value": cp / cdt, "unit": "pairs/s", "cores": 1, "kind": "port",
+               "queries_per_s": cq / cdt,
+               "sample": "first %d of 24 chromosomes (%d reads) x their annotations, NCLS build + all_overlaps_both, "
+                         "%.1f s on 1 core" % (done, cq, cdt)}
+
+    if rank == 0:
+        line = {
+            "metric": "join overlap pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": join_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args, world),
+            "pairs_per_step": pairs_all, "count_overlaps_queries_per_s": count_qps,
+            "count_overlaps_ms_per_step": count_ms / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

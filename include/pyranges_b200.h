@@ -119,6 +119,8 @@ typedef struct iv_queries {
 int iv_abi_version(void);
 const char* iv_last_error_string(void);
 int iv_set_device(int device);
+/* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
+uint64_t iv_launch_count(void);
 
 /* ---- building blocks (exported for tests and the bench) -------------------------------------- */
 

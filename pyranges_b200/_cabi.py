@@ -41,6 +41,7 @@ PROTOTYPES = {
     "iv_abi_version": (C.c_int, []),
     "iv_last_error_string": (C.c_char_p, []),
     "iv_set_device": (C.c_int, [C.c_int]),
+    "iv_launch_count": (C.c_uint64, []),
     "iv_sort_workspace_bytes": (_sz, [_i64, _i32]),
     "iv_radix_sort_u64": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
     "iv_segment_bounds": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),

@@ -5,6 +5,7 @@
 
 namespace iv {
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -19,3 +20,4 @@ extern "C" int iv_set_device(int device) {
     IV_CUDA(cudaSetDevice(device));
     return IV_OK;
 }
+extern "C" uint64_t iv_launch_count(void) { return __atomic_load_n(&iv::g_launches, __ATOMIC_RELAXED); }

@@ -21,7 +21,13 @@ void set_error(const char* fmt, ...);
         }                                                                                          \
     } while (0)
 
-#define IV_LAUNCH_CHECK() IV_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here; iv_launch_count() reports the tally
+extern unsigned long long g_launches;
+#define IV_LAUNCH_CHECK()                                                                          \
+    do {                                                                                           \
+        __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);                               \
+        IV_CUDA(cudaGetLastError());                                                               \
+    } while (0)
 
 #define IV_REQUIRE(cond, code, ...)                                                                \
     do {                                                                                           \

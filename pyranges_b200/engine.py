@@ -74,9 +74,25 @@ class DeviceIntervals:
         assert self.seg_off[0] == 0 and self.seg_off[-1] == self.n
         self.n_seg = len(self.seg_off) - 1
         self.seg_off_dev = _to_dev(self.seg_off, self.device)
-        if bounds is None:
-            bounds = self._bounds()
-        self.lo, self.hi, self.maxlen = bounds
+        self._b = bounds  # (lo, hi, maxlen) per segment; computed on first use (subjects / unary ops only)
+
+    @property
+    def bounds(self):
+        if self._b is None:
+            self._b = self._bounds()
+        return self._b
+
+    @property
+    def lo(self):
+        return self.bounds[0]
+
+    @property
+    def hi(self):
+        return self.bounds[1]
+
+    @property
+    def maxlen(self):
+        return self.bounds[2]
 
     @classmethod
     def from_numpy(cls, starts, ends, seg_off, device="cuda", pinned=False):

@@ -1,0 +1,71 @@
+"""Synthetic "hg38-shaped" interval sets of the benchmark configs, modelled on
+pr.random (pyranges/__init__.py:305-331): chromosome ~ Categorical(p proportional to size), strand uniform,
+rows left in generation order inside a key.  Host-side numpy only."""
+import numpy as np
+
+HG38 = [("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 190214555), ("chr5", 181538259),
+        ("chr6", 170805979), ("chr7", 159345973), ("chr8", 145138636), ("chr9", 138394717), ("chr10", 133797422),
+        ("chr11", 135086622), ("chr12", 133275309), ("chr13", 114364328), ("chr14", 107043718),
+        ("chr15", 101991189), ("chr16", 90338345), ("chr17", 83257441), ("chr18", 80373285), ("chr19", 58617616),
+        ("chr20", 64444167), ("chr21", 46709983), ("chr22", 50818468), ("chrX", 156040895), ("chrY", 57227415)]
+SIZES = np.asarray([s for _, s in HG38], dtype=np.int64)
+STRANDS = ("+", "-")
+
+
+def keys(stranded=True):
+    """natsorted key list: (chrom, '+'), (chrom, '-') ... or chrom."""
+    if stranded:
+        return [(c, s) for c, _ in HG38 for s in STRANDS]
+    return [c for c, _ in HG38]
+
+
+class KeyedArrays:
+    """starts/ends grouped by (chromosome, strand) key: segment k = rows [seg_off[k], seg_off[k+1])."""
+
+    def __init__(self, starts, ends, key_id, n_keys):
+        order = np.argsort(key_id, kind="stable")
+        self.starts = np.ascontiguousarray(starts[order])
+        self.ends = np.ascontiguousarray(ends[order])
+        self.seg_off = np.zeros(n_keys + 1, np.int64)
+        np.cumsum(np.bincount(key_id, minlength=n_keys), out=self.seg_off[1:])
+        self.n = len(starts)
+        self.n_keys = n_keys
+
+    def chrom_ranges(self):
+        """segment ranges of the per-chromosome groups (both strands of a chromosome are adjacent)."""
+        return [(2 * c, 2 * c + 2) for c in range(self.n_keys // 2)]
+
+
+def _chrom(rng, n):
+    return rng.choice(len(SIZES), size=n, p=SIZES / SIZES.sum())
+
+
+def reads(n, seed=1, length=100, min_len=None, max_len=None):
+    """n reads: Start ~ U[0, size-len), fixed length (or U{min_len..max_len})."""
+    rng = np.random.default_rng(seed)
+    c = _chrom(rng, n)
+    strand = rng.integers(0, 2, n)
+    ln = np.full(n, length, np.int64) if min_len is None else rng.integers(min_len, max_len + 1, n)
+    s = np.floor(rng.random(n) * (SIZES[c] - ln)).astype(np.int64)
+    return KeyedArrays(s, s + ln, c * 2 + strand, 2 * len(SIZES))
+
+
+def annotations(n, seed=2):
+    """10 % genes (log-normal length, 0.5 kb .. 2 Mb), 90 % exons nested inside a random gene."""
+    rng = np.random.default_rng(seed)
+    ng = max(1, n // 10)
+    ne = n - ng
+    gc = _chrom(rng, ng)
+    gstrand = rng.integers(0, 2, ng)
+    glen = np.clip(np.floor(rng.lognormal(np.log(25000.0), 1.2, ng)), 500, 2000000).astype(np.int64)
+    glen = np.minimum(glen, SIZES[gc] - 1)
+    gs = np.floor(rng.random(ng) * (SIZES[gc] - glen)).astype(np.int64)
+    parent = rng.integers(0, ng, ne)
+    elen = np.clip(np.floor(rng.lognormal(np.log(150.0), 0.8, ne)), 20, 10000).astype(np.int64)
+    elen = np.minimum(elen, glen[parent])
+    es = gs[parent] + np.floor(rng.random(ne) * (glen[parent] - elen + 1)).astype(np.int64)
+    s = np.concatenate([gs, es])
+    e = np.concatenate([gs + glen, es + elen])
+    key = np.concatenate([gc * 2 + gstrand, gc[parent] * 2 + gstrand[parent]])
+    perm = rng.permutation(n)  # interleave genes and exons: rows are unsorted
+    return KeyedArrays(s[perm], e[perm], key[perm], 2 * len(SIZES))
