@@ -1,0 +1,549 @@
+"""Batched GPU replacement of the reference's per-key dispatcher.
+
+Same two entry points, same signatures and the same result contract as
+pyranges/multithreaded.py:182-303 (``pyrange_apply``) and :306-372 (``pyrange_apply_single``):
+a dict {key -> DataFrame} holding only the non-empty results, each with a RangeIndex.  Where the
+reference loops over the (chromosome[, strand]) keys and calls ``function(df, odf, **kwargs)`` once per
+key (building an NCLS per key), this module recognises the hot-path callables by name
+
+    _write_both, _number_overlapping, _overlap, _coverage, _nearest      (binary)
+    _cluster, _merge, coverage (pyrle.methods.coverage)                   (unary)
+
+concatenates the Start/End columns of all keys into device-resident int64 columns and runs ONE batched
+kernel sequence (pyranges_b200.engine) for every key; the pandas glue around the index arrays (row
+gathers, suffix joins, -1 fillers) follows pyranges/methods/*.py.  Any other callable raises
+NotImplementedError -- there is no CPU fallback.
+"""
+import numpy as np
+import pandas as pd
+
+from . import engine as E
+from ._natsort import natsorted
+
+_OTHER_STRAND = {"+": "-", "-": "+"}
+_SAME_STRAND = {"+": "+", "-": "-"}
+
+
+def _name(function):
+    return function if isinstance(function, str) else getattr(function, "__name__", repr(function))
+
+
+# ---- plumbing shared with the reference --------------------------------------------------------------
+def merge_dfs(df1, df2):
+    """pyranges/multithreaded.py:64-74"""
+    if not df1.empty and not df2.empty:
+        return pd.concat([df1, df2], sort=False).reset_index(drop=True)
+    elif df1.empty and df2.empty:
+        return None
+    elif df1.empty:
+        return df2
+    return df1
+
+
+def process_results(results, keys):
+    """pyranges/multithreaded.py:77-103: drop None/empty, deep copy, RangeIndex."""
+    results_dict = {k: r for k, r in zip(keys, results) if r is not None}
+    try:
+        first_item = next(iter(results_dict.values()))
+    except StopIteration:
+        return results_dict
+    if not isinstance(first_item, pd.DataFrame):
+        return results_dict
+    out = {}
+    for k, v in results_dict.items():
+        if v is None or v.empty:
+            continue
+        v = v.copy(deep=True)
+        v.index = range(len(v))
+        out[k] = v
+    return out
+
+
+def make_sparse(df):
+    cols = "Chromosome Start End Strand".split() if "Strand" in df else "Chromosome Start End".split()
+    return df[cols]
+
+
+def _dummy():
+    return pd.DataFrame(columns="Chromosome Start End".split())
+
+
+def _is_stranded(gr):
+    keys = list(gr.dfs.keys())
+    return True if not keys else isinstance(keys[0], tuple)
+
+
+# ---- device ingest --------------------------------------------------------------------------------------
+class _Frames:
+    """A list of (key, DataFrame) in natsorted key order plus their concatenated device columns."""
+
+    def __init__(self, items, device):
+        self.keys = [k for k, _ in items]
+        self.dfs = [d for _, d in items]
+        lens = np.asarray([len(d) for d in self.dfs], dtype=np.int64)
+        self.seg_off = np.zeros(len(lens) + 1, np.int64)
+        np.cumsum(lens, out=self.seg_off[1:])
+        if len(self.dfs):
+            s = np.concatenate([np.asarray(d["Start"].values, dtype=np.int64) for d in self.dfs])
+            e = np.concatenate([np.asarray(d["End"].values, dtype=np.int64) for d in self.dfs])
+        else:
+            s = e = np.zeros(0, np.int64)
+        self.starts, self.ends = s, e
+        self.iv = E.DeviceIntervals.from_numpy(s, e, self.seg_off, device)
+
+
+def _device_of(kwargs):
+    import torch
+
+    dev = kwargs.get("device")
+    if dev is None:
+        if not torch.cuda.is_available():
+            raise E.cabi.CabiError("pyranges_b200 needs a CUDA device (B200); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class _Plan:
+    """Partner selection of pyrange_apply (pyranges/multithreaded.py:221-294) for all keys at once."""
+
+    def __init__(self, self_gr, other_gr, strandedness, device):
+        assert strandedness in ["same", "opposite", False, None]
+        self_stranded, other_stranded = _is_stranded(self_gr), _is_stranded(other_gr)
+        if strandedness:
+            assert self_stranded and other_stranded, \
+                "Can only do stranded operations when both PyRanges contain strand info"
+        self.q = _Frames(natsorted(self_gr.dfs.items()), device)
+        o_items = natsorted(other_gr.dfs.items())
+        self.s = _Frames(o_items, device)
+        okeys = self.s.keys
+        if strandedness or not other_stranded:
+            # every key of other is one partner frame
+            self.group_ranges = [(i, i + 1) for i in range(len(okeys))]
+            gkey = {k: i for i, k in enumerate(okeys)}
+            self._frames = list(self.s.dfs)
+        else:
+            # strand ignored, other stranded: partner = '+' and '-' frames of the chromosome, concatenated
+            self.group_ranges, gkey, self._frames = [], {}, []
+            i = 0
+            while i < len(okeys):
+                j = i
+                while j < len(okeys) and okeys[j][0] == okeys[i][0]:
+                    j += 1
+                gkey[okeys[i][0]] = len(self.group_ranges)
+                self.group_ranges.append((i, j))
+                self._frames.append(None)  # merged lazily
+                i = j
+        strand_dict = _OTHER_STRAND if strandedness == "opposite" else _SAME_STRAND
+        sg = []
+        for k in self.q.keys:
+            if strandedness:
+                pk = (k[0], strand_dict[k[1]])
+            elif other_stranded:
+                pk = k[0] if self_stranded else k
+            else:
+                pk = k[0] if self_stranded else k
+            sg.append(gkey.get(pk, -1))
+        self.seg_group = np.asarray(sg, dtype=np.int32)
+        self.group_row_off = np.asarray([self.s.seg_off[r[0]] for r in self.group_ranges] + [self.s.iv.n], dtype=np.int64)
+
+    def partner(self, k):
+        """partner DataFrame of self key number k (0-row dummy when other has none)."""
+        g = self.seg_group[k]
+        if g < 0:
+            return _dummy()
+        f = self._frames[g]
+        if f is None:
+            a, b = self.group_ranges[g]
+            dfs = self.s.dfs[a:b]
+            f = dfs[0] if len(dfs) == 1 else merge_dfs(dfs[0], dfs[1])
+            self._frames[g] = f
+        return f
+
+    def index(self, ends_perm=False):
+        return E.SubjectIndex(self.s.iv, self.group_ranges if self.group_ranges else None, ends_perm=ends_perm)
+
+    def queries(self, seg_mode=None, slack=0):
+        return E.Queries(self.q.iv, self.seg_group, seg_mode=seg_mode, slack=slack)
+
+
+def _sparse(kwargs, df, odf):
+    sparse = kwargs.get("sparse")
+    if not sparse:
+        return df, odf
+    if sparse.get("self"):
+        df = make_sparse(df)
+    if sparse.get("other") and odf is not None and len(odf.columns):
+        odf = make_sparse(odf)
+    return df, odf
+
+
+# ---- binary operations --------------------------------------------------------------------------------------
+def null_types(h):
+    """pyranges/methods/join.py:62-92: one-row frame of "missing" values (-1 / "-1")."""
+    h2 = h.copy()
+    for n, d in zip(h, h.dtypes):
+        if n in ["Chromosome", "Strand"]:
+            continue
+        d = str(d)
+        if "bool" in d:
+            h2[n] = h2[n].astype("category")
+            d = "category"
+        if "int" in d or "float" in d:
+            null = -1
+        elif "string" in d or d in ("object", "str"):
+            null = "-1"
+        elif d == "category":
+            h2[n] = h2[n].cat.add_categories("-1")
+            null = "-1"
+        else:
+            raise Exception("Unknown dtype {} in a column {}".format(d, n))
+        h2.loc[:, n] = null
+    return h2
+
+
+def _take_with_null(df, pos):
+    """df.reindex(labels) of the reference with positions: -1 selects the null row."""
+    pos = np.asarray(pos, dtype=np.int64)
+    if (pos < 0).any():
+        nh = null_types(df.head(1))
+        df = pd.concat([df, nh])
+        pos = np.where(pos < 0, len(df) - 1, pos)
+    return df.take(pos)
+
+
+def _join_frames(scdf, ocdf, self_pos, other_pos, counts_self, kwargs):
+    """_both_indexes tail + _both_dfs + _write_both (pyranges/methods/join.py:22-154) given the inner pairs
+    as row positions into scdf / ocdf."""
+    how = kwargs.get("how")
+    suffix = kwargs.get("suffix", "_b") if not kwargs.get("new_pos") else kwargs.get("suffixes", "_a _b".split())[1]
+    if how in ["outer", "left", "right"]:
+        slab, olab = scdf.index.values, ocdf.index.values
+        ms = np.flatnonzero(counts_self == 0)
+        ms = ms[np.argsort(slab[ms], kind="stable")]  # Index.difference returns sorted labels
+        hit_o = np.zeros(len(ocdf), dtype=bool)
+        hit_o[other_pos] = True
+        mo = np.flatnonzero(~hit_o)
+        mo = mo[np.argsort(olab[mo], kind="stable")]
+        fs, fo = np.full(len(mo), -1, np.int64), np.full(len(ms), -1, np.int64)
+        if how == "outer":
+            self_pos, other_pos = np.concatenate([self_pos, ms, fs]), np.concatenate([other_pos, fo, mo])
+        elif how == "left":
+            self_pos, other_pos = np.concatenate([self_pos, ms]), np.concatenate([other_pos, fo])
+        else:
+            self_pos, other_pos = np.concatenate([self_pos, fs]), np.concatenate([other_pos, mo])
+        if kwargs.get("preserve_order"):
+            sl = np.where(self_pos >= 0, slab[np.maximum(self_pos, 0)], -1) if len(slab) else self_pos
+            ol = np.where(other_pos >= 0, olab[np.maximum(other_pos, 0)], -1) if len(olab) else other_pos
+            if how == "outer":
+                o = np.lexsort([ol, ol < 0, sl, sl < 0])
+            elif how == "left":
+                o = np.argsort(sl, kind="stable")
+            else:
+                o = np.argsort(ol, kind="stable")
+            self_pos, other_pos = self_pos[o], other_pos[o]
+        s2, o2 = _take_with_null(scdf, self_pos), _take_with_null(ocdf, other_pos)
+        if "Strand" in s2 and "Strand" in o2:
+            if how == "left":
+                x = other_pos < 0
+                if x.any():
+                    o2 = o2.copy()
+                    o2["Strand"] = np.where(x, s2["Strand"].astype(object).values, o2["Strand"].astype(object).values)
+            elif how == "right":
+                x = self_pos < 0
+                if x.any():
+                    s2 = s2.copy()
+                    s2["Strand"] = np.where(x, o2["Strand"].astype(object).values, s2["Strand"].astype(object).values)
+    else:
+        s2, o2 = scdf.take(self_pos), ocdf.take(other_pos)
+    nix = pd.RangeIndex(len(s2))
+    s2.index = nix
+    o2.index = nix
+    o2 = o2.drop("Chromosome", axis=1)
+    df = s2.join(o2, rsuffix=suffix)
+    if kwargs.get("report_overlap"):
+        df["Overlap"] = df[["End", "End" + suffix]].min(axis=1) - df[["Start", "Start" + suffix]].max(axis=1)
+    return df
+
+
+def _b_write_both(plan, kwargs):
+    """join: pyranges/methods/join.py:125-154 for all keys."""
+    how = kwargs.get("how")
+    assert (how in "containment first last outer right left".split() + [False, None]) or isinstance(how, int)
+    if how == "last":
+        raise NotImplementedError("join(how='last') is not part of the B200 hot path")
+    mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
+    ix = plan.index()
+    counts, out_q, out_s = ix.pairs(plan.queries(), mode)
+    counts, out_q, out_s = counts.cpu().numpy(), out_q.cpu().numpy(), out_s.cpu().numpy()
+    first = np.searchsorted(out_q, plan.q.seg_off)  # pairs are emitted in query-row order
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        ocdf = plan.partner(k)
+        scdf, ocdf = _sparse(kwargs, scdf, ocdf)
+        a, b = first[k], first[k + 1]
+        if scdf.empty or ocdf.empty:
+            if how in ["left", "outer"] and ocdf.empty:
+                ocdf = null_types(kwargs["example_header_other"])
+                cs = np.zeros(len(scdf), np.int64)
+                results.append(_join_frames(scdf, ocdf, np.zeros(0, np.int64), np.zeros(0, np.int64), cs, kwargs))
+            else:
+                results.append(None)
+            continue
+        g = plan.seg_group[k]
+        self_pos = out_q[a:b] - plan.q.seg_off[k]
+        other_pos = out_s[a:b] - plan.group_row_off[g]
+        cs = counts[plan.q.seg_off[k]:plan.q.seg_off[k + 1]]
+        results.append(_join_frames(scdf, ocdf, self_pos, other_pos, cs, kwargs))
+    return results
+
+
+def _b_number_overlapping(plan, kwargs):
+    """count_overlaps: pyranges/methods/coverage.py:6-45 for all keys (no pair materialisation)."""
+    keep = kwargs.get("keep_nonoverlapping", True)
+    col = kwargs.get("overlap_col", True)
+    counts, _, _ = plan.index().count(plan.queries(), E.IV_MODE_ALL, for_emit=False)
+    counts = counts.cpu().numpy()
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        ocdf = plan.partner(k)
+        if scdf.empty or (ocdf.empty and not keep):
+            results.append(None)
+            continue
+        df = scdf.copy()
+        df.insert(df.shape[1], col, counts[plan.q.seg_off[k]:plan.q.seg_off[k + 1]])
+        results.append(df if keep else df[df[col] != 0])
+    return results
+
+
+def _b_overlap(plan, kwargs):
+    """overlap: pyranges/methods/intersection.py:58-83 for all keys; only counts are needed."""
+    how = kwargs["how"]
+    assert how in "containment first".split() + [False, None]
+    mode = E.IV_MODE_ALL if not how else (E.IV_MODE_CONTAIN if how == "containment" else E.IV_MODE_ANY)
+    counts, _, _ = plan.index().count(plan.queries(), mode, for_emit=False)
+    counts = counts.cpu().numpy()
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        ocdf = plan.partner(k)
+        scdf, ocdf = _sparse(kwargs, scdf, ocdf)
+        if scdf.empty or ocdf.empty:
+            results.append(None)
+            continue
+        c = counts[plan.q.seg_off[k]:plan.q.seg_off[k + 1]]
+        pos = np.repeat(np.arange(len(c)), c)
+        if kwargs.get("return_indexes", False):
+            results.append(scdf.index.values[pos])
+        else:
+            results.append(scdf.take(pos))
+    return results
+
+
+def _b_coverage(plan, kwargs):
+    """coverage fraction: pyranges/methods/coverage.py:48-74 for all keys."""
+    col = kwargs["fraction_col"]
+    _, frac = plan.index().coverage_bp(plan.queries())
+    frac = frac.cpu().numpy()
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        if scdf.empty:
+            results.append(None)
+            continue
+        df = scdf.copy()
+        f = frac[plan.q.seg_off[k]:plan.q.seg_off[k + 1]] if not plan.partner(k).empty else 0.0
+        df.insert(df.shape[1], col, f)
+        results.append(df)
+    return results
+
+
+def _distance_name(ocdf, suffix):
+    """pyranges/methods/nearest.py:9-26"""
+    if "Distance" not in ocdf:
+        return "Distance"
+    if "Distance" + suffix not in ocdf:
+        return "Distance" + suffix
+    i = 1
+    while "Distance" + str(i) in ocdf:
+        i += 1
+    return "Distance" + str(i)
+
+
+def _b_nearest(plan, kwargs):
+    """nearest: pyranges/methods/nearest.py:77-132 for all keys."""
+    overlap, how, suffix = kwargs["overlap"], kwargs["how"], kwargs["suffix"]
+    modes = []
+    for k, key in enumerate(plan.q.keys):
+        h = how
+        if how in ("upstream", "downstream"):
+            strand = key[1] if isinstance(key, tuple) else plan.q.dfs[k].Strand.iloc[0]
+            h = ({"+": "previous", "-": "next"} if how == "upstream" else {"+": "next", "-": "previous"})[strand]
+        modes.append({"previous": E.IV_NEAREST_PREVIOUS, "next": E.IV_NEAREST_NEXT}.get(h, E.IV_NEAREST_BOTH))
+    row, dist = plan.index(ends_perm=True).nearest(plan.queries(seg_mode=np.asarray(modes, np.int32)), overlap=overlap)
+    row, dist = row.cpu().numpy(), dist.cpu().numpy()
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        ocdf = plan.partner(k)
+        if scdf.empty or ocdf.empty:
+            results.append(None)
+            continue
+        ocdf = ocdf.reset_index(drop=True)
+        sl = slice(plan.q.seg_off[k], plan.q.seg_off[k + 1])
+        r = row[sl] - plan.group_row_off[plan.seg_group[k]]
+        d = dist[sl]
+        hit = np.flatnonzero(d == 0)  # overlapping rows first, in self order (nearest.py:29-53)
+        rest = np.flatnonzero(d > 0)
+        if len(rest):
+            # the reference sorts the remaining rows by (Start, End) (sort_one_by_one, nearest.py:100)
+            s, e = scdf.Start.values[rest], scdf.End.values[rest]
+            rest = rest[np.lexsort([e, s])]
+        sel = np.concatenate([hit, rest])
+        if not len(sel):
+            results.append(None)
+            continue
+        o2 = ocdf.take(r[sel])
+        o2.index = pd.RangeIndex(len(sel))
+        o2.insert(o2.shape[1], _distance_name(o2, suffix), d[sel])
+        s2 = scdf.take(sel)
+        s2.index = o2.index
+        df = s2.join(o2, rsuffix=suffix)
+        df = df.drop("Chromosome" + suffix, axis=1)
+        results.append(df)
+    return results
+
+
+_BINARY = {
+    "_write_both": _b_write_both,
+    "_number_overlapping": _b_number_overlapping,
+    "_overlap": _b_overlap,
+    "_coverage": _b_coverage,
+    "_nearest": _b_nearest,
+}
+
+
+def pyrange_apply(function, self, other, **kwargs):
+    """Drop-in for pyranges.multithreaded.pyrange_apply (pyranges/multithreaded.py:182-303).
+
+    `function` is one of the reference's per-key callables (or its name); `self` / `other` are
+    PyRanges-like objects exposing ``.dfs``.  ``nb_cpu`` is accepted and ignored: all keys run in one
+    batched launch sequence on the current CUDA device."""
+    name = _name(function)
+    if name not in _BINARY:
+        raise NotImplementedError(
+            "pyranges_b200.pyrange_apply: %r is not on the B200 hot path (supported: %s); no CPU fallback"
+            % (name, ", ".join(sorted(_BINARY))))
+    plan = _Plan(self, other, kwargs["strandedness"], _device_of(kwargs))
+    results = _BINARY[name](plan, kwargs)
+    return process_results(results, plan.q.keys)
+
+
+# ---- unary operations -----------------------------------------------------------------------------------
+class _UnaryPlan:
+    """Key iteration of pyrange_apply_single (pyranges/multithreaded.py:324-363)."""
+
+    def __init__(self, self_gr, strand, device):
+        stranded = _is_stranded(self_gr)
+        if strand:
+            assert stranded, "Can only do stranded operation when PyRange contains strand info"
+        items = natsorted(self_gr.dfs.items())
+        self.f = _Frames(items, device)
+        keys = self.f.keys
+        if strand or not stranded:
+            self.group_ranges = [(i, i + 1) for i in range(len(keys))]
+            self.out_keys = list(keys)
+            self.frames = list(self.f.dfs)
+            self.chrom = [k[0] if isinstance(k, tuple) else k for k in keys]
+            self.strand = [k[1] if (strand and isinstance(k, tuple)) else None for k in keys]
+        else:
+            self.group_ranges, self.out_keys, self.frames, self.chrom, self.strand = [], [], [], [], []
+            i = 0
+            while i < len(keys):
+                j = i
+                while j < len(keys) and keys[j][0] == keys[i][0]:
+                    j += 1
+                self.group_ranges.append((i, j))
+                self.out_keys.append(keys[i][0])
+                dfs = self.f.dfs[i:j]
+                self.frames.append(dfs[0] if len(dfs) == 1 else merge_dfs(dfs[0], dfs[1]))
+                self.chrom.append(keys[i][0])
+                self.strand.append(None)
+                i = j
+        self.row_off = np.asarray([self.f.seg_off[r[0]] for r in self.group_ranges] + [self.f.iv.n], dtype=np.int64)
+
+
+def _u_cluster(plan, kwargs):
+    """cluster: pyranges/methods/cluster.py:4-22 per key; ids are LOCAL (1-based per key) exactly like the
+    reference's per-key result -- PyRanges.cluster adds the running offsets (pyranges_main.py:1210-1223)."""
+    slack, count = kwargs.get("slack", 0), kwargs.get("count", False)
+    row, cid, _ = E.cluster(plan.f.iv, plan.group_ranges or None, slack)
+    row, cid = row.cpu().numpy(), cid.cpu().numpy()
+    results = []
+    for g, df in enumerate(plan.frames):
+        a, b = plan.row_off[g], plan.row_off[g + 1]
+        if a == b:
+            results.append(None)
+            continue
+        if kwargs.get("sparse", {}).get("self"):
+            df = make_sparse(df)
+        cdf = df.take(row[a:b] - a)
+        ids = cid[a:b] - cid[a] + 1
+        cdf.insert(cdf.shape[1], "Cluster", ids)
+        if count:
+            cdf.insert(cdf.shape[1], "Count", np.bincount(ids)[ids])
+        results.append(cdf)
+    return results
+
+
+def _u_merge(plan, kwargs):
+    """merge: pyranges/methods/merge.py:5-38 per key."""
+    slack = kwargs.get("slack", 0)
+    st, en, cnt, grp = E.merge(plan.f.iv, plan.group_ranges or None, slack, want_count=bool(kwargs["count"]))
+    st, en, grp = st.cpu().numpy(), en.cpu().numpy(), grp.cpu().numpy()
+    cnt = cnt.cpu().numpy() if cnt is not None else None
+    first = np.searchsorted(grp, np.arange(len(plan.frames) + 1))
+    results = []
+    for g in range(len(plan.frames)):
+        a, b = first[g], first[g + 1]
+        if a == b:
+            results.append(None)
+            continue
+        nidx = pd.RangeIndex(b - a)
+        d = {"Chromosome": pd.Series(plan.chrom[g], dtype="category", index=nidx), "Start": st[a:b], "End": en[a:b]}
+        if plan.strand[g]:
+            d["Strand"] = pd.Series(plan.strand[g], dtype="category", index=nidx)
+        cdf = pd.DataFrame(d)
+        if kwargs["count"]:
+            cdf.insert(cdf.shape[1], kwargs["count_col"], cnt[a:b])
+        results.append(cdf)
+    return results
+
+
+def _u_coverage(plan, kwargs):
+    """to_rle: pyrle.methods.coverage (pyranges/methods/to_rle.py:18) per key, unit weights."""
+    from .rle import Rle
+
+    if kwargs.get("value_col"):
+        raise NotImplementedError("to_rle(value_col=...) is not on the B200 path yet (float weights are not bit-exact)")
+    run_off, runs, vals = E.coverage_rle(plan.f.iv, plan.group_ranges or None)
+    runs, vals = runs.cpu().numpy(), vals.cpu().numpy()
+    results = []
+    for g in range(len(plan.frames)):
+        if plan.row_off[g] == plan.row_off[g + 1]:
+            results.append(None)
+            continue
+        a, b = run_off[g], run_off[g + 1]
+        results.append(Rle(runs[a:b].copy(), vals[a:b].copy()))
+    return results
+
+
+_UNARY = {"_cluster": _u_cluster, "_merge": _u_merge, "coverage": _u_coverage}
+
+
+def pyrange_apply_single(function, self, **kwargs):
+    """Drop-in for pyranges.multithreaded.pyrange_apply_single (pyranges/multithreaded.py:306-372)."""
+    name = _name(function)
+    if name not in _UNARY:
+        raise NotImplementedError(
+            "pyranges_b200.pyrange_apply_single: %r is not on the B200 hot path (supported: %s); no CPU fallback"
+            % (name, ", ".join(sorted(_UNARY))))
+    plan = _UnaryPlan(self, kwargs["strand"], _device_of(kwargs))
+    results = _UNARY[name](plan, kwargs)
+    return process_results(results, plan.out_keys)

@@ -1,0 +1,145 @@
+"""ORACLE-BACKED stand-in for pyranges_b200.engine -- TEST INFRASTRUCTURE ONLY.
+
+The CPU test-suite (-m "not gpu") monkeypatches it into pyranges_b200.multithreaded so that the host
+logic (key order, partner selection, -1 fillers, frame glue) can be checked against the golden fixtures
+without a GPU.  The product never imports this module; on a GPU box the same golden cases run through the
+real CUDA engine (tests/test_gpu_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import oracle as orc
+
+IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN = 0, 1, 2
+IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+class DeviceIntervals:
+    def __init__(self, s, e, seg_off):
+        self.s, self.e, self.seg_off = np.asarray(s, np.int64), np.asarray(e, np.int64), np.asarray(seg_off, np.int64)
+        self.n, self.n_seg = len(self.s), len(self.seg_off) - 1
+
+    @classmethod
+    def from_numpy(cls, s, e, seg_off, device=None):
+        return cls(s, e, seg_off)
+
+
+class Queries:
+    def __init__(self, iv, seg_group, seg_mode=None, slack=0, label=None):
+        self.iv, self.seg_group, self.seg_mode, self.slack = iv, np.asarray(seg_group), seg_mode, slack
+
+
+class SubjectIndex:
+    def __init__(self, iv, seg_ranges=None, ends_perm=False):
+        self.iv = iv
+        if seg_ranges is None:
+            seg_ranges = [(i, i + 1) for i in range(iv.n_seg)]
+        self.off = np.asarray([iv.seg_off[a] for a, _ in seg_ranges] + [iv.n], np.int64)
+
+    def _per_key(self, q):
+        for k in range(q.iv.n_seg):
+            g = q.seg_group[k]
+            a, b = q.iv.seg_off[k], q.iv.seg_off[k + 1]
+            if g < 0 or a == b or self.off[g] == self.off[g + 1]:
+                continue
+            sa, sb = self.off[g], self.off[g + 1]
+            s, e = q.iv.s[a:b].copy(), q.iv.e[a:b].copy()
+            if q.slack:
+                s, e = np.maximum(s - q.slack, 0), e + q.slack
+            yield k, a, b, sa, sb, s, e, orc.NCLS(self.iv.s[sa:sb], self.iv.e[sa:sb], np.arange(sa, sb, dtype=np.int64))
+
+    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None):
+        A, B = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)]
+        for k, a, b, sa, sb, s, e, t in self._per_key(q):
+            ids = np.arange(a, b, dtype=np.int64)
+            fn = {IV_MODE_ALL: t.all_overlaps_both, IV_MODE_CONTAIN: t.all_containments_both,
+                  IV_MODE_ANY: t.first_overlap_both}[mode]
+            x, y = fn(s, e, ids)
+            o = np.argsort(x, kind="stable")
+            A.append(x[o])
+            B.append(y[o])
+        A, B = np.concatenate(A), np.concatenate(B)
+        return _t(np.bincount(A, minlength=q.iv.n).astype(np.int64)), _t(A), _t(B)
+
+    def count(self, q, mode=IV_MODE_ALL, for_emit=True):
+        c, _, _ = self.pairs(q, mode)
+        return c, None, _t(np.asarray([int(c.sum())]))
+
+    def coverage_bp(self, q, want_fraction=True):
+        bp = np.zeros(q.iv.n, np.int64)
+        for k, a, b, sa, sb, s, e, t in self._per_key(q):
+            bp[a:b] = t.coverage(s, e, np.arange(a, b))
+        ln = (q.iv.e - q.iv.s).astype(np.float64)
+        with np.errstate(all="ignore"):
+            fr = np.nan_to_num(bp / ln)
+        return _t(bp), _t(fr)
+
+    def nearest(self, q, overlap=True):
+        row = np.full(q.iv.n, -1, np.int64)
+        dist = np.full(q.iv.n, -1, np.int64)
+        for k, a, b, sa, sb, s, e, t in self._per_key(q):
+            S, En = self.iv.s[sa:sb], self.iv.e[sa:sb]
+            mode = IV_NEAREST_BOTH if q.seg_mode is None else q.seg_mode[k]
+            hit = np.zeros(b - a, bool)
+            if overlap:
+                x, y = t.first_overlap_both(s, e, np.arange(b - a, dtype=np.int64))
+                hit[x] = True
+                row[a + x], dist[a + x] = y, 0
+            rest = np.flatnonzero(~hit)
+            o_e, o_s = np.argsort(En, kind="stable"), np.argsort(S, kind="stable")
+            ls, le = np.argsort(s[rest], kind="stable"), np.argsort(e[rest], kind="stable")
+            pi, pd_ = orc.nearest_previous_nonoverlapping(s[rest][ls], En[o_e] - 1, o_e)
+            ni, nd = orc.nearest_next_nonoverlapping(e[rest][le] - 1, S[o_s], o_s)
+            pi2, pd2, ni2, nd2 = (np.empty(len(rest), np.int64) for _ in range(4))
+            pi2[ls], pd2[ls], ni2[le], nd2[le] = pi, pd_, ni, nd
+            if mode == IV_NEAREST_PREVIOUS:
+                ri, rd = pi2, pd2
+            elif mode == IV_NEAREST_NEXT:
+                ri, rd = ni2, nd2
+            else:
+                ri, rd = orc.nearest_nonoverlapping(pi2, pd2, ni2, nd2)
+            row[a + rest] = np.where(ri >= 0, ri + sa, -1)
+            dist[a + rest] = rd
+        return _t(row), _t(dist)
+
+
+def _ranges(iv, seg_ranges):
+    if seg_ranges is None:
+        seg_ranges = [(i, i + 1) for i in range(iv.n_seg)]
+    return [(iv.seg_off[a], iv.seg_off[b]) for a, b in seg_ranges]
+
+
+def cluster(iv, seg_ranges=None, slack=0):
+    rows, ids, base = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)], 0
+    for a, b in _ranges(iv, seg_ranges):
+        if a == b:
+            continue
+        o = np.lexsort([np.arange(a, b), iv.e[a:b], iv.s[a:b]])
+        c = orc.annotate_clusters(iv.s[a:b][o], iv.e[a:b][o], slack)
+        rows.append(o + a)
+        ids.append(c + base)
+        base += c.max()
+    return _t(np.concatenate(rows)), _t(np.concatenate(ids)), _t(np.asarray([base]))
+
+
+def merge(iv, seg_ranges=None, slack=0, want_count=True):
+    S, En, N, G = ([np.zeros(0, np.int64)] for _ in range(4))
+    for g, (a, b) in enumerate(_ranges(iv, seg_ranges)):
+        if a == b:
+            continue
+        o = np.lexsort([iv.e[a:b], iv.s[a:b]])
+        cs, ce, cn = orc.find_clusters(iv.s[a:b][o], iv.e[a:b][o], slack)
+        S.append(cs), En.append(ce), N.append(cn), G.append(np.full(len(cs), g, np.int64))
+    return _t(np.concatenate(S)), _t(np.concatenate(En)), _t(np.concatenate(N)), _t(np.concatenate(G).astype(np.int32))
+
+
+def coverage_rle(iv, seg_ranges=None):
+    off, R, V = [0], [np.zeros(0, np.int64)], [np.zeros(0, np.float64)]
+    for a, b in _ranges(iv, seg_ranges):
+        r, v = orc.coverage_rle(iv.s[a:b], iv.e[a:b]) if b > a else (np.zeros(0, np.int64), np.zeros(0))
+        R.append(r), V.append(v)
+        off.append(off[-1] + len(r))
+    return np.asarray(off, np.int64), _t(np.concatenate(R)), _t(np.concatenate(V))
