@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define IV_ABI_VERSION 1
+#define IV_ABI_VERSION 2
 
 #define IV_OK 0
 #define IV_ERR_INVALID (-1)   /* bad argument */
@@ -72,7 +72,9 @@ extern "C" {
 
 /* Row groups of a set of intervals.  Group g owns rows [row_off[g], row_off[g+1]).
  * lo[g] <= every start, hi[g] >= every end of the group.  base[] is the flattened-coordinate origin:
- * base[0] = 0, base[g+1] >= base[g] + (hi[g]-lo[g]) + gap, base[n_groups] = total_span. */
+ * base[0] = 0, base[g+1] >= base[g] + (hi[g]-lo[g]) + gap, base[n_groups] = total_span.
+ * sum_len >= sum over all rows of (end - start): sizes the stabbing lists of iv_index_build;
+ * max_len >= the largest (end - start), <= 0 = unknown (both ignored by the unary operations). */
 typedef struct iv_groups {
     int32_t n_groups;
     int32_t _pad;
@@ -81,24 +83,43 @@ typedef struct iv_groups {
     const int64_t* hi;      /* [n_groups]   */
     const int64_t* base;    /* [n_groups+1] */
     int64_t total_span;     /* host copy of base[n_groups] */
+    int64_t sum_len;
+    int64_t max_len;
 } iv_groups_t;
+
+/* One 32-byte record (= one L2 sector) per coordinate bin b = flattened coordinate >> shift. */
+typedef struct iv_binrec {
+    uint32_t bs, be;   /* #starts < b<<shift, #ends < b<<shift             */
+    uint32_t bs1, be1; /* the same ranks at the next bin boundary           */
+    uint32_t co, co1;  /* stabbing list of the bin: cross[co, co1)           */
+    uint32_t _pad[2];
+} iv_binrec_t;
+
+/* Stabbing-list entry: a subject that starts before the bin and ends after the bin's first coordinate. */
+typedef struct iv_cross {
+    uint32_t row;  /* subject row */
+    uint32_t eoff; /* min(flattened end - (b<<shift), 2^32-1) */
+} iv_cross_t;
 
 /* Subject index descriptor, filled by iv_index_build; all arrays live in the caller's workspace. */
 typedef struct iv_index {
     int64_t n;             /* subjects */
     int64_t total_span;
-    int32_t shift;         /* bin = flattened coordinate >> shift */
+    int32_t shift;         /* bin = flattened coordinate >> shift (shift <= 31) */
     int32_t flags;
-    int64_t n_bins;        /* bin tables hold n_bins + 1 entries */
+    int64_t n_bins;        /* bins[] holds n_bins + 1 records */
+    int64_t cross_cap;     /* capacity of cross[] */
     const uint64_t* key_s; /* [n] flattened starts, ascending */
     const uint32_t* row_s; /* [n] subject row of each entry of key_s */
     const uint64_t* end_s; /* [n] flattened end of the same entries (start order) */
     const uint64_t* key_e; /* [n] flattened ends, ascending */
     const uint32_t* row_e; /* [n] subject row of key_e entries (IV_INDEX_ENDS_PERM) or NULL */
-    const uint64_t* max1;  /* [ceil(n/64)]   max end_s per 64 entries   (skip index) */
-    const uint64_t* max2;  /* [ceil(n/4096)] max end_s per 4096 entries (skip index) */
-    const uint32_t* bin_s; /* [n_bins+1] #key_s < (b << shift) */
-    const uint32_t* bin_e; /* [n_bins+1] #key_e < (b << shift) */
+    const uint32_t* soff;  /* [n] key_s - (bin << shift)                      (start order) */
+    const uint32_t* seoff; /* [n] min(end_s - (bin of key_s << shift), 2^32-1) (start order) */
+    const uint32_t* eoff;  /* [n] key_e - (bin << shift)                      (end order)   */
+    const iv_binrec_t* bins;
+    const iv_cross_t* cross;
+    const uint32_t* cross_p; /* start-order position of every cross[] entry */
     iv_groups_t groups;
 } iv_index_t;
 
@@ -130,14 +151,14 @@ size_t iv_sort_workspace_bytes(int64_t n, int32_t value_bytes);
 int iv_radix_sort_u64(uint64_t* keys, void* values, int32_t value_bytes, int64_t n, int32_t begin_bit,
                       int32_t end_bit, void* ws, size_t ws_bytes, void* stream);
 
-/* out_lo[k] = min start, out_hi[k] = max end, out_maxlen[k] = max(end-start) of segment k
- * (INT64_MAX / INT64_MIN / 0 for an empty segment). */
+/* out_lo[k] = min start, out_hi[k] = max end, out_maxlen[k] = max(end-start), out_sumlen[k] = sum(end-start)
+ * of segment k (INT64_MAX / INT64_MIN / 0 / 0 for an empty segment). */
 int iv_segment_bounds(const int64_t* starts, const int64_t* ends, const int64_t* seg_off, int32_t n_seg,
-                      int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, void* stream);
+                      int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, int64_t* out_sumlen, void* stream);
 
 /* ---- binary operations ------------------------------------------------------------------------ */
 
-size_t iv_index_workspace_bytes(int64_t n, int64_t total_span, int32_t flags);
+size_t iv_index_workspace_bytes(int64_t n, int64_t total_span, int64_t sum_len, int32_t flags);
 int iv_index_build(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups,
                    int32_t flags, void* ws, size_t ws_bytes, iv_index_t* out, void* stream);
 

@@ -13,20 +13,21 @@ IV_OK = 0
 IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN = 0, 1, 2
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
-IV_ABI_VERSION = 1
+IV_ABI_VERSION = 2
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
 
 
 class IvGroups(C.Structure):
     _fields_ = [("n_groups", _i32), ("_pad", _i32), ("row_off", _vp), ("lo", _vp), ("hi", _vp), ("base", _vp),
-                ("total_span", _i64)]
+                ("total_span", _i64), ("sum_len", _i64), ("max_len", _i64)]
 
 
 class IvIndex(C.Structure):
     _fields_ = [("n", _i64), ("total_span", _i64), ("shift", _i32), ("flags", _i32), ("n_bins", _i64),
-                ("key_s", _vp), ("row_s", _vp), ("end_s", _vp), ("key_e", _vp), ("row_e", _vp), ("max1", _vp),
-                ("max2", _vp), ("bin_s", _vp), ("bin_e", _vp), ("groups", IvGroups)]
+                ("cross_cap", _i64), ("key_s", _vp), ("row_s", _vp), ("end_s", _vp), ("key_e", _vp), ("row_e", _vp),
+                ("soff", _vp), ("seoff", _vp), ("eoff", _vp), ("bins", _vp), ("cross", _vp), ("cross_p", _vp),
+                ("groups", IvGroups)]
 
 
 class IvQueries(C.Structure):
@@ -44,8 +45,8 @@ PROTOTYPES = {
     "iv_launch_count": (C.c_uint64, []),
     "iv_sort_workspace_bytes": (_sz, [_i64, _i32]),
     "iv_radix_sort_u64": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
-    "iv_segment_bounds": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
-    "iv_index_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "iv_segment_bounds": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "iv_index_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "iv_index_build": (C.c_int, [_vp, _vp, _i64, _PG, _i32, _vp, _sz, _PI, _vp]),
     "iv_overlap_workspace_bytes": (_sz, [_i64]),
     "iv_count_overlaps": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _sz, _vp, _vp]),

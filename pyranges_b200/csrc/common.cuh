@@ -63,6 +63,15 @@ static inline int bits_for(uint64_t v) {  // number of bits needed to represent 
 size_t radix_sort_temp_bytes(int64_t n);
 // Sorts keys (+ optional 4/8-byte values) on bits [begin_bit, end_bit) ping-ponging between
 // (k0,v0) and (k1,v1); input is in (k0,v0).  *result_buf = 0/1 says where the sorted data is.
+// several independent sorts of the same length in one launch sequence (blockIdx.y = job)
+constexpr int RS_MAX_JOBS = 2;
+struct SortJob {
+    uint64_t *k0, *k1;
+    void *v0, *v1;
+    int vb;
+};
+int radix_sort_multi(const SortJob* jobs, int njobs, int64_t n, int begin_bit, int end_bit, void* temp,
+                     size_t temp_bytes, cudaStream_t stream, int* result_buf);
 int radix_sort_pingpong(uint64_t* k0, uint64_t* k1, void* v0, void* v1, int value_bytes, int64_t n,
                         int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t stream,
                         int* result_buf);

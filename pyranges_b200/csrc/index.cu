@@ -4,9 +4,16 @@
 // All keys (chromosome/strand groups) are indexed at once in a FLATTENED coordinate:
 //     x' = clamp(x, lo[g], hi[g]) - lo[g] + base[g]
 // so that one global sorted array serves every group and a query never needs a per-group search.
-// Pieces:  key_s/row_s  starts sorted (+ subject row),  end_s  ends in start order,
-//          key_e[/row_e] ends sorted,  max1/max2  block maxima of end_s (skip index for the
-//          stabbing scan),  bin_s/bin_e  direct-address rank tables (bin = x' >> shift).
+// Pieces:  key_s/row_s  starts sorted (+ subject row),  end_s  ends in start order,  key_e[/row_e] ends
+//          sorted;  soff/seoff/eoff  the same values as 32-bit offsets from their bin origin;
+//          bins[]   one 32-byte record per coordinate bin (bin = x' >> shift): start rank, end rank and
+//                   stabbing-list range at the bin's origin and at the next one (one L2 sector answers
+//                   "how many starts / ends lie before x" up to a scan of the bin's own few entries);
+//          cross[]  per-bin stabbing lists: the subjects that start before the bin and are still open at
+//                   its origin.  A query starting in bin b overlaps, besides the starts inside
+//                   [s, e), exactly the members of cross[b] that end after s and the bin's own earlier
+//                   starts that end after s -- no scan over non-hits (the NCLS nesting replaced by
+//                   direct addressing).  sum(len)/binwidth + n bounds the list storage.
 #include "common.cuh"
 
 namespace iv {
@@ -14,48 +21,53 @@ namespace iv {
 constexpr int IX_THREADS = 256;
 
 // ---- per-segment bounds (ingest-time metadata) ------------------------------------------------------------------
-__global__ void k_bounds_init(int64_t* lo, int64_t* hi, int64_t* ml, int n) {
+__global__ void k_bounds_init(int64_t* lo, int64_t* hi, int64_t* ml, int64_t* sl, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         lo[i] = INT64_MAX;
         hi[i] = INT64_MIN;
         ml[i] = 0;
+        sl[i] = 0;
     }
 }
 
 constexpr int BD_SPLIT = 64;
 __global__ void __launch_bounds__(IX_THREADS)
 k_bounds(const int64_t* __restrict__ s, const int64_t* __restrict__ e, const int64_t* __restrict__ seg_off,
-         int64_t* lo, int64_t* hi, int64_t* ml) {
-    __shared__ long long sm[3][IX_THREADS / 32];
+         int64_t* lo, int64_t* hi, int64_t* ml, int64_t* sl) {
+    __shared__ long long sm[4][IX_THREADS / 32];
     int seg = blockIdx.x;
     int64_t a = seg_off[seg], b = seg_off[seg + 1];
     int64_t len = b - a;
     int64_t chunk = (len + BD_SPLIT - 1) / BD_SPLIT;
     int64_t ca = a + chunk * blockIdx.y, cb = ca + chunk < b ? ca + chunk : b;
-    long long mn = INT64_MAX, mx = INT64_MIN, m = 0;
+    long long mn = INT64_MAX, mx = INT64_MIN, m = 0, sum = 0;
     for (int64_t i = ca + threadIdx.x; i < cb; i += IX_THREADS) {
         long long x = s[i], y = e[i];
         mn = x < mn ? x : mn;
         mx = y > mx ? y : mx;
         m = (y - x) > m ? (y - x) : m;
+        sum += y > x ? y - x : 0;
     }
     mn = warp_min(mn);
     mx = warp_max(mx);
     m = warp_max(m);
+    sum = warp_sum(sum);
     int w = threadIdx.x >> 5;
-    if (lane_id() == 0) { sm[0][w] = mn; sm[1][w] = mx; sm[2][w] = m; }
+    if (lane_id() == 0) { sm[0][w] = mn; sm[1][w] = mx; sm[2][w] = m; sm[3][w] = sum; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < IX_THREADS / 32; k++) {
             mn = sm[0][k] < mn ? sm[0][k] : mn;
             mx = sm[1][k] > mx ? sm[1][k] : mx;
             m = sm[2][k] > m ? sm[2][k] : m;
+            sum += sm[3][k];
         }
         if (ca < cb) {
             atomicMin((long long*)lo + seg, mn);
             atomicMax((long long*)hi + seg, mx);
             atomicMax((long long*)ml + seg, m);
+            atomicAdd((unsigned long long*)sl + seg, (unsigned long long)sum);
         }
     }
 }
@@ -64,7 +76,7 @@ k_bounds(const int64_t* __restrict__ s, const int64_t* __restrict__ e, const int
 __global__ void __launch_bounds__(IX_THREADS)
 k_flatten_subjects(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, iv_groups_t G,
                    uint64_t* __restrict__ key_s, uint32_t* __restrict__ row_s, uint64_t* __restrict__ key_e,
-                   uint32_t* __restrict__ row_e) {
+                   uint32_t* __restrict__ row_e) {  // row_e is always written (the batched sort carries it)
     __shared__ int span[2];
     int64_t first = (int64_t)blockIdx.x * IX_THREADS;
     int64_t last = first + IX_THREADS - 1 < n - 1 ? first + IX_THREADS - 1 : n - 1;
@@ -79,99 +91,141 @@ k_flatten_subjects(const int64_t* __restrict__ s, const int64_t* __restrict__ e,
     if (row_e) row_e[i] = (uint32_t)i;
 }
 
-// end_s[p] = flattened end of the subject at start-sorted position p; block maxima per 64 / 4096
+// Per start-sorted position p: exact flattened end, 32-bit bin offsets, and the rank fields of every bin
+// whose origin falls between the previous key and this one (bs of bin b = first p with bin(key) >= b).
+// blockIdx.y == 0: start order (also counts the bins every subject crosses); == 1: end order.
 __global__ void __launch_bounds__(IX_THREADS)
-k_gather_ends(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const uint32_t* __restrict__ row_s,
-              uint64_t* __restrict__ end_s, uint64_t* __restrict__ max1, uint64_t* __restrict__ max2) {
+k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const uint64_t* __restrict__ key_s,
+               const uint32_t* __restrict__ row_s, const uint64_t* __restrict__ key_e, int shift, int64_t n_bins,
+               uint64_t* __restrict__ end_s, uint32_t* __restrict__ soff, uint32_t* __restrict__ seoff,
+               uint32_t* __restrict__ eoff, iv_binrec_t* __restrict__ bins, uint32_t* __restrict__ ccnt) {
     __shared__ int span[2];
-    __shared__ unsigned long long m1[64];
-    int64_t first = (int64_t)blockIdx.x * 4096;
-    int64_t last = first + 4095 < n - 1 ? first + 4095 : n - 1;
-    // sorted position p of group g lies in the same row range as the group's rows
-    SegSpan sp = block_seg_span(G.row_off, G.n_groups, first, last, span);
-    if (threadIdx.x < 64) m1[threadIdx.x] = 0;
-    __syncthreads();
-#pragma unroll 4
-    for (int it = 0; it < 16; it++) {
-        int li = it * IX_THREADS + threadIdx.x;
-        int64_t p = first + li;
-        unsigned long long v = 0;
-        if (p < n) {
-            int g = sp.of(G.row_off, p);
-            v = (unsigned long long)(e[__ldg(row_s + p)] + (__ldg(G.base + g) - __ldg(G.lo + g)));
-            end_s[p] = v;
+    const int64_t first = (int64_t)blockIdx.x * IX_THREADS;
+    const int64_t p = first + threadIdx.x;
+    if (blockIdx.y == 0) {
+        // sorted position p of group g lies in the same row range as the group's rows
+        const int64_t last = first + IX_THREADS - 1 < n - 1 ? first + IX_THREADS - 1 : n - 1;
+        SegSpan sp = block_seg_span(G.row_off, G.n_groups, first, last, span);
+        if (p >= n) return;
+        const int g = sp.of(G.row_off, p);
+        const uint64_t k = key_s[p];
+        const uint64_t E = (uint64_t)(e[__ldg(row_s + p)] + (__ldg(G.base + g) - __ldg(G.lo + g)));
+        end_s[p] = E;
+        const int64_t b = (int64_t)(k >> shift);
+        const uint64_t origin = (uint64_t)b << shift;
+        soff[p] = (uint32_t)(k - origin);
+        const uint64_t d = E - origin;
+        seoff[p] = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
+        const int64_t bprev = p ? (int64_t)(key_s[p - 1] >> shift) : -1;
+        for (int64_t bb = bprev + 1; bb <= b; bb++) {
+            bins[bb].bs = (uint32_t)p;
+            if (bb) bins[bb - 1].bs1 = (uint32_t)p;
         }
-        // 64-entry chunk = two warps; reduce per warp then one smem atomic
-        unsigned long long wm = warp_max(v);
-        if (lane_id() == 0) atomicMax(&m1[li >> 6], wm);
-    }
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        int64_t c = (first >> 6) + threadIdx.x;
-        if ((c << 6) < n) max1[c] = m1[threadIdx.x];
-    }
-    if (threadIdx.x < 32) {
-        unsigned long long a = m1[threadIdx.x], b = m1[threadIdx.x + 32];
-        a = a > b ? a : b;
-        a = warp_max(a);
-        if (threadIdx.x == 0) max2[blockIdx.x] = a;
+        if (p == n - 1)
+            for (int64_t bb = b + 1; bb <= n_bins + 1; bb++) {
+                if (bb <= n_bins) bins[bb].bs = (uint32_t)n;
+                bins[bb - 1].bs1 = (uint32_t)n;
+            }
+        // bins b+1 .. bin(E-1) are crossed: the subject is open at their origin
+        if (E > k) {
+            const int64_t bl = (int64_t)((E - 1) >> shift);
+            for (int64_t bb = b + 1; bb <= bl; bb++) atomicAdd(ccnt + bb, 1u);
+        }
+    } else {
+        if (p >= n) return;
+        const uint64_t k = key_e[p];
+        const int64_t b = (int64_t)(k >> shift);
+        eoff[p] = (uint32_t)(k - ((uint64_t)b << shift));
+        const int64_t bprev = p ? (int64_t)(key_e[p - 1] >> shift) : -1;
+        for (int64_t bb = bprev + 1; bb <= b; bb++) {
+            bins[bb].be = (uint32_t)p;
+            if (bb) bins[bb - 1].be1 = (uint32_t)p;
+        }
+        if (p == n - 1)
+            for (int64_t bb = b + 1; bb <= n_bins + 1; bb++) {
+                if (bb <= n_bins) bins[bb].be = (uint32_t)n;
+                bins[bb - 1].be1 = (uint32_t)n;
+            }
     }
 }
 
-// bin[b] = #keys < (b << shift)   for b in [0, n_bins]
+// stabbing lists: entry order inside a list is arbitrary (atomic cursor)
 __global__ void __launch_bounds__(IX_THREADS)
-k_build_bins(const uint64_t* __restrict__ key_s, const uint64_t* __restrict__ key_e, int64_t n, int shift,
-             int64_t n_bins, uint32_t* __restrict__ bin_s, uint32_t* __restrict__ bin_e) {
-    int64_t b = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
-    if (b > n_bins) return;
-    uint64_t x = (uint64_t)b << shift;
-    const uint64_t* keys = blockIdx.y == 0 ? key_s : key_e;
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (__ldg(keys + mid) < x) lo = mid + 1; else hi = mid;
+k_cross_fill(int64_t n, const uint64_t* __restrict__ key_s, const uint64_t* __restrict__ end_s,
+             const uint32_t* __restrict__ row_s, int shift, const uint32_t* __restrict__ coff,
+             uint32_t* __restrict__ cursor, int64_t cap, iv_cross_t* __restrict__ cross, uint32_t* __restrict__ cross_p) {
+    const int64_t p = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
+    if (p >= n) return;
+    const uint64_t k = key_s[p], E = end_s[p];
+    if (E <= k) return;
+    const int64_t b = (int64_t)(k >> shift), bl = (int64_t)((E - 1) >> shift);
+    const uint32_t row = __ldg(row_s + p);
+    for (int64_t bb = b + 1; bb <= bl; bb++) {
+        const uint64_t d = E - ((uint64_t)bb << shift);
+        const int64_t at = (int64_t)__ldg(coff + bb) + atomicAdd(cursor + bb, 1u);
+        if (at < cap) {
+            iv_cross_t c;
+            c.row = row;
+            c.eoff = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
+            cross[at] = c;
+            cross_p[at] = (uint32_t)p;
+        }
     }
-    (blockIdx.y == 0 ? bin_s : bin_e)[b] = (uint32_t)lo;
+}
+
+__global__ void __launch_bounds__(IX_THREADS)
+k_bins_cross(int64_t n_bins, const uint32_t* __restrict__ coff, iv_binrec_t* __restrict__ bins) {
+    const int64_t b = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
+    if (b > n_bins) return;
+    bins[b].co = coff[b];
+    bins[b].co1 = coff[b + 1];
 }
 
 struct IndexLayout {
-    uint64_t *ks0, *ks1, *ke0, *ke1, *end_s, *max1, *max2;
-    uint32_t *rs0, *rs1, *re0, *re1, *bin_s, *bin_e;
+    uint64_t *ks0, *ks1, *ke0, *ke1, *end_s;
+    uint32_t *rs0, *rs1, *re0, *re1, *soff, *seoff, *eoff, *ccnt, *cursor, *cross_p, *scan_tmp;
+    iv_binrec_t* bins;
+    iv_cross_t* cross;
     void* sort_temp;
     int shift;
-    int64_t n_bins;
+    int64_t n_bins, cross_cap;
 };
 
-static void choose_bins(int64_t n, int64_t span, int* shift, int64_t* n_bins) {
-    // about two bins per subject, between 2^10 and 2^26 bins
+// about two bins per subject (2^10 .. 2^26 bins), coarser when long subjects would blow the stabbing lists up
+static void choose_bins(int64_t n, int64_t span, int64_t sum_len, int* shift, int64_t* n_bins, int64_t* cross_cap) {
     int64_t target = 1024;
     while (target < 2 * n && target < ((int64_t)1 << 26)) target <<= 1;
     int s = 0;
     while ((span >> s) > target) s++;
+    if (sum_len < 0) sum_len = 0;
+    while (s < 31 && (sum_len >> s) > 6 * (n > 1024 ? n : 1024)) s++;
+    if (s > 31) s = 31;  // bin offsets are 32-bit
     *shift = s;
     *n_bins = (span >> s) + 1;
+    *cross_cap = (sum_len >> s) + n + 16;
 }
 
-static void plan_index(int64_t n, int64_t span, int flags, Bump& b, IndexLayout& L) {
+static void plan_index(int64_t n, int64_t span, int64_t sum_len, int flags, Bump& b, IndexLayout& L) {
     size_t nn = (size_t)(n > 0 ? n : 1);
-    choose_bins(n, span, &L.shift, &L.n_bins);
+    choose_bins(n, span, sum_len, &L.shift, &L.n_bins, &L.cross_cap);
     L.ks0 = b.take<uint64_t>(nn);
     L.ks1 = b.take<uint64_t>(nn);
     L.rs0 = b.take<uint32_t>(nn);
     L.rs1 = b.take<uint32_t>(nn);
     L.ke0 = b.take<uint64_t>(nn);
     L.ke1 = b.take<uint64_t>(nn);
-    if (flags & IV_INDEX_ENDS_PERM) {
-        L.re0 = b.take<uint32_t>(nn);
-        L.re1 = b.take<uint32_t>(nn);
-    } else {
-        L.re0 = L.re1 = nullptr;
-    }
+    L.re0 = b.take<uint32_t>(nn);
+    L.re1 = b.take<uint32_t>(nn);
     L.end_s = b.take<uint64_t>(nn);
-    L.max1 = b.take<uint64_t>((size_t)cdiv(nn, 64) + 64);
-    L.max2 = b.take<uint64_t>((size_t)cdiv(nn, 4096) + 1);
-    L.bin_s = b.take<uint32_t>((size_t)L.n_bins + 2);
-    L.bin_e = b.take<uint32_t>((size_t)L.n_bins + 2);
+    L.soff = b.take<uint32_t>(nn);
+    L.seoff = b.take<uint32_t>(nn);
+    L.eoff = b.take<uint32_t>(nn);
+    L.bins = b.take<iv_binrec_t>((size_t)L.n_bins + 2);
+    L.ccnt = b.take<uint32_t>((size_t)L.n_bins + 4);
+    L.cursor = b.take<uint32_t>((size_t)L.n_bins + 4);
+    L.scan_tmp = b.take<uint32_t>(scan_u32_large_temp_elems(L.n_bins + 2) + 64);
+    L.cross = b.take<iv_cross_t>((size_t)L.cross_cap);
+    L.cross_p = b.take<uint32_t>((size_t)L.cross_cap);
     L.sort_temp = b.take<char>(radix_sort_temp_bytes(n));
 }
 
@@ -180,21 +234,24 @@ static void plan_index(int64_t n, int64_t span, int flags, Bump& b, IndexLayout&
 using namespace iv;
 
 extern "C" int iv_segment_bounds(const int64_t* starts, const int64_t* ends, const int64_t* seg_off, int32_t n_seg,
-                                 int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, void* stream) {
+                                 int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, int64_t* out_sumlen,
+                                 void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     IV_REQUIRE(n_seg >= 0, IV_ERR_INVALID, "iv_segment_bounds: n_seg < 0");
     if (n_seg == 0) return IV_OK;
-    k_bounds_init<<<(n_seg + 255) / 256, 256, 0, st>>>(out_lo, out_hi, out_maxlen, n_seg);
+    IV_REQUIRE(out_lo && out_hi && out_maxlen && out_sumlen, IV_ERR_INVALID, "iv_segment_bounds: null output");
+    k_bounds_init<<<(n_seg + 255) / 256, 256, 0, st>>>(out_lo, out_hi, out_maxlen, out_sumlen, n_seg);
     IV_LAUNCH_CHECK();
-    k_bounds<<<dim3((unsigned)n_seg, BD_SPLIT), IX_THREADS, 0, st>>>(starts, ends, seg_off, out_lo, out_hi, out_maxlen);
+    k_bounds<<<dim3((unsigned)n_seg, BD_SPLIT), IX_THREADS, 0, st>>>(starts, ends, seg_off, out_lo, out_hi, out_maxlen,
+                                                                      out_sumlen);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }
 
-extern "C" size_t iv_index_workspace_bytes(int64_t n, int64_t total_span, int32_t flags) {
+extern "C" size_t iv_index_workspace_bytes(int64_t n, int64_t total_span, int64_t sum_len, int32_t flags) {
     Bump b(nullptr, 0);
     IndexLayout L;
-    plan_index(n, total_span > 0 ? total_span : 1, flags, b, L);
+    plan_index(n, total_span > 0 ? total_span : 1, sum_len, flags, b, L);
     return b.off + 256;
 }
 
@@ -205,11 +262,13 @@ extern "C" int iv_index_build(const int64_t* starts, const int64_t* ends, int64_
     IV_REQUIRE(n < ((int64_t)1 << 31), IV_ERR_RANGE, "iv_index_build: more than 2^31-1 subjects");
     const iv_groups_t& G = *groups;
     int64_t span = G.total_span > 0 ? G.total_span : 1;
-    IV_REQUIRE(span < ((int64_t)1 << 62), IV_ERR_RANGE, "iv_index_build: flattened span too large");
+    IV_REQUIRE(span < ((int64_t)1 << 56), IV_ERR_RANGE, "iv_index_build: flattened span too large");
     Bump b(ws, ws_bytes);
     IndexLayout L;
-    plan_index(n, span, flags, b, L);
+    plan_index(n, span, G.sum_len, flags, b, L);
     IV_REQUIRE(b.fits(), IV_ERR_WORKSPACE, "iv_index_build: workspace %zu < %zu", ws_bytes, b.off);
+    IV_REQUIRE(L.cross_cap < ((int64_t)1 << 32), IV_ERR_RANGE, "iv_index_build: stabbing lists exceed 2^32 entries");
+    IV_REQUIRE(L.n_bins <= ((int64_t)1 << 28), IV_ERR_RANGE, "iv_index_build: flattened span needs too many bins");
 
     memset(out, 0, sizeof(*out));
     out->n = n;
@@ -217,12 +276,13 @@ extern "C" int iv_index_build(const int64_t* starts, const int64_t* ends, int64_
     out->shift = L.shift;
     out->flags = flags;
     out->n_bins = L.n_bins;
+    out->cross_cap = L.cross_cap;
     out->groups = G;
     out->key_s = L.ks0; out->row_s = L.rs0; out->key_e = L.ke0; out->row_e = L.re0;
-    out->end_s = L.end_s; out->max1 = L.max1; out->max2 = L.max2; out->bin_s = L.bin_s; out->bin_e = L.bin_e;
+    out->end_s = L.end_s; out->soff = L.soff; out->seoff = L.seoff; out->eoff = L.eoff;
+    out->bins = L.bins; out->cross = L.cross; out->cross_p = L.cross_p;
     if (n == 0) {
-        IV_CUDA(cudaMemsetAsync(L.bin_s, 0, ((size_t)L.n_bins + 2) * 4, st));
-        IV_CUDA(cudaMemsetAsync(L.bin_e, 0, ((size_t)L.n_bins + 2) * 4, st));
+        IV_CUDA(cudaMemsetAsync(L.bins, 0, ((size_t)L.n_bins + 2) * sizeof(iv_binrec_t), st));
         return IV_OK;
     }
     unsigned nb = (unsigned)cdiv(n, IX_THREADS);
@@ -230,20 +290,23 @@ extern "C" int iv_index_build(const int64_t* starts, const int64_t* ends, int64_
     IV_LAUNCH_CHECK();
     int bits = bits_for((uint64_t)span);
     int res = 0;
-    size_t tb = radix_sort_temp_bytes(n);
-    int rc = radix_sort_pingpong(L.ks0, L.ks1, L.rs0, L.rs1, 4, n, 0, bits, L.sort_temp, tb, st, &res);
+    SortJob jobs[2] = {{L.ks0, L.ks1, L.rs0, L.rs1, 4},
+                       {L.ke0, L.ke1, L.re0, L.re1, (flags & IV_INDEX_ENDS_PERM) ? 4 : 0}};
+    int rc = radix_sort_multi(jobs, 2, n, 0, bits, L.sort_temp, radix_sort_temp_bytes(n), st, &res);
     if (rc != IV_OK) return rc;
-    if (res) { out->key_s = L.ks1; out->row_s = L.rs1; }
-    if (flags & IV_INDEX_ENDS_PERM)
-        rc = radix_sort_pingpong(L.ke0, L.ke1, L.re0, L.re1, 4, n, 0, bits, L.sort_temp, tb, st, &res);
-    else
-        rc = radix_sort_pingpong(L.ke0, L.ke1, nullptr, nullptr, 0, n, 0, bits, L.sort_temp, tb, st, &res);
-    if (rc != IV_OK) return rc;
-    if (res) { out->key_e = L.ke1; out->row_e = (flags & IV_INDEX_ENDS_PERM) ? L.re1 : nullptr; }
-    k_gather_ends<<<(unsigned)cdiv(n, 4096), IX_THREADS, 0, st>>>(ends, n, G, out->row_s, L.end_s, L.max1, L.max2);
+    if (res) { out->key_s = L.ks1; out->row_s = L.rs1; out->key_e = L.ke1; out->row_e = L.re1; }
+    if (!(flags & IV_INDEX_ENDS_PERM)) out->row_e = nullptr;
+    // ccnt and cursor are adjacent in the workspace: one memset clears both
+    IV_CUDA(cudaMemsetAsync(L.ccnt, 0, (size_t)((char*)L.scan_tmp - (char*)L.ccnt), st));
+    k_index_arrays<<<dim3(nb, 2), IX_THREADS, 0, st>>>(ends, n, G, out->key_s, out->row_s, out->key_e, L.shift, L.n_bins,
+                                                       L.end_s, L.soff, L.seoff, L.eoff, L.bins, L.ccnt);
     IV_LAUNCH_CHECK();
-    k_build_bins<<<dim3((unsigned)cdiv(L.n_bins + 1, IX_THREADS), 2), IX_THREADS, 0, st>>>(
-        out->key_s, out->key_e, n, L.shift, L.n_bins, L.bin_s, L.bin_e);
+    rc = scan_exclusive_u32_large(L.ccnt, L.n_bins + 2, L.scan_tmp, st);
+    if (rc != IV_OK) return rc;
+    k_cross_fill<<<nb, IX_THREADS, 0, st>>>(n, out->key_s, L.end_s, out->row_s, L.shift, L.ccnt, L.cursor, L.cross_cap,
+                                            L.cross, L.cross_p);
+    IV_LAUNCH_CHECK();
+    k_bins_cross<<<(unsigned)cdiv(L.n_bins + 1, IX_THREADS), IX_THREADS, 0, st>>>(L.n_bins, L.ccnt, L.bins);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -7,10 +7,11 @@
 //   NCLS.coverage               pyranges/methods/coverage.py:64
 //   nearest_previous/next/_nonoverlapping   pyranges/methods/nearest.py:59,69,113
 //
-// count   = #{S' < e'} - #{E' <= s'}         two rank look-ups through the bin tables, no scan
+// count   = #{S' < e'} - #{E' <= s'}         two rank look-ups: one 32-byte bin record each (usually the
+//                                            same record) + the bin's own few 32-bit offsets; no scan
 // hits    = class A: s' <= S' < e'  (contiguous in start order, all of them overlap)
-//         + class B: S' < s' < E'   (stabbing set: backward scan from rank(s') with the 64/4096
-//                                    block-max skip index, stops after the known number of hits)
+//         + class B: S' < s' < E'   (stabbing set) = members of the bin's stabbing list that end after s'
+//                                    + earlier starts of the same bin that end after s'
 // emit    = count -> per-tile sums -> exclusive scan of tile sums -> emit kernel re-scans the counts of
 //           its tile in shared memory (no global offsets array).
 #include "common.cuh"
@@ -21,16 +22,36 @@ constexpr int OV_THREADS = 256;
 constexpr int OV_ITEMS = 4;
 constexpr int OV_TILE = OV_THREADS * OV_ITEMS;  // 1024 queries per block
 
-// #keys < x  via the direct-address bin table, then a short binary search inside the bin
-__device__ __forceinline__ uint32_t rank_lt(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bins,
-                                            int shift, uint64_t x) {
-    uint64_t b = x >> shift;
-    uint32_t lo = __ldg(bins + b), hi = __ldg(bins + b + 1);
+// first 16 bytes of a bin record: bs, be, bs1, be1
+__device__ __forceinline__ uint4 bin_ranks(const iv_index_t& ix, uint64_t b) {
+    return __ldg(reinterpret_cast<const uint4*>(ix.bins + b));
+}
+__device__ __forceinline__ uint2 bin_cross(const iv_index_t& ix, uint64_t b) {
+    return __ldg(reinterpret_cast<const uint2*>(ix.bins + b) + 2);
+}
+// lo + #{off[p] < rel : p in [lo, hi)}   (off ascending inside a bin)
+__device__ __forceinline__ uint32_t rank_in(const uint32_t* __restrict__ off, uint32_t lo, uint32_t hi, uint32_t rel) {
+    if (hi - lo <= 8) {
+        uint32_t r = lo;
+        for (uint32_t p = lo; p < hi; p++) r += __ldg(off + p) < rel ? 1u : 0u;
+        return r;
+    }
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(keys + mid) < x) lo = mid + 1; else hi = mid;
+        if (__ldg(off + mid) < rel) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+// #starts < x, #ends < x  (x: flattened coordinate)
+__device__ __forceinline__ uint32_t rank_s_lt(const iv_index_t& ix, uint64_t x) {
+    uint64_t b = x >> ix.shift;
+    uint4 r = bin_ranks(ix, b);
+    return rank_in(ix.soff, r.x, r.z, (uint32_t)(x - (b << ix.shift)));
+}
+__device__ __forceinline__ uint32_t rank_e_lt(const iv_index_t& ix, uint64_t x) {
+    uint64_t b = x >> ix.shift;
+    uint4 r = bin_ranks(ix, b);
+    return rank_in(ix.eoff, r.y, r.w, (uint32_t)(x - (b << ix.shift)));
 }
 
 struct QGeom {
@@ -64,26 +85,34 @@ __device__ __forceinline__ QGeom make_geom(const iv_index_t& ix, const iv_querie
 
 __device__ __forceinline__ int64_t count_all(const iv_index_t& ix, const QGeom& g) {
     if (g.g < 0 || ix.n == 0) return 0;
-    int64_t c = (int64_t)rank_lt(ix.key_s, ix.bin_s, ix.shift, g.ec) -
-                (int64_t)rank_lt(ix.key_e, ix.bin_e, ix.shift, g.sc + 1);
+    const uint64_t xe = g.ec, xs = g.sc + 1;
+    const uint64_t b1 = xe >> ix.shift, b0 = xs >> ix.shift;
+    const uint4 r1 = bin_ranks(ix, b1);
+    const uint4 r0 = b0 == b1 ? r1 : bin_ranks(ix, b0);
+    int64_t c = (int64_t)rank_in(ix.soff, r1.x, r1.z, (uint32_t)(xe - (b1 << ix.shift))) -
+                (int64_t)rank_in(ix.eoff, r0.y, r0.w, (uint32_t)(xs - (b0 << ix.shift)));
     return c > 0 ? c : 0;
 }
 
-// visit every subject (by start-sorted position) overlapping the query; cnt = count_all()
-template <typename F>
-__device__ __forceinline__ void for_each_hit(const iv_index_t& ix, uint64_t sc, uint64_t ec, int64_t cnt, F&& f) {
-    uint32_t pS = rank_lt(ix.key_s, ix.bin_s, ix.shift, sc);
-    uint32_t pE = rank_lt(ix.key_s, ix.bin_s, ix.shift, ec);
-    for (uint32_t j = pS; j < pE; j++) f((int64_t)j);
-    int64_t need = cnt - (int64_t)(pE - pS);
-    int64_t j = (int64_t)pS - 1;
-    while (need > 0 && j >= 0) {
-        if ((j & 63) == 63) {
-            if ((j & 4095) == 4095 && __ldg(ix.max2 + (j >> 12)) <= sc) { j -= 4096; continue; }
-            if (__ldg(ix.max1 + (j >> 6)) <= sc) { j -= 64; continue; }
-        }
-        if (__ldg(ix.end_s + j) > sc) { f(j); need--; }
-        j--;
+// Visit every subject overlapping [sc, ec).  WANT_P: f(position in start order), else f(subject row).
+template <bool WANT_P, typename F>
+__device__ __forceinline__ void for_each_hit(const iv_index_t& ix, uint64_t sc, uint64_t ec, F&& f) {
+    const uint64_t b = sc >> ix.shift;
+    const uint32_t rel = (uint32_t)(sc - (b << ix.shift));
+    const uint4 r = bin_ranks(ix, b);
+    const uint32_t pS = rank_in(ix.soff, r.x, r.z, rel);
+    const uint64_t b1 = ec >> ix.shift;
+    const uint32_t pE = b1 == b ? rank_in(ix.soff, r.x, r.z, (uint32_t)(ec - (b << ix.shift))) : rank_s_lt(ix, ec);
+    for (uint32_t p = pS; p < pE; p++) f(WANT_P ? p : __ldg(ix.row_s + p));  // class A
+    uint32_t pL = r.x;  // class B, started in this bin: only starts later than s' - max_len can still be open
+    if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
+        pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
+    for (uint32_t p = pL; p < pS; p++)
+        if (__ldg(ix.seoff + p) > rel) f(WANT_P ? p : __ldg(ix.row_s + p));
+    const uint2 c = bin_cross(ix, b);
+    for (uint32_t j = c.x; j < c.y; j++) {                                    // class B, open at the bin origin
+        const uint2 en = __ldg(reinterpret_cast<const uint2*>(ix.cross) + j);
+        if (en.y > rel) f(WANT_P ? __ldg(ix.cross_p + j) : en.x);
     }
 }
 
@@ -94,7 +123,7 @@ struct FirstHit {
     uint32_t brow;
     bool any;
     __device__ FirstHit(const iv_index_t& i) : ix(i), bs(0), be(0), brow(0), any(false) {}
-    __device__ __forceinline__ void operator()(int64_t j) {
+    __device__ __forceinline__ void operator()(uint32_t j) {
         uint64_t s = __ldg(ix.key_s + j), e = __ldg(ix.end_s + j);
         uint32_t r = __ldg(ix.row_s + j);
         bool better = !any || s < bs || (s == bs && (e > be || (e == be && r < brow)));
@@ -149,7 +178,7 @@ k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count
                 if (ca > 0 && !g.clamped) {
                     int64_t k = 0;
                     uint64_t sc = g.sc, ec = g.ec;
-                    for_each_hit(ix, sc, ec, ca, [&](int64_t p) {
+                    for_each_hit<true>(ix, sc, ec, [&](uint32_t p) {
                         k += (__ldg(ix.key_s + p) <= sc && ec <= __ldg(ix.end_s + p)) ? 1 : 0;
                     });
                     c[j] = k;
@@ -201,25 +230,24 @@ k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ coun
         const int64_t i = i0 + j;
         const int64_t ql = q.label ? __ldg(q.label + i) : i;
         QGeom g = make_geom(ix, q, sp.of(q.seg_off, i), s[j], e[j]);
-        const int64_t ca = count_all(ix, g);
         if (MODE == IV_MODE_ALL) {
-            for_each_hit(ix, g.sc, g.ec, ca, [&](int64_t p) {
+            for_each_hit<false>(ix, g.sc, g.ec, [&](uint32_t r) {
                 if (out_q) out_q[o] = ql;
-                if (out_s) { int64_t r = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + r) : r; }
+                if (out_s) out_s[o] = s_label ? __ldg(s_label + r) : (int64_t)r;
                 o++;
             });
         } else if (MODE == IV_MODE_ANY) {
             if (out_q) out_q[o] = ql;
             if (out_s) {
                 FirstHit fh(ix);
-                for_each_hit(ix, g.sc, g.ec, ca, fh);
+                for_each_hit<true>(ix, g.sc, g.ec, fh);
                 int64_t r = fh.brow;
                 out_s[o] = s_label ? __ldg(s_label + r) : r;
             }
             o++;
         } else {
             uint64_t sc = g.sc, ec = g.ec;
-            for_each_hit(ix, sc, ec, ca, [&](int64_t p) {
+            for_each_hit<true>(ix, sc, ec, [&](uint32_t p) {
                 if (__ldg(ix.key_s + p) <= sc && ec <= __ldg(ix.end_s + p)) {
                     if (out_q) out_q[o] = ql;
                     if (out_s) { int64_t r = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + r) : r; }
@@ -245,7 +273,7 @@ k_coverage(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_bp, double* 
     int64_t bp = 0;
     if (ca > 0) {
         uint64_t sc = g.sc, ec = g.ec;
-        for_each_hit(ix, sc, ec, ca, [&](int64_t p) {
+        for_each_hit<true>(ix, sc, ec, [&](uint32_t p) {
             uint64_t S = __ldg(ix.key_s + p), E = __ldg(ix.end_s + p);
             bp += (int64_t)((E < ec ? E : ec) - (S > sc ? S : sc));
         });
@@ -277,7 +305,7 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
             int64_t ca = count_all(ix, g);
             if (ca > 0) {
                 FirstHit fh(ix);
-                for_each_hit(ix, g.sc, g.ec, ca, fh);
+                for_each_hit<true>(ix, g.sc, g.ec, fh);
                 row = fh.brow; dist = 0; done = true;
             }
         }
@@ -287,17 +315,17 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
             if (mode != IV_NEAREST_NEXT && g.s >= g.lo) {
                 // last subject end <= s ; ties: first of the equal run (earliest row, stable sort)
                 uint64_t sc = (uint64_t)((g.s > g.hi ? g.hi : g.s) - g.lo + g.base);
-                int64_t r = rank_lt(ix.key_e, ix.bin_e, ix.shift, sc + 1);
+                int64_t r = rank_e_lt(ix, sc + 1);
                 if (r > g_first) {
                     uint64_t ev = __ldg(ix.key_e + (r - 1));
-                    int64_t jf = rank_lt(ix.key_e, ix.bin_e, ix.shift, ev);
+                    int64_t jf = rank_e_lt(ix, ev);
                     prow = __ldg(ix.row_e + jf);
                     pdist = g.s - ((int64_t)ev - g.base + g.lo) + 1;
                 }
             }
             if (mode != IV_NEAREST_PREVIOUS && g.e <= g.hi) {
                 uint64_t ec = (uint64_t)((g.e < g.lo ? g.lo : g.e) - g.lo + g.base);
-                int64_t j = rank_lt(ix.key_s, ix.bin_s, ix.shift, ec);
+                int64_t j = rank_s_lt(ix, ec);
                 if (j < g_end) {
                     nrow = __ldg(ix.row_s + j);
                     ndist = ((int64_t)__ldg(ix.key_s + j) - g.base + g.lo) - g.e + 1;

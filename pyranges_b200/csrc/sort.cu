@@ -15,32 +15,39 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per block
 constexpr int RS_RADIX = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_FUSED_TILES = 128;  // up to this many tiles the scatter kernel scans the histograms itself
 
+struct SortJobs {
+    const uint64_t* kin[RS_MAX_JOBS];
+    uint64_t* kout[RS_MAX_JOBS];
+    const void* vin[RS_MAX_JOBS];
+    void* vout[RS_MAX_JOBS];
+    int vb[RS_MAX_JOBS];
+};
+
+// hist[job][digit][tile]
 __global__ void __launch_bounds__(RS_THREADS)
-k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t mask, uint32_t* __restrict__ hist,
-          int64_t ntiles) {
+k_rs_hist(SortJobs J, int64_t n, int shift, uint32_t mask, uint32_t* __restrict__ hist, int64_t ntiles) {
     __shared__ uint32_t h[RS_RADIX];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, job = blockIdx.y;
+    const uint64_t* __restrict__ keys = J.kin[job];
     h[tid] = 0;
     __syncthreads();
     const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; it++) {
         int64_t idx = tbase + it * RS_THREADS + tid;
-        bool ok = idx < n;
-        uint32_t d = ok ? (uint32_t)((__ldg(keys + idx) >> shift) & mask) : 0xffffffffu;
-        unsigned m = __match_any_sync(FULL, d);
-        if (ok && (int)(__ffs(m) - 1) == lane_id()) atomicAdd(&h[d], (uint32_t)__popc(m));
+        if (idx < n) atomicAdd(&h[(uint32_t)((__ldg(keys + idx) >> shift) & mask)], 1u);
     }
     __syncthreads();
-    hist[(int64_t)tid * ntiles + blockIdx.x] = h[tid];
+    hist[((int64_t)job * RS_RADIX + tid) * ntiles + blockIdx.x] = h[tid];
 }
 
-template <int VB>
+// FUSED: hist holds raw per-tile counts and every block derives its own offsets (small inputs);
+// otherwise hist holds the device-wide exclusive scan over [job][digit][tile].
+template <bool FUSED>
 __global__ void __launch_bounds__(RS_THREADS)
-k_rs_scatter(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const void* __restrict__ vin,
-             void* __restrict__ vout, int64_t n, int shift, uint32_t mask,
-             const uint32_t* __restrict__ hist_scanned, int64_t ntiles) {
+k_rs_scatter(SortJobs J, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ hist, int64_t ntiles) {
     __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
     __shared__ uint32_t digit_base[RS_RADIX];
     __shared__ uint32_t gbase[RS_RADIX];
@@ -48,7 +55,10 @@ k_rs_scatter(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, cons
     __shared__ uint8_t sdig[RS_TILE];
     __shared__ uint32_t wsum[RS_WARPS + 1];
 
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, job = blockIdx.y;
+    const uint64_t* __restrict__ kin = J.kin[job];
+    uint64_t* __restrict__ kout = J.kout[job];
+    const int VB = J.vb[job];
     const int64_t tile = blockIdx.x;
     const int64_t tbase = tile * RS_TILE;
     const int nvalid = (int)((n - tbase) < (int64_t)RS_TILE ? (n - tbase) : (int64_t)RS_TILE);
@@ -90,7 +100,22 @@ k_rs_scatter(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, cons
         uint32_t tot;
         uint32_t ex = block_excl_sum<uint32_t, RS_THREADS>(run, wsum, tot);
         digit_base[tid] = ex;
-        gbase[tid] = __ldg(hist_scanned + (int64_t)tid * ntiles + tile) - ex;
+        const uint32_t* hrow = hist + ((int64_t)job * RS_RADIX + tid) * ntiles;
+        uint32_t goff;
+        if (FUSED) {
+            uint32_t before = 0, total = 0;
+            for (int64_t t = 0; t < ntiles; t++) {
+                uint32_t c = __ldg(hrow + t);
+                before += t < tile ? c : 0;
+                total += c;
+            }
+            uint32_t tt;
+            uint32_t dstart = block_excl_sum<uint32_t, RS_THREADS>(total, wsum, tt);
+            goff = dstart + before;
+        } else {
+            goff = __ldg(hrow + tile) - (uint32_t)((int64_t)job * n);
+        }
+        gbase[tid] = goff - ex;
     }
     __syncthreads();
     uint32_t pos[RS_ITEMS];
@@ -105,8 +130,8 @@ k_rs_scatter(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, cons
     for (int k = tid; k < nvalid; k += RS_THREADS) kout[gbase[sdig[k]] + (uint32_t)k] = sbuf[k];
     if (VB == 8) {
         __syncthreads();
-        const uint64_t* vi = (const uint64_t*)vin;
-        uint64_t* vo = (uint64_t*)vout;
+        const uint64_t* vi = (const uint64_t*)J.vin[job];
+        uint64_t* vo = (uint64_t*)J.vout[job];
 #pragma unroll
         for (int it = 0; it < RS_ITEMS; it++) {
             int li = w * (RS_ITEMS * 32) + it * 32 + lane;
@@ -116,8 +141,8 @@ k_rs_scatter(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, cons
         for (int k = tid; k < nvalid; k += RS_THREADS) vo[gbase[sdig[k]] + (uint32_t)k] = sbuf[k];
     } else if (VB == 4) {
         __syncthreads();
-        const uint32_t* vi = (const uint32_t*)vin;
-        uint32_t* vo = (uint32_t*)vout;
+        const uint32_t* vi = (const uint32_t*)J.vin[job];
+        uint32_t* vo = (uint32_t*)J.vout[job];
         uint32_t* sb32 = (uint32_t*)sbuf;
 #pragma unroll
         for (int it = 0; it < RS_ITEMS; it++) {
@@ -233,44 +258,58 @@ int scan_exclusive_i64_inplace(int64_t* data, int64_t n, int64_t* out_total, cud
 // ---- host driver ---------------------------------------------------------------------------------------------
 size_t radix_sort_temp_bytes(int64_t n) {
     int64_t ntiles = cdiv(n > 0 ? n : 1, RS_TILE);
-    size_t hist = (size_t)ntiles * RS_RADIX;
-    return (hist + scan_u32_large_temp_elems((int64_t)hist)) * sizeof(uint32_t) + 512;
+    size_t hist = (size_t)ntiles * RS_RADIX * RS_MAX_JOBS;
+    return (hist + scan_u32_large_temp_elems((int64_t)hist) + 64) * sizeof(uint32_t) + 512;
 }
 
-int radix_sort_pingpong(uint64_t* k0, uint64_t* k1, void* v0, void* v1, int value_bytes, int64_t n, int begin_bit,
-                        int end_bit, void* temp, size_t temp_bytes, cudaStream_t stream, int* result_buf) {
+int radix_sort_multi(const SortJob* jobs, int njobs, int64_t n, int begin_bit, int end_bit, void* temp,
+                     size_t temp_bytes, cudaStream_t stream, int* result_buf) {
     *result_buf = 0;
-    if (n <= 1 || end_bit <= begin_bit) return IV_OK;
-    IV_REQUIRE(n < ((int64_t)1 << 32) - RS_TILE, IV_ERR_RANGE, "radix sort: n=%lld exceeds 2^32", (long long)n);
-    IV_REQUIRE(value_bytes == 0 || value_bytes == 4 || value_bytes == 8, IV_ERR_INVALID, "radix sort: value_bytes");
+    if (n <= 1 || end_bit <= begin_bit || njobs <= 0) return IV_OK;
+    IV_REQUIRE(njobs <= RS_MAX_JOBS, IV_ERR_INVALID, "radix sort: too many jobs");
+    IV_REQUIRE((int64_t)njobs * n < ((int64_t)1 << 32) - RS_TILE, IV_ERR_RANGE, "radix sort: n=%lld exceeds 2^32",
+               (long long)n);
+    for (int j = 0; j < njobs; j++)
+        IV_REQUIRE(jobs[j].vb == 0 || jobs[j].vb == 4 || jobs[j].vb == 8, IV_ERR_INVALID, "radix sort: value_bytes");
     IV_REQUIRE(temp_bytes >= radix_sort_temp_bytes(n), IV_ERR_WORKSPACE, "radix sort: temp too small");
     int64_t ntiles = cdiv(n, RS_TILE);
     uint32_t* hist = (uint32_t*)temp;
-    int64_t nh = ntiles * RS_RADIX;
+    int64_t nh = ntiles * RS_RADIX * njobs;
     uint32_t* partials = hist + ((nh + 63) & ~(int64_t)63);
+    const bool fused = ntiles <= RS_FUSED_TILES;
     int cur = 0;
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         int bits = end_bit - shift < 8 ? end_bit - shift : 8;
         uint32_t mask = (1u << bits) - 1u;
-        const uint64_t* kin = cur ? k1 : k0;
-        uint64_t* kout = cur ? k0 : k1;
-        const void* vin = cur ? v1 : v0;
-        void* vout = cur ? v0 : v1;
-        k_rs_hist<<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, n, shift, mask, hist, ntiles);
+        SortJobs J;
+        for (int j = 0; j < njobs; j++) {
+            J.kin[j] = cur ? jobs[j].k1 : jobs[j].k0;
+            J.kout[j] = cur ? jobs[j].k0 : jobs[j].k1;
+            J.vin[j] = cur ? jobs[j].v1 : jobs[j].v0;
+            J.vout[j] = cur ? jobs[j].v0 : jobs[j].v1;
+            J.vb[j] = jobs[j].vb;
+        }
+        dim3 grid((unsigned)ntiles, (unsigned)njobs);
+        k_rs_hist<<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
         IV_LAUNCH_CHECK();
-        int rc = scan_exclusive_u32_large(hist, nh, partials, stream);
-        if (rc != IV_OK) return rc;
-        if (value_bytes == 0)
-            k_rs_scatter<0><<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, kout, nullptr, nullptr, n, shift, mask, hist, ntiles);
-        else if (value_bytes == 4)
-            k_rs_scatter<4><<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, kout, vin, vout, n, shift, mask, hist, ntiles);
-        else
-            k_rs_scatter<8><<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(kin, kout, vin, vout, n, shift, mask, hist, ntiles);
+        if (fused) {
+            k_rs_scatter<true><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
+        } else {
+            int rc = scan_exclusive_u32_large(hist, nh, partials, stream);
+            if (rc != IV_OK) return rc;
+            k_rs_scatter<false><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
+        }
         IV_LAUNCH_CHECK();
         cur ^= 1;
     }
     *result_buf = cur;
     return IV_OK;
+}
+
+int radix_sort_pingpong(uint64_t* k0, uint64_t* k1, void* v0, void* v1, int value_bytes, int64_t n, int begin_bit,
+                        int end_bit, void* temp, size_t temp_bytes, cudaStream_t stream, int* result_buf) {
+    SortJob j{k0, k1, v0, v1, value_bytes};
+    return radix_sort_multi(&j, 1, n, begin_bit, end_bit, temp, temp_bytes, stream, result_buf);
 }
 
 }  // namespace iv

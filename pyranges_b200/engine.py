@@ -74,7 +74,7 @@ class DeviceIntervals:
         assert self.seg_off[0] == 0 and self.seg_off[-1] == self.n
         self.n_seg = len(self.seg_off) - 1
         self.seg_off_dev = _to_dev(self.seg_off, self.device)
-        self._b = bounds  # (lo, hi, maxlen) per segment; computed on first use (subjects / unary ops only)
+        self._b = bounds  # (lo, hi, maxlen, sumlen) per segment; computed on first use (subjects / unary ops)
 
     @property
     def bounds(self):
@@ -94,6 +94,10 @@ class DeviceIntervals:
     def maxlen(self):
         return self.bounds[2]
 
+    @property
+    def sumlen(self):
+        return self.bounds[3]
+
     @classmethod
     def from_numpy(cls, starts, ends, seg_off, device="cuda", pinned=False):
         dev = _use(device)
@@ -105,13 +109,14 @@ class DeviceIntervals:
         k = self.n_seg
         if k == 0:
             z = np.zeros(0, np.int64)
-            return z, z.copy(), z.copy()
-        out = torch.empty(3 * k, dtype=torch.int64, device=self.device)
+            return z, z.copy(), z.copy(), z.copy()
+        out = torch.empty(4 * k, dtype=torch.int64, device=self.device)
+        p = out.data_ptr()
         cabi.check(cabi.lib().iv_segment_bounds(_ptr(self.start), _ptr(self.end), _ptr(self.seg_off_dev), k,
-                                                C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr() + 8 * k),
-                                                C.c_void_p(out.data_ptr() + 16 * k), _stream()), "iv_segment_bounds")
+                                                C.c_void_p(p), C.c_void_p(p + 8 * k), C.c_void_p(p + 16 * k),
+                                                C.c_void_p(p + 24 * k), _stream()), "iv_segment_bounds")
         h = out.cpu().numpy()
-        return h[:k].copy(), h[k:2 * k].copy(), h[2 * k:].copy()
+        return h[:k].copy(), h[k:2 * k].copy(), h[2 * k:3 * k].copy(), h[3 * k:].copy()
 
 
 class Groups:
@@ -144,6 +149,7 @@ class Groups:
                 raise ValueError("coverage needs non-negative coordinates")
             lo = np.zeros(g, np.int64)
         self.lo, self.hi, self.maxlen = lo, hi, int(ml.max()) if g else 0
+        self.sumlen = int(iv.sumlen.sum()) if k else 0
         base = np.zeros(g + 1, np.int64)
         np.cumsum((hi - lo) + int(gap), out=base[1:])
         self.base = base
@@ -151,7 +157,8 @@ class Groups:
         packed = np.concatenate([self.row_off, lo, hi, base]).astype(np.int64)
         self.dev = _to_dev(packed, iv.device)
         p = self.dev.data_ptr()
-        self.c = IvGroups(g, 0, p, p + 8 * (g + 1), p + 8 * (2 * g + 1), p + 8 * (3 * g + 1), self.total_span)
+        self.c = IvGroups(g, 0, p, p + 8 * (g + 1), p + 8 * (2 * g + 1), p + 8 * (3 * g + 1), self.total_span,
+                          self.sumlen, self.maxlen)
 
 
 class Queries:
@@ -180,7 +187,7 @@ class SubjectIndex:
         self.groups = Groups(iv, seg_ranges, gap=1)
         self.flags = IV_INDEX_ENDS_PERM if ends_perm else 0
         L = cabi.lib()
-        nbytes = L.iv_index_workspace_bytes(iv.n, self.groups.total_span, self.flags)
+        nbytes = L.iv_index_workspace_bytes(iv.n, self.groups.total_span, self.groups.sumlen, self.flags)
         self.ws = _bytes(nbytes, iv.device)
         self.c = IvIndex()
         cabi.check(L.iv_index_build(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(self.groups.c), self.flags,

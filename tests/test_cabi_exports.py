@@ -29,7 +29,7 @@ def test_abi_version_and_sizes():
 
     L = _cabi.lib()
     assert L.iv_abi_version() == _cabi.IV_ABI_VERSION
-    a, b = L.iv_index_workspace_bytes(1000, 1 << 20, 0), L.iv_index_workspace_bytes(1000000, 1 << 32, 1)
+    a, b = L.iv_index_workspace_bytes(1000, 1 << 20, 100000, 0), L.iv_index_workspace_bytes(1000000, 1 << 32, 10**9, 1)
     assert 0 < a < b
     assert L.iv_overlap_workspace_bytes(10_000_000) >= 8 * (10_000_000 // 1024)
     assert L.iv_cluster_workspace_bytes(1000) > 0 and L.iv_rle_workspace_bytes(1000, 4) > 0
@@ -43,7 +43,7 @@ def test_argument_errors_without_gpu():
     L = _cabi.lib()
     rc = L.iv_count_overlaps(None, None, 0, None, None, 0, None, None)
     assert rc == -1 and b"null" in L.iv_last_error_string()
-    g = _cabi.IvGroups(0, 0, None, None, None, None, 1 << 63 - 1)
+    g = _cabi.IvGroups(0, 0, None, None, None, None, 1 << 40, 0, 0)
     assert L.iv_index_build(None, None, -5, C.byref(g), 0, None, 0, None, None) == -1
     assert L.iv_rle_count(None, None, 1 << 31, C.byref(g), None, 0, C.c_void_p(8), None) == -4
 
