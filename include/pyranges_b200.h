@@ -87,13 +87,19 @@ typedef struct iv_groups {
     int64_t max_len;
 } iv_groups_t;
 
-/* One 32-byte record (= one L2 sector) per coordinate bin b = flattened coordinate >> shift. */
+/* One 32-byte record (= one L2 sector, fetched with a single 256-bit load) per coordinate bin
+ * b = flattened coordinate >> shift.  It answers "how many starts / ends lie before x" for any x of the
+ * bin without touching another array as long as the bin holds at most four starts and four ends. */
 typedef struct iv_binrec {
-    uint32_t bs, be;   /* #starts < b<<shift, #ends < b<<shift             */
-    uint32_t bs1, be1; /* the same ranks at the next bin boundary           */
-    uint32_t co, co1;  /* stabbing list of the bin: cross[co, co1)           */
-    uint32_t _pad[2];
+    uint32_t bs, be;  /* #starts < b<<shift, #ends < b<<shift                                   */
+    uint32_t co;      /* stabbing list of the bin: cross[co, co + nc)                            */
+    uint8_t ns, ne, nc; /* starts / ends / stabbing entries of the bin; 255 = "255 or more": the
+                           exact count is the difference to the next record                      */
+    uint8_t flags;    /* bit 0: so[] / eo[] are valid (shift <= 15: offsets are 15-bit)            */
+    uint16_t so[4];   /* offsets (x - (b<<shift)) of the bin's first four starts, 0x7FFF = none   */
+    uint16_t eo[4];   /* ... and first four ends                                                  */
 } iv_binrec_t;
+#define IV_BIN_INLINE 1
 
 /* Stabbing-list entry: a subject that starts before the bin and ends after the bin's first coordinate. */
 typedef struct iv_cross {

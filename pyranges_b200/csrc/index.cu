@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(IX_THREADS)
 k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const uint64_t* __restrict__ key_s,
                const uint32_t* __restrict__ row_s, const uint64_t* __restrict__ key_e, int shift, int64_t n_bins,
                uint64_t* __restrict__ end_s, uint32_t* __restrict__ soff, uint32_t* __restrict__ seoff,
-               uint32_t* __restrict__ eoff, iv_binrec_t* __restrict__ bins, uint32_t* __restrict__ ccnt) {
+               uint32_t* __restrict__ eoff, uint32_t* __restrict__ bsarr, uint32_t* __restrict__ bearr,
+               uint32_t* __restrict__ ccnt) {
     __shared__ int span[2];
     const int64_t first = (int64_t)blockIdx.x * IX_THREADS;
     const int64_t p = first + threadIdx.x;
@@ -117,15 +118,9 @@ k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const ui
         const uint64_t d = E - origin;
         seoff[p] = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
         const int64_t bprev = p ? (int64_t)(key_s[p - 1] >> shift) : -1;
-        for (int64_t bb = bprev + 1; bb <= b; bb++) {
-            bins[bb].bs = (uint32_t)p;
-            if (bb) bins[bb - 1].bs1 = (uint32_t)p;
-        }
+        for (int64_t bb = bprev + 1; bb <= b; bb++) bsarr[bb] = (uint32_t)p;
         if (p == n - 1)
-            for (int64_t bb = b + 1; bb <= n_bins + 1; bb++) {
-                if (bb <= n_bins) bins[bb].bs = (uint32_t)n;
-                bins[bb - 1].bs1 = (uint32_t)n;
-            }
+            for (int64_t bb = b + 1; bb <= n_bins + 1; bb++) bsarr[bb] = (uint32_t)n;
         // bins b+1 .. bin(E-1) are crossed: the subject is open at their origin
         if (E > k) {
             const int64_t bl = (int64_t)((E - 1) >> shift);
@@ -137,15 +132,9 @@ k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const ui
         const int64_t b = (int64_t)(k >> shift);
         eoff[p] = (uint32_t)(k - ((uint64_t)b << shift));
         const int64_t bprev = p ? (int64_t)(key_e[p - 1] >> shift) : -1;
-        for (int64_t bb = bprev + 1; bb <= b; bb++) {
-            bins[bb].be = (uint32_t)p;
-            if (bb) bins[bb - 1].be1 = (uint32_t)p;
-        }
+        for (int64_t bb = bprev + 1; bb <= b; bb++) bearr[bb] = (uint32_t)p;
         if (p == n - 1)
-            for (int64_t bb = b + 1; bb <= n_bins + 1; bb++) {
-                if (bb <= n_bins) bins[bb].be = (uint32_t)n;
-                bins[bb - 1].be1 = (uint32_t)n;
-            }
+            for (int64_t bb = b + 1; bb <= n_bins + 1; bb++) bearr[bb] = (uint32_t)n;
     }
 }
 
@@ -173,17 +162,36 @@ k_cross_fill(int64_t n, const uint64_t* __restrict__ key_s, const uint64_t* __re
     }
 }
 
+// assemble the 32-byte bin records from the rank / stabbing-list offsets and the first offsets of each bin
 __global__ void __launch_bounds__(IX_THREADS)
-k_bins_cross(int64_t n_bins, const uint32_t* __restrict__ coff, iv_binrec_t* __restrict__ bins) {
+k_bins_finalize(int64_t n_bins, int shift, const uint32_t* __restrict__ bsarr, const uint32_t* __restrict__ bearr,
+                const uint32_t* __restrict__ coff, const uint32_t* __restrict__ soff, const uint32_t* __restrict__ eoff,
+                iv_binrec_t* __restrict__ bins) {
     const int64_t b = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
     if (b > n_bins) return;
-    bins[b].co = coff[b];
-    bins[b].co1 = coff[b + 1];
+    const uint32_t bs = bsarr[b], be = bearr[b], co = coff[b];
+    const uint32_t ns = bsarr[b + 1] - bs, ne = bearr[b + 1] - be, nc = coff[b + 1] - co;
+    const bool inl = shift <= 15;  // inline offsets are 15-bit (SWAR compares in the count kernel)
+    uint32_t so[4], eo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        so[i] = (inl && (uint32_t)i < ns) ? __ldg(soff + bs + i) : 0x7fffu;
+        eo[i] = (inl && (uint32_t)i < ne) ? __ldg(eoff + be + i) : 0x7fffu;
+    }
+    uint4 a, c;
+    a.x = bs; a.y = be; a.z = co;
+    a.w = (ns < 255 ? ns : 255u) | ((ne < 255 ? ne : 255u) << 8) | ((nc < 255 ? nc : 255u) << 16) |
+          ((inl ? (uint32_t)IV_BIN_INLINE : 0u) << 24);
+    c.x = so[0] | (so[1] << 16); c.y = so[2] | (so[3] << 16);
+    c.z = eo[0] | (eo[1] << 16); c.w = eo[2] | (eo[3] << 16);
+    uint4* out = reinterpret_cast<uint4*>(bins + b);
+    out[0] = a;
+    out[1] = c;
 }
 
 struct IndexLayout {
     uint64_t *ks0, *ks1, *ke0, *ke1, *end_s;
-    uint32_t *rs0, *rs1, *re0, *re1, *soff, *seoff, *eoff, *ccnt, *cursor, *cross_p, *scan_tmp;
+    uint32_t *rs0, *rs1, *re0, *re1, *soff, *seoff, *eoff, *bsarr, *bearr, *ccnt, *cursor, *cross_p, *scan_tmp;
     iv_binrec_t* bins;
     iv_cross_t* cross;
     void* sort_temp;
@@ -221,6 +229,8 @@ static void plan_index(int64_t n, int64_t span, int64_t sum_len, int flags, Bump
     L.seoff = b.take<uint32_t>(nn);
     L.eoff = b.take<uint32_t>(nn);
     L.bins = b.take<iv_binrec_t>((size_t)L.n_bins + 2);
+    L.bsarr = b.take<uint32_t>((size_t)L.n_bins + 4);
+    L.bearr = b.take<uint32_t>((size_t)L.n_bins + 4);
     L.ccnt = b.take<uint32_t>((size_t)L.n_bins + 4);
     L.cursor = b.take<uint32_t>((size_t)L.n_bins + 4);
     L.scan_tmp = b.take<uint32_t>(scan_u32_large_temp_elems(L.n_bins + 2) + 64);
@@ -299,14 +309,15 @@ extern "C" int iv_index_build(const int64_t* starts, const int64_t* ends, int64_
     // ccnt and cursor are adjacent in the workspace: one memset clears both
     IV_CUDA(cudaMemsetAsync(L.ccnt, 0, (size_t)((char*)L.scan_tmp - (char*)L.ccnt), st));
     k_index_arrays<<<dim3(nb, 2), IX_THREADS, 0, st>>>(ends, n, G, out->key_s, out->row_s, out->key_e, L.shift, L.n_bins,
-                                                       L.end_s, L.soff, L.seoff, L.eoff, L.bins, L.ccnt);
+                                                       L.end_s, L.soff, L.seoff, L.eoff, L.bsarr, L.bearr, L.ccnt);
     IV_LAUNCH_CHECK();
     rc = scan_exclusive_u32_large(L.ccnt, L.n_bins + 2, L.scan_tmp, st);
     if (rc != IV_OK) return rc;
     k_cross_fill<<<nb, IX_THREADS, 0, st>>>(n, out->key_s, L.end_s, out->row_s, L.shift, L.ccnt, L.cursor, L.cross_cap,
                                             L.cross, L.cross_p);
     IV_LAUNCH_CHECK();
-    k_bins_cross<<<(unsigned)cdiv(L.n_bins + 1, IX_THREADS), IX_THREADS, 0, st>>>(L.n_bins, L.ccnt, L.bins);
+    k_bins_finalize<<<(unsigned)cdiv(L.n_bins + 1, IX_THREADS), IX_THREADS, 0, st>>>(L.n_bins, L.shift, L.bsarr, L.bearr,
+                                                                                     L.ccnt, L.soff, L.eoff, L.bins);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -7,13 +7,17 @@
 //   NCLS.coverage               pyranges/methods/coverage.py:64
 //   nearest_previous/next/_nonoverlapping   pyranges/methods/nearest.py:59,69,113
 //
-// count   = #{S' < e'} - #{E' <= s'}         two rank look-ups: one 32-byte bin record each (usually the
-//                                            same record) + the bin's own few 32-bit offsets; no scan
+// count   = #{S' < e'} - #{E' <= s'}         ONE 256-bit gather per query: the 32-byte record of the bin of
+//                                            e' holds both ranks at the bin origin plus the bin's first four
+//                                            start / end offsets (s'+1 almost always lies in the same bin)
 // hits    = class A: s' <= S' < e'  (contiguous in start order, all of them overlap)
 //         + class B: S' < s' < E'   (stabbing set) = members of the bin's stabbing list that end after s'
 //                                    + earlier starts of the same bin that end after s'
 // emit    = count -> per-tile sums -> exclusive scan of tile sums -> emit kernel re-scans the counts of
 //           its tile in shared memory (no global offsets array).
+//
+// Kernels are instantiated for 32-bit flattened coordinates (total span < 2^32: any single genome) and for
+// 64-bit ones; the 32-bit instantiation halves the integer work per query.
 #include "common.cuh"
 
 namespace iv {
@@ -21,18 +25,29 @@ namespace iv {
 constexpr int OV_THREADS = 256;
 constexpr int OV_ITEMS = 4;
 constexpr int OV_TILE = OV_THREADS * OV_ITEMS;  // 1024 queries per block
+constexpr int OV_BATCH = 2;                       // record gathers a thread keeps in flight
 
-// first 16 bytes of a bin record: bs, be, bs1, be1
-__device__ __forceinline__ uint4 bin_ranks(const iv_index_t& ix, uint64_t b) {
-    return __ldg(reinterpret_cast<const uint4*>(ix.bins + b));
+// ---- bin records ----------------------------------------------------------------------------------------------
+// w[0]=bs w[1]=be w[2]=co w[3]=ns|ne<<8|nc<<16|flags<<24 w[4..5]=so[0..3] w[6..7]=eo[0..3]
+struct Rec { uint32_t w[8]; };
+
+// one 256-bit load = one L2 sector per look-up (LDG.E.256 on sm_100a)
+__device__ __forceinline__ Rec load_rec(const iv_index_t& ix, uint64_t b) {
+    Rec r;
+    const iv_binrec_t* p = ix.bins + b;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+        : "l"(p));
+    return r;
 }
-__device__ __forceinline__ uint2 bin_cross(const iv_index_t& ix, uint64_t b) {
-    return __ldg(reinterpret_cast<const uint2*>(ix.bins + b) + 2);
+__device__ __forceinline__ uint32_t cnt4(uint32_t a, uint32_t b, uint32_t rel) {
+    return ((a & 0xffffu) < rel) + ((a >> 16) < rel) + ((b & 0xffffu) < rel) + ((b >> 16) < rel);
 }
 // lo + #{off[p] < rel : p in [lo, hi)}   (off ascending inside a bin)
-__device__ __forceinline__ uint32_t rank_in(const uint32_t* __restrict__ off, uint32_t lo, uint32_t hi, uint32_t rel) {
-    if (hi - lo <= 8) {
+__device__ __noinline__ uint32_t rank_in(const uint32_t* __restrict__ off, uint32_t lo, uint32_t hi, uint32_t rel) {
+    if (hi - lo <= 32) {  // independent loads over at most a few sectors: one round trip, not log2(n) dependent ones
         uint32_t r = lo;
+#pragma unroll 8
         for (uint32_t p = lo; p < hi; p++) r += __ldg(off + p) < rel ? 1u : 0u;
         return r;
     }
@@ -42,78 +57,127 @@ __device__ __forceinline__ uint32_t rank_in(const uint32_t* __restrict__ off, ui
     }
     return lo;
 }
+__device__ __forceinline__ bool rec_inline_s(const Rec& r) { return (r.w[3] & (IV_BIN_INLINE << 24)) && (r.w[3] & 0xffu) <= 4; }
+__device__ __forceinline__ bool rec_inline_e(const Rec& r) { return (r.w[3] & (IV_BIN_INLINE << 24)) && ((r.w[3] >> 8) & 0xffu) <= 4; }
+// #starts < origin(b) + rel,  #ends < origin(b) + rel   (r = record of bin b)
+__device__ __forceinline__ uint32_t rec_rank_s(const iv_index_t& ix, const Rec& r, uint64_t b, uint32_t rel) {
+    if (rec_inline_s(r)) return r.w[0] + cnt4(r.w[4], r.w[5], rel);
+    const uint32_t n = r.w[3] & 0xffu;
+    const uint32_t hi = n < 255 ? r.w[0] + n : __ldg(&ix.bins[b + 1].bs);
+    return rank_in(ix.soff, r.w[0], hi, rel);
+}
+__device__ __forceinline__ uint32_t rec_rank_e(const iv_index_t& ix, const Rec& r, uint64_t b, uint32_t rel) {
+    if (rec_inline_e(r)) return r.w[1] + cnt4(r.w[6], r.w[7], rel);
+    const uint32_t n = (r.w[3] >> 8) & 0xffu;
+    const uint32_t hi = n < 255 ? r.w[1] + n : __ldg(&ix.bins[b + 1].be);
+    return rank_in(ix.eoff, r.w[1], hi, rel);
+}
+template <typename X> __device__ __forceinline__ uint32_t rel_of(const iv_index_t& ix, X x) {
+    return (uint32_t)x & ((1u << ix.shift) - 1u);  // shift <= 31
+}
 // #starts < x, #ends < x  (x: flattened coordinate)
-__device__ __forceinline__ uint32_t rank_s_lt(const iv_index_t& ix, uint64_t x) {
-    uint64_t b = x >> ix.shift;
-    uint4 r = bin_ranks(ix, b);
-    return rank_in(ix.soff, r.x, r.z, (uint32_t)(x - (b << ix.shift)));
+template <typename X> __device__ __forceinline__ uint32_t rank_s_lt(const iv_index_t& ix, X x) {
+    const uint64_t b = x >> ix.shift;
+    return rec_rank_s(ix, load_rec(ix, b), b, rel_of(ix, x));
 }
-__device__ __forceinline__ uint32_t rank_e_lt(const iv_index_t& ix, uint64_t x) {
-    uint64_t b = x >> ix.shift;
-    uint4 r = bin_ranks(ix, b);
-    return rank_in(ix.eoff, r.y, r.w, (uint32_t)(x - (b << ix.shift)));
+template <typename X> __device__ __forceinline__ uint32_t rank_e_lt(const iv_index_t& ix, X x) {
+    const uint64_t b = x >> ix.shift;
+    return rec_rank_e(ix, load_rec(ix, b), b, rel_of(ix, x));
 }
 
-struct QGeom {
-    int g;           // partner group, -1 = none
-    int64_t s, e;    // raw (slack-extended) coordinates
-    int64_t lo, hi, base;
-    uint64_t sc, ec; // flattened, clamped
-    bool clamped;    // query sticks out of [lo, hi]
-};
-
-__device__ __forceinline__ QGeom make_geom(const iv_index_t& ix, const iv_queries_t& q, int seg, int64_t s, int64_t e) {
-    QGeom r;
-    r.g = __ldg(q.seg_group + seg);
-    if (q.slack != 0) {
-        s -= q.slack;
-        if (s < 0) s = 0;
-        e += q.slack;
+// ---- query geometry ---------------------------------------------------------------------------------------------
+// x' = base + clamp(x - lo, 0, width): the partner group's window of the flattened axis
+template <typename X> struct Flat {
+    int64_t lo;
+    uint64_t width;
+    X base;
+    int g;  // partner group, -1 = none (lo = width = base = 0: every count comes out 0)
+    __device__ __forceinline__ X at(int64_t x) const {
+        uint64_t d = (uint64_t)(x - lo);
+        d = x < lo ? 0ull : d;
+        d = d > width ? width : d;
+        return base + (X)d;
     }
-    r.s = s; r.e = e;
-    if (r.g < 0) { r.lo = r.hi = r.base = 0; r.sc = r.ec = 0; r.clamped = true; return r; }
-    r.lo = __ldg(ix.groups.lo + r.g);
-    r.hi = __ldg(ix.groups.hi + r.g);
-    r.base = __ldg(ix.groups.base + r.g);
-    int64_t cs = s < r.lo ? r.lo : (s > r.hi ? r.hi : s);
-    int64_t ce = e < r.lo ? r.lo : (e > r.hi ? r.hi : e);
-    r.clamped = (cs != s) || (ce != e);
-    r.sc = (uint64_t)(cs - r.lo + r.base);
-    r.ec = (uint64_t)(ce - r.lo + r.base);
-    return r;
+    __device__ __forceinline__ bool outside(int64_t x) const { return x < lo || (uint64_t)(x - lo) > width; }
+    __device__ __forceinline__ int64_t raw(uint64_t xf) const { return (int64_t)(xf - (uint64_t)base) + lo; }
+};
+template <typename X> __device__ __forceinline__ Flat<X> load_flat(const iv_index_t& ix, const iv_queries_t& q, int seg) {
+    Flat<X> f;
+    f.g = __ldg(q.seg_group + seg);
+    f.lo = 0; f.width = 0; f.base = 0;
+    if (f.g >= 0 && ix.n > 0) {
+        f.lo = __ldg(ix.groups.lo + f.g);
+        f.width = (uint64_t)(__ldg(ix.groups.hi + f.g) - f.lo);
+        f.base = (X)__ldg(ix.groups.base + f.g);
+    } else {
+        f.g = -1;
+    }
+    return f;
+}
+// per-thread cache: most blocks sit inside one query segment
+template <typename X> struct FlatCache {
+    SegSpan sp;
+    Flat<X> f0;
+    __device__ __forceinline__ FlatCache(const iv_index_t& ix, const iv_queries_t& q, SegSpan s) : sp(s) {
+        f0 = load_flat<X>(ix, q, sp.klo);
+    }
+    __device__ __forceinline__ Flat<X> of(const iv_index_t& ix, const iv_queries_t& q, int64_t i, int* seg_out = nullptr) const {
+        if (sp.klo == sp.khi) { if (seg_out) *seg_out = sp.klo; return f0; }
+        int seg = find_seg_range(q.seg_off, sp.klo, sp.khi, i);
+        if (seg_out) *seg_out = seg;
+        return seg == sp.klo ? f0 : load_flat<X>(ix, q, seg);
+    }
+};
+__device__ __forceinline__ void apply_slack(int64_t slack, int64_t& s, int64_t& e) {
+    if (slack != 0) {  // join(slack=k): pyranges/multithreaded.py:420-423
+        s -= slack;
+        if (s < 0) s = 0;
+        e += slack;
+    }
 }
 
-__device__ __forceinline__ int64_t count_all(const iv_index_t& ix, const QGeom& g) {
-    if (g.g < 0 || ix.n == 0) return 0;
-    const uint64_t xe = g.ec, xs = g.sc + 1;
-    const uint64_t b1 = xe >> ix.shift, b0 = xs >> ix.shift;
-    const uint4 r1 = bin_ranks(ix, b1);
-    const uint4 r0 = b0 == b1 ? r1 : bin_ranks(ix, b0);
-    int64_t c = (int64_t)rank_in(ix.soff, r1.x, r1.z, (uint32_t)(xe - (b1 << ix.shift))) -
-                (int64_t)rank_in(ix.eoff, r0.y, r0.w, (uint32_t)(xs - (b0 << ix.shift)));
-    return c > 0 ? c : 0;
+// count from the record of bin(ec); general fallback when s'+1 sits in another bin or a bin overflows
+template <typename X>
+__device__ __forceinline__ int64_t count_rec(const iv_index_t& ix, X sc, X ec, const Rec& r, uint64_t b1) {
+    const X xs = sc + 1;
+    const uint64_t b0 = xs >> ix.shift;
+    if (b0 == b1 && rec_inline_s(r) && rec_inline_e(r)) {
+        int c = (int)(r.w[0] + cnt4(r.w[4], r.w[5], rel_of(ix, ec))) - (int)(r.w[1] + cnt4(r.w[6], r.w[7], rel_of(ix, xs)));
+        return c > 0 ? c : 0;
+    }
+    int64_t pe = rec_rank_s(ix, r, b1, rel_of(ix, ec));
+    int64_t re = b0 == b1 ? rec_rank_e(ix, r, b1, rel_of(ix, xs)) : rank_e_lt<X>(ix, xs);
+    return pe > re ? pe - re : 0;
 }
-
-// Visit every subject overlapping [sc, ec).  WANT_P: f(position in start order), else f(subject row).
-template <bool WANT_P, typename F>
-__device__ __forceinline__ void for_each_hit(const iv_index_t& ix, uint64_t sc, uint64_t ec, F&& f) {
-    const uint64_t b = sc >> ix.shift;
-    const uint32_t rel = (uint32_t)(sc - (b << ix.shift));
-    const uint4 r = bin_ranks(ix, b);
-    const uint32_t pS = rank_in(ix.soff, r.x, r.z, rel);
+template <typename X> __device__ __forceinline__ int64_t count_all(const iv_index_t& ix, X sc, X ec) {
     const uint64_t b1 = ec >> ix.shift;
-    const uint32_t pE = b1 == b ? rank_in(ix.soff, r.x, r.z, (uint32_t)(ec - (b << ix.shift))) : rank_s_lt(ix, ec);
+    return count_rec<X>(ix, sc, ec, load_rec(ix, b1), b1);
+}
+
+// Visit every subject overlapping [sc, ec); r = record of bin(sc).
+// WANT_P: f(position in start order), else f(subject row).
+template <typename X, bool WANT_P, typename F>
+__device__ __forceinline__ void for_each_hit_rec(const iv_index_t& ix, X sc, X ec, const Rec& r, F&& f) {
+    const uint64_t b = sc >> ix.shift;
+    const uint32_t rel = rel_of(ix, sc);
+    const uint32_t pS = rec_rank_s(ix, r, b, rel);
+    const uint32_t pE = (ec >> ix.shift) == b ? rec_rank_s(ix, r, b, rel_of(ix, ec)) : rank_s_lt<X>(ix, ec);
     for (uint32_t p = pS; p < pE; p++) f(WANT_P ? p : __ldg(ix.row_s + p));  // class A
-    uint32_t pL = r.x;  // class B, started in this bin: only starts later than s' - max_len can still be open
+    uint32_t pL = r.w[0];  // class B, started in this bin: only starts later than s' - max_len can still be open
     if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
         pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
     for (uint32_t p = pL; p < pS; p++)
         if (__ldg(ix.seoff + p) > rel) f(WANT_P ? p : __ldg(ix.row_s + p));
-    const uint2 c = bin_cross(ix, b);
-    for (uint32_t j = c.x; j < c.y; j++) {                                    // class B, open at the bin origin
+    const uint32_t nc = (r.w[3] >> 16) & 0xffu;
+    const uint32_t c0 = r.w[2], c1 = nc < 255 ? c0 + nc : __ldg(&ix.bins[b + 1].co);
+    for (uint32_t j = c0; j < c1; j++) {                                      // class B, open at the bin origin
         const uint2 en = __ldg(reinterpret_cast<const uint2*>(ix.cross) + j);
         if (en.y > rel) f(WANT_P ? __ldg(ix.cross_p + j) : en.x);
     }
+}
+template <typename X, bool WANT_P, typename F>
+__device__ __forceinline__ void for_each_hit(const iv_index_t& ix, X sc, X ec, F&& f) {
+    for_each_hit_rec<X, WANT_P>(ix, sc, ec, load_rec(ix, sc >> ix.shift), f);
 }
 
 // first hit in nested-containment-list order: smallest start, then largest end, then smallest row
@@ -153,37 +217,57 @@ __device__ __forceinline__ void store_items(int64_t* __restrict__ p, int64_t i0,
 }
 
 // ---- count ----------------------------------------------------------------------------------------------------------
-template <int MODE>
+template <typename X, int MODE>
 __global__ void __launch_bounds__(OV_THREADS)
-k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count, int64_t* __restrict__ tile_sums) {
+k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count, int64_t* __restrict__ tile_sums,
+        int64_t first_tile) {
     __shared__ int span[2];
     __shared__ int64_t red[OV_THREADS / 32];
-    const int64_t tbase = (int64_t)blockIdx.x * OV_TILE;
+    const int64_t tile = first_tile + blockIdx.x;
+    const int64_t tbase = tile * OV_TILE;
     const int64_t last = tbase + OV_TILE - 1 < q.n - 1 ? tbase + OV_TILE - 1 : q.n - 1;
-    SegSpan sp = block_seg_span(q.seg_off, q.n_seg, tbase, last, span);
+    const FlatCache<X> fc(ix, q, block_seg_span(q.seg_off, q.n_seg, tbase, last, span));
     const int64_t i0 = tbase + (int64_t)threadIdx.x * OV_ITEMS;
     int64_t s[OV_ITEMS], e[OV_ITEMS], c[OV_ITEMS];
     load_items(q.start, i0, q.n, vec, s);
     load_items(q.end, i0, q.n, vec, e);
+    // two half-batches: flatten, issue one record gather per query (all in flight together), then count;
+    // dead rows use a harmless geometry
     int64_t tsum = 0;
 #pragma unroll
-    for (int j = 0; j < OV_ITEMS; j++) {
-        c[j] = 0;
-        if (i0 + j < q.n) {
-            QGeom g = make_geom(ix, q, sp.of(q.seg_off, i0 + j), s[j], e[j]);
-            int64_t ca = count_all(ix, g);
+    for (int h = 0; h < OV_ITEMS; h += OV_BATCH) {
+        X sc[OV_BATCH], ec[OV_BATCH];
+        Rec r[OV_BATCH];
+        bool out[OV_BATCH];
+#pragma unroll
+        for (int k = 0; k < OV_BATCH; k++) {
+            const int j = h + k;
+            const int64_t i = i0 + j < q.n ? i0 + j : q.n - 1;
+            const Flat<X> f = fc.of(ix, q, i);
+            apply_slack(q.slack, s[j], e[j]);
+            sc[k] = f.at(s[j]);
+            ec[k] = f.at(e[j]);
+            out[k] = MODE == IV_MODE_CONTAIN ? (f.g < 0 || f.outside(s[j]) || f.outside(e[j])) : false;
+            r[k] = load_rec(ix, ec[k] >> ix.shift);
+        }
+#pragma unroll
+        for (int k = 0; k < OV_BATCH; k++) {
+            const int j = h + k;
+            const int64_t ca = count_rec<X>(ix, sc[k], ec[k], r[k], ec[k] >> ix.shift);
             if (MODE == IV_MODE_ALL) c[j] = ca;
             else if (MODE == IV_MODE_ANY) c[j] = ca > 0 ? 1 : 0;
-            else {  // containment: subject.start <= q.start && q.end <= subject.end (raw coordinates)
-                if (ca > 0 && !g.clamped) {
-                    int64_t k = 0;
-                    uint64_t sc = g.sc, ec = g.ec;
-                    for_each_hit<true>(ix, sc, ec, [&](uint32_t p) {
-                        k += (__ldg(ix.key_s + p) <= sc && ec <= __ldg(ix.end_s + p)) ? 1 : 0;
+            else {
+                // containment: subject.start <= q.start && q.end <= subject.end (raw coordinates)
+                int64_t cnt = 0;
+                if (ca > 0 && !out[k]) {
+                    const uint64_t qs = sc[k], qe = ec[k];
+                    for_each_hit<X, true>(ix, sc[k], ec[k], [&](uint32_t p) {
+                        cnt += (__ldg(ix.key_s + p) <= qs && qe <= __ldg(ix.end_s + p)) ? 1 : 0;
                     });
-                    c[j] = k;
                 }
+                c[j] = cnt;
             }
+            if (i0 + j >= q.n) c[j] = 0;
             tsum += c[j];
         }
     }
@@ -195,22 +279,152 @@ k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count
         if (threadIdx.x < 32) {
             int64_t x = threadIdx.x < OV_THREADS / 32 ? red[threadIdx.x] : 0;
             x = warp_sum(x);
-            if (threadIdx.x == 0) tile_sums[blockIdx.x] = x;
+            if (threadIdx.x == 0) tile_sums[tile] = x;
         }
     }
 }
 
+// ---- count, lean: the throughput kernel for full, 16-byte aligned tiles ----------------------------------------------
+// The record gather runs at ~1 sector / cycle / SM whatever its width (tools/gather_bench.cu: 253 G gathers/s),
+// so the budget per query is set by INSTRUCTIONS: this kernel keeps them to a few dozen -- 32-bit clamps when the
+// coordinates fit, one 256-bit record gather, SWAR compares of the inline 15-bit offsets, vector loads / stores --
+// and keeps 48+ warps per SM resident.  The rare queries that need more than the one record (s'+1 in another bin, a
+// bin with more than four starts / ends) go to a per-warp queue in shared memory and are counted 32 at a time by
+// the full warp, so the long path never runs with one or two active lanes.
+constexpr int LN_THREADS = 256;
+constexpr int LN_TILES = 4;                        // consecutive 1024-row tiles per block
+constexpr int LN_QCAP = 64;                        // slow queue entries per warp
+
+// #{15-bit offsets of (a, b) that are < rel}: per 16-bit half, bit 15 of (rel + 0x7fff - x) is set iff x < rel
+__device__ __forceinline__ uint32_t swar_cnt4(uint32_t a, uint32_t b, uint32_t rel) {
+    const uint32_t c = (rel + 0x7fffu) * 0x10001u;
+    return __popc(((c - a) & 0x80008000u) | (((c - b) & 0x80008000u) >> 1));
+}
+__device__ __forceinline__ bool rec_fast(const Rec& r) {
+    // inline flag set, at most four starts and four ends
+    return (r.w[3] & (IV_BIN_INLINE << 24)) && (r.w[3] & 0xffu) <= 4 && ((r.w[3] >> 8) & 0xffu) <= 4;
+}
+
+template <typename X, int MODE>
+__global__ void __launch_bounds__(LN_THREADS, 6)
+k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, unsigned long long* __restrict__ tile_sums) {
+    __shared__ X q_sc[LN_THREADS / 32][LN_QCAP], q_ec[LN_THREADS / 32][LN_QCAP];
+    __shared__ uint32_t q_row[LN_THREADS / 32][LN_QCAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t bbase = (int64_t)blockIdx.x * (LN_TILES * OV_TILE);
+    const int shift = ix.shift;
+    const uint32_t mask = (1u << shift) - 1u;
+    const iv_binrec_t* __restrict__ bins = ix.bins;
+    int q_head = 0, q_tail = 0;  // warp-uniform ring positions of the slow queue
+    auto count_slow = [&](int n_valid) {
+        if (lane < n_valid) {
+            const int at = (q_head + lane) % LN_QCAP;
+            const int64_t row = bbase + q_row[warp][at];
+            int64_t c = count_all<X>(ix, q_sc[warp][at], q_ec[warp][at]);
+            if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
+            out_count[row] = c;
+            if (c && tile_sums) atomicAdd(tile_sums + row / OV_TILE, (unsigned long long)c);
+        }
+        q_head += n_valid;
+        __syncwarp();
+    };
+    // segment geometry: re-derived only when the block crosses a key boundary (uniform per half-tile otherwise)
+    int seg = find_seg(q.seg_off, q.n_seg, bbase), f_seg = -1;
+    Flat<X> f0;
+    uint32_t lo32 = 0, hi32 = 0, off32 = 0;
+    bool geo32 = false;
+    for (int t = 0; t < LN_TILES; t++) {
+        unsigned long long tsum = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int64_t hbase = bbase + t * OV_TILE + h * (OV_TILE / 2);  // 512 rows: 2 per thread
+            while (seg + 1 < q.n_seg && __ldg(q.seg_off + seg + 1) <= hbase) seg++;
+            if (seg != f_seg) {
+                f0 = load_flat<X>(ix, q, seg);
+                f_seg = seg;
+                const uint64_t hi = (uint64_t)f0.lo + f0.width;
+                geo32 = sizeof(X) == 4 && f0.lo >= 0 && hi <= 0xffffffffull;
+                lo32 = (uint32_t)f0.lo;
+                hi32 = (uint32_t)hi;
+                off32 = (uint32_t)f0.base - lo32;
+            }
+            const bool uniform = __ldg(q.seg_off + seg + 1) >= hbase + OV_TILE / 2;
+            const int64_t i0 = hbase + 2 * threadIdx.x;
+            const longlong2 s2 = __ldg(reinterpret_cast<const longlong2*>(q.start + i0));
+            const longlong2 e2 = __ldg(reinterpret_cast<const longlong2*>(q.end + i0));
+            int64_t s[2] = {s2.x, s2.y}, e[2] = {e2.x, e2.y};
+            X sc[2], ec[2];
+            Rec r[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                apply_slack(q.slack, s[k], e[k]);
+                if (uniform && geo32 && (((uint64_t)s[k] | (uint64_t)e[k]) >> 32) == 0) {
+                    // x' = clamp(x, lo, hi) + (base - lo), all in 32 bits
+                    sc[k] = (X)(min(max((uint32_t)s[k], lo32), hi32) + off32);
+                    ec[k] = (X)(min(max((uint32_t)e[k], lo32), hi32) + off32);
+                } else {
+                    Flat<X> f = f0;
+                    if (!uniform) {
+                        int sg = find_seg_range(q.seg_off, seg, q.n_seg - 1, i0 + k);
+                        if (sg != seg) f = load_flat<X>(ix, q, sg);
+                    }
+                    sc[k] = f.at(s[k]);
+                    ec[k] = f.at(e[k]);
+                }
+                r[k] = load_rec(ix, ec[k] >> shift);
+            }
+            int cc[2];
+            bool fast[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const X xs = sc[k] + 1;
+                fast[k] = (xs >> shift) == (ec[k] >> shift) && rec_fast(r[k]);
+                int c = (int)(r[k].w[0] - r[k].w[1]) + (int)swar_cnt4(r[k].w[4], r[k].w[5], (uint32_t)ec[k] & mask) -
+                        (int)swar_cnt4(r[k].w[6], r[k].w[7], (uint32_t)xs & mask);
+                c = c > 0 ? c : 0;
+                if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
+                cc[k] = fast[k] ? c : 0;
+            }
+            // rows i0, i0+1: one 16-byte store; queued rows are rewritten by count_slow (same warp, later)
+            *reinterpret_cast<longlong2*>(out_count + i0) = make_longlong2(cc[0], cc[1]);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const unsigned m = __ballot_sync(FULL, !fast[k]);
+                if (m) {  // queue the others (flattened coordinates + row); the whole warp counts them 32 at a time
+                    if (!fast[k]) {
+                        const int at = (q_tail + __popc(m & ((1u << lane) - 1u))) % LN_QCAP;
+                        q_sc[warp][at] = sc[k];
+                        q_ec[warp][at] = ec[k];
+                        q_row[warp][at] = (uint32_t)(i0 + k - bbase);
+                    }
+                    q_tail += __popc(m);
+                    __syncwarp();
+                    if (q_tail - q_head >= 32) count_slow(32);
+                }
+            }
+            tsum += (unsigned)(cc[0] + cc[1]);
+        }
+        tsum = warp_sum(tsum);
+        if (lane == 0 && tsum && tile_sums) atomicAdd(tile_sums + bbase / OV_TILE + t, tsum);
+    }
+    if (q_tail - q_head > 0) count_slow(q_tail - q_head);
+}
+
 // ---- emit -----------------------------------------------------------------------------------------------------------
-template <int MODE>
+template <typename X, int MODE>
 __global__ void __launch_bounds__(OV_THREADS)
 k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ counts,
        const int64_t* __restrict__ tile_off, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
        const int64_t* __restrict__ s_label) {
     __shared__ int span[2];
     __shared__ int64_t sm[OV_THREADS / 32 + 1];
+    __shared__ int64_t hit_off[OV_TILE];
+    __shared__ uint16_t hit_li[OV_TILE];
+    __shared__ int hit_n;
     const int64_t tbase = (int64_t)blockIdx.x * OV_TILE;
     const int64_t last = tbase + OV_TILE - 1 < q.n - 1 ? tbase + OV_TILE - 1 : q.n - 1;
-    SegSpan sp = block_seg_span(q.seg_off, q.n_seg, tbase, last, span);
+    if (threadIdx.x == 0) hit_n = 0;
+    const SegSpan sp = block_seg_span(q.seg_off, q.n_seg, tbase, last, span);
     const int64_t i0 = tbase + (int64_t)threadIdx.x * OV_ITEMS;
     int64_t c[OV_ITEMS];
     load_items(counts, i0, q.n, vec, c);
@@ -220,37 +434,49 @@ k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ coun
     int64_t tot;
     int64_t o = block_excl_sum<int64_t, OV_THREADS>(tsum, sm, tot) + __ldg(tile_off + blockIdx.x);
     if (tot == 0) return;
-    if (tsum == 0) return;
-    int64_t s[OV_ITEMS], e[OV_ITEMS];
-    load_items(q.start, i0, q.n, vec, s);
-    load_items(q.end, i0, q.n, vec, e);
+    // compact the hit queries of the tile (with their output offsets) so that consecutive threads work on
+    // consecutive HIT queries: most queries of a sparse join have no hit at all
 #pragma unroll
     for (int j = 0; j < OV_ITEMS; j++) {
-        if (c[j] == 0) continue;
-        const int64_t i = i0 + j;
+        if (c[j] > 0) {
+            const int k = atomicAdd(&hit_n, 1);
+            hit_li[k] = (uint16_t)(threadIdx.x * OV_ITEMS + j);
+            hit_off[k] = o;
+            o += c[j];
+        }
+    }
+    __syncthreads();
+    const FlatCache<X> fc(ix, q, sp);
+    const int nh = hit_n;
+    for (int k = threadIdx.x; k < nh; k += OV_THREADS) {
+        const int64_t i = tbase + hit_li[k];
+        o = hit_off[k];
+        int64_t s = __ldg(q.start + i), e = __ldg(q.end + i);
+        const Flat<X> f = fc.of(ix, q, i);
+        apply_slack(q.slack, s, e);
+        const X sc = f.at(s), ec = f.at(e);
+        const Rec r = load_rec(ix, sc >> ix.shift);
         const int64_t ql = q.label ? __ldg(q.label + i) : i;
-        QGeom g = make_geom(ix, q, sp.of(q.seg_off, i), s[j], e[j]);
         if (MODE == IV_MODE_ALL) {
-            for_each_hit<false>(ix, g.sc, g.ec, [&](uint32_t r) {
+            for_each_hit_rec<X, false>(ix, sc, ec, r, [&](uint32_t row) {
                 if (out_q) out_q[o] = ql;
-                if (out_s) out_s[o] = s_label ? __ldg(s_label + r) : (int64_t)r;
+                if (out_s) out_s[o] = s_label ? __ldg(s_label + row) : (int64_t)row;
                 o++;
             });
         } else if (MODE == IV_MODE_ANY) {
             if (out_q) out_q[o] = ql;
             if (out_s) {
                 FirstHit fh(ix);
-                for_each_hit<true>(ix, g.sc, g.ec, fh);
-                int64_t r = fh.brow;
-                out_s[o] = s_label ? __ldg(s_label + r) : r;
+                for_each_hit_rec<X, true>(ix, sc, ec, r, fh);
+                int64_t row = fh.brow;
+                out_s[o] = s_label ? __ldg(s_label + row) : row;
             }
-            o++;
         } else {
-            uint64_t sc = g.sc, ec = g.ec;
-            for_each_hit<true>(ix, sc, ec, [&](uint32_t p) {
-                if (__ldg(ix.key_s + p) <= sc && ec <= __ldg(ix.end_s + p)) {
+            const uint64_t qs = sc, qe = ec;
+            for_each_hit_rec<X, true>(ix, sc, ec, r, [&](uint32_t p) {
+                if (__ldg(ix.key_s + p) <= qs && qe <= __ldg(ix.end_s + p)) {
                     if (out_q) out_q[o] = ql;
-                    if (out_s) { int64_t r = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + r) : r; }
+                    if (out_s) { int64_t row = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + row) : row; }
                     o++;
                 }
             });
@@ -259,76 +485,77 @@ k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ coun
 }
 
 // ---- NCLS.coverage -----------------------------------------------------------------------------------------------
+template <typename X>
 __global__ void __launch_bounds__(OV_THREADS)
 k_coverage(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_bp, double* __restrict__ out_frac) {
     __shared__ int span[2];
     const int64_t tbase = (int64_t)blockIdx.x * OV_THREADS;
     const int64_t last = tbase + OV_THREADS - 1 < q.n - 1 ? tbase + OV_THREADS - 1 : q.n - 1;
-    SegSpan sp = block_seg_span(q.seg_off, q.n_seg, tbase, last, span);
+    const FlatCache<X> fc(ix, q, block_seg_span(q.seg_off, q.n_seg, tbase, last, span));
     const int64_t i = tbase + threadIdx.x;
     if (i >= q.n) return;
-    int64_t s = __ldg(q.start + i), e = __ldg(q.end + i);
-    QGeom g = make_geom(ix, q, sp.of(q.seg_off, i), s, e);
-    int64_t ca = count_all(ix, g);
+    const int64_t s0 = __ldg(q.start + i), e0 = __ldg(q.end + i);
+    int64_t s = s0, e = e0;
+    apply_slack(q.slack, s, e);
+    const Flat<X> f = fc.of(ix, q, i);
+    const X sc = f.at(s), ec = f.at(e);
     int64_t bp = 0;
-    if (ca > 0) {
-        uint64_t sc = g.sc, ec = g.ec;
-        for_each_hit<true>(ix, sc, ec, [&](uint32_t p) {
+    if (count_all<X>(ix, sc, ec) > 0) {
+        const uint64_t qs = sc, qe = ec;
+        for_each_hit<X, true>(ix, sc, ec, [&](uint32_t p) {
             uint64_t S = __ldg(ix.key_s + p), E = __ldg(ix.end_s + p);
-            bp += (int64_t)((E < ec ? E : ec) - (S > sc ? S : sc));
+            bp += (int64_t)((E < qe ? E : qe) - (S > qs ? S : qs));
         });
     }
     if (out_bp) out_bp[i] = bp;
     if (out_frac) {
-        int64_t len = e - s;
+        int64_t len = e0 - s0;
         out_frac[i] = len == 0 ? 0.0 : (double)bp / (double)len;
     }
 }
 
 // ---- nearest --------------------------------------------------------------------------------------------------------
+template <typename X>
 __global__ void __launch_bounds__(OV_THREADS)
 k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_row, int64_t* __restrict__ out_dist) {
     __shared__ int span[2];
     const int64_t tbase = (int64_t)blockIdx.x * OV_THREADS;
     const int64_t last = tbase + OV_THREADS - 1 < q.n - 1 ? tbase + OV_THREADS - 1 : q.n - 1;
-    SegSpan sp = block_seg_span(q.seg_off, q.n_seg, tbase, last, span);
+    const FlatCache<X> fc(ix, q, block_seg_span(q.seg_off, q.n_seg, tbase, last, span));
     const int64_t i = tbase + threadIdx.x;
     if (i >= q.n) return;
-    const int seg = sp.of(q.seg_off, i);
+    int seg;
+    const Flat<X> f = fc.of(ix, q, i, &seg);
     int64_t s = __ldg(q.start + i), e = __ldg(q.end + i);
-    QGeom g = make_geom(ix, q, seg, s, e);
+    apply_slack(q.slack, s, e);
     int64_t row = -1, dist = -1;
-    if (g.g >= 0 && ix.n > 0) {
+    if (f.g >= 0) {
         const int mode = q.seg_mode ? __ldg(q.seg_mode + seg) : IV_NEAREST_BOTH;
+        const X sc = f.at(s), ec = f.at(e);
         bool done = false;
-        if (overlap) {
-            int64_t ca = count_all(ix, g);
-            if (ca > 0) {
-                FirstHit fh(ix);
-                for_each_hit<true>(ix, g.sc, g.ec, fh);
-                row = fh.brow; dist = 0; done = true;
-            }
+        if (overlap && count_all<X>(ix, sc, ec) > 0) {
+            FirstHit fh(ix);
+            for_each_hit<X, true>(ix, sc, ec, fh);
+            row = fh.brow; dist = 0; done = true;
         }
         if (!done) {
-            const int64_t g_first = __ldg(ix.groups.row_off + g.g), g_end = __ldg(ix.groups.row_off + g.g + 1);
+            const int64_t g_first = __ldg(ix.groups.row_off + f.g), g_end = __ldg(ix.groups.row_off + f.g + 1);
             int64_t prow = -1, pdist = -1, nrow = -1, ndist = -1;
-            if (mode != IV_NEAREST_NEXT && g.s >= g.lo) {
+            if (mode != IV_NEAREST_NEXT && s >= f.lo) {
                 // last subject end <= s ; ties: first of the equal run (earliest row, stable sort)
-                uint64_t sc = (uint64_t)((g.s > g.hi ? g.hi : g.s) - g.lo + g.base);
-                int64_t r = rank_e_lt(ix, sc + 1);
+                const int64_t r = rank_e_lt<X>(ix, (X)(sc + 1));
                 if (r > g_first) {
-                    uint64_t ev = __ldg(ix.key_e + (r - 1));
-                    int64_t jf = rank_e_lt(ix, ev);
+                    const uint64_t ev = __ldg(ix.key_e + (r - 1));
+                    const int64_t jf = rank_e_lt<X>(ix, (X)ev);
                     prow = __ldg(ix.row_e + jf);
-                    pdist = g.s - ((int64_t)ev - g.base + g.lo) + 1;
+                    pdist = s - f.raw(ev) + 1;
                 }
             }
-            if (mode != IV_NEAREST_PREVIOUS && g.e <= g.hi) {
-                uint64_t ec = (uint64_t)((g.e < g.lo ? g.lo : g.e) - g.lo + g.base);
-                int64_t j = rank_s_lt(ix, ec);
+            if (mode != IV_NEAREST_PREVIOUS && !(e > f.lo && (uint64_t)(e - f.lo) > f.width)) {
+                const int64_t j = rank_s_lt<X>(ix, ec);
                 if (j < g_end) {
                     nrow = __ldg(ix.row_s + j);
-                    ndist = ((int64_t)__ldg(ix.key_s + j) - g.base + g.lo) - g.e + 1;
+                    ndist = f.raw(__ldg(ix.key_s + j)) - e + 1;
                 }
             }
             if (prow >= 0 && (nrow < 0 || pdist <= ndist)) { row = prow; dist = pdist; }
@@ -340,6 +567,7 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
 }
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+static bool narrow(const iv_index_t* ix) { return ix->total_span < (int64_t)0xfffffff0ll; }
 
 static int check_query(const iv_index_t* ix, const iv_queries_t* q, const char* who) {
     IV_REQUIRE(ix && q, IV_ERR_INVALID, "%s: null argument", who);
@@ -348,9 +576,46 @@ static int check_query(const iv_index_t* ix, const iv_queries_t* q, const char* 
     return IV_OK;
 }
 
+int g_debug = 0;
+
+template <typename X>
+static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, int64_t* out_count,
+                         int64_t* tile_sums, unsigned ntiles, cudaStream_t st) {
+    int64_t first = 0;
+    const int64_t nblk = q.n / (LN_TILES * OV_TILE);
+    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16 && g_debug != 9) {
+        // full, aligned 4096-row blocks go through the lean kernel, the remainder through the generic one;
+        // its warps add their partial sums with atomics: clear the tile sums of that range first
+        if (tile_sums) cudaMemsetAsync(tile_sums, 0, (size_t)(nblk * LN_TILES) * sizeof(int64_t), st);
+        unsigned long long* ts = reinterpret_cast<unsigned long long*>(tile_sums);
+        if (mode == IV_MODE_ALL) k_count_lean<X, IV_MODE_ALL><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts);
+        else k_count_lean<X, IV_MODE_ANY><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts);
+        __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
+        first = nblk * LN_TILES;
+        if (first >= (int64_t)ntiles) return;
+    }
+    const unsigned nb = (unsigned)(ntiles - first);
+    if (mode == IV_MODE_ALL) k_count<X, IV_MODE_ALL><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, first);
+    else if (mode == IV_MODE_ANY) k_count<X, IV_MODE_ANY><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, first);
+    else k_count<X, IV_MODE_CONTAIN><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, first);
+}
+template <typename X>
+static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, const int64_t* counts,
+                        const int64_t* tile_off, int64_t* out_q, int64_t* out_s, const int64_t* s_label,
+                        unsigned ntiles, cudaStream_t st) {
+    if (mode == IV_MODE_ALL)
+        k_emit<X, IV_MODE_ALL><<<ntiles, OV_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, out_q, out_s, s_label);
+    else if (mode == IV_MODE_ANY)
+        k_emit<X, IV_MODE_ANY><<<ntiles, OV_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, out_q, out_s, s_label);
+    else
+        k_emit<X, IV_MODE_CONTAIN><<<ntiles, OV_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, out_q, out_s, s_label);
+}
+
 }  // namespace iv
 
 using namespace iv;
+
+extern "C" void iv_debug_set(int v) { iv::g_debug = v; }
 
 extern "C" size_t iv_overlap_workspace_bytes(int64_t n_queries) {
     return (size_t)(cdiv(n_queries > 0 ? n_queries : 1, OV_TILE) + 2) * sizeof(int64_t) + 256;
@@ -371,12 +636,8 @@ extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q,
     int64_t ntiles = cdiv(q->n, OV_TILE);
     int64_t* tile_sums = (int64_t*)ws;
     bool vec = aligned16(q->start) && aligned16(q->end) && aligned16(out_count);
-    if (mode == IV_MODE_ALL)
-        k_count<IV_MODE_ALL><<<(unsigned)ntiles, OV_THREADS, 0, st>>>(*index, *q, vec, out_count, tile_sums);
-    else if (mode == IV_MODE_ANY)
-        k_count<IV_MODE_ANY><<<(unsigned)ntiles, OV_THREADS, 0, st>>>(*index, *q, vec, out_count, tile_sums);
-    else
-        k_count<IV_MODE_CONTAIN><<<(unsigned)ntiles, OV_THREADS, 0, st>>>(*index, *q, vec, out_count, tile_sums);
+    if (narrow(index)) launch_count<uint32_t>(*index, *q, mode, vec, out_count, tile_sums, (unsigned)ntiles, st);
+    else launch_count<uint64_t>(*index, *q, mode, vec, out_count, tile_sums, (unsigned)ntiles, st);
     IV_LAUNCH_CHECK();
     if (tile_sums) {
         rc = scan_exclusive_i64_inplace(tile_sums, ntiles, out_total, st);
@@ -396,12 +657,8 @@ extern "C" int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int
     int64_t ntiles = cdiv(q->n, OV_TILE);
     const int64_t* tile_off = (const int64_t*)ws;
     bool vec = aligned16(q->start) && aligned16(q->end) && aligned16(counts);
-    if (mode == IV_MODE_ALL)
-        k_emit<IV_MODE_ALL><<<(unsigned)ntiles, OV_THREADS, 0, st>>>(*index, *q, vec, counts, tile_off, out_q, out_s, s_label);
-    else if (mode == IV_MODE_ANY)
-        k_emit<IV_MODE_ANY><<<(unsigned)ntiles, OV_THREADS, 0, st>>>(*index, *q, vec, counts, tile_off, out_q, out_s, s_label);
-    else
-        k_emit<IV_MODE_CONTAIN><<<(unsigned)ntiles, OV_THREADS, 0, st>>>(*index, *q, vec, counts, tile_off, out_q, out_s, s_label);
+    if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, (unsigned)ntiles, st);
+    else launch_emit<uint64_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, (unsigned)ntiles, st);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }
@@ -412,7 +669,9 @@ extern "C" int iv_coverage_bp(const iv_index_t* index, const iv_queries_t* q, in
     int rc = check_query(index, q, "iv_coverage_bp");
     if (rc != IV_OK) return rc;
     if (q->n == 0) return IV_OK;
-    k_coverage<<<(unsigned)cdiv(q->n, OV_THREADS), OV_THREADS, 0, st>>>(*index, *q, out_bp, out_fraction);
+    unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
+    if (narrow(index)) k_coverage<uint32_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, out_bp, out_fraction);
+    else k_coverage<uint64_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, out_bp, out_fraction);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }
@@ -425,7 +684,9 @@ extern "C" int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_
     if (q->n == 0) return IV_OK;
     IV_REQUIRE(out_row && out_dist, IV_ERR_INVALID, "iv_nearest: null output");
     IV_REQUIRE(index->n == 0 || index->row_e, IV_ERR_INVALID, "iv_nearest: index built without IV_INDEX_ENDS_PERM");
-    k_nearest<<<(unsigned)cdiv(q->n, OV_THREADS), OV_THREADS, 0, st>>>(*index, *q, overlap, out_row, out_dist);
+    unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
+    if (narrow(index)) k_nearest<uint32_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, overlap, out_row, out_dist);
+    else k_nearest<uint64_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, overlap, out_row, out_dist);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -240,3 +240,31 @@ def test_coverage_rle(eng, seed, n_seg, n, maxpos, maxlen):
         sl = slice(run_off[k], run_off[k + 1])
         assert np.array_equal(runs[sl], wr), k
         assert np.array_equal(vals[sl], wv), k
+
+
+def test_large_staged_paths(eng):
+    """sizes above the staged-kernel threshold (>= 64 tiles of 2048 rows), ragged tail, several key segments,
+    a key without partner: counts / pairs must equal the oracle."""
+    rng = np.random.default_rng(5)
+    kq, ks = 6, 5
+    n_per = [40000, 1, 70001, 0, 35000, 20011]
+    qs, qe, qoff = [], [], [0]
+    for n in n_per:
+        s = rng.integers(0, 2_000_000, n)
+        qs.append(s)
+        qe.append(s + rng.integers(1, 300, n))
+        qoff.append(qoff[-1] + n)
+    qs, qe, qoff = np.concatenate(qs).astype(np.int64), np.concatenate(qe).astype(np.int64), np.asarray(qoff, np.int64)
+    ss, se, soff = gen_segments(77, ks, 6000, 2_000_000, 3000)
+    sg = np.asarray([0, 1, 2, 3, -1, 4], np.int32)
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff))
+    for mode, name in [(eng.IV_MODE_ALL, "all"), (eng.IV_MODE_ANY, "any")]:
+        c, _, total = ix.count(q, mode)
+        want = oracle_counts(qs, qe, qoff, sg, ss, se, soff, name)
+        assert np.array_equal(c.cpu().numpy(), want), name
+        assert int(total.item()) == int(want.sum())
+    _, a, b = ix.pairs(q, eng.IV_MODE_ALL)
+    wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "all"))
+    ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
+    assert np.array_equal(ga, wa) and np.array_equal(gb, wb)

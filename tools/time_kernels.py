@@ -1,0 +1,72 @@
+"""Steady-state device time of the individual C-ABI calls on the bench workload (CUDA events, back-to-back
+launches so that host overhead is hidden).  Usage: python tools/time_kernels.py [reads] [annot]"""
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from pyranges_b200 import _cabi as cabi
+from pyranges_b200 import engine as E
+from pyranges_b200 import synthetic as S
+
+nr = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+na = int(sys.argv[2]) if len(sys.argv) > 2 else 200_000
+reads, annot = S.reads(nr), S.annotations(na)
+sg = (np.arange(reads.n_keys) // 2).astype(np.int32)
+q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off)
+s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off)
+L = cabi.lib()
+ix = E.SubjectIndex(s_iv, annot.chrom_ranges())
+q = E.Queries(q_iv, sg)
+counts, ws, total = ix.count(q)
+p = int(total.item())
+out_q = torch.empty(p, dtype=torch.int64, device="cuda")
+out_s = torch.empty(p, dtype=torch.int64, device="cuda")
+st = E._stream()
+
+
+def timeit(name, fn, reps=20, alg_bytes=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / reps
+    extra = "  %.0f GB/s algorithmic" % (alg_bytes / us / 1e3) if alg_bytes else ""
+    print("%-28s %9.1f us%s" % (name, us, extra))
+
+
+def f_count():
+    cabi.check(L.iv_count_overlaps(C.byref(ix.c), C.byref(q.c), 0, E._ptr(counts), E._ptr(ws), ws.numel(), E._ptr(total), st))
+
+
+def f_count_only():
+    cabi.check(L.iv_count_overlaps(C.byref(ix.c), C.byref(q.c), 0, E._ptr(counts), None, 0, None, st))
+
+
+def f_emit():
+    cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), 0, E._ptr(counts), E._ptr(ws), E._ptr(out_q), E._ptr(out_s), None, st))
+
+
+def f_build():
+    E.SubjectIndex(s_iv, annot.chrom_ranges())
+
+
+print("reads %d annotations %d pairs %d" % (nr, na, p))
+import ctypes
+for dbg in (9, 0):
+    ctypes.CDLL(cabi.LIB_PATH).iv_debug_set(dbg)
+    timeit("count dbg=%d" % dbg, f_count_only, alg_bytes=24 * nr)
+timeit("iv_count_overlaps (+scan)", f_count, alg_bytes=24 * nr)
+timeit("iv_count_overlaps (no sums)", f_count_only, alg_bytes=24 * nr)
+timeit("iv_emit_pairs", f_emit, alg_bytes=24 * nr + 16 * p)
+timeit("iv_index_build (python)", f_build, reps=10)
+x = torch.empty(nr * 3, dtype=torch.int64, device="cuda")
+y = torch.empty_like(x)
+timeit("torch copy 240 MB (rd+wr)", lambda: y.copy_(x), alg_bytes=2 * 24 * nr)
