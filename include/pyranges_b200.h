@@ -95,11 +95,12 @@ typedef struct iv_binrec {
     uint32_t co;      /* stabbing list of the bin: cross[co, co + nc)                            */
     uint8_t ns, ne, nc; /* starts / ends / stabbing entries of the bin; 255 = "255 or more": the
                            exact count is the difference to the next record                      */
-    uint8_t flags;    /* bit 0: so[] / eo[] are valid (shift <= 15: offsets are 15-bit)            */
+    uint8_t flags;    /* IV_BIN_INLINE: so[] / eo[] are valid (shift <= 15: offsets are 15-bit); IV_BIN_FAST */
     uint16_t so[4];   /* offsets (x - (b<<shift)) of the bin's first four starts, 0x7FFF = none   */
     uint16_t eo[4];   /* ... and first four ends                                                  */
 } iv_binrec_t;
 #define IV_BIN_INLINE 1
+#define IV_BIN_FAST 2 /* inline and ns <= 4 and ne <= 4: both ranks come out of the record alone */
 
 /* Stabbing-list entry: a subject that starts before the bin and ends after the bin's first coordinate. */
 typedef struct iv_cross {

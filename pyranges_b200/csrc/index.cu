@@ -93,13 +93,12 @@ k_flatten_subjects(const int64_t* __restrict__ s, const int64_t* __restrict__ e,
 
 // Per start-sorted position p: exact flattened end, 32-bit bin offsets, and the rank fields of every bin
 // whose origin falls between the previous key and this one (bs of bin b = first p with bin(key) >= b).
-// blockIdx.y == 0: start order (also counts the bins every subject crosses); == 1: end order.
+// blockIdx.y == 0: start order; == 1: end order.
 __global__ void __launch_bounds__(IX_THREADS)
 k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const uint64_t* __restrict__ key_s,
                const uint32_t* __restrict__ row_s, const uint64_t* __restrict__ key_e, int shift, int64_t n_bins,
                uint64_t* __restrict__ end_s, uint32_t* __restrict__ soff, uint32_t* __restrict__ seoff,
-               uint32_t* __restrict__ eoff, uint32_t* __restrict__ bsarr, uint32_t* __restrict__ bearr,
-               uint32_t* __restrict__ ccnt) {
+               uint32_t* __restrict__ eoff, uint32_t* __restrict__ bsarr, uint32_t* __restrict__ bearr) {
     __shared__ int span[2];
     const int64_t first = (int64_t)blockIdx.x * IX_THREADS;
     const int64_t p = first + threadIdx.x;
@@ -121,11 +120,6 @@ k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const ui
         for (int64_t bb = bprev + 1; bb <= b; bb++) bsarr[bb] = (uint32_t)p;
         if (p == n - 1)
             for (int64_t bb = b + 1; bb <= n_bins + 1; bb++) bsarr[bb] = (uint32_t)n;
-        // bins b+1 .. bin(E-1) are crossed: the subject is open at their origin
-        if (E > k) {
-            const int64_t bl = (int64_t)((E - 1) >> shift);
-            for (int64_t bb = b + 1; bb <= bl; bb++) atomicAdd(ccnt + bb, 1u);
-        }
     } else {
         if (p >= n) return;
         const uint64_t k = key_e[p];
@@ -138,26 +132,57 @@ k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const ui
     }
 }
 
-// stabbing lists: entry order inside a list is arbitrary (atomic cursor)
+// Stabbing list of bin b = the subjects with S' < origin(b) <= E'.  Its length needs no counting pass:
+// #{S' < o} - #{E' < o} = bsarr[b] - bearr[b].  (A member with E' == o can never be a hit -- its eoff is 0 --
+// and is filtered like every member that ends before the query starts.)
+__global__ void __launch_bounds__(IX_THREADS)
+k_cross_counts(int64_t n_bins, const uint32_t* __restrict__ bsarr, const uint32_t* __restrict__ bearr,
+               uint32_t* __restrict__ ccnt) {
+    const int64_t b = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
+    if (b <= n_bins + 1) ccnt[b] = b <= n_bins ? bsarr[b] - bearr[b] : 0u;
+}
+
+// Fill: every (subject, crossed bin) pair is one unit of work, spread over the block's threads whatever the
+// subject lengths (a 2 Mb gene crosses hundreds of bins, an exon none).  Entry order inside a list is arbitrary
+// (atomic cursor).
 __global__ void __launch_bounds__(IX_THREADS)
 k_cross_fill(int64_t n, const uint64_t* __restrict__ key_s, const uint64_t* __restrict__ end_s,
              const uint32_t* __restrict__ row_s, int shift, const uint32_t* __restrict__ coff,
              uint32_t* __restrict__ cursor, int64_t cap, iv_cross_t* __restrict__ cross, uint32_t* __restrict__ cross_p) {
+    __shared__ uint32_t pre[IX_THREADS + 1];
+    __shared__ uint32_t wsum[IX_THREADS / 32 + 1];
+    __shared__ uint64_t sE[IX_THREADS];
+    __shared__ int64_t sB[IX_THREADS];
+    __shared__ uint32_t sRow[IX_THREADS];
     const int64_t p = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
-    if (p >= n) return;
-    const uint64_t k = key_s[p], E = end_s[p];
-    if (E <= k) return;
-    const int64_t b = (int64_t)(k >> shift), bl = (int64_t)((E - 1) >> shift);
-    const uint32_t row = __ldg(row_s + p);
-    for (int64_t bb = b + 1; bb <= bl; bb++) {
-        const uint64_t d = E - ((uint64_t)bb << shift);
+    uint32_t cnt = 0;
+    if (p < n) {
+        const uint64_t k = key_s[p], E = end_s[p];
+        const int64_t b = (int64_t)(k >> shift);
+        sE[threadIdx.x] = E;
+        sB[threadIdx.x] = b + 1;
+        sRow[threadIdx.x] = __ldg(row_s + p);
+        if (E > k) cnt = (uint32_t)((int64_t)(E >> shift) - b);
+    }
+    uint32_t tot;
+    pre[threadIdx.x] = block_excl_sum<uint32_t, IX_THREADS>(cnt, wsum, tot);
+    if (threadIdx.x == 0) pre[IX_THREADS] = tot;
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < tot; u += IX_THREADS) {
+        int lo = 0, hi = IX_THREADS;  // owner = last thread whose prefix <= u
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (pre[mid] <= u) lo = mid; else hi = mid;
+        }
+        const int64_t bb = sB[lo] + (u - pre[lo]);
+        const uint64_t d = sE[lo] - ((uint64_t)bb << shift);
         const int64_t at = (int64_t)__ldg(coff + bb) + atomicAdd(cursor + bb, 1u);
         if (at < cap) {
             iv_cross_t c;
-            c.row = row;
+            c.row = sRow[lo];
             c.eoff = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
             cross[at] = c;
-            cross_p[at] = (uint32_t)p;
+            cross_p[at] = (uint32_t)(blockIdx.x * IX_THREADS + lo);
         }
     }
 }
@@ -181,7 +206,7 @@ k_bins_finalize(int64_t n_bins, int shift, const uint32_t* __restrict__ bsarr, c
     uint4 a, c;
     a.x = bs; a.y = be; a.z = co;
     a.w = (ns < 255 ? ns : 255u) | ((ne < 255 ? ne : 255u) << 8) | ((nc < 255 ? nc : 255u) << 16) |
-          ((inl ? (uint32_t)IV_BIN_INLINE : 0u) << 24);
+          ((inl ? (uint32_t)IV_BIN_INLINE | ((ns <= 4 && ne <= 4) ? (uint32_t)IV_BIN_FAST : 0u) : 0u) << 24);
     c.x = so[0] | (so[1] << 16); c.y = so[2] | (so[3] << 16);
     c.z = eo[0] | (eo[1] << 16); c.w = eo[2] | (eo[3] << 16);
     uint4* out = reinterpret_cast<uint4*>(bins + b);
@@ -210,7 +235,7 @@ static void choose_bins(int64_t n, int64_t span, int64_t sum_len, int* shift, in
     if (s > 31) s = 31;  // bin offsets are 32-bit
     *shift = s;
     *n_bins = (span >> s) + 1;
-    *cross_cap = (sum_len >> s) + n + 16;
+    *cross_cap = (sum_len >> s) + 2 * n + 16;  // bin(E) - bin(S) <= len / binwidth + 1 per subject
 }
 
 static void plan_index(int64_t n, int64_t span, int64_t sum_len, int flags, Bump& b, IndexLayout& L) {
@@ -306,10 +331,11 @@ extern "C" int iv_index_build(const int64_t* starts, const int64_t* ends, int64_
     if (rc != IV_OK) return rc;
     if (res) { out->key_s = L.ks1; out->row_s = L.rs1; out->key_e = L.ke1; out->row_e = L.re1; }
     if (!(flags & IV_INDEX_ENDS_PERM)) out->row_e = nullptr;
-    // ccnt and cursor are adjacent in the workspace: one memset clears both
-    IV_CUDA(cudaMemsetAsync(L.ccnt, 0, (size_t)((char*)L.scan_tmp - (char*)L.ccnt), st));
+    IV_CUDA(cudaMemsetAsync(L.cursor, 0, ((size_t)L.n_bins + 4) * sizeof(uint32_t), st));
     k_index_arrays<<<dim3(nb, 2), IX_THREADS, 0, st>>>(ends, n, G, out->key_s, out->row_s, out->key_e, L.shift, L.n_bins,
-                                                       L.end_s, L.soff, L.seoff, L.eoff, L.bsarr, L.bearr, L.ccnt);
+                                                       L.end_s, L.soff, L.seoff, L.eoff, L.bsarr, L.bearr);
+    IV_LAUNCH_CHECK();
+    k_cross_counts<<<(unsigned)cdiv(L.n_bins + 2, IX_THREADS), IX_THREADS, 0, st>>>(L.n_bins, L.bsarr, L.bearr, L.ccnt);
     IV_LAUNCH_CHECK();
     rc = scan_exclusive_u32_large(L.ccnt, L.n_bins + 2, L.scan_tmp, st);
     if (rc != IV_OK) return rc;

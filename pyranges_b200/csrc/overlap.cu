@@ -314,7 +314,6 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
     const int64_t bbase = (int64_t)blockIdx.x * (LN_TILES * OV_TILE);
     const int shift = ix.shift;
     const uint32_t mask = (1u << shift) - 1u;
-    const iv_binrec_t* __restrict__ bins = ix.bins;
     int q_head = 0, q_tail = 0;  // warp-uniform ring positions of the slow queue
     auto count_slow = [&](int n_valid) {
         if (lane < n_valid) {
@@ -576,14 +575,12 @@ static int check_query(const iv_index_t* ix, const iv_queries_t* q, const char* 
     return IV_OK;
 }
 
-int g_debug = 0;
-
 template <typename X>
 static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, int64_t* out_count,
                          int64_t* tile_sums, unsigned ntiles, cudaStream_t st) {
     int64_t first = 0;
     const int64_t nblk = q.n / (LN_TILES * OV_TILE);
-    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16 && g_debug != 9) {
+    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16) {
         // full, aligned 4096-row blocks go through the lean kernel, the remainder through the generic one;
         // its warps add their partial sums with atomics: clear the tile sums of that range first
         if (tile_sums) cudaMemsetAsync(tile_sums, 0, (size_t)(nblk * LN_TILES) * sizeof(int64_t), st);
@@ -614,8 +611,6 @@ static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, b
 }  // namespace iv
 
 using namespace iv;
-
-extern "C" void iv_debug_set(int v) { iv::g_debug = v; }
 
 extern "C" size_t iv_overlap_workspace_bytes(int64_t n_queries) {
     return (size_t)(cdiv(n_queries > 0 ? n_queries : 1, OV_TILE) + 2) * sizeof(int64_t) + 256;

@@ -2,20 +2,21 @@
 // it needs.  Replaces libc qsort inside NCLS construction and pandas sort_values in
 // pyranges/methods/{cluster,merge,nearest}.py and the mergesort of pyrle's event list.
 //
-// Per 8-bit digit: (1) per-tile digit histogram, digit-major; (2) exclusive scan of the 256 x n_tiles
-// table = global scatter offsets; (3) scatter: warp-level multi-split ranks (__match_any_sync), keys
-// staged through shared memory in digit order so that global writes are coalesced runs.
+// Per 8-bit digit, three launches whatever the size: (1) per-tile digit histogram, digit-major; (2) one warp
+// per digit row: exclusive prefix along the tiles + row total; (3) scatter: every block scans the 256 row
+// totals itself, warp-level multi-split ranks (__match_any_sync), keys staged through shared memory in digit
+// order so that global writes are coalesced runs.  Several sorts of equal length share the launches
+// (blockIdx.y).  Small inputs use 1024-key tiles so that they still spread over the 148 SMs.
 // No inter-block dependencies (no spin waits), so it cannot hang.
 #include "common.cuh"
 
 namespace iv {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per block
+constexpr int RS_ITEMS_BIG = 16;   // 4096 keys per block: large inputs
+constexpr int RS_ITEMS_SMALL = 4;  // 1024 keys per block: small inputs still fill the 148 SMs
 constexpr int RS_RADIX = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_FUSED_TILES = 128;  // up to this many tiles the scatter kernel scans the histograms itself
 
 struct SortJobs {
     const uint64_t* kin[RS_MAX_JOBS];
@@ -26,11 +27,13 @@ struct SortJobs {
 };
 
 // hist[job][digit][tile]
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist(SortJobs J, int64_t n, int shift, uint32_t mask, uint32_t* __restrict__ hist, int64_t ntiles) {
     __shared__ uint32_t h[RS_RADIX];
     const int tid = threadIdx.x, job = blockIdx.y;
     const uint64_t* __restrict__ keys = J.kin[job];
+    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     h[tid] = 0;
     __syncthreads();
     const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
@@ -43,11 +46,31 @@ k_rs_hist(SortJobs J, int64_t n, int shift, uint32_t mask, uint32_t* __restrict_
     hist[((int64_t)job * RS_RADIX + tid) * ntiles + blockIdx.x] = h[tid];
 }
 
-// FUSED: hist holds raw per-tile counts and every block derives its own offsets (small inputs);
-// otherwise hist holds the device-wide exclusive scan over [job][digit][tile].
-template <bool FUSED>
+// One warp per (job, digit) row of the histogram table: exclusive prefix along the tiles (in place) and the
+// row total.  With the exclusive scan of the 256 totals (done by every scatter block for itself) this replaces a
+// device-wide scan of the table: three launches per digit whatever the input size.
 __global__ void __launch_bounds__(RS_THREADS)
-k_rs_scatter(SortJobs J, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ hist, int64_t ntiles) {
+k_rs_prefix(uint32_t* __restrict__ hist, int64_t ntiles, uint32_t* __restrict__ totals, int nrows) {
+    const int row = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t* h = hist + (int64_t)row * ntiles;
+    uint32_t run = 0;
+    for (int64_t base = 0; base < ntiles; base += 32) {
+        const int64_t t = base + lane;
+        const uint32_t v = t < ntiles ? h[t] : 0u;
+        const uint32_t inc = warp_incl_sum(v);
+        if (t < ntiles) h[t] = run + inc - v;
+        run += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) totals[row] = run;
+}
+
+template <int RS_ITEMS>
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(SortJobs J, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ hist,
+             const uint32_t* __restrict__ totals, int64_t ntiles) {
+    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
     __shared__ uint32_t digit_base[RS_RADIX];
     __shared__ uint32_t gbase[RS_RADIX];
@@ -100,22 +123,10 @@ k_rs_scatter(SortJobs J, int64_t n, int shift, uint32_t mask, const uint32_t* __
         uint32_t tot;
         uint32_t ex = block_excl_sum<uint32_t, RS_THREADS>(run, wsum, tot);
         digit_base[tid] = ex;
-        const uint32_t* hrow = hist + ((int64_t)job * RS_RADIX + tid) * ntiles;
-        uint32_t goff;
-        if (FUSED) {
-            uint32_t before = 0, total = 0;
-            for (int64_t t = 0; t < ntiles; t++) {
-                uint32_t c = __ldg(hrow + t);
-                before += t < tile ? c : 0;
-                total += c;
-            }
-            uint32_t tt;
-            uint32_t dstart = block_excl_sum<uint32_t, RS_THREADS>(total, wsum, tt);
-            goff = dstart + before;
-        } else {
-            goff = __ldg(hrow + tile) - (uint32_t)((int64_t)job * n);
-        }
-        gbase[tid] = goff - ex;
+        // global offset of (digit, tile) = digits before (scan of the row totals) + same digit in earlier tiles
+        uint32_t tt;
+        const uint32_t dstart = block_excl_sum<uint32_t, RS_THREADS>(__ldg(totals + job * RS_RADIX + tid), wsum, tt);
+        gbase[tid] = dstart + __ldg(hist + ((int64_t)job * RS_RADIX + tid) * ntiles + tile) - ex;
     }
     __syncthreads();
     uint32_t pos[RS_ITEMS];
@@ -256,27 +267,23 @@ int scan_exclusive_i64_inplace(int64_t* data, int64_t n, int64_t* out_total, cud
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------------
+static int items_for(int64_t n) { return n <= ((int64_t)1 << 20) ? RS_ITEMS_SMALL : RS_ITEMS_BIG; }
+
 size_t radix_sort_temp_bytes(int64_t n) {
-    int64_t ntiles = cdiv(n > 0 ? n : 1, RS_TILE);
+    int64_t ntiles = cdiv(n > 0 ? n : 1, (int64_t)RS_THREADS * items_for(n));
     size_t hist = (size_t)ntiles * RS_RADIX * RS_MAX_JOBS;
-    return (hist + scan_u32_large_temp_elems((int64_t)hist) + 64) * sizeof(uint32_t) + 512;
+    return (hist + RS_RADIX * RS_MAX_JOBS + 128) * sizeof(uint32_t) + 512;
 }
 
-int radix_sort_multi(const SortJob* jobs, int njobs, int64_t n, int begin_bit, int end_bit, void* temp,
-                     size_t temp_bytes, cudaStream_t stream, int* result_buf) {
-    *result_buf = 0;
-    if (n <= 1 || end_bit <= begin_bit || njobs <= 0) return IV_OK;
-    IV_REQUIRE(njobs <= RS_MAX_JOBS, IV_ERR_INVALID, "radix sort: too many jobs");
-    IV_REQUIRE((int64_t)njobs * n < ((int64_t)1 << 32) - RS_TILE, IV_ERR_RANGE, "radix sort: n=%lld exceeds 2^32",
-               (long long)n);
-    for (int j = 0; j < njobs; j++)
-        IV_REQUIRE(jobs[j].vb == 0 || jobs[j].vb == 4 || jobs[j].vb == 8, IV_ERR_INVALID, "radix sort: value_bytes");
-    IV_REQUIRE(temp_bytes >= radix_sort_temp_bytes(n), IV_ERR_WORKSPACE, "radix sort: temp too small");
-    int64_t ntiles = cdiv(n, RS_TILE);
+template <int ITEMS>
+static int radix_sort_multi_t(const SortJob* jobs, int njobs, int64_t n, int begin_bit, int end_bit, void* temp,
+                              cudaStream_t stream, int* result_buf) {
+    constexpr int TILE = RS_THREADS * ITEMS;
+    int64_t ntiles = cdiv(n, TILE);
     uint32_t* hist = (uint32_t*)temp;
     int64_t nh = ntiles * RS_RADIX * njobs;
-    uint32_t* partials = hist + ((nh + 63) & ~(int64_t)63);
-    const bool fused = ntiles <= RS_FUSED_TILES;
+    uint32_t* totals = hist + ((nh + 63) & ~(int64_t)63);
+    const int nrows = RS_RADIX * njobs;
     int cur = 0;
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         int bits = end_bit - shift < 8 ? end_bit - shift : 8;
@@ -290,20 +297,31 @@ int radix_sort_multi(const SortJob* jobs, int njobs, int64_t n, int begin_bit, i
             J.vb[j] = jobs[j].vb;
         }
         dim3 grid((unsigned)ntiles, (unsigned)njobs);
-        k_rs_hist<<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
+        k_rs_hist<ITEMS><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
         IV_LAUNCH_CHECK();
-        if (fused) {
-            k_rs_scatter<true><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
-        } else {
-            int rc = scan_exclusive_u32_large(hist, nh, partials, stream);
-            if (rc != IV_OK) return rc;
-            k_rs_scatter<false><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
-        }
+        k_rs_prefix<<<(unsigned)cdiv(nrows, RS_WARPS), RS_THREADS, 0, stream>>>(hist, ntiles, totals, nrows);
+        IV_LAUNCH_CHECK();
+        k_rs_scatter<ITEMS><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, totals, ntiles);
         IV_LAUNCH_CHECK();
         cur ^= 1;
     }
     *result_buf = cur;
     return IV_OK;
+}
+
+int radix_sort_multi(const SortJob* jobs, int njobs, int64_t n, int begin_bit, int end_bit, void* temp,
+                     size_t temp_bytes, cudaStream_t stream, int* result_buf) {
+    *result_buf = 0;
+    if (n <= 1 || end_bit <= begin_bit || njobs <= 0) return IV_OK;
+    IV_REQUIRE(njobs <= RS_MAX_JOBS, IV_ERR_INVALID, "radix sort: too many jobs");
+    IV_REQUIRE((int64_t)njobs * n < ((int64_t)1 << 32) - 4096, IV_ERR_RANGE, "radix sort: n=%lld exceeds 2^32",
+               (long long)n);
+    for (int j = 0; j < njobs; j++)
+        IV_REQUIRE(jobs[j].vb == 0 || jobs[j].vb == 4 || jobs[j].vb == 8, IV_ERR_INVALID, "radix sort: value_bytes");
+    IV_REQUIRE(temp_bytes >= radix_sort_temp_bytes(n), IV_ERR_WORKSPACE, "radix sort: temp too small");
+    if (items_for(n) == RS_ITEMS_SMALL)
+        return radix_sort_multi_t<RS_ITEMS_SMALL>(jobs, njobs, n, begin_bit, end_bit, temp, stream, result_buf);
+    return radix_sort_multi_t<RS_ITEMS_BIG>(jobs, njobs, n, begin_bit, end_bit, temp, stream, result_buf);
 }
 
 int radix_sort_pingpong(uint64_t* k0, uint64_t* k1, void* v0, void* v1, int value_bytes, int64_t n, int begin_bit,

@@ -75,6 +75,15 @@ class DeviceIntervals:
         self.n_seg = len(self.seg_off) - 1
         self.seg_off_dev = _to_dev(self.seg_off, self.device)
         self._b = bounds  # (lo, hi, maxlen, sumlen) per segment; computed on first use (subjects / unary ops)
+        self._groups = {}
+
+    def groups(self, seg_ranges=None, gap=1, zero_lo=False):
+        """iv_groups_t descriptor of these rows (ingest-time metadata: memoised per grouping)."""
+        key = (None if seg_ranges is None else tuple(map(tuple, seg_ranges)), int(gap), bool(zero_lo))
+        g = self._groups.get(key)
+        if g is None:
+            g = self._groups[key] = Groups(self, seg_ranges, gap=gap, zero_lo=zero_lo)
+        return g
 
     @property
     def bounds(self):
@@ -184,14 +193,21 @@ class SubjectIndex:
 
     def __init__(self, iv, seg_ranges=None, ends_perm=False):
         self.iv = iv
-        self.groups = Groups(iv, seg_ranges, gap=1)
+        self.groups = iv.groups(seg_ranges, gap=1)
         self.flags = IV_INDEX_ENDS_PERM if ends_perm else 0
         L = cabi.lib()
         nbytes = L.iv_index_workspace_bytes(iv.n, self.groups.total_span, self.groups.sumlen, self.flags)
         self.ws = _bytes(nbytes, iv.device)
         self.c = IvIndex()
-        cabi.check(L.iv_index_build(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(self.groups.c), self.flags,
-                                    _ptr(self.ws), self.ws.numel(), C.byref(self.c), _stream()), "iv_index_build")
+        self.build()
+
+    def build(self):
+        """(re)run the device build into this index' workspace: sorts, bin records, stabbing lists"""
+        iv = self.iv
+        cabi.check(cabi.lib().iv_index_build(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(self.groups.c), self.flags,
+                                             _ptr(self.ws), self.ws.numel(), C.byref(self.c), _stream()),
+                   "iv_index_build")
+        return self
 
     # -- counts ------------------------------------------------------------------------------------
     def count(self, q, mode=IV_MODE_ALL, for_emit=True):
@@ -242,7 +258,7 @@ class SubjectIndex:
 
 # ---- unary operations -------------------------------------------------------------------------------
 def _cluster_groups(iv, seg_ranges, slack):
-    g = Groups(iv, seg_ranges, gap=max(int(slack), 0) + 1)
+    g = iv.groups(seg_ranges, gap=max(int(slack), 0) + 1)
     return g, bits_for(g.maxlen)
 
 
@@ -286,7 +302,7 @@ def coverage_rle(iv, seg_ranges=None):
     """pyrle.methods.coverage with unit weights (pyranges/methods/to_rle.py:18) for all groups at once.
     -> (run_off int64[n_groups+1] host, runs int64[R], values float64[R])."""
     L = cabi.lib()
-    g = Groups(iv, seg_ranges, gap=1, zero_lo=True)
+    g = iv.groups(seg_ranges, gap=1, zero_lo=True)
     dev = iv.device
     ws = _bytes(L.iv_rle_workspace_bytes(iv.n, g.n_groups), dev)
     run_off = torch.zeros(g.n_groups + 1, dtype=torch.int64, device=dev)

@@ -59,14 +59,11 @@ def f_build():
 
 
 print("reads %d annotations %d pairs %d" % (nr, na, p))
-import ctypes
-for dbg in (9, 0):
-    ctypes.CDLL(cabi.LIB_PATH).iv_debug_set(dbg)
-    timeit("count dbg=%d" % dbg, f_count_only, alg_bytes=24 * nr)
 timeit("iv_count_overlaps (+scan)", f_count, alg_bytes=24 * nr)
 timeit("iv_count_overlaps (no sums)", f_count_only, alg_bytes=24 * nr)
 timeit("iv_emit_pairs", f_emit, alg_bytes=24 * nr + 16 * p)
-timeit("iv_index_build (python)", f_build, reps=10)
+timeit("SubjectIndex() python", f_build, reps=10)
+timeit("iv_index_build (C call)", ix.build, reps=10, alg_bytes=24 * na)
 x = torch.empty(nr * 3, dtype=torch.int64, device="cuda")
 y = torch.empty_like(x)
 timeit("torch copy 240 MB (rd+wr)", lambda: y.copy_(x), alg_bytes=2 * 24 * nr)
