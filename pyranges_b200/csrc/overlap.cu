@@ -25,6 +25,7 @@ namespace iv {
 constexpr int OV_THREADS = 256;
 constexpr int OV_ITEMS = 4;
 constexpr int OV_TILE = OV_THREADS * OV_ITEMS;  // 1024 queries per block
+constexpr int OV_GRAN = 64;                       // rows per emit warp: the count kernels also leave their sums
 constexpr int OV_BATCH = 2;                       // record gathers a thread keeps in flight
 
 // ---- bin records ----------------------------------------------------------------------------------------------
@@ -220,7 +221,7 @@ __device__ __forceinline__ void store_items(int64_t* __restrict__ p, int64_t i0,
 template <typename X, int MODE>
 __global__ void __launch_bounds__(OV_THREADS)
 k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count, int64_t* __restrict__ tile_sums,
-        int64_t first_tile) {
+        int64_t* __restrict__ gran_sums, int64_t first_tile) {
     __shared__ int span[2];
     __shared__ int64_t red[OV_THREADS / 32];
     const int64_t tile = first_tile + blockIdx.x;
@@ -272,6 +273,12 @@ k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count
         }
     }
     store_items(out_count, i0, q.n, vec, c);
+    if (gran_sums) {  // 64 rows = 16 consecutive threads
+        int64_t g = tsum;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) g += __shfl_xor_sync(FULL, g, o);
+        if ((lane_id() & 15) == 0 && i0 < q.n) gran_sums[i0 / OV_GRAN] = g;
+    }
     if (tile_sums) {
         tsum = warp_sum(tsum);
         if (lane_id() == 0) red[threadIdx.x >> 5] = tsum;
@@ -307,7 +314,8 @@ __device__ __forceinline__ bool rec_fast(const Rec& r) {
 
 template <typename X, int MODE>
 __global__ void __launch_bounds__(LN_THREADS, 6)
-k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, unsigned long long* __restrict__ tile_sums) {
+k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, unsigned long long* __restrict__ tile_sums,
+             unsigned long long* __restrict__ gran_sums) {
     __shared__ X q_sc[LN_THREADS / 32][LN_QCAP], q_ec[LN_THREADS / 32][LN_QCAP];
     __shared__ uint32_t q_row[LN_THREADS / 32][LN_QCAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -322,7 +330,10 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
             int64_t c = count_all<X>(ix, q_sc[warp][at], q_ec[warp][at]);
             if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
             out_count[row] = c;
-            if (c && tile_sums) atomicAdd(tile_sums + row / OV_TILE, (unsigned long long)c);
+            if (c && tile_sums) {
+                atomicAdd(tile_sums + row / OV_TILE, (unsigned long long)c);
+                atomicAdd(gran_sums + row / OV_GRAN, (unsigned long long)c);
+            }
         }
         q_head += n_valid;
         __syncwarp();
@@ -401,81 +412,173 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
                     if (q_tail - q_head >= 32) count_slow(32);
                 }
             }
-            tsum += (unsigned)(cc[0] + cc[1]);
+            // this warp's 64 rows are one emit granule
+            const unsigned long long g = warp_sum((unsigned long long)(unsigned)(cc[0] + cc[1]));
+            if (lane == 0 && g && tile_sums) atomicAdd(gran_sums + hbase / OV_GRAN + warp, g);
+            tsum += g;
         }
-        tsum = warp_sum(tsum);
         if (lane == 0 && tsum && tile_sums) atomicAdd(tile_sums + bbase / OV_TILE + t, tsum);
     }
     if (q_tail - q_head > 0) count_slow(q_tail - q_head);
 }
 
 // ---- emit -----------------------------------------------------------------------------------------------------------
+// One WARP per 64-row granule, no block-wide barrier: the warp's output offset is the tile offset (scan of the tile
+// sums) plus the sums of the granules before it in the tile (both left by the count kernel); a shuffle scan of the
+// 64 counts gives every query its offset.  Most queries of a sparse join have no hit and the hit ones differ in how
+// many candidates they walk, so the warp first compacts its hit queries into a small shared-memory queue and then
+// gives every lane one HIT query per round.
+constexpr int EM_THREADS = 256;
+constexpr int EM_WARPS = EM_THREADS / 32;
+
 template <typename X, int MODE>
-__global__ void __launch_bounds__(OV_THREADS)
+__global__ void __launch_bounds__(EM_THREADS)
 k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ counts,
-       const int64_t* __restrict__ tile_off, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
-       const int64_t* __restrict__ s_label) {
-    __shared__ int span[2];
-    __shared__ int64_t sm[OV_THREADS / 32 + 1];
-    __shared__ int64_t hit_off[OV_TILE];
-    __shared__ uint16_t hit_li[OV_TILE];
-    __shared__ int hit_n;
-    const int64_t tbase = (int64_t)blockIdx.x * OV_TILE;
-    const int64_t last = tbase + OV_TILE - 1 < q.n - 1 ? tbase + OV_TILE - 1 : q.n - 1;
-    if (threadIdx.x == 0) hit_n = 0;
-    const SegSpan sp = block_seg_span(q.seg_off, q.n_seg, tbase, last, span);
-    const int64_t i0 = tbase + (int64_t)threadIdx.x * OV_ITEMS;
-    int64_t c[OV_ITEMS];
-    load_items(counts, i0, q.n, vec, c);
-    int64_t tsum = 0;
-#pragma unroll
-    for (int j = 0; j < OV_ITEMS; j++) tsum += c[j];
-    int64_t tot;
-    int64_t o = block_excl_sum<int64_t, OV_THREADS>(tsum, sm, tot) + __ldg(tile_off + blockIdx.x);
-    if (tot == 0) return;
-    // compact the hit queries of the tile (with their output offsets) so that consecutive threads work on
-    // consecutive HIT queries: most queries of a sparse join have no hit at all
-#pragma unroll
-    for (int j = 0; j < OV_ITEMS; j++) {
-        if (c[j] > 0) {
-            const int k = atomicAdd(&hit_n, 1);
-            hit_li[k] = (uint16_t)(threadIdx.x * OV_ITEMS + j);
-            hit_off[k] = o;
-            o += c[j];
-        }
+       const int64_t* __restrict__ tile_off, const int64_t* __restrict__ gran_sums, int64_t* __restrict__ out_q,
+       int64_t* __restrict__ out_s, const int64_t* __restrict__ s_label) {
+    __shared__ int64_t h_off[EM_WARPS][OV_GRAN];
+    __shared__ X h_sc[EM_WARPS][OV_GRAN], h_ec[EM_WARPS][OV_GRAN];
+    __shared__ uint8_t h_row[EM_WARPS][OV_GRAN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gran = (int64_t)blockIdx.x * EM_WARPS + warp;
+    const int64_t gbase = gran * OV_GRAN;
+    if (gbase >= q.n) return;
+    const int64_t tile = gbase / OV_TILE;
+    constexpr int GPT = OV_TILE / OV_GRAN;  // 16 granules per tile
+    // output offset of the granule
+    int64_t pre = lane < (int)(gran % GPT) ? __ldg(gran_sums + tile * GPT + lane) : 0;
+    pre = warp_sum(pre) + __ldg(tile_off + tile);
+    // the 64 counts: two per lane
+    const int64_t i0 = gbase + 2 * lane;
+    int64_t c0 = 0, c1 = 0;
+    if (vec && i0 + 1 < q.n) {
+        const longlong2 cv = __ldg(reinterpret_cast<const longlong2*>(counts + i0));
+        c0 = cv.x; c1 = cv.y;
+    } else {
+        if (i0 < q.n) c0 = __ldg(counts + i0);
+        if (i0 + 1 < q.n) c1 = __ldg(counts + i0 + 1);
     }
-    __syncthreads();
-    const FlatCache<X> fc(ix, q, sp);
-    const int nh = hit_n;
-    for (int k = threadIdx.x; k < nh; k += OV_THREADS) {
-        const int64_t i = tbase + hit_li[k];
-        o = hit_off[k];
-        int64_t s = __ldg(q.start + i), e = __ldg(q.end + i);
-        const Flat<X> f = fc.of(ix, q, i);
-        apply_slack(q.slack, s, e);
-        const X sc = f.at(s), ec = f.at(e);
-        const Rec r = load_rec(ix, sc >> ix.shift);
-        const int64_t ql = q.label ? __ldg(q.label + i) : i;
+    const int64_t mine = c0 + c1;
+    const int64_t inc = warp_incl_sum(mine);
+    if (__shfl_sync(FULL, inc, 31) == 0) return;  // no hit in the granule
+    int64_t o = pre + inc - mine;
+    // segment geometry of the granule (usually one segment)
+    const int seg0 = find_seg(q.seg_off, q.n_seg, gbase);
+    const Flat<X> f0 = load_flat<X>(ix, q, seg0);
+    const bool one_seg = __ldg(q.seg_off + seg0 + 1) >= gbase + OV_GRAN;
+    const uint64_t hi0 = (uint64_t)f0.lo + f0.width;
+    const bool tight = sizeof(X) == 4 && one_seg && f0.lo >= 0 && hi0 <= 0xffffffffull;
+    const uint32_t lo32 = (uint32_t)f0.lo, hi32 = (uint32_t)hi0, off32 = (uint32_t)f0.base - lo32;
+    const int shift = ix.shift;
+    const uint32_t mask = (1u << shift) - 1u;
+    // the lane's two rows, read coalesced and flattened here: the hit ones travel through the queue, so the
+    // round loop below does no scattered reads of the query columns
+    int64_t s0 = 0, s1 = 0, e0 = 0, e1 = 0;
+    if (vec && i0 + 1 < q.n) {
+        const longlong2 sv = __ldg(reinterpret_cast<const longlong2*>(q.start + i0));
+        const longlong2 ev = __ldg(reinterpret_cast<const longlong2*>(q.end + i0));
+        s0 = sv.x; s1 = sv.y; e0 = ev.x; e1 = ev.y;
+    } else {
+        if (i0 < q.n) { s0 = __ldg(q.start + i0); e0 = __ldg(q.end + i0); }
+        if (i0 + 1 < q.n) { s1 = __ldg(q.start + i0 + 1); e1 = __ldg(q.end + i0 + 1); }
+    }
+    apply_slack(q.slack, s0, e0);
+    apply_slack(q.slack, s1, e1);
+    X sc0, ec0, sc1, ec1;
+    if (tight && (((uint64_t)s0 | (uint64_t)e0 | (uint64_t)s1 | (uint64_t)e1) >> 32) == 0) {
+        sc0 = (X)(min(max((uint32_t)s0, lo32), hi32) + off32);
+        ec0 = (X)(min(max((uint32_t)e0, lo32), hi32) + off32);
+        sc1 = (X)(min(max((uint32_t)s1, lo32), hi32) + off32);
+        ec1 = (X)(min(max((uint32_t)e1, lo32), hi32) + off32);
+    } else {
+        const int64_t ra = i0 < q.n ? i0 : q.n - 1, rb = i0 + 1 < q.n ? i0 + 1 : q.n - 1;
+        const Flat<X> fa = one_seg ? f0 : load_flat<X>(ix, q, find_seg_range(q.seg_off, seg0, q.n_seg - 1, ra));
+        const Flat<X> fb = one_seg ? f0 : load_flat<X>(ix, q, find_seg_range(q.seg_off, seg0, q.n_seg - 1, rb));
+        sc0 = fa.at(s0); ec0 = fa.at(e0);
+        sc1 = fb.at(s1); ec1 = fb.at(e1);
+    }
+    // compact the hit queries
+    const unsigned m0 = __ballot_sync(FULL, c0 > 0), m1 = __ballot_sync(FULL, c1 > 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (c0 > 0) {
+        const int k = __popc(m0 & lt);
+        h_row[warp][k] = (uint8_t)(2 * lane); h_off[warp][k] = o; h_sc[warp][k] = sc0; h_ec[warp][k] = ec0;
+    }
+    if (c1 > 0) {
+        const int k = __popc(m0) + __popc(m1 & lt);
+        h_row[warp][k] = (uint8_t)(2 * lane + 1); h_off[warp][k] = o + c0; h_sc[warp][k] = sc1; h_ec[warp][k] = ec1;
+    }
+    const int nh = __popc(m0) + __popc(m1);
+    __syncwarp();
+    for (int k = lane; k < nh; k += 32) {
+        const int64_t row = gbase + h_row[warp][k];
+        o = h_off[warp][k];
+        const X sc = h_sc[warp][k], ec = h_ec[warp][k];
+        const uint64_t b = sc >> shift;
+        const uint32_t rel = (uint32_t)sc & mask;
+        const Rec r = load_rec(ix, b);
+        const int64_t ql = q.label ? __ldg(q.label + row) : row;
         if (MODE == IV_MODE_ALL) {
-            for_each_hit_rec<X, false>(ix, sc, ec, r, [&](uint32_t row) {
+            auto put = [&](uint32_t srow) {
                 if (out_q) out_q[o] = ql;
-                if (out_s) out_s[o] = s_label ? __ldg(s_label + row) : (int64_t)row;
+                if (out_s) out_s[o] = s_label ? __ldg(s_label + srow) : (int64_t)srow;
                 o++;
-            });
+            };
+            uint32_t pS, pE;
+            if (rec_inline_s(r)) {
+                pS = r.w[0] + swar_cnt4(r.w[4], r.w[5], rel);
+                pE = (ec >> shift) == b ? r.w[0] + swar_cnt4(r.w[4], r.w[5], (uint32_t)ec & mask) : rank_s_lt<X>(ix, ec);
+            } else {
+                pS = rec_rank_s(ix, r, b, rel);
+                pE = (ec >> shift) == b ? rec_rank_s(ix, r, b, (uint32_t)ec & mask) : rank_s_lt<X>(ix, ec);
+            }
+            // candidates in start order: [pL, pS) started in this bin before s' (class B if still open),
+            // [pS, pE) start inside the query (class A).  Four at a time, loads first: one latency per chunk.
+            uint32_t pL = r.w[0];
+            if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
+                pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
+            for (uint32_t p = pL; p < pS; p += 4) {  // started before s': open iff its end offset is beyond s'
+                uint32_t so[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) so[u] = p + u < pS ? __ldg(ix.seoff + p + u) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (so[u] > rel) put(__ldg(ix.row_s + p + u));
+            }
+            for (uint32_t p = pS; p < pE; p += 4) {  // start inside the query: all hits
+                uint32_t rw[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) rw[u] = p + u < pE ? __ldg(ix.row_s + p + u) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (p + u < pE) put(rw[u]);
+            }
+            // class B, open at the bin origin: the bin's stabbing list
+            const uint32_t nc = (r.w[3] >> 16) & 0xffu;
+            const uint32_t x0 = r.w[2], x1 = nc < 255 ? x0 + nc : __ldg(&ix.bins[b + 1].co);
+            for (uint32_t j = x0; j < x1; j += 4) {
+                uint2 en[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    en[u] = j + u < x1 ? __ldg(reinterpret_cast<const uint2*>(ix.cross) + j + u) : make_uint2(0u, 0u);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (en[u].y > rel) put(en[u].x);
+            }
         } else if (MODE == IV_MODE_ANY) {
             if (out_q) out_q[o] = ql;
             if (out_s) {
                 FirstHit fh(ix);
                 for_each_hit_rec<X, true>(ix, sc, ec, r, fh);
-                int64_t row = fh.brow;
-                out_s[o] = s_label ? __ldg(s_label + row) : row;
+                const int64_t srow = fh.brow;
+                out_s[o] = s_label ? __ldg(s_label + srow) : srow;
             }
         } else {
             const uint64_t qs = sc, qe = ec;
             for_each_hit_rec<X, true>(ix, sc, ec, r, [&](uint32_t p) {
                 if (__ldg(ix.key_s + p) <= qs && qe <= __ldg(ix.end_s + p)) {
                     if (out_q) out_q[o] = ql;
-                    if (out_s) { int64_t row = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + row) : row; }
+                    if (out_s) { int64_t srow = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + srow) : srow; }
                     o++;
                 }
             });
@@ -575,37 +678,46 @@ static int check_query(const iv_index_t* ix, const iv_queries_t* q, const char* 
     return IV_OK;
 }
 
+// workspace of count / emit: [tile sums -> tile offsets (n/1024 + 2)] [granule sums (n/64 + 2)]
+static size_t ws_tiles(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_TILE) + 2; }
+static size_t ws_grans(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_GRAN) + 2; }
+
 template <typename X>
 static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, int64_t* out_count,
                          int64_t* tile_sums, unsigned ntiles, cudaStream_t st) {
+    int64_t* gran_sums = tile_sums ? tile_sums + ws_tiles(q.n) : nullptr;
     int64_t first = 0;
     const int64_t nblk = q.n / (LN_TILES * OV_TILE);
     if (mode != IV_MODE_CONTAIN && vec && nblk >= 16) {
         // full, aligned 4096-row blocks go through the lean kernel, the remainder through the generic one;
-        // its warps add their partial sums with atomics: clear the tile sums of that range first
-        if (tile_sums) cudaMemsetAsync(tile_sums, 0, (size_t)(nblk * LN_TILES) * sizeof(int64_t), st);
+        // its warps add their partial sums with atomics: clear the sums first
+        if (tile_sums) cudaMemsetAsync(tile_sums, 0, (ws_tiles(q.n) + ws_grans(q.n)) * sizeof(int64_t), st);
         unsigned long long* ts = reinterpret_cast<unsigned long long*>(tile_sums);
-        if (mode == IV_MODE_ALL) k_count_lean<X, IV_MODE_ALL><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts);
-        else k_count_lean<X, IV_MODE_ANY><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts);
+        unsigned long long* gs = reinterpret_cast<unsigned long long*>(gran_sums);
+        if (mode == IV_MODE_ALL) k_count_lean<X, IV_MODE_ALL><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts, gs);
+        else k_count_lean<X, IV_MODE_ANY><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts, gs);
         __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
         first = nblk * LN_TILES;
         if (first >= (int64_t)ntiles) return;
     }
     const unsigned nb = (unsigned)(ntiles - first);
-    if (mode == IV_MODE_ALL) k_count<X, IV_MODE_ALL><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, first);
-    else if (mode == IV_MODE_ANY) k_count<X, IV_MODE_ANY><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, first);
-    else k_count<X, IV_MODE_CONTAIN><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, first);
+    if (mode == IV_MODE_ALL) k_count<X, IV_MODE_ALL><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, gran_sums, first);
+    else if (mode == IV_MODE_ANY) k_count<X, IV_MODE_ANY><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, gran_sums, first);
+    else k_count<X, IV_MODE_CONTAIN><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, gran_sums, first);
 }
+
 template <typename X>
 static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, const int64_t* counts,
                         const int64_t* tile_off, int64_t* out_q, int64_t* out_s, const int64_t* s_label,
-                        unsigned ntiles, cudaStream_t st) {
+                        cudaStream_t st) {
+    const int64_t* gran_sums = tile_off + ws_tiles(q.n);
+    const unsigned nb = (unsigned)cdiv(cdiv(q.n, OV_GRAN), EM_WARPS);
     if (mode == IV_MODE_ALL)
-        k_emit<X, IV_MODE_ALL><<<ntiles, OV_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, out_q, out_s, s_label);
+        k_emit<X, IV_MODE_ALL><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label);
     else if (mode == IV_MODE_ANY)
-        k_emit<X, IV_MODE_ANY><<<ntiles, OV_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, out_q, out_s, s_label);
+        k_emit<X, IV_MODE_ANY><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label);
     else
-        k_emit<X, IV_MODE_CONTAIN><<<ntiles, OV_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, out_q, out_s, s_label);
+        k_emit<X, IV_MODE_CONTAIN><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label);
 }
 
 }  // namespace iv
@@ -613,7 +725,7 @@ static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, b
 using namespace iv;
 
 extern "C" size_t iv_overlap_workspace_bytes(int64_t n_queries) {
-    return (size_t)(cdiv(n_queries > 0 ? n_queries : 1, OV_TILE) + 2) * sizeof(int64_t) + 256;
+    return (ws_tiles(n_queries) + ws_grans(n_queries)) * sizeof(int64_t) + 256;
 }
 
 extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mode, int64_t* out_count,
@@ -652,8 +764,8 @@ extern "C" int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int
     int64_t ntiles = cdiv(q->n, OV_TILE);
     const int64_t* tile_off = (const int64_t*)ws;
     bool vec = aligned16(q->start) && aligned16(q->end) && aligned16(counts);
-    if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, (unsigned)ntiles, st);
-    else launch_emit<uint64_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, (unsigned)ntiles, st);
+    if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, st);
+    else launch_emit<uint64_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, st);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }
