@@ -36,26 +36,54 @@ class KeyedArrays:
         return [(2 * c, 2 * c + 2) for c in range(self.n_keys // 2)]
 
 
+def shard_chromosomes(world, rank):
+    """chromosome ids owned by `rank`: size-balanced (LPT) assignment, both strands of a chromosome together"""
+    from .sharding import lpt_assign
+
+    a = lpt_assign(SIZES, world)
+    return [c for c in range(len(SIZES)) if a[c] == rank]
+
+
+def _split_counts(n_total):
+    """rows per chromosome, proportional to size, summing to n_total exactly"""
+    w = SIZES / SIZES.sum()
+    c = np.floor(w * n_total).astype(np.int64)
+    c[: int(n_total - c.sum())] += 1
+    return c
+
+
+def _chrom_for(rng, n_total, chroms):
+    per = _split_counts(n_total)
+    c = np.repeat(np.asarray(chroms, dtype=np.int64), per[chroms])
+    return c[rng.permutation(len(c))]
+
+
 def _chrom(rng, n):
     return rng.choice(len(SIZES), size=n, p=SIZES / SIZES.sum())
 
 
-def reads(n, seed=1, length=100, min_len=None, max_len=None):
-    """n reads: Start ~ U[0, size-len), fixed length (or U{min_len..max_len})."""
+def reads(n, seed=1, length=100, min_len=None, max_len=None, chroms=None):
+    """n reads: Start ~ U[0, size-len), fixed length (or U{min_len..max_len}).
+    chroms: only the rows of these chromosome ids of an n-row genome-wide set (a rank's shard)."""
     rng = np.random.default_rng(seed)
-    c = _chrom(rng, n)
+    c = _chrom(rng, n) if chroms is None else _chrom_for(rng, n, chroms)
+    n = len(c)
     strand = rng.integers(0, 2, n)
     ln = np.full(n, length, np.int64) if min_len is None else rng.integers(min_len, max_len + 1, n)
     s = np.floor(rng.random(n) * (SIZES[c] - ln)).astype(np.int64)
     return KeyedArrays(s, s + ln, c * 2 + strand, 2 * len(SIZES))
 
 
-def annotations(n, seed=2):
-    """10 % genes (log-normal length, 0.5 kb .. 2 Mb), 90 % exons nested inside a random gene."""
+def annotations(n, seed=2, chroms=None):
+    """10 % genes (log-normal length, 0.5 kb .. 2 Mb), 90 % exons nested inside a random gene.
+    chroms: only the genes (and their exons) on these chromosome ids of an n-row genome-wide set."""
     rng = np.random.default_rng(seed)
     ng = max(1, n // 10)
+    gc = _chrom(rng, ng) if chroms is None else _chrom_for(rng, ng, chroms)
+    if chroms is not None:
+        n = int(round(n * len(gc) / ng))
+    ng = len(gc)
     ne = n - ng
-    gc = _chrom(rng, ng)
     gstrand = rng.integers(0, 2, ng)
     glen = np.clip(np.floor(rng.lognormal(np.log(25000.0), 1.2, ng)), 500, 2000000).astype(np.int64)
     glen = np.minimum(glen, SIZES[gc] - 1)
