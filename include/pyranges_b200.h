@@ -33,7 +33,8 @@
  *     (structs live in host memory, their members are device pointers / scalars);
  *   - all coordinates, labels, counts are int64 (pyranges/methods/init.py:13-16);
  *   - the caller owns every buffer including the workspace (size from *_workspace_bytes); the library
- *     never allocates or frees device memory and never synchronises the stream;
+ *     never allocates or frees device memory and does not synchronise the stream (one exception:
+ *     iv_cluster / iv_merge_count read back one flag to skip the sort of already sorted input);
  *   - `stream` is a cudaStream_t passed as void*;
  *   - return value: IV_OK or a negative error; iv_last_error_string() describes the last failure of
  *     the calling thread.

@@ -21,7 +21,7 @@ constexpr int CL_TILE = CL_THREADS * CL_ITEMS;  // 2048 rows per block
 
 __global__ void __launch_bounds__(CL_THREADS)
 k_cluster_keys(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, iv_groups_t G, int lbits,
-               uint64_t* __restrict__ keys, uint32_t* __restrict__ rows) {
+               uint64_t* __restrict__ keys, uint32_t* __restrict__ rows, int* __restrict__ unsorted) {
     __shared__ int span[2];
     int64_t first = (int64_t)blockIdx.x * CL_THREADS;
     int64_t last = first + CL_THREADS - 1 < n - 1 ? first + CL_THREADS - 1 : n - 1;
@@ -31,8 +31,17 @@ k_cluster_keys(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int
     int g = sp.of(G.row_off, i);
     int64_t a = s[i], b = e[i];
     uint64_t len = b > a ? (uint64_t)(b - a) : 0;
-    keys[i] = ((uint64_t)(a - __ldg(G.lo + g) + __ldg(G.base + g)) << lbits) | len;
+    const uint64_t key = ((uint64_t)(a - __ldg(G.lo + g) + __ldg(G.base + g)) << lbits) | len;
+    keys[i] = key;
     rows[i] = (uint32_t)i;
+    // already in (group, Start, End) order?  then the stable sort is the identity and is skipped
+    if (i > 0) {
+        int64_t pa = s[i - 1], pb = e[i - 1];
+        int pg = sp.of(G.row_off, i - 1);
+        uint64_t plen = pb > pa ? (uint64_t)(pb - pa) : 0;
+        uint64_t pkey = ((uint64_t)(pa - __ldg(G.lo + pg) + __ldg(G.base + pg)) << lbits) | plen;
+        if (pkey > key && *unsorted == 0) *unsorted = 1;
+    }
 }
 
 // single block exclusive max scan (identity INT64_MIN)
@@ -195,6 +204,7 @@ struct ClusterLayout {
     uint32_t *r0, *r1;
     uint8_t* flags;
     int64_t *tile_max, *tile_cnt, *c_first;
+    int* unsorted;  // device flag written by k_cluster_keys; its host copy decides about the sort
     void* sort_temp;
 };
 
@@ -209,6 +219,7 @@ static void plan_cluster(int64_t n, Bump& b, ClusterLayout& L) {
     L.tile_max = b.take<int64_t>(nt);
     L.tile_cnt = b.take<int64_t>(nt);
     L.c_first = b.take<int64_t>(nn);
+    L.unsorted = b.take<int>(64);
     L.sort_temp = b.take<char>(radix_sort_temp_bytes(n));
 }
 
@@ -231,10 +242,22 @@ static int cluster_phase1(const int64_t* starts, const int64_t* ends, int64_t n,
         *res = 0;
         return IV_OK;
     }
-    k_cluster_keys<<<(unsigned)cdiv(n, CL_THREADS), CL_THREADS, 0, st>>>(starts, ends, n, *G, len_bits, L.k0, L.r0);
+    IV_CUDA(cudaMemsetAsync(L.unsorted, 0, sizeof(int), st));
+    k_cluster_keys<<<(unsigned)cdiv(n, CL_THREADS), CL_THREADS, 0, st>>>(starts, ends, n, *G, len_bits, L.k0, L.r0,
+                                                                          L.unsorted);
     IV_LAUNCH_CHECK();
-    int rc = radix_sort_pingpong(L.k0, L.k1, L.r0, L.r1, 4, n, 0, tbits, L.sort_temp, radix_sort_temp_bytes(n), st, res);
-    if (rc != IV_OK) return rc;
+    // one small host read (the only synchronisation of the call): sorted input skips all radix passes.
+    // unsorted[1] records which buffer holds the sorted keys for iv_merge_emit.
+    int h_unsorted = 1;
+    IV_CUDA(cudaMemcpyAsync(&h_unsorted, L.unsorted, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IV_CUDA(cudaStreamSynchronize(st));
+    int rc = IV_OK;
+    *res = 0;
+    if (h_unsorted) {
+        rc = radix_sort_pingpong(L.k0, L.k1, L.r0, L.r1, 4, n, 0, tbits, L.sort_temp, radix_sort_temp_bytes(n), st, res);
+        if (rc != IV_OK) return rc;
+    }
+    IV_CUDA(cudaMemcpyAsync(L.unsorted + 1, res, sizeof(int), cudaMemcpyHostToDevice, st));
     const uint64_t* keys = *res ? L.k1 : L.k0;
     unsigned nt = (unsigned)cdiv(n, CL_TILE);
     k_cl_tilemax<<<nt, CL_THREADS, 0, st>>>(keys, n, len_bits, L.tile_max);
@@ -291,8 +314,9 @@ extern "C" int iv_merge_emit(int64_t n, int64_t n_clusters, const iv_groups_t* g
     Bump b((void*)ws, (size_t)-1);
     ClusterLayout L;
     plan_cluster(n, b, L);
-    int passes = (cluster_total_bits(groups, len_bits) + 7) / 8;
-    int res = passes & 1;
+    int res = 0;  // which ping-pong buffer holds the sorted keys: left by iv_merge_count in the workspace
+    IV_CUDA(cudaMemcpyAsync(&res, L.unsorted + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IV_CUDA(cudaStreamSynchronize(st));
     unsigned nt = (unsigned)cdiv(n, CL_TILE);
     // out_end doubles as the atomicMax accumulator of the flattened cluster end: 0x80.. = very negative
     IV_CUDA(cudaMemsetAsync(out_end, 0x80, (size_t)n_clusters * 8, st));

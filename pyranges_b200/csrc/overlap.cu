@@ -348,6 +348,7 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int64_t hbase = bbase + t * OV_TILE + h * (OV_TILE / 2);  // 512 rows: 2 per thread
+            if (hbase >= q.n) break;  // ragged last block
             while (seg + 1 < q.n_seg && __ldg(q.seg_off + seg + 1) <= hbase) seg++;
             if (seg != f_seg) {
                 f0 = load_flat<X>(ix, q, seg);
@@ -360,9 +361,14 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
             }
             const bool uniform = __ldg(q.seg_off + seg + 1) >= hbase + OV_TILE / 2;
             const int64_t i0 = hbase + 2 * threadIdx.x;
-            const longlong2 s2 = __ldg(reinterpret_cast<const longlong2*>(q.start + i0));
-            const longlong2 e2 = __ldg(reinterpret_cast<const longlong2*>(q.end + i0));
-            int64_t s[2] = {s2.x, s2.y}, e[2] = {e2.x, e2.y};
+            int64_t s[2] = {0, 0}, e[2] = {0, 0};
+            if (i0 + 1 < q.n) {
+                const longlong2 s2 = __ldg(reinterpret_cast<const longlong2*>(q.start + i0));
+                const longlong2 e2 = __ldg(reinterpret_cast<const longlong2*>(q.end + i0));
+                s[0] = s2.x; s[1] = s2.y; e[0] = e2.x; e[1] = e2.y;
+            } else if (i0 < q.n) {
+                s[0] = __ldg(q.start + i0); e[0] = __ldg(q.end + i0);
+            }
             X sc[2], ec[2];
             Rec r[2];
 #pragma unroll
@@ -388,15 +394,17 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const X xs = sc[k] + 1;
-                fast[k] = (xs >> shift) == (ec[k] >> shift) && rec_fast(r[k]);
+                const bool dead = i0 + k >= q.n;  // beyond the ragged end: count 0, never queued
+                fast[k] = dead || ((xs >> shift) == (ec[k] >> shift) && rec_fast(r[k]));
                 int c = (int)(r[k].w[0] - r[k].w[1]) + (int)swar_cnt4(r[k].w[4], r[k].w[5], (uint32_t)ec[k] & mask) -
                         (int)swar_cnt4(r[k].w[6], r[k].w[7], (uint32_t)xs & mask);
                 c = c > 0 ? c : 0;
                 if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
-                cc[k] = fast[k] ? c : 0;
+                cc[k] = (fast[k] && !dead) ? c : 0;
             }
             // rows i0, i0+1: one 16-byte store; queued rows are rewritten by count_slow (same warp, later)
-            *reinterpret_cast<longlong2*>(out_count + i0) = make_longlong2(cc[0], cc[1]);
+            if (i0 + 1 < q.n) *reinterpret_cast<longlong2*>(out_count + i0) = make_longlong2(cc[0], cc[1]);
+            else if (i0 < q.n) out_count[i0] = cc[0];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const unsigned m = __ballot_sync(FULL, !fast[k]);
@@ -687,9 +695,9 @@ static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, 
                          int64_t* tile_sums, unsigned ntiles, cudaStream_t st) {
     int64_t* gran_sums = tile_sums ? tile_sums + ws_tiles(q.n) : nullptr;
     int64_t first = 0;
-    const int64_t nblk = q.n / (LN_TILES * OV_TILE);
+    const int64_t nblk = cdiv(q.n, LN_TILES * OV_TILE);
     if (mode != IV_MODE_CONTAIN && vec && nblk >= 16) {
-        // full, aligned 4096-row blocks go through the lean kernel, the remainder through the generic one;
+        // large aligned inputs go through the lean kernel (ragged last block included);
         // its warps add their partial sums with atomics: clear the sums first
         if (tile_sums) cudaMemsetAsync(tile_sums, 0, (ws_tiles(q.n) + ws_grans(q.n)) * sizeof(int64_t), st);
         unsigned long long* ts = reinterpret_cast<unsigned long long*>(tile_sums);
