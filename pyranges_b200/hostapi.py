@@ -14,6 +14,17 @@ def _host_tensor(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64))
 
 
+_streams = {}
+
+
+def _side_streams(dev):
+    """copy-in / copy-out streams, created once per device"""
+    key = (dev.type, dev.index)
+    if key not in _streams:
+        _streams[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _streams[key]
+
+
 def _to_device(a, device):
     t = _host_tensor(a)
     return t.to(device, non_blocking=t.is_pinned())
@@ -34,17 +45,73 @@ class NCLSBatch:
         q = E.DeviceIntervals(_to_device(starts, self.device), _to_device(ends, self.device), seg_off)
         return E.Queries(q, seg_group, slack=slack)
 
-    def all_overlaps_both(self, starts, ends, seg_off, seg_group, slack=0, out=None):
-        """-> (query rows, subject rows) host int64 arrays, query order (NCLS.all_overlaps_both)."""
-        q = self._queries(starts, ends, seg_off, seg_group, slack)
-        _, a, b = self.index.pairs(q, E.IV_MODE_ALL)
-        if out is not None:  # pinned staging buffers supplied by the caller
-            p = a.numel()
-            out[0][:p].copy_(a, non_blocking=True)
-            out[1][:p].copy_(b, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return out[0][:p], out[1][:p]
-        return a.cpu().numpy(), b.cpu().numpy()
+    def all_overlaps_both(self, starts, ends, seg_off, seg_group, slack=0, out=None, chunks=None):
+        """-> (query rows, subject rows) host int64 arrays, query order (NCLS.all_overlaps_both).
+
+        Large pinned inputs are processed in row chunks on three streams: the host->device copies of all
+        chunks are queued up front on a copy stream, every chunk is counted / emitted as soon as it has
+        landed, and its pairs travel back on a third stream while the next chunk is computed -- PCIe runs in
+        both directions and the kernels hide behind it."""
+        hs, he = _host_tensor(starts), _host_tensor(ends)
+        n = hs.numel()
+        seg_off = np.asarray(seg_off, dtype=np.int64)
+        if chunks is None:
+            chunks = 8 if (n >= (1 << 21) and hs.is_pinned() and he.is_pinned() and out is not None) else 1
+        if chunks <= 1:
+            q = self._queries(hs, he, seg_off, seg_group, slack)
+            _, a, b = self.index.pairs(q, E.IV_MODE_ALL)
+            if out is not None:  # pinned staging buffers supplied by the caller
+                p = a.numel()
+                out[0][:p].copy_(a, non_blocking=True)
+                out[1][:p].copy_(b, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return out[0][:p], out[1][:p]
+            return a.cpu().numpy(), b.cpu().numpy()
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        s_copy, s_back = _side_streams(dev)
+        step = -(-n // chunks)
+        step = (step + 4095) // 4096 * 4096  # chunk edges on the count kernel's 4096-row blocks
+        bounds = [(a, min(a + step, n)) for a in range(0, n, step)]
+        # device columns from the main stream's pool (reused call after call), filled on the copy stream
+        d_s = torch.empty(n, dtype=torch.int64, device=dev)
+        d_e = torch.empty(n, dtype=torch.int64, device=dev)
+        d_s.record_stream(s_copy)
+        d_e.record_stream(s_copy)
+        s_copy.wait_stream(main)
+        landed = []
+        with torch.cuda.stream(s_copy):
+            for a, b in bounds:
+                d_s[a:b].copy_(hs[a:b], non_blocking=True)
+                d_e[a:b].copy_(he[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_copy)
+                landed.append((d_s[a:b], d_e[a:b], ev))
+        pos = 0
+        keep = []
+        for (a, b), (ds, de, ev) in zip(bounds, landed):
+            main.wait_event(ev)
+            off = np.clip(seg_off, a, b) - a  # the chunk's own segment offsets (empty segments allowed)
+            q = E.Queries(E.DeviceIntervals(ds, de, off), seg_group, slack=slack)
+            _, qa, qb = self.index.pairs(q, E.IV_MODE_ALL)  # host waits for this chunk's total only
+            if a:
+                qa.add_(a)
+            p = qa.numel()
+            if pos + p > out[0].numel():
+                raise ValueError("all_overlaps_both: output buffers too small (%d pairs so far)" % (pos + p))
+            done = torch.cuda.Event()
+            done.record(main)
+            s_back.wait_event(done)
+            with torch.cuda.stream(s_back):
+                out[0][pos:pos + p].copy_(qa, non_blocking=True)
+                out[1][pos:pos + p].copy_(qb, non_blocking=True)
+            qa.record_stream(s_back)
+            qb.record_stream(s_back)
+            keep.append((q, qa, qb))
+            pos += p
+        s_back.synchronize()
+        main.wait_stream(s_copy)
+        return out[0][:pos], out[1][:pos]
 
     def count(self, starts, ends, seg_off, seg_group, slack=0, out=None):
         """-> overlaps per query, host int64 array (the NumberOverlaps column, coverage.py:26-40)."""

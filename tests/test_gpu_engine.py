@@ -268,3 +268,29 @@ def test_large_staged_paths(eng):
     wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "all"))
     ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
     assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
+
+
+def test_hostapi_chunked_pipeline(eng):
+    """numpy/pinned host facade: the chunked three-stream pipeline returns the same pairs as one shot."""
+    import torch
+
+    from pyranges_b200 import hostapi
+
+    rng = np.random.default_rng(9)
+    n = 300_000
+    s = rng.integers(0, 5_000_000, n).astype(np.int64)
+    e = s + rng.integers(1, 400, n)
+    qoff = np.asarray([0, 100_000, 100_000, 220_001, n], np.int64)
+    ss, se, soff = gen_segments(91, 3, 20000, 5_000_000, 5000)
+    sg = np.asarray([0, 1, 2, -1], np.int32)
+    nb = hostapi.NCLSBatch(ss, se, soff)
+    a1, b1 = nb.all_overlaps_both(s, e, qoff, sg)
+    hs, he = torch.from_numpy(s).pin_memory(), torch.from_numpy(e).pin_memory()
+    out = (torch.empty(len(a1) + 10, dtype=torch.int64).pin_memory(), torch.empty(len(a1) + 10, dtype=torch.int64).pin_memory())
+    a2, b2 = nb.all_overlaps_both(hs, he, qoff, sg, out=out, chunks=5)
+    assert np.array_equal(a1, a2.numpy()) and np.array_equal(b1, b2.numpy())
+    wa, wb = canon_pairs(*oracle_pairs(s, e, qoff, sg, ss, se, soff, "all"))
+    ga, gb = canon_pairs(a1, b1)
+    assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
+    c = nb.count(s, e, qoff, sg)
+    assert np.array_equal(c, np.bincount(wa, minlength=n))
