@@ -9,8 +9,8 @@ pyranges/methods/join.py:12) -> count -> scan -> emit of all (query row, subject
   python bench.py [--gpus N --steps K --warmup W]             this repo's CUDA path
   python bench.py --impl reference [...]                       CPU restatement of ncls on the host cores
 
-N > 1 (torchrun): the genome-wide set grows with N (N x 10 M reads, N x 200 k annotations: per-GPU work fixed =
-weak scaling); chromosomes are assigned to ranks by a size-balanced (LPT) rule, every rank joins its own
+N > 1 (torchrun): the read set grows with N (N x 10 M reads against the same 200 k annotations: reads and pairs
+per GPU stay fixed = weak scaling); chromosomes are assigned to ranks by a size-balanced (LPT) rule, every rank joins its own
 chromosomes with no data-path collective, and the ranks exchange only their per-key pair counts (one small NCCL
 all-reduce per step) from which every rank knows the global output offsets.
 """
@@ -101,7 +101,7 @@ def make_workload(args, rank, world=1):
 
     chroms = None if world == 1 else S.shard_chromosomes(world, rank)
     reads = S.reads(args.reads * world, seed=1, chroms=chroms)
-    annot = S.annotations(args.annot * world, seed=2, chroms=chroms)
+    annot = S.annotations(args.annot, seed=2, chroms=chroms)  # the genome annotation does not grow with N
     seg_group = (np.arange(reads.n_keys) // 2).astype(np.int32)  # strandedness=None: partner = whole chromosome
     return reads, annot, seg_group
 
@@ -189,11 +189,11 @@ def run_reference(args, rank, world):
 def workload_config(args, n_gpus):
     return {"workload": "synthetic hg38-shaped %d reads (100 bp) x %d gene/exon annotations: join (+ count_overlaps), "
                         "strandedness=None, per GPU" % (args.reads, args.annot),
-            "reads_per_gpu": args.reads, "annotations_per_gpu": args.annot, "keys": 48,
+            "reads_per_gpu": args.reads, "annotations_genome_wide": args.annot, "keys": 48,
             "l2": "inputs (%.0f MB of int64 query columns) exceed the 126 MB L2; no flush" % (16 * args.reads / 1e6),
             "index_build": "inside the timed region",
-            "parallelism": "chromosomes sharded over %d GPU(s) by size (LPT); genome-wide set = %d x the per-GPU size"
-                           % (n_gpus, n_gpus)}
+            "parallelism": "chromosomes sharded over %d GPU(s) by size (LPT); %d x %d reads genome-wide against the "
+                           "same %d annotations" % (n_gpus, n_gpus, args.reads, args.annot)}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1,0 +1,93 @@
+"""GPU, BASELINE.json config sizes (10 M reads x 200 k annotations): the oracle is too slow to replay them in a
+test, so parity is checked through size-independent properties + an oracle check of a random sample of keys."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    import torch
+
+    from pyranges_b200 import engine as E
+    from pyranges_b200 import synthetic as S
+
+    reads, annot = S.reads(10_000_000, seed=1), S.annotations(200_000, seed=2)
+    sg = (np.arange(reads.n_keys) // 2).astype(np.int32)
+    q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off)
+    s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off)
+    ix = E.SubjectIndex(s_iv, annot.chrom_ranges(), ends_perm=True)
+    return E, torch, reads, annot, sg, q_iv, s_iv, ix
+
+
+def test_join_properties_full_size(c2):
+    E, torch, reads, annot, sg, q_iv, s_iv, ix = c2
+    q = E.Queries(q_iv, sg)
+    counts, a, b = ix.pairs(q, E.IV_MODE_ALL)
+    p = a.numel()
+    assert int(counts.sum().item()) == p and p > 1_000_000
+    assert bool((a[1:] >= a[:-1]).all()), "pairs come out in query order"
+    # every pair is a true overlap inside the right chromosome group, no pair is emitted twice
+    qs, qe, ss, se = q_iv.start[a], q_iv.end[a], s_iv.start[b], s_iv.end[b]
+    assert bool(((ss < qe) & (qs < se)).all())
+    grp_off = torch.from_numpy(annot.seg_off[::2].copy()).cuda()  # chromosome groups = pairs of strand keys
+    key_of_q = torch.searchsorted(q_iv.seg_off_dev, a, right=True) - 1
+    grp_of_s = torch.searchsorted(grp_off, b, right=True) - 1
+    assert bool((grp_of_s == key_of_q // 2).all())
+    packed = a * annot.n + b
+    assert int(torch.unique(packed).numel()) == p
+    # counts = bincount of the emitted query rows; ANY = counts > 0
+    assert bool((torch.bincount(a, minlength=reads.n) == counts).all())
+    any_c, _, _ = ix.count(q, E.IV_MODE_ANY, for_emit=False)
+    assert bool((any_c == (counts > 0).long()).all())
+
+
+def test_counts_vs_oracle_on_sampled_keys(c2):
+    from oracle import oracle as orc
+
+    E, torch, reads, annot, sg, q_iv, s_iv, ix = c2
+    counts, _, _ = ix.count(E.Queries(q_iv, sg), E.IV_MODE_ALL, for_emit=False)
+    counts = counts.cpu().numpy()
+    for k in (0, 17, 47):  # chr1 +, chr9 -, chrY -
+        g = k // 2
+        a, b = annot.seg_off[2 * g], annot.seg_off[2 * g + 2]
+        t = orc.NCLS(annot.starts[a:b], annot.ends[a:b], np.arange(a, b))
+        sl = slice(reads.seg_off[k], reads.seg_off[k + 1])
+        assert np.array_equal(counts[sl], t.count(reads.starts[sl], reads.ends[sl]))
+
+
+def test_nearest_properties_full_size(c2):
+    E, torch, reads, annot, sg, q_iv, s_iv, ix = c2
+    q = E.Queries(q_iv, sg)
+    row, dist = ix.nearest(q, overlap=True)
+    counts, _, _ = ix.count(q, E.IV_MODE_ALL, for_emit=False)
+    assert bool(((dist == 0) == (counts > 0)).all())
+    ok = row >= 0
+    assert bool(ok.all())  # every chromosome has annotations
+    S, En, s, e = s_iv.start[row], s_iv.end[row], q_iv.start, q_iv.end
+    gap = torch.where(En <= s, s - En + 1, torch.where(S >= e, S - e + 1, torch.zeros_like(s)))
+    assert bool((gap == dist).all())
+
+
+def test_cluster_merge_rle_properties_full_size(c2):
+    E, torch, reads, annot, sg, q_iv, s_iv, ix = c2
+    row, cid, nc = E.cluster(q_iv)
+    ms, me, mc, mg = E.merge(q_iv)
+    m = int(nc.item())
+    assert ms.numel() == m and int(mc.sum().item()) == reads.n
+    assert bool((cid[1:] >= cid[:-1]).all()) and int(cid[0].item()) == 1 and int(cid[-1].item()) == m
+    assert bool((torch.sort(row).values == torch.arange(reads.n, device=row.device)).all())
+    # idempotence: merging the merged intervals changes nothing
+    off2 = np.concatenate([[0], np.cumsum(np.bincount(mg.cpu().numpy(), minlength=reads.n_keys))])
+    again = E.merge(E.DeviceIntervals(ms, me, off2))
+    assert bool((again[0] == ms).all()) and bool((again[1] == me).all()) and bool((again[2] == 1).all())
+    # coverage: runs of a key sum to its largest End; sum(run * value) = covered bases = sum of lengths
+    run_off, runs, vals = E.coverage_rle(q_iv)
+    hi = q_iv.hi
+    for k in (0, 5, 47):
+        sl = slice(int(run_off[k]), int(run_off[k + 1]))
+        assert int(runs[sl].sum().item()) == int(hi[k])
+        a, b = reads.seg_off[k], reads.seg_off[k + 1]
+        assert float((runs[sl].double() * vals[sl]).sum().item()) == float((reads.ends[a:b] - reads.starts[a:b]).sum())
+        assert bool((vals[sl][1:] != vals[sl][:-1]).all())  # equal neighbours are coalesced
