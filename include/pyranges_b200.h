@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define IV_ABI_VERSION 2
+#define IV_ABI_VERSION 3
 
 #define IV_OK 0
 #define IV_ERR_INVALID (-1)   /* bad argument */
@@ -175,11 +175,15 @@ size_t iv_overlap_workspace_bytes(int64_t n_queries);
  * iv_emit_pairs needs in ws and the grand total in *out_total (device). */
 int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mode, int64_t* out_count,
                       void* ws, size_t ws_bytes, int64_t* out_total, void* stream);
-/* Writes sum(out_count) entries.  out_q gets the query label, out_s the subject row (or
- * s_label[row]).  Either may be NULL.  In mode ANY out_s receives the FIRST hit: smallest start,
- * then largest end, then smallest row (the head of the nested-containment-list traversal). */
+/* Writes min(sum(out_count), out_capacity) entries.  out_q gets the query label, out_s the subject row (or
+ * s_label[row]).  Either may be NULL.  out_capacity = entries the output buffers hold: the exact total read back
+ * from iv_count_overlaps, or a guess when the emit is launched speculatively before the total is known (entries
+ * beyond the capacity are dropped, never written; the caller compares the total and repeats the call if needed).
+ * In mode ANY out_s receives the FIRST hit: smallest start, then largest end, then smallest row (the head of the
+ * nested-containment-list traversal). */
 int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int32_t mode, const int64_t* counts,
-                  const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label, void* stream);
+                  const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label, int64_t out_capacity,
+                  void* stream);
 /* out_bp[i] = sum over hits of min(e,E)-max(s,S); out_fraction[i] = out_bp / (end-start), NaN -> 0 */
 int iv_coverage_bp(const iv_index_t* index, const iv_queries_t* q, int64_t* out_bp, double* out_fraction,
                    void* stream);

@@ -443,7 +443,7 @@ template <typename X, int MODE>
 __global__ void __launch_bounds__(EM_THREADS)
 k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ counts,
        const int64_t* __restrict__ tile_off, const int64_t* __restrict__ gran_sums, int64_t* __restrict__ out_q,
-       int64_t* __restrict__ out_s, const int64_t* __restrict__ s_label) {
+       int64_t* __restrict__ out_s, const int64_t* __restrict__ s_label, int64_t cap) {
     __shared__ int64_t h_off[EM_WARPS][OV_GRAN];
     __shared__ X h_sc[EM_WARPS][OV_GRAN], h_ec[EM_WARPS][OV_GRAN];
     __shared__ uint8_t h_row[EM_WARPS][OV_GRAN];
@@ -528,8 +528,10 @@ k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ coun
         const int64_t ql = q.label ? __ldg(q.label + row) : row;
         if (MODE == IV_MODE_ALL) {
             auto put = [&](uint32_t srow) {
-                if (out_q) out_q[o] = ql;
-                if (out_s) out_s[o] = s_label ? __ldg(s_label + srow) : (int64_t)srow;
+                if (o < cap) {  // cap: entries the caller's buffers hold (speculative emission)
+                    if (out_q) out_q[o] = ql;
+                    if (out_s) out_s[o] = s_label ? __ldg(s_label + srow) : (int64_t)srow;
+                }
                 o++;
             };
             uint32_t pS, pE;
@@ -574,19 +576,23 @@ k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ coun
                     if (en[u].y > rel) put(en[u].x);
             }
         } else if (MODE == IV_MODE_ANY) {
-            if (out_q) out_q[o] = ql;
-            if (out_s) {
-                FirstHit fh(ix);
-                for_each_hit_rec<X, true>(ix, sc, ec, r, fh);
-                const int64_t srow = fh.brow;
-                out_s[o] = s_label ? __ldg(s_label + srow) : srow;
+            if (o < cap) {
+                if (out_q) out_q[o] = ql;
+                if (out_s) {
+                    FirstHit fh(ix);
+                    for_each_hit_rec<X, true>(ix, sc, ec, r, fh);
+                    const int64_t srow = fh.brow;
+                    out_s[o] = s_label ? __ldg(s_label + srow) : srow;
+                }
             }
         } else {
             const uint64_t qs = sc, qe = ec;
             for_each_hit_rec<X, true>(ix, sc, ec, r, [&](uint32_t p) {
                 if (__ldg(ix.key_s + p) <= qs && qe <= __ldg(ix.end_s + p)) {
-                    if (out_q) out_q[o] = ql;
-                    if (out_s) { int64_t srow = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + srow) : srow; }
+                    if (o < cap) {
+                        if (out_q) out_q[o] = ql;
+                        if (out_s) { int64_t srow = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + srow) : srow; }
+                    }
                     o++;
                 }
             });
@@ -716,16 +722,16 @@ static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, 
 
 template <typename X>
 static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, const int64_t* counts,
-                        const int64_t* tile_off, int64_t* out_q, int64_t* out_s, const int64_t* s_label,
+                        const int64_t* tile_off, int64_t* out_q, int64_t* out_s, const int64_t* s_label, int64_t cap,
                         cudaStream_t st) {
     const int64_t* gran_sums = tile_off + ws_tiles(q.n);
     const unsigned nb = (unsigned)cdiv(cdiv(q.n, OV_GRAN), EM_WARPS);
     if (mode == IV_MODE_ALL)
-        k_emit<X, IV_MODE_ALL><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label);
+        k_emit<X, IV_MODE_ALL><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label, cap);
     else if (mode == IV_MODE_ANY)
-        k_emit<X, IV_MODE_ANY><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label);
+        k_emit<X, IV_MODE_ANY><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label, cap);
     else
-        k_emit<X, IV_MODE_CONTAIN><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label);
+        k_emit<X, IV_MODE_CONTAIN><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label, cap);
 }
 
 }  // namespace iv
@@ -762,18 +768,20 @@ extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q,
 }
 
 extern "C" int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int32_t mode, const int64_t* counts,
-                             const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label, void* stream) {
+                             const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label,
+                             int64_t out_capacity, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_query(index, q, "iv_emit_pairs");
     if (rc != IV_OK) return rc;
     IV_REQUIRE(mode >= IV_MODE_ALL && mode <= IV_MODE_CONTAIN, IV_ERR_INVALID, "iv_emit_pairs: mode");
     if (q->n == 0) return IV_OK;
     IV_REQUIRE(counts && ws, IV_ERR_INVALID, "iv_emit_pairs: counts / ws is null");
+    IV_REQUIRE(out_capacity >= 0, IV_ERR_INVALID, "iv_emit_pairs: negative out_capacity");
     int64_t ntiles = cdiv(q->n, OV_TILE);
     const int64_t* tile_off = (const int64_t*)ws;
     bool vec = aligned16(q->start) && aligned16(q->end) && aligned16(counts);
-    if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, st);
-    else launch_emit<uint64_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, st);
+    if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, out_capacity, st);
+    else launch_emit<uint64_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, out_capacity, st);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

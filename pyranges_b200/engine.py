@@ -178,7 +178,13 @@ class Queries:
         sg = np.ascontiguousarray(seg_group, dtype=np.int32)
         assert len(sg) == iv.n_seg
         arr = sg if seg_mode is None else np.concatenate([sg, np.ascontiguousarray(seg_mode, dtype=np.int32)])
-        self.dev = _to_dev(arr, iv.device) if len(arr) else torch.zeros(1, dtype=torch.int32, device=iv.device)
+        # the partner map is a few hundred bytes; its device copy is memoised on the columns (a pageable
+        # host->device copy would otherwise synchronise the stream on every call)
+        key = arr.tobytes()
+        cache = iv.__dict__.setdefault("_qdesc", {})
+        if key not in cache:
+            cache[key] = _to_dev(arr, iv.device) if len(arr) else torch.zeros(1, dtype=torch.int32, device=iv.device)
+        self.dev = cache[key]
         p = self.dev.data_ptr()
         self.label = label
         self.c = IvQueries(iv.n, iv.start.data_ptr(), iv.end.data_ptr(), label.data_ptr() if label is not None else None,
@@ -223,17 +229,35 @@ class SubjectIndex:
                    "iv_count_overlaps")
         return counts, ws, total
 
-    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None):
+    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None, capacity=None):
         """All (query row | label, subject row | label) pairs in query order: count -> scan -> emit
-        (NCLS.all_overlaps_both / all_containments_both / first_overlap_both, join.py:15-23)."""
+        (NCLS.all_overlaps_both / all_containments_both / first_overlap_both, join.py:15-23).
+
+        The output size is only known after the count, which costs one host sync before the emit can be
+        launched.  `capacity` (e.g. the pair count of a previous, similar join) lets the emit be launched
+        speculatively into buffers of that size right behind the count; the total is read afterwards and the
+        emit is simply repeated into exact buffers if the guess was too small."""
         counts, ws, total = self.count(q, mode, for_emit=True)
-        p = int(total.item())  # the one host sync: output size
         dev = self.iv.device
-        out_q = torch.empty(p, dtype=torch.int64, device=dev) if want_q else None
-        out_s = torch.empty(p, dtype=torch.int64, device=dev) if want_s else None
-        if p:
+
+        def emit(n):
+            oq = torch.empty(n, dtype=torch.int64, device=dev) if want_q else None
+            os_ = torch.empty(n, dtype=torch.int64, device=dev) if want_s else None
             cabi.check(cabi.lib().iv_emit_pairs(C.byref(self.c), C.byref(q.c), mode, _ptr(counts), _ptr(ws),
-                                                _ptr(out_q), _ptr(out_s), _ptr(s_label), _stream()), "iv_emit_pairs")
+                                                _ptr(oq), _ptr(os_), _ptr(s_label), n, _stream()), "iv_emit_pairs")
+            return oq, os_
+
+        if capacity is not None and capacity > 0:
+            out_q, out_s = emit(int(capacity))
+            p = int(total.item())
+            if p <= capacity:
+                return counts, (out_q[:p] if want_q else None), (out_s[:p] if want_s else None)
+            # guess too small: the kernel dropped the entries beyond `capacity`; emit again into exact buffers
+        p = int(total.item())  # the one host sync: output size
+        if p == 0:
+            z = torch.empty(0, dtype=torch.int64, device=dev)
+            return counts, (z if want_q else None), (z.clone() if want_s else None)
+        out_q, out_s = emit(p)
         return counts, out_q, out_s
 
     def coverage_bp(self, q, want_fraction=True):

@@ -89,11 +89,13 @@ class NCLSBatch:
                 landed.append((d_s[a:b], d_e[a:b], ev))
         pos = 0
         keep = []
+        hint = None  # pairs of the previous chunk: the next chunk's emit is launched before its total is known
         for (a, b), (ds, de, ev) in zip(bounds, landed):
             main.wait_event(ev)
             off = np.clip(seg_off, a, b) - a  # the chunk's own segment offsets (empty segments allowed)
             q = E.Queries(E.DeviceIntervals(ds, de, off), seg_group, slack=slack)
-            _, qa, qb = self.index.pairs(q, E.IV_MODE_ALL)  # host waits for this chunk's total only
+            _, qa, qb = self.index.pairs(q, E.IV_MODE_ALL, capacity=hint)
+            hint = int(qa.numel() * 1.25) + 4096
             if a:
                 qa.add_(a)
             p = qa.numel()

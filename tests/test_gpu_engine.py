@@ -294,3 +294,15 @@ def test_hostapi_chunked_pipeline(eng):
     assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
     c = nb.count(s, e, qoff, sg)
     assert np.array_equal(c, np.bincount(wa, minlength=n))
+
+
+def test_pairs_capacity_hint(eng):
+    """speculative emission: any capacity guess gives the exact result (too small -> repeated)."""
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, CASES[2])
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff))
+    _, a0, b0 = ix.pairs(q, eng.IV_MODE_ALL)
+    for cap in (1, a0.numel() // 2, a0.numel(), a0.numel() + 1000):
+        _, a, b = ix.pairs(q, eng.IV_MODE_ALL, capacity=cap)
+        assert a.numel() == a0.numel()
+        assert bool((a == a0).all()) and bool((b.sort().values == b0.sort().values).all())

@@ -51,7 +51,7 @@ def f_count_only():
 
 
 def f_emit():
-    cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), 0, E._ptr(counts), E._ptr(ws), E._ptr(out_q), E._ptr(out_s), None, st))
+    cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), 0, E._ptr(counts), E._ptr(ws), E._ptr(out_q), E._ptr(out_s), None, out_q.numel(), st))
 
 
 def f_build():
