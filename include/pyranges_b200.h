@@ -217,6 +217,15 @@ int iv_rle_count(const int64_t* starts, const int64_t* ends, int64_t n, const iv
 int iv_rle_emit(int64_t n, const iv_groups_t* groups, const void* ws, int64_t n_runs, const int64_t* run_off,
                 int64_t* out_runs, double* out_values, void* stream);
 
+/* to_rle(value_col=...): the same with float64 weights per row (pyranges/pyranges_main.py:5838-5856).  The level
+ * is a float64 sum restarted at every group; a parallel sum can differ from pyrle's sequential one in the last
+ * bits (exact for integer-valued weights). */
+size_t iv_rle_weighted_workspace_bytes(int64_t n, int32_t n_groups);
+int iv_rle_weighted_count(const int64_t* starts, const int64_t* ends, const double* weights, int64_t n,
+                          const iv_groups_t* groups, void* ws, size_t ws_bytes, int64_t* out_run_off, void* stream);
+int iv_rle_weighted_emit(int64_t n, const iv_groups_t* groups, const void* ws, int64_t n_runs, const int64_t* run_off,
+                         int64_t* out_runs, double* out_values, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

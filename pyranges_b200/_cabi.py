@@ -60,6 +60,9 @@ PROTOTYPES = {
     "iv_rle_workspace_bytes": (_sz, [_i64, _i32]),
     "iv_rle_count": (C.c_int, [_vp, _vp, _i64, _PG, _vp, _sz, _vp, _vp]),
     "iv_rle_emit": (C.c_int, [_i64, _PG, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "iv_rle_weighted_workspace_bytes": (_sz, [_i64, _i32]),
+    "iv_rle_weighted_count": (C.c_int, [_vp, _vp, _vp, _i64, _PG, _vp, _sz, _vp, _vp]),
+    "iv_rle_weighted_emit": (C.c_int, [_i64, _PG, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

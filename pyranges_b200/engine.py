@@ -322,22 +322,30 @@ def merge(iv, seg_ranges=None, slack=0, want_count=True):
     return st, en, cnt, grp
 
 
-def coverage_rle(iv, seg_ranges=None):
-    """pyrle.methods.coverage with unit weights (pyranges/methods/to_rle.py:18) for all groups at once.
+def coverage_rle(iv, seg_ranges=None, weights=None):
+    """pyrle.methods.coverage (pyranges/methods/to_rle.py:18) for all groups at once; weights = float64 device
+    tensor aligned with the rows (value_col), None = unit weights (bit-exact integer levels).
     -> (run_off int64[n_groups+1] host, runs int64[R], values float64[R])."""
     L = cabi.lib()
     g = iv.groups(seg_ranges, gap=1, zero_lo=True)
     dev = iv.device
-    ws = _bytes(L.iv_rle_workspace_bytes(iv.n, g.n_groups), dev)
     run_off = torch.zeros(g.n_groups + 1, dtype=torch.int64, device=dev)
-    cabi.check(L.iv_rle_count(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(g.c), _ptr(ws), ws.numel(), _ptr(run_off),
-                              _stream()), "iv_rle_count")
+    if weights is None:
+        ws = _bytes(L.iv_rle_workspace_bytes(iv.n, g.n_groups), dev)
+        cabi.check(L.iv_rle_count(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(g.c), _ptr(ws), ws.numel(), _ptr(run_off),
+                                  _stream()), "iv_rle_count")
+    else:
+        assert weights.dtype == torch.float64 and weights.numel() == iv.n and weights.is_cuda
+        weights = weights.contiguous()
+        ws = _bytes(L.iv_rle_weighted_workspace_bytes(iv.n, g.n_groups), dev)
+        cabi.check(L.iv_rle_weighted_count(_ptr(iv.start), _ptr(iv.end), _ptr(weights), iv.n, C.byref(g.c), _ptr(ws),
+                                           ws.numel(), _ptr(run_off), _stream()), "iv_rle_weighted_count")
     off_h = run_off.cpu().numpy()
     r = int(off_h[-1])
     runs = torch.empty(r, dtype=torch.int64, device=dev)
     vals = torch.empty(r, dtype=torch.float64, device=dev)
-    cabi.check(L.iv_rle_emit(iv.n, C.byref(g.c), _ptr(ws), r, _ptr(run_off), _ptr(runs), _ptr(vals), _stream()),
-               "iv_rle_emit")
+    emit = L.iv_rle_emit if weights is None else L.iv_rle_weighted_emit
+    cabi.check(emit(iv.n, C.byref(g.c), _ptr(ws), r, _ptr(run_off), _ptr(runs), _ptr(vals), _stream()), "iv_rle_emit")
     return off_h, runs, vals
 
 

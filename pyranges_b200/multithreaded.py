@@ -517,12 +517,20 @@ def _u_merge(plan, kwargs):
 
 
 def _u_coverage(plan, kwargs):
-    """to_rle: pyrle.methods.coverage (pyranges/methods/to_rle.py:18) per key, unit weights."""
+    """to_rle: pyrle.methods.coverage (pyranges/methods/to_rle.py:18) per key; unit weights or value_col."""
     from .rle import Rle
 
+    weights = None
     if kwargs.get("value_col"):
-        raise NotImplementedError("to_rle(value_col=...) is not on the B200 path yet (float weights are not bit-exact)")
-    run_off, runs, vals = E.coverage_rle(plan.f.iv, plan.group_ranges or None)
+        import torch
+
+        col = kwargs["value_col"]
+        w = np.concatenate([np.asarray(d[col].values, dtype=np.float64) for d in plan.f.dfs]) if plan.f.dfs else np.zeros(0)
+        weights = torch.from_numpy(np.ascontiguousarray(w))
+        dev = getattr(plan.f.iv, "device", None)
+        if dev is not None:
+            weights = weights.to(dev)
+    run_off, runs, vals = E.coverage_rle(plan.f.iv, plan.group_ranges or None, weights)
     runs, vals = runs.cpu().numpy(), vals.cpu().numpy()
     results = []
     for g in range(len(plan.frames)):

@@ -136,10 +136,12 @@ def merge(iv, seg_ranges=None, slack=0, want_count=True):
     return _t(np.concatenate(S)), _t(np.concatenate(En)), _t(np.concatenate(N)), _t(np.concatenate(G).astype(np.int32))
 
 
-def coverage_rle(iv, seg_ranges=None):
+def coverage_rle(iv, seg_ranges=None, weights=None):
     off, R, V = [0], [np.zeros(0, np.int64)], [np.zeros(0, np.float64)]
+    w = None if weights is None else weights.numpy()
     for a, b in _ranges(iv, seg_ranges):
-        r, v = orc.coverage_rle(iv.s[a:b], iv.e[a:b]) if b > a else (np.zeros(0, np.int64), np.zeros(0))
+        r, v = (orc.coverage_rle(iv.s[a:b], iv.e[a:b], None if w is None else w[a:b]) if b > a
+                else (np.zeros(0, np.int64), np.zeros(0)))
         R.append(r), V.append(v)
         off.append(off[-1] + len(r))
     return np.asarray(off, np.int64), _t(np.concatenate(R)), _t(np.concatenate(V))

@@ -306,3 +306,32 @@ def test_pairs_capacity_hint(eng):
         _, a, b = ix.pairs(q, eng.IV_MODE_ALL, capacity=cap)
         assert a.numel() == a0.numel()
         assert bool((a == a0).all()) and bool((b.sort().values == b0.sort().values).all())
+
+
+@pytest.mark.parametrize("seed,n_seg,n,maxpos,maxlen", [(1, 1, 5, 30, 10), (3, 5, 3000, 50000, 300), (5, 2, 5000, 400, 100)])
+@pytest.mark.parametrize("integer_weights", [True, False])
+def test_coverage_rle_weighted(eng, seed, n_seg, n, maxpos, maxlen, integer_weights):
+    """to_rle(value_col): integer-valued weights are exact; general float weights within 1e-9 (a parallel float64
+    sum is not bit-identical to pyrle's sequential one)."""
+    import torch
+
+    from oracle import oracle as orc
+
+    s, e, off = gen_segments(seed, n_seg, n, maxpos, maxlen, empty_every=3)
+    rng = np.random.default_rng(seed)
+    w = rng.integers(0, 1000, len(s)).astype(np.float64) if integer_weights else rng.random(len(s)) * 10 + 0.5
+    iv = _dev(eng, s, e, off)
+    run_off, runs, vals = eng.coverage_rle(iv, None, torch.from_numpy(w).cuda())
+    runs, vals = runs.cpu().numpy(), vals.cpu().numpy()
+    for k in range(n_seg):
+        a, b = off[k], off[k + 1]
+        wr, wv = orc.coverage_rle(s[a:b], e[a:b], w[a:b]) if b > a else (np.zeros(0, np.int64), np.zeros(0))
+        sl = slice(run_off[k], run_off[k + 1])
+        if integer_weights:
+            assert np.array_equal(runs[sl], wr) and np.array_equal(vals[sl], wv), k
+        else:
+            # run boundaries can only differ where a level changes by rounding noise: compare the step functions
+            def expand(r, v):
+                return np.repeat(v, r)
+            assert int(runs[sl].sum()) == int(wr.sum())
+            assert np.allclose(expand(runs[sl], vals[sl]), expand(wr, wv), rtol=1e-9, atol=1e-9), k

@@ -19,6 +19,4 @@ def oracle_engine(monkeypatch):
 def test_golden_host(name):
     from pyranges_b200.pyranges_main import PyRanges
 
-    if name == "rle_value_synth":
-        pytest.skip("to_rle(value_col=...) float weights: next (SURVEY.md 8(f))")
     check_case(name, PyRanges)
