@@ -78,6 +78,9 @@ int radix_sort_pingpong(uint64_t* k0, uint64_t* k1, void* v0, void* v1, int valu
 
 // single-block exclusive scans over small/medium arrays (scan.cu)
 int scan_exclusive_i64_inplace(int64_t* data, int64_t n, int64_t* out_total, cudaStream_t stream);
+// long arrays: three launches, partials = scan_i64_large_temp_elems(n) int64 of scratch
+size_t scan_i64_large_temp_elems(int64_t n);
+int scan_exclusive_i64_large(int64_t* data, int64_t n, int64_t* partials, int64_t* out_total, cudaStream_t stream);
 int scan_exclusive_u32_large(uint32_t* data, int64_t n, uint32_t* temp_partials, cudaStream_t stream);
 size_t scan_u32_large_temp_elems(int64_t n);
 

@@ -692,7 +692,7 @@ static int check_query(const iv_index_t* ix, const iv_queries_t* q, const char* 
     return IV_OK;
 }
 
-// workspace of count / emit: [tile sums -> tile offsets (n/1024 + 2)] [granule sums (n/64 + 2)]
+// workspace of count / emit: [tile sums -> tile offsets (n/1024 + 2)] [granule sums (n/64 + 2)] [scan scratch]
 static size_t ws_tiles(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_TILE) + 2; }
 static size_t ws_grans(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_GRAN) + 2; }
 
@@ -739,7 +739,8 @@ static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, b
 using namespace iv;
 
 extern "C" size_t iv_overlap_workspace_bytes(int64_t n_queries) {
-    return (ws_tiles(n_queries) + ws_grans(n_queries)) * sizeof(int64_t) + 256;
+    return (ws_tiles(n_queries) + ws_grans(n_queries) + scan_i64_large_temp_elems((int64_t)ws_tiles(n_queries))) *
+               sizeof(int64_t) + 256;
 }
 
 extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mode, int64_t* out_count,
@@ -761,7 +762,7 @@ extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q,
     else launch_count<uint64_t>(*index, *q, mode, vec, out_count, tile_sums, (unsigned)ntiles, st);
     IV_LAUNCH_CHECK();
     if (tile_sums) {
-        rc = scan_exclusive_i64_inplace(tile_sums, ntiles, out_total, st);
+        rc = scan_exclusive_i64_large(tile_sums, ntiles, tile_sums + ws_tiles(q->n) + ws_grans(q->n), out_total, st);
         if (rc != IV_OK) return rc;
     }
     return IV_OK;

@@ -260,6 +260,61 @@ int scan_exclusive_u32_large(uint32_t* data, int64_t n, uint32_t* temp_partials,
     return IV_OK;
 }
 
+// device-wide exclusive sum of int64 for long arrays: tile sums -> single-block scan of the sums -> apply
+__global__ void __launch_bounds__(SC_THREADS)
+k_i64_tile_sums(const int64_t* __restrict__ in, int64_t n, int64_t* __restrict__ partials) {
+    __shared__ int64_t sm[SC_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SC_TILE;
+    int64_t s = 0;
+#pragma unroll
+    for (int it = 0; it < SC_ITEMS; it++) {
+        int64_t i = base + it * SC_THREADS + threadIdx.x;
+        if (i < n) s += __ldg(in + i);
+    }
+    s = warp_sum(s);
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int64_t x = threadIdx.x < SC_THREADS / 32 ? sm[threadIdx.x] : 0;
+        x = warp_sum(x);
+        if (threadIdx.x == 0) partials[blockIdx.x] = x;
+    }
+}
+__global__ void __launch_bounds__(SC_THREADS)
+k_i64_apply(int64_t* __restrict__ data, int64_t n, const int64_t* __restrict__ partials) {
+    __shared__ int64_t sm[SC_THREADS / 32 + 1];
+    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    int64_t v[SC_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        int64_t i = base + j;
+        v[j] = i < n ? data[i] : 0;
+        s += v[j];
+    }
+    int64_t tot;
+    int64_t ex = block_excl_sum<int64_t, SC_THREADS>(s, sm, tot);
+    int64_t run = __ldg(partials + blockIdx.x) + ex;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        int64_t i = base + j;
+        if (i < n) data[i] = run;
+        run += v[j];
+    }
+}
+size_t scan_i64_large_temp_elems(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, SC_TILE) + 2; }
+int scan_exclusive_i64_large(int64_t* data, int64_t n, int64_t* partials, int64_t* out_total, cudaStream_t stream) {
+    if (n <= 4 * SC_TILE) return scan_exclusive_i64_inplace(data, n, out_total, stream);
+    int64_t nt = cdiv(n, SC_TILE);
+    k_i64_tile_sums<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, partials);
+    IV_LAUNCH_CHECK();
+    k_scan_small<int64_t><<<1, 1024, 0, stream>>>(partials, nt, out_total);
+    IV_LAUNCH_CHECK();
+    k_i64_apply<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, partials);
+    IV_LAUNCH_CHECK();
+    return IV_OK;
+}
+
 int scan_exclusive_i64_inplace(int64_t* data, int64_t n, int64_t* out_total, cudaStream_t stream) {
     k_scan_small<int64_t><<<1, 1024, 0, stream>>>(data, n > 0 ? n : 0, out_total);
     IV_LAUNCH_CHECK();
