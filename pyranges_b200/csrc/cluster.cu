@@ -44,6 +44,34 @@ k_cluster_keys(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int
     }
 }
 
+// ---- wide case: (flattened start, length) does not fit one 64-bit key.  Two stable sorts instead -- by length,
+// then by flattened start -- and the flattened ends kept in an array of their own.
+__global__ void __launch_bounds__(CL_THREADS)
+k_cluster_len_keys(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, uint64_t* __restrict__ keys,
+                   uint32_t* __restrict__ rows) {
+    int64_t i = (int64_t)blockIdx.x * CL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int64_t a = s[i], b = e[i];
+    keys[i] = b > a ? (uint64_t)(b - a) : 0;
+    rows[i] = (uint32_t)i;
+}
+// ENDS=false: keys[p] = flattened start of rows[p];  ENDS=true: ends[p] = keys[p] + length of rows[p]
+template <bool ENDS>
+__global__ void __launch_bounds__(CL_THREADS)
+k_cluster_gather(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, iv_groups_t G,
+                 const uint32_t* __restrict__ rows, uint64_t* __restrict__ keys, uint64_t* __restrict__ ends) {
+    int64_t p = (int64_t)blockIdx.x * CL_THREADS + threadIdx.x;
+    if (p >= n) return;
+    const int64_t r = rows[p];
+    const int64_t a = s[r], b = e[r];
+    if (!ENDS) {
+        const int g = find_seg(G.row_off, G.n_groups, r);
+        keys[p] = (uint64_t)(a - __ldg(G.lo + g) + __ldg(G.base + g));
+    } else {
+        ends[p] = keys[p] + (b > a ? (uint64_t)(b - a) : 0);
+    }
+}
+
 // single block exclusive max scan (identity INT64_MIN)
 __global__ void __launch_bounds__(1024) k_scan_small_max(int64_t* __restrict__ data, int64_t m) {
     __shared__ int64_t sm[1024 / 32 + 1];
@@ -65,7 +93,8 @@ __global__ void __launch_bounds__(1024) k_scan_small_max(int64_t* __restrict__ d
 }
 
 __global__ void __launch_bounds__(CL_THREADS)
-k_cl_tilemax(const uint64_t* __restrict__ keys, int64_t n, int lbits, int64_t* __restrict__ tile_max) {
+k_cl_tilemax(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ends_opt, int64_t n, int lbits,
+             int64_t* __restrict__ tile_max) {
     __shared__ int64_t red[CL_THREADS / 32];
     const uint64_t lmask = lbits ? ((1ull << lbits) - 1) : 0;
     int64_t base = (int64_t)blockIdx.x * CL_TILE;
@@ -75,7 +104,7 @@ k_cl_tilemax(const uint64_t* __restrict__ keys, int64_t n, int lbits, int64_t* _
         int64_t i = base + it * CL_THREADS + threadIdx.x;
         if (i < n) {
             uint64_t k = __ldg(keys + i);
-            int64_t E = (int64_t)((k >> lbits) + (k & lmask));
+            int64_t E = ends_opt ? (int64_t)__ldg(ends_opt + i) : (int64_t)((k >> lbits) + (k & lmask));
             m = E > m ? E : m;
         }
     }
@@ -90,7 +119,7 @@ k_cl_tilemax(const uint64_t* __restrict__ keys, int64_t n, int lbits, int64_t* _
 
 // flags[p] = 1 iff sorted row p opens a cluster; tile_cnt = flags per tile
 __global__ void __launch_bounds__(CL_THREADS)
-k_cl_flags(const uint64_t* __restrict__ keys, int64_t n, int lbits, int64_t slack,
+k_cl_flags(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ends_opt, int64_t n, int lbits, int64_t slack,
            const int64_t* __restrict__ tile_max_excl, uint8_t* __restrict__ flags, int64_t* __restrict__ tile_cnt) {
     __shared__ int64_t sm[CL_THREADS / 32 + 1];
     __shared__ int64_t thr_inc[CL_THREADS];
@@ -103,7 +132,7 @@ k_cl_flags(const uint64_t* __restrict__ keys, int64_t n, int lbits, int64_t slac
         if (p0 + j < n) {
             uint64_t k = __ldg(keys + p0 + j);
             S[j] = (int64_t)(k >> lbits);
-            E[j] = S[j] + (int64_t)(k & lmask);
+            E[j] = ends_opt ? (int64_t)__ldg(ends_opt + p0 + j) : S[j] + (int64_t)(k & lmask);
             tmax = E[j] > tmax ? E[j] : tmax;
         } else { S[j] = 0; E[j] = INT64_MIN; }
     }
@@ -148,8 +177,8 @@ k_cl_flags(const uint64_t* __restrict__ keys, int64_t n, int lbits, int64_t slac
 // MERGE=false: out_id / out_row.  MERGE=true: per-cluster start / group / first index / max end.
 template <bool MERGE>
 __global__ void __launch_bounds__(CL_THREADS)
-k_cl_ids(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ rows, const uint8_t* __restrict__ flags,
-         int64_t n, int lbits, iv_groups_t G, const int64_t* __restrict__ tile_off, int64_t* __restrict__ out_row,
+k_cl_ids(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ends_opt, const uint32_t* __restrict__ rows,
+         const uint8_t* __restrict__ flags, int64_t n, int lbits, iv_groups_t G, const int64_t* __restrict__ tile_off, int64_t* __restrict__ out_row,
          int64_t* __restrict__ out_id, int64_t* __restrict__ c_start, int32_t* __restrict__ c_group,
          int64_t* __restrict__ c_first, int64_t* __restrict__ c_end) {
     __shared__ int64_t sm[CL_THREADS / 32 + 1];
@@ -175,7 +204,7 @@ k_cl_ids(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ rows, c
         } else {
             uint64_t k = __ldg(keys + p);
             int64_t S = (int64_t)(k >> lbits);
-            int64_t E = S + (int64_t)(k & lmask);
+            int64_t E = ends_opt ? (int64_t)__ldg(ends_opt + p) : S + (int64_t)(k & lmask);
             if (f[j]) {
                 // group of a flattened coordinate: largest g with base[g] <= S
                 int g = find_seg(G.base, G.n_groups, S);
@@ -202,9 +231,11 @@ __global__ void k_merge_finish(int64_t n, int64_t nc, iv_groups_t G,
 struct ClusterLayout {
     uint64_t *k0, *k1;
     uint32_t *r0, *r1;
+    uint64_t* e_sorted;  // wide case only: flattened ends in sorted order
     uint8_t* flags;
     int64_t *tile_max, *tile_cnt, *c_first;
-    int* unsorted;  // device flag written by k_cluster_keys; its host copy decides about the sort
+    int* unsorted;  // [0] device flag written by k_cluster_keys (its host copy decides about the sort),
+                    // [1] which ping-pong buffer holds the sorted keys, [2] wide case -- for iv_merge_emit
     void* sort_temp;
 };
 
@@ -215,6 +246,7 @@ static void plan_cluster(int64_t n, Bump& b, ClusterLayout& L) {
     L.k1 = b.take<uint64_t>(nn);
     L.r0 = b.take<uint32_t>(nn);
     L.r1 = b.take<uint32_t>(nn);
+    L.e_sorted = b.take<uint64_t>(nn);
     L.flags = b.take<uint8_t>(nn + 8);
     L.tile_max = b.take<int64_t>(nt);
     L.tile_cnt = b.take<int64_t>(nt);
@@ -223,48 +255,69 @@ static void plan_cluster(int64_t n, Bump& b, ClusterLayout& L) {
     L.sort_temp = b.take<char>(radix_sort_temp_bytes(n));
 }
 
-static int cluster_total_bits(const iv_groups_t* G, int len_bits) { return bits_for((uint64_t)G->total_span) + len_bits; }
-
 // sort + flags + scan; leaves tile offsets in L.tile_cnt and the total in *out_n_clusters
 static int cluster_phase1(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* G, int64_t slack,
-                          int len_bits, void* ws, size_t ws_bytes, ClusterLayout& L, int* res, int64_t* out_n_clusters,
-                          cudaStream_t st, const char* who) {
+                          int len_bits, void* ws, size_t ws_bytes, ClusterLayout& L, int* res, bool* wide_out,
+                          int64_t* out_n_clusters, cudaStream_t st, const char* who) {
     IV_REQUIRE(G && n >= 0 && len_bits >= 0, IV_ERR_INVALID, "%s: bad arguments", who);
     IV_REQUIRE(n < ((int64_t)1 << 31), IV_ERR_RANGE, "%s: more than 2^31-1 rows", who);
-    int tbits = cluster_total_bits(G, len_bits);
-    IV_REQUIRE(tbits <= 63, IV_ERR_RANGE, "%s: span (%d bits) x max length (%d bits) does not fit a 64-bit key", who,
-               tbits - len_bits, len_bits);
+    const int sbits = bits_for((uint64_t)G->total_span);
+    const int tbits = sbits + len_bits;
+    const bool wide = tbits > 63;
+    IV_REQUIRE(sbits <= 62 && len_bits <= 62, IV_ERR_RANGE, "%s: span (%d bits) / max length (%d bits) too large", who,
+               sbits, len_bits);
     Bump b(ws, ws_bytes);
     plan_cluster(n, b, L);
     IV_REQUIRE(b.fits(), IV_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, b.off);
+    *wide_out = wide;
     if (n == 0) {
         IV_CUDA(cudaMemsetAsync(out_n_clusters, 0, 8, st));
         *res = 0;
         return IV_OK;
     }
-    IV_CUDA(cudaMemsetAsync(L.unsorted, 0, sizeof(int), st));
-    k_cluster_keys<<<(unsigned)cdiv(n, CL_THREADS), CL_THREADS, 0, st>>>(starts, ends, n, *G, len_bits, L.k0, L.r0,
-                                                                          L.unsorted);
-    IV_LAUNCH_CHECK();
-    // one small host read (the only synchronisation of the call): sorted input skips all radix passes.
-    // unsorted[1] records which buffer holds the sorted keys for iv_merge_emit.
-    int h_unsorted = 1;
-    IV_CUDA(cudaMemcpyAsync(&h_unsorted, L.unsorted, sizeof(int), cudaMemcpyDeviceToHost, st));
-    IV_CUDA(cudaStreamSynchronize(st));
+    const unsigned nb = (unsigned)cdiv(n, CL_THREADS);
     int rc = IV_OK;
     *res = 0;
-    if (h_unsorted) {
-        rc = radix_sort_pingpong(L.k0, L.k1, L.r0, L.r1, 4, n, 0, tbits, L.sort_temp, radix_sort_temp_bytes(n), st, res);
+    if (!wide) {
+        IV_CUDA(cudaMemsetAsync(L.unsorted, 0, sizeof(int), st));
+        k_cluster_keys<<<nb, CL_THREADS, 0, st>>>(starts, ends, n, *G, len_bits, L.k0, L.r0, L.unsorted);
+        IV_LAUNCH_CHECK();
+        // one small host read (the only synchronisation of the call): sorted input skips all radix passes
+        int h_unsorted = 1;
+        IV_CUDA(cudaMemcpyAsync(&h_unsorted, L.unsorted, sizeof(int), cudaMemcpyDeviceToHost, st));
+        IV_CUDA(cudaStreamSynchronize(st));
+        if (h_unsorted) {
+            rc = radix_sort_pingpong(L.k0, L.k1, L.r0, L.r1, 4, n, 0, tbits, L.sort_temp, radix_sort_temp_bytes(n), st, res);
+            if (rc != IV_OK) return rc;
+        }
+    } else {
+        k_cluster_len_keys<<<nb, CL_THREADS, 0, st>>>(starts, ends, n, L.k0, L.r0);
+        IV_LAUNCH_CHECK();
+        int r1 = 0, r2 = 0;
+        rc = radix_sort_pingpong(L.k0, L.k1, L.r0, L.r1, 4, n, 0, len_bits, L.sort_temp, radix_sort_temp_bytes(n), st, &r1);
         if (rc != IV_OK) return rc;
+        uint64_t *ka = r1 ? L.k1 : L.k0, *kb = r1 ? L.k0 : L.k1;
+        uint32_t *ra = r1 ? L.r1 : L.r0, *rb = r1 ? L.r0 : L.r1;
+        k_cluster_gather<false><<<nb, CL_THREADS, 0, st>>>(starts, ends, n, *G, ra, ka, nullptr);
+        IV_LAUNCH_CHECK();
+        rc = radix_sort_pingpong(ka, kb, ra, rb, 4, n, 0, sbits, L.sort_temp, radix_sort_temp_bytes(n), st, &r2);
+        if (rc != IV_OK) return rc;
+        *res = r2 ? (r1 ? 0 : 1) : r1;  // index of the buffer (k0/r0 = 0, k1/r1 = 1) holding the result
+        k_cluster_gather<true><<<nb, CL_THREADS, 0, st>>>(starts, ends, n, *G, *res ? L.r1 : L.r0, *res ? L.k1 : L.k0,
+                                                          L.e_sorted);
+        IV_LAUNCH_CHECK();
     }
-    IV_CUDA(cudaMemcpyAsync(L.unsorted + 1, res, sizeof(int), cudaMemcpyHostToDevice, st));
+    int h_state[2] = {*res, wide ? 1 : 0};
+    IV_CUDA(cudaMemcpyAsync(L.unsorted + 1, h_state, sizeof(h_state), cudaMemcpyHostToDevice, st));
     const uint64_t* keys = *res ? L.k1 : L.k0;
+    const uint64_t* eopt = wide ? L.e_sorted : nullptr;
+    const int lb = wide ? 0 : len_bits;
     unsigned nt = (unsigned)cdiv(n, CL_TILE);
-    k_cl_tilemax<<<nt, CL_THREADS, 0, st>>>(keys, n, len_bits, L.tile_max);
+    k_cl_tilemax<<<nt, CL_THREADS, 0, st>>>(keys, eopt, n, lb, L.tile_max);
     IV_LAUNCH_CHECK();
     k_scan_small_max<<<1, 1024, 0, st>>>(L.tile_max, nt);
     IV_LAUNCH_CHECK();
-    k_cl_flags<<<nt, CL_THREADS, 0, st>>>(keys, n, len_bits, slack, L.tile_max, L.flags, L.tile_cnt);
+    k_cl_flags<<<nt, CL_THREADS, 0, st>>>(keys, eopt, n, lb, slack, L.tile_max, L.flags, L.tile_cnt);
     IV_LAUNCH_CHECK();
     return scan_exclusive_i64_inplace(L.tile_cnt, nt, out_n_clusters, st);
 }
@@ -286,11 +339,14 @@ extern "C" int iv_cluster(const int64_t* starts, const int64_t* ends, int64_t n,
     cudaStream_t st = (cudaStream_t)stream;
     ClusterLayout L;
     int res = 0;
-    int rc = cluster_phase1(starts, ends, n, groups, slack, len_bits, ws, ws_bytes, L, &res, out_n_clusters, st, "iv_cluster");
+    bool wide = false;
+    int rc = cluster_phase1(starts, ends, n, groups, slack, len_bits, ws, ws_bytes, L, &res, &wide, out_n_clusters, st,
+                            "iv_cluster");
     if (rc != IV_OK || n == 0) return rc;
     unsigned nt = (unsigned)cdiv(n, CL_TILE);
-    k_cl_ids<false><<<nt, CL_THREADS, 0, st>>>(res ? L.k1 : L.k0, res ? L.r1 : L.r0, L.flags, n, len_bits, *groups,
-                                                L.tile_cnt, out_row, out_id, nullptr, nullptr, nullptr, nullptr);
+    k_cl_ids<false><<<nt, CL_THREADS, 0, st>>>(res ? L.k1 : L.k0, wide ? L.e_sorted : nullptr, res ? L.r1 : L.r0, L.flags, n,
+                                                wide ? 0 : len_bits, *groups, L.tile_cnt, out_row, out_id, nullptr, nullptr,
+                                                nullptr, nullptr);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }
@@ -300,7 +356,8 @@ extern "C" int iv_merge_count(const int64_t* starts, const int64_t* ends, int64_
                               void* stream) {
     ClusterLayout L;
     int res = 0;
-    return cluster_phase1(starts, ends, n, groups, slack, len_bits, ws, ws_bytes, L, &res, out_n_clusters,
+    bool wide = false;
+    return cluster_phase1(starts, ends, n, groups, slack, len_bits, ws, ws_bytes, L, &res, &wide, out_n_clusters,
                           (cudaStream_t)stream, "iv_merge_count");
 }
 
@@ -314,14 +371,17 @@ extern "C" int iv_merge_emit(int64_t n, int64_t n_clusters, const iv_groups_t* g
     Bump b((void*)ws, (size_t)-1);
     ClusterLayout L;
     plan_cluster(n, b, L);
-    int res = 0;  // which ping-pong buffer holds the sorted keys: left by iv_merge_count in the workspace
-    IV_CUDA(cudaMemcpyAsync(&res, L.unsorted + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int h_state[2] = {0, 0};  // sorted-keys buffer and wide flag: left by iv_merge_count in the workspace
+    IV_CUDA(cudaMemcpyAsync(h_state, L.unsorted + 1, sizeof(h_state), cudaMemcpyDeviceToHost, st));
     IV_CUDA(cudaStreamSynchronize(st));
+    const int res = h_state[0];
+    const bool wide = h_state[1] != 0;
     unsigned nt = (unsigned)cdiv(n, CL_TILE);
     // out_end doubles as the atomicMax accumulator of the flattened cluster end: 0x80.. = very negative
     IV_CUDA(cudaMemsetAsync(out_end, 0x80, (size_t)n_clusters * 8, st));
-    k_cl_ids<true><<<nt, CL_THREADS, 0, st>>>(res ? L.k1 : L.k0, res ? L.r1 : L.r0, L.flags, n, len_bits, *groups,
-                                               L.tile_cnt, nullptr, nullptr, out_start, out_group, L.c_first, out_end);
+    k_cl_ids<true><<<nt, CL_THREADS, 0, st>>>(res ? L.k1 : L.k0, wide ? L.e_sorted : nullptr, res ? L.r1 : L.r0, L.flags, n,
+                                               wide ? 0 : len_bits, *groups, L.tile_cnt, nullptr, nullptr, out_start,
+                                               out_group, L.c_first, out_end);
     IV_LAUNCH_CHECK();
     unsigned nb = (unsigned)cdiv(n_clusters, 256);
     if (nb > 65535u * 16u) nb = 65535u * 16u;
