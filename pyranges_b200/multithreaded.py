@@ -6,7 +6,7 @@ a dict {key -> DataFrame} holding only the non-empty results, each with a RangeI
 reference loops over the (chromosome[, strand]) keys and calls ``function(df, odf, **kwargs)`` once per
 key (building an NCLS per key), this module recognises the hot-path callables by name
 
-    _write_both, _number_overlapping, _overlap, _coverage, _nearest      (binary)
+    _write_both, _number_overlapping, _overlap, _count_overlaps, _coverage, _nearest      (binary)
     _cluster, _merge, coverage (pyrle.methods.coverage)                   (unary)
 
 concatenates the Start/End columns of all keys into device-resident int64 columns and runs ONE batched
@@ -338,6 +338,26 @@ def _b_overlap(plan, kwargs):
     return results
 
 
+def _b_count_overlaps(plan, kwargs):
+    """pr.count_overlaps helper: pyranges/methods/intersection.py:86-99 for all keys -- overlaps per row according to
+    `how` as an int32 column kwargs["name"].  The reference inserts into the caller's frame in place; here the key's
+    frame is copied (Appendix B quirk 6 consciously not kept)."""
+    how = kwargs.get("how")
+    mode = E.IV_MODE_ALL if not how else (E.IV_MODE_CONTAIN if how == "containment" else E.IV_MODE_ANY)
+    counts, _, _ = plan.index().count(plan.queries(), mode, for_emit=False)
+    counts = counts.cpu().numpy()
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        if scdf.empty:
+            results.append(None)
+            continue
+        c = counts[plan.q.seg_off[k]:plan.q.seg_off[k + 1]] if not plan.partner(k).empty else np.zeros(len(scdf), np.int64)
+        df = scdf.copy()
+        df.insert(df.shape[1], kwargs["name"], c.astype(np.int32))
+        results.append(df)
+    return results
+
+
 def _b_coverage(plan, kwargs):
     """coverage fraction: pyranges/methods/coverage.py:48-74 for all keys."""
     col = kwargs["fraction_col"]
@@ -414,6 +434,7 @@ _BINARY = {
     "_write_both": _b_write_both,
     "_number_overlapping": _b_number_overlapping,
     "_overlap": _b_overlap,
+    "_count_overlaps": _b_count_overlaps,
     "_coverage": _b_coverage,
     "_nearest": _b_nearest,
 }
