@@ -648,10 +648,15 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
     if (f.g >= 0) {
         const int mode = q.seg_mode ? __ldg(q.seg_mode + seg) : IV_NEAREST_BOTH;
         const X sc = f.at(s), ec = f.at(e);
+        // the record of bin(e') serves the overlap count, the rank of the next start and, when s'+1 shares the
+        // bin (the usual case), the rank of the previous end and the first-hit walk as well
+        const uint64_t b1 = ec >> ix.shift;
+        const Rec r1 = load_rec(ix, b1);
         bool done = false;
-        if (overlap && count_all<X>(ix, sc, ec) > 0) {
+        if (overlap && count_rec<X>(ix, sc, ec, r1, b1) > 0) {
             FirstHit fh(ix);
-            for_each_hit<X, true>(ix, sc, ec, fh);
+            if ((uint64_t)(sc >> ix.shift) == b1) for_each_hit_rec<X, true>(ix, sc, ec, r1, fh);
+            else for_each_hit<X, true>(ix, sc, ec, fh);
             row = fh.brow; dist = 0; done = true;
         }
         if (!done) {
@@ -659,16 +664,18 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
             int64_t prow = -1, pdist = -1, nrow = -1, ndist = -1;
             if (mode != IV_NEAREST_NEXT && s >= f.lo) {
                 // last subject end <= s ; ties: first of the equal run (earliest row, stable sort)
-                const int64_t r = rank_e_lt<X>(ix, (X)(sc + 1));
+                const X xs = (X)(sc + 1);
+                const int64_t r = (uint64_t)(xs >> ix.shift) == b1 ? rec_rank_e(ix, r1, b1, rel_of(ix, xs)) : rank_e_lt<X>(ix, xs);
                 if (r > g_first) {
                     const uint64_t ev = __ldg(ix.key_e + (r - 1));
-                    const int64_t jf = rank_e_lt<X>(ix, (X)ev);
+                    int64_t jf = r - 1;
+                    if (r - 2 >= g_first && __ldg(ix.key_e + (r - 2)) == ev) jf = rank_e_lt<X>(ix, (X)ev);  // duplicate ends
                     prow = __ldg(ix.row_e + jf);
                     pdist = s - f.raw(ev) + 1;
                 }
             }
             if (mode != IV_NEAREST_PREVIOUS && !(e > f.lo && (uint64_t)(e - f.lo) > f.width)) {
-                const int64_t j = rank_s_lt<X>(ix, ec);
+                const int64_t j = rec_rank_s(ix, r1, b1, rel_of(ix, ec));
                 if (j < g_end) {
                     nrow = __ldg(ix.row_s + j);
                     ndist = f.raw(__ldg(ix.key_s + j)) - e + 1;
