@@ -14,6 +14,7 @@
  *                                NCLS.all_containments_both              pyranges/methods/join.py:17, intersection.py:76
  *                                NCLS.first_overlap_both                 pyranges/methods/join.py:19 (via nearest.py:32)
  *   iv_coverage_bp            <- NCLS.coverage                           pyranges/methods/coverage.py:64-68
+ *   iv_subtract_count/_emit   <- NCLS.set_difference_helper              pyranges/methods/subtraction.py:63-65
  *   iv_nearest                <- first_overlap_both + nearest_previous_nonoverlapping +
  *                                nearest_next_nonoverlapping + nearest_nonoverlapping
  *                                                                        pyranges/methods/nearest.py:29-53,59,69,113
@@ -187,6 +188,16 @@ int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int32_t mode, 
 /* out_bp[i] = sum over hits of min(e,E)-max(s,S); out_fraction[i] = out_bp / (end-start), NaN -> 0 */
 int iv_coverage_bp(const iv_index_t* index, const iv_queries_t* q, int64_t* out_bp, double* out_fraction,
                    void* stream);
+/* subtract: NCLS.set_difference_helper (pyranges/methods/subtraction.py:63-65).  The index must hold DISJOINT
+ * subjects per group (the caller merges `other` first, pyranges/pyranges_main.py:4868).  Phase 1 leaves the
+ * exclusive piece offsets in out_offsets[nq] and the number of pieces in *out_total (device); phase 2 writes one
+ * (query label, start, end) per surviving piece, query order.  A query without overlap survives as one piece, a
+ * completely covered query yields none. */
+size_t iv_subtract_workspace_bytes(int64_t n_queries);
+int iv_subtract_count(const iv_index_t* index, const iv_queries_t* q, int64_t* out_offsets, void* ws, size_t ws_bytes,
+                      int64_t* out_total, void* stream);
+int iv_subtract_emit(const iv_index_t* index, const iv_queries_t* q, const int64_t* offsets, int64_t* out_q,
+                     int64_t* out_start, int64_t* out_end, void* stream);
 /* out_row[i] = subject row of the nearest interval or -1, out_dist[i] = 0 (overlap), gap+1, or -1 */
 int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_t overlap, int64_t* out_row,
                int64_t* out_dist, void* stream);

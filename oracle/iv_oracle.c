@@ -199,6 +199,39 @@ void ivo_ncls_coverage(const ncls_t *t, const i64 *qs, const i64 *qe, i64 nq, i6
     }
 }
 
+/* NCLS.set_difference_helper(starts, ends, indexes, num)  methods/subtraction.py:63-65
+ * The subjects are the MERGED other intervals (pyranges_main.py:4868: disjoint).  For every query with at
+ * least one hit: the parts of [s, e) not covered by its hits, in coordinate order, as (id, start, end);
+ * a query that is covered completely yields one (id, -1, -1) marker (dropped by the caller,
+ * subtraction.py:69-73).  Queries without hit are not reported (they survive unchanged, :67). */
+static int cmp_i64_pair(const void *a, const void *b) {
+    const i64 *x = (const i64 *)a, *y = (const i64 *)b;
+    return x[0] < y[0] ? -1 : (x[0] > y[0] ? 1 : 0);
+}
+typedef struct { const ncls_t *t; vec64 *h; } dctx;
+static void hit_collect(void *c, i64 pos) { dctx *x = (dctx *)c; vpush(x->h, x->t->start[pos]); vpush(x->h, x->t->end[pos]); }
+i64 ivo_ncls_set_difference(const ncls_t *t, const i64 *qs, const i64 *qe, const i64 *qid, i64 nq,
+                            i64 **out_id, i64 **out_s, i64 **out_e) {
+    vec64 vi = {0, 0, 0}, vs = {0, 0, 0}, ve = {0, 0, 0}, h = {0, 0, 0};
+    dctx c; c.t = t; c.h = &h;
+    for (i64 i = 0; i < nq && t->n > 0; i++) {
+        h.n = 0;
+        ncls_walk(t, 0, t->n_top, qs[i], qe[i], hit_collect, &c);
+        if (h.n == 0) continue;
+        qsort(h.p, (size_t)(h.n / 2), 2 * sizeof(i64), cmp_i64_pair);
+        i64 cur = qs[i], pieces = 0;
+        for (i64 k = 0; k < h.n; k += 2) {
+            if (h.p[k] > cur) { vpush(&vi, qid[i]); vpush(&vs, cur); vpush(&ve, h.p[k]); pieces++; }
+            if (h.p[k + 1] > cur) cur = h.p[k + 1];
+        }
+        if (cur < qe[i]) { vpush(&vi, qid[i]); vpush(&vs, cur); vpush(&ve, qe[i]); pieces++; }
+        if (!pieces) { vpush(&vi, qid[i]); vpush(&vs, -1); vpush(&ve, -1); }
+    }
+    free(h.p);
+    *out_id = vi.p; *out_s = vs.p; *out_e = ve.p;
+    return vi.n;
+}
+
 /* ------------------------------------------------------------------ */
 /* sorted_nearest restatement                                            */
 /* ------------------------------------------------------------------ */

@@ -144,6 +144,11 @@ def known_answers():
     assert gr.overlap(gr2, how=None).df.ID.tolist() == ["a", "a", "a", "a", "b"]
     assert gr.overlap(gr2, how="containment").df.ID.tolist() == ["b"]
     assert gr.overlap(gr2, invert=True).df.ID.tolist() == ["c", "d"]
+    # subtract doctest :4819-4860: [1,3) a, [4,9) b, [10,11) c minus [2,3), [2,9), [9,10) -> [1,2) a, [10,11) c
+    sa = pr.from_dict({"Chromosome": ["chr1"] * 3, "Start": [1, 4, 10], "End": [3, 9, 11], "ID": ["a", "b", "c"]})
+    sb = pr.from_dict({"Chromosome": ["chr1"] * 3, "Start": [2, 2, 9], "End": [3, 9, 10]})
+    sub = sa.subtract(sb).df
+    assert sub[["Start", "End", "ID"]].values.tolist() == [[1, 2, "a"], [10, 11, "c"]], sub
     # cluster doctests :1111-1184
     g = pr.from_dict({"Chromosome": [1, 1, 1, 1], "Start": [1, 2, 3, 9], "End": [3, 3, 10, 12],
                       "Gene": [1, 2, 3, 3]})
@@ -197,8 +202,15 @@ def run_case(name, op, kwargs, sdf, odf=None, note=""):
     s = mk(sdf)
     o = mk(odf) if odf is not None else None
     kw = dict(kwargs)
-    if op in ("join", "overlap", "count_overlaps", "coverage", "nearest"):
-        res = getattr(s, op)(o, **kw)
+    if op in ("join", "overlap", "count_overlaps", "coverage", "nearest", "intersect", "set_intersect", "set_union", "subtract"):
+        try:
+            res = getattr(s, op)(o, **kw)
+        except AssertionError as exc:
+            if op != "set_union":
+                raise
+            # the reference's own pr.concat trips over pandas >= 3 for some stranded inputs: no fixture then
+            print("%-44s %-15s SKIPPED (reference fails here: %s)" % (name, op, str(exc)[:60]))
+            return
     else:
         res = getattr(s, op)(**kw)
     m = save(name, op, kwargs, stag, otag, res, note)
@@ -258,6 +270,18 @@ def main():
             run_case("overlap_invert_%s" % tag, "overlap", {"invert": True}, s, o)
             run_case("count_drop_%s" % tag, "count_overlaps", {"keep_nonoverlapping": False, "overlap_col": "C"}, s, o)
             run_case("nearest_nooverlap_%s" % tag, "nearest", {"overlap": False}, s, o)
+        # compositions of pairs / merge
+        for st in strands:
+            sn = {None: "none", "same": "same", "opposite": "opp"}[st]
+            run_case("intersect_%s_%s" % (tag, sn), "intersect", {"strandedness": st}, s, o)
+            run_case("set_intersect_%s_%s" % (tag, sn), "set_intersect", {"strandedness": st}, s, o)
+            run_case("set_union_%s_%s" % (tag, sn), "set_union", {"strandedness": st}, s, o)
+            run_case("subtract_%s_%s" % (tag, sn), "subtract", {"strandedness": st}, s, o)
+        if tag in ("f1f2", "synth", "synth_uu", "pile"):
+            run_case("intersect_first_%s" % tag, "intersect", {"how": "first"}, s, o)
+            run_case("intersect_contain_%s" % tag, "intersect", {"how": "containment"}, s, o)
+            run_case("intersect_invert_%s" % tag, "intersect", {"invert": True}, s, o)
+            run_case("set_intersect_contain_%s" % tag, "set_intersect", {"how": "containment"}, s, o)
         if both_stranded:
             for how in ("upstream", "downstream"):
                 for st in ("same", None, "opposite"):

@@ -44,6 +44,9 @@ def lib():
         for f in (L.ivo_ncls_all_overlaps_both, L.ivo_ncls_first_overlap_both):
             f.restype = C.c_int64
             f.argtypes = [C.c_void_p, _P64, _P64, _P64, C.c_int64, C.c_int, C.POINTER(_P64), C.POINTER(_P64)]
+        L.ivo_ncls_set_difference.restype = C.c_int64
+        L.ivo_ncls_set_difference.argtypes = [C.c_void_p, _P64, _P64, _P64, C.c_int64, C.POINTER(_P64), C.POINTER(_P64),
+                                              C.POINTER(_P64)]
         L.ivo_ncls_count.argtypes = [C.c_void_p, _P64, _P64, C.c_int64, _P64]
         L.ivo_ncls_coverage.argtypes = [C.c_void_p, _P64, _P64, C.c_int64, _P64]
         L.ivo_annotate_clusters.argtypes = [_P64, _P64, C.c_int64, C.c_int64, _P64]
@@ -121,6 +124,13 @@ class NCLS:
 
     def has_overlaps(self, starts, ends, indexes):
         return _a64(indexes)[self.count(starts, ends) > 0]
+
+    def set_difference_helper(self, starts, ends, indexes, num=None):
+        """-> (idx, new_starts, new_ends); see iv_oracle.c (reference call site methods/subtraction.py:63-65)"""
+        s, e, i = _a64(starts), _a64(ends), _a64(indexes)
+        oi, os_, oe = _P64(), _P64(), _P64()
+        n = lib().ivo_ncls_set_difference(self._h, _p(s), _p(e), _p(i), len(s), C.byref(oi), C.byref(os_), C.byref(oe))
+        return _take(oi, n), _take(os_, n), _take(oe, n)
 
     def coverage(self, starts, ends, indexes):
         s, e = _a64(starts), _a64(ends)

@@ -52,6 +52,9 @@ PROTOTYPES = {
     "iv_count_overlaps": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _sz, _vp, _vp]),
     "iv_emit_pairs": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "iv_coverage_bp": (C.c_int, [_PI, _PQ, _vp, _vp, _vp]),
+    "iv_subtract_workspace_bytes": (_sz, [_i64]),
+    "iv_subtract_count": (C.c_int, [_PI, _PQ, _vp, _vp, _sz, _vp, _vp]),
+    "iv_subtract_emit": (C.c_int, [_PI, _PQ, _vp, _vp, _vp, _vp, _vp]),
     "iv_nearest": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _vp]),
     "iv_cluster_workspace_bytes": (_sz, [_i64]),
     "iv_cluster": (C.c_int, [_vp, _vp, _i64, _PG, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),

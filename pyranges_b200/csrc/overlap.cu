@@ -689,6 +689,50 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
     out_dist[i] = dist;
 }
 
+// ---- subtract -------------------------------------------------------------------------------------------------------
+// NCLS.set_difference_helper (pyranges/methods/subtraction.py:63-65): the parts of every query not covered by the
+// subjects.  The subjects are the MERGED other intervals (pyranges/pyranges_main.py:4868), i.e. disjoint: the hits
+// of a query are then the `count` consecutive entries of the start order that follow the #{E' <= s'} subjects lying
+// entirely before it.  A query without hit survives as one piece, a completely covered one yields none.
+template <typename X, bool EMIT>
+__global__ void __launch_bounds__(OV_THREADS)
+k_subtract(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ pieces, const int64_t* __restrict__ offsets,
+           int64_t* __restrict__ out_q, int64_t* __restrict__ out_start, int64_t* __restrict__ out_end) {
+    __shared__ int span[2];
+    const int64_t tbase = (int64_t)blockIdx.x * OV_THREADS;
+    const int64_t last = tbase + OV_THREADS - 1 < q.n - 1 ? tbase + OV_THREADS - 1 : q.n - 1;
+    const FlatCache<X> fc(ix, q, block_seg_span(q.seg_off, q.n_seg, tbase, last, span));
+    const int64_t i = tbase + threadIdx.x;
+    if (i >= q.n) return;
+    const Flat<X> f = fc.of(ix, q, i);
+    const int64_t s = __ldg(q.start + i), e = __ldg(q.end + i);
+    int64_t o = EMIT ? __ldg(offsets + i) : 0, np = 0;
+    const int64_t ql = (EMIT && q.label) ? __ldg(q.label + i) : i;
+    auto piece = [&](int64_t a, int64_t b) {
+        if (EMIT) { out_q[o] = ql; out_start[o] = a; out_end[o] = b; o++; }
+        np++;
+    };
+    int64_t cnt = 0;
+    uint32_t p0 = 0;
+    if (f.g >= 0) {
+        const X sc = f.at(s), ec = f.at(e);
+        cnt = count_all<X>(ix, sc, ec);
+        if (cnt > 0) p0 = rank_e_lt<X>(ix, (X)(sc + 1));
+    }
+    if (cnt == 0) {
+        piece(s, e);
+    } else {
+        int64_t cur = s;
+        for (int64_t j = 0; j < cnt; j++) {
+            const int64_t S = f.raw(__ldg(ix.key_s + p0 + j)), En = f.raw(__ldg(ix.end_s + p0 + j));
+            if (S > cur) piece(cur, S);
+            cur = En > cur ? En : cur;
+        }
+        if (cur < e) piece(cur, e);
+    }
+    if (!EMIT) pieces[i] = np;
+}
+
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 static bool narrow(const iv_index_t* ix) { return ix->total_span < (int64_t)0xfffffff0ll; }
 
@@ -803,6 +847,42 @@ extern "C" int iv_coverage_bp(const iv_index_t* index, const iv_queries_t* q, in
     unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
     if (narrow(index)) k_coverage<uint32_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, out_bp, out_fraction);
     else k_coverage<uint64_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, out_bp, out_fraction);
+    IV_LAUNCH_CHECK();
+    return IV_OK;
+}
+
+extern "C" size_t iv_subtract_workspace_bytes(int64_t n_queries) {
+    return scan_i64_large_temp_elems(n_queries > 0 ? n_queries : 1) * sizeof(int64_t) + 256;
+}
+
+extern "C" int iv_subtract_count(const iv_index_t* index, const iv_queries_t* q, int64_t* out_offsets, void* ws,
+                                 size_t ws_bytes, int64_t* out_total, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_query(index, q, "iv_subtract_count");
+    if (rc != IV_OK) return rc;
+    IV_REQUIRE(out_total && ws && ws_bytes >= iv_subtract_workspace_bytes(q->n), IV_ERR_WORKSPACE, "iv_subtract_count: workspace");
+    if (q->n == 0) {
+        IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
+        return IV_OK;
+    }
+    IV_REQUIRE(out_offsets, IV_ERR_INVALID, "iv_subtract_count: out_offsets is null");
+    unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
+    if (narrow(index)) k_subtract<uint32_t, false><<<nb, OV_THREADS, 0, st>>>(*index, *q, out_offsets, nullptr, nullptr, nullptr, nullptr);
+    else k_subtract<uint64_t, false><<<nb, OV_THREADS, 0, st>>>(*index, *q, out_offsets, nullptr, nullptr, nullptr, nullptr);
+    IV_LAUNCH_CHECK();
+    return scan_exclusive_i64_large(out_offsets, q->n, (int64_t*)ws, out_total, st);
+}
+
+extern "C" int iv_subtract_emit(const iv_index_t* index, const iv_queries_t* q, const int64_t* offsets, int64_t* out_q,
+                                int64_t* out_start, int64_t* out_end, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_query(index, q, "iv_subtract_emit");
+    if (rc != IV_OK) return rc;
+    if (q->n == 0) return IV_OK;
+    IV_REQUIRE(offsets && out_q && out_start && out_end, IV_ERR_INVALID, "iv_subtract_emit: null argument");
+    unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
+    if (narrow(index)) k_subtract<uint32_t, true><<<nb, OV_THREADS, 0, st>>>(*index, *q, nullptr, offsets, out_q, out_start, out_end);
+    else k_subtract<uint64_t, true><<<nb, OV_THREADS, 0, st>>>(*index, *q, nullptr, offsets, out_q, out_start, out_end);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -269,6 +269,25 @@ class SubjectIndex:
                    "iv_coverage_bp")
         return bp, fr
 
+    def subtract(self, q):
+        """NCLS.set_difference_helper (pyranges/methods/subtraction.py:63-65); the index must hold disjoint
+        (merged) subjects.  -> (query row, start, end) of every surviving piece, query order."""
+        L = cabi.lib()
+        dev = self.iv.device
+        off = torch.empty(max(q.iv.n, 1), dtype=torch.int64, device=dev)
+        ws = _bytes(L.iv_subtract_workspace_bytes(q.iv.n), dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        cabi.check(L.iv_subtract_count(C.byref(self.c), C.byref(q.c), _ptr(off), _ptr(ws), ws.numel(), _ptr(total),
+                                       _stream()), "iv_subtract_count")
+        m = int(total.item())
+        oq = torch.empty(m, dtype=torch.int64, device=dev)
+        os_ = torch.empty(m, dtype=torch.int64, device=dev)
+        oe = torch.empty(m, dtype=torch.int64, device=dev)
+        if m:
+            cabi.check(L.iv_subtract_emit(C.byref(self.c), C.byref(q.c), _ptr(off), _ptr(oq), _ptr(os_), _ptr(oe),
+                                          _stream()), "iv_subtract_emit")
+        return oq, os_, oe
+
     def nearest(self, q, overlap=True):
         """-> (subject row or -1, distance) per query (pyranges/methods/nearest.py:29-53,59,69,113)."""
         assert self.flags & IV_INDEX_ENDS_PERM, "build the index with ends_perm=True for nearest"

@@ -6,7 +6,8 @@ a dict {key -> DataFrame} holding only the non-empty results, each with a RangeI
 reference loops over the (chromosome[, strand]) keys and calls ``function(df, odf, **kwargs)`` once per
 key (building an NCLS per key), this module recognises the hot-path callables by name
 
-    _write_both, _number_overlapping, _overlap, _count_overlaps, _coverage, _nearest      (binary)
+    _write_both, _number_overlapping, _overlap, _intersection, _subtraction, _count_overlaps, _coverage,
+    _nearest                                                                (binary)
     _cluster, _merge, coverage (pyrle.methods.coverage)                   (unary)
 
 concatenates the Start/End columns of all keys into device-resident int64 columns and runs ONE batched
@@ -338,6 +339,56 @@ def _b_overlap(plan, kwargs):
     return results
 
 
+def _b_intersection(plan, kwargs):
+    """intersect / set_intersect: pyranges/methods/intersection.py:6-55 for all keys -- the self rows of every
+    overlapping pair, clipped to the overlap."""
+    how = kwargs["how"]
+    assert how in "containment first last".split() + [False, None]
+    if how == "last":
+        raise NotImplementedError("intersect(how='last') is not part of the B200 hot path")
+    mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
+    _, out_q, out_s = plan.index().pairs(plan.queries(), mode)
+    out_q, out_s = out_q.cpu().numpy(), out_s.cpu().numpy()
+    first = np.searchsorted(out_q, plan.q.seg_off)
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        ocdf = plan.partner(k)
+        scdf, ocdf = _sparse(kwargs, scdf, ocdf)
+        a, b = first[k], first[k + 1]
+        if scdf.empty or ocdf.empty or a == b:
+            results.append(None)
+            continue
+        sp = out_q[a:b] - plan.q.seg_off[k]
+        op = out_s[a:b] - plan.group_row_off[plan.seg_group[k]]
+        df = scdf.take(sp)
+        in_dtype = ocdf.Start.dtype
+        os_, oe = ocdf.Start.values[op], ocdf.End.values[op]
+        df["Start"] = np.maximum(df.Start.values, os_).astype(in_dtype)
+        df["End"] = np.minimum(df.End.values, oe).astype(in_dtype)
+        results.append(df)
+    return results
+
+
+def _b_subtraction(plan, kwargs):
+    """subtract: pyranges/methods/subtraction.py:47-89 for all keys.  `other` must already be merged (disjoint), as
+    PyRanges.subtract does (pyranges/pyranges_main.py:4868).  Rows without overlap come back unchanged, overlapped
+    rows once per surviving piece with the piece's Start / End, completely covered rows not at all."""
+    oq, os_, oe = plan.index().subtract(plan.queries())
+    oq, os_, oe = oq.cpu().numpy(), os_.cpu().numpy(), oe.cpu().numpy()
+    first = np.searchsorted(oq, plan.q.seg_off)
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        a, b = first[k], first[k + 1]
+        if scdf.empty or a == b:
+            results.append(None)
+            continue
+        df = scdf.take(oq[a:b] - plan.q.seg_off[k])
+        df["Start"] = os_[a:b].astype(scdf.Start.dtype)
+        df["End"] = oe[a:b].astype(scdf.End.dtype)
+        results.append(df)
+    return results
+
+
 def _b_count_overlaps(plan, kwargs):
     """pr.count_overlaps helper: pyranges/methods/intersection.py:86-99 for all keys -- overlaps per row according to
     `how` as an int32 column kwargs["name"].  The reference inserts into the caller's frame in place; here the key's
@@ -434,6 +485,8 @@ _BINARY = {
     "_write_both": _b_write_both,
     "_number_overlapping": _b_number_overlapping,
     "_overlap": _b_overlap,
+    "_intersection": _b_intersection,
+    "_subtraction": _b_subtraction,
     "_count_overlaps": _b_count_overlaps,
     "_coverage": _b_coverage,
     "_nearest": _b_nearest,

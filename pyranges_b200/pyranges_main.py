@@ -58,6 +58,32 @@ def _check_strandedness(df):
     return bool(df["Strand"].astype(str).isin(["+", "-"]).all())
 
 
+def concat(pyranges, strand=None):
+    """pr.concat (pyranges/methods/concat.py:8-51): per-key concatenation of several PyRanges."""
+    pyranges = [gr for gr in pyranges if not gr.empty]
+    if not pyranges:
+        return PyRanges()
+    strand_info = [gr.stranded for gr in pyranges]
+    if strand is None:
+        strand = all(strand_info)
+    per_key = {}
+    if strand:
+        assert all(strand_info), "Cannot do stranded concat, not all pyranges contain strand info."
+        for gr in pyranges:
+            for k, df in gr.dfs.items():
+                per_key.setdefault(k, []).append(df)
+    else:
+        for gr in pyranges:
+            for c in gr.chromosomes:
+                per_key.setdefault(c, []).append(gr[c].df)
+    dfs = {k: pd.concat(v, sort=False).reset_index(drop=True) for k, v in per_key.items()}
+    if any(strand_info) and not all(strand_info):
+        for k, v in dfs.items():
+            if "Strand" in v:
+                dfs[k] = v.assign(Strand=v.Strand.astype(object).where(v.Strand.notna(), "."))
+    return PyRanges(dfs)
+
+
 class PyRanges:
     def __init__(self, df=None, chromosomes=None, starts=None, ends=None, strands=None, int64=False, copy_df=True):
         if isinstance(df, PyRanges):
@@ -299,6 +325,52 @@ class PyRanges:
             result = self[~self.__ix__.isin(found_idxs)]
             result = result.drop("__ix__")
         return result
+
+    def intersect(self, other, strandedness=None, how=None, invert=False, nb_cpu=1):
+        """pyranges/pyranges_main.py:2092-2217 (pairs + elementwise clip)"""
+        kwargs = fill_kwargs({"how": how, "strandedness": strandedness, "nb_cpu": nb_cpu})
+        kwargs["sparse"] = {"self": False, "other": True}
+        if len(self) == 0:
+            return self
+        if invert:
+            self = self.copy()
+            self.__ix__ = np.arange(len(self))
+        result = PyRanges(pyrange_apply("_intersection", self, other, **kwargs))
+        if invert:
+            found_idxs = getattr(result, "__ix__", []) if len(result) else []
+            result = self[~self.__ix__.isin(found_idxs)]
+            result = result.drop("__ix__")
+        return result
+
+    def set_intersect(self, other, strandedness=None, how=None, new_pos=False, nb_cpu=1):
+        """pyranges/pyranges_main.py:3865-3981: intersect of the two merged sets"""
+        kwargs = fill_kwargs({"strandedness": strandedness, "how": how, "nb_cpu": nb_cpu, "new_pos": new_pos})
+        strand = True if strandedness else False
+        self_clusters = self.merge(strand=strand)
+        other_clusters = other.merge(strand=strand)
+        return PyRanges(pyrange_apply("_intersection", self_clusters, other_clusters, **kwargs))
+
+    def set_union(self, other, strandedness=None, nb_cpu=1):
+        """pyranges/pyranges_main.py:3983-4073: merge of the concatenation"""
+        if self.empty and other.empty:
+            return PyRanges()
+        strand = True if strandedness else False
+        if not strand:
+            self = self.unstrand()
+            other = other.unstrand()
+        if strandedness == "opposite" and len(other):
+            other = other.copy()
+            other.Strand = other.Strand.astype(str).replace({"+": "-", "-": "+"})
+        return concat([self, other], strand).merge(strand=strand)
+
+    def subtract(self, other, strandedness=None, nb_cpu=1):
+        """pyranges/pyranges_main.py:4802-4879.  (The reference first annotates self with a __num__ overlap count
+        for NCLS.set_difference_helper; the batched kernel does not need it.)"""
+        kwargs = fill_kwargs({"strandedness": strandedness})
+        kwargs["sparse"] = {"self": False, "other": True}
+        strand = True if strandedness else False
+        other_clusters = other.merge(strand=strand)
+        return PyRanges(pyrange_apply("_subtraction", self, other_clusters, **kwargs))
 
     def count_overlaps(self, other, strandedness=None, keep_nonoverlapping=True, overlap_col="NumberOverlaps"):
         """pyranges/pyranges_main.py:1293-1386"""

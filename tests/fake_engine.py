@@ -77,6 +77,29 @@ class SubjectIndex:
             fr = np.nan_to_num(bp / ln)
         return _t(bp), _t(fr)
 
+    def subtract(self, q):
+        Q, S, En = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)], [np.zeros(0, np.int64)]
+        hit_keys = {}
+        for k, a, b, sa, sb, s, e, t in self._per_key(q):
+            hit_keys[k] = (a, b, s, e, t)
+        for k in range(q.iv.n_seg):
+            a, b = q.iv.seg_off[k], q.iv.seg_off[k + 1]
+            s, e = q.iv.s[a:b], q.iv.e[a:b]
+            rows = np.arange(a, b, dtype=np.int64)
+            if k not in hit_keys:
+                Q.append(rows), S.append(s), En.append(e)
+                continue
+            t = hit_keys[k][4]
+            idx, ns, ne = t.set_difference_helper(s, e, rows)
+            untouched = np.setdiff1d(rows, idx)
+            keep = ns != -1
+            qq = np.concatenate([untouched, idx[keep]])
+            ss = np.concatenate([q.iv.s[untouched], ns[keep]])
+            ee = np.concatenate([q.iv.e[untouched], ne[keep]])
+            o = np.lexsort([ss, qq])
+            Q.append(qq[o]), S.append(ss[o]), En.append(ee[o])
+        return _t(np.concatenate(Q)), _t(np.concatenate(S)), _t(np.concatenate(En))
+
     def nearest(self, q, overlap=True):
         row = np.full(q.iv.n, -1, np.int64)
         dist = np.full(q.iv.n, -1, np.int64)

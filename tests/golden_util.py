@@ -49,6 +49,10 @@ def load_case(name):
     return meta, res
 
 
+BINARY_OPS = ("join", "overlap", "count_overlaps", "coverage", "nearest", "intersect", "set_intersect", "set_union",
+              "subtract")
+
+
 def run_case(meta, PyRanges):
     s = PyRanges(load_input(meta["self"]))
     kw = dict(meta["kwargs"])

@@ -335,3 +335,43 @@ def test_coverage_rle_weighted(eng, seed, n_seg, n, maxpos, maxlen, integer_weig
                 return np.repeat(v, r)
             assert int(runs[sl].sum()) == int(wr.sum())
             assert np.allclose(expand(runs[sl], vals[sl]), expand(wr, wv), rtol=1e-9, atol=1e-9), k
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_subtract(eng, seed):
+    """iv_subtract_count/_emit vs the oracle's set_difference_helper on merged (disjoint) subjects."""
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(seed)
+    maxpos = int(rng.choice([500, 100_000, 8_000_000_000]))
+    qs, qe, qoff = gen_segments(seed, 4, 2000, min(maxpos, 10**9), 300)
+    ss, se, soff = gen_segments(seed + 9, 3, 800, min(maxpos, 10**9), 300)
+    if maxpos > 2**32:
+        qs, qe, ss, se = qs * 9, qe * 9, ss * 9, se * 9
+    # merge the subjects per key on the device first (PyRanges.subtract does the same)
+    ms, me, _, mg = eng.merge(_dev(eng, ss, se, soff))
+    moff = np.concatenate([[0], np.cumsum(np.bincount(mg.cpu().numpy(), minlength=3))])
+    ix = eng.SubjectIndex(eng.DeviceIntervals(ms, me, moff))
+    sg = np.asarray([0, 1, -1, 2], np.int32)
+    oq, os_, oe = ix.subtract(eng.Queries(_dev(eng, qs, qe, qoff), sg))
+    oq, os_, oe = oq.cpu().numpy(), os_.cpu().numpy(), oe.cpu().numpy()
+    ms, me = ms.cpu().numpy(), me.cpu().numpy()
+    WQ, WS, WE = [], [], []
+    for k in range(4):
+        a, b = qoff[k], qoff[k + 1]
+        rows = np.arange(a, b)
+        g = sg[k]
+        if g < 0 or moff[g] == moff[g + 1]:
+            WQ.append(rows), WS.append(qs[a:b]), WE.append(qe[a:b])
+            continue
+        t = orc.NCLS(ms[moff[g]:moff[g + 1]], me[moff[g]:moff[g + 1]], np.arange(moff[g], moff[g + 1]))
+        idx, ns, ne = t.set_difference_helper(qs[a:b], qe[a:b], rows)
+        untouched = np.setdiff1d(rows, idx)
+        keep = ns != -1
+        q2 = np.concatenate([untouched, idx[keep]])
+        s2 = np.concatenate([qs[untouched], ns[keep]])
+        e2 = np.concatenate([qe[untouched], ne[keep]])
+        o = np.lexsort([s2, q2])
+        WQ.append(q2[o]), WS.append(s2[o]), WE.append(e2[o])
+    assert np.array_equal(oq, np.concatenate(WQ))
+    assert np.array_equal(os_, np.concatenate(WS)) and np.array_equal(oe, np.concatenate(WE))
