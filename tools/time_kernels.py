@@ -64,6 +64,15 @@ timeit("iv_count_overlaps (no sums)", f_count_only, alg_bytes=24 * nr)
 timeit("iv_emit_pairs", f_emit, alg_bytes=24 * nr + 16 * p)
 timeit("SubjectIndex() python", f_build, reps=10)
 timeit("iv_index_build (C call)", ix.build, reps=10, alg_bytes=24 * na)
+# subtract against the merged annotations (strand ignored -> chromosome groups)
+ms, me, _, mg = E.merge(s_iv, annot.chrom_ranges())
+moff = np.concatenate([[0], np.cumsum(np.bincount(mg.cpu().numpy(), minlength=len(annot.chrom_ranges())))])
+m_iv = E.DeviceIntervals(ms, me, moff)
+m_iv.bounds
+mix = E.SubjectIndex(m_iv)
+oq, _, _ = mix.subtract(q)
+timeit("merge annotations (%d -> %d)" % (na, ms.numel()), lambda: E.merge(s_iv, annot.chrom_ranges()), reps=10)
+timeit("subtract (count+scan+emit, %d pieces)" % oq.numel(), lambda: mix.subtract(q), reps=10, alg_bytes=16 * nr + 24 * oq.numel())
 x = torch.empty(nr * 3, dtype=torch.int64, device="cuda")
 y = torch.empty_like(x)
 timeit("torch copy 240 MB (rd+wr)", lambda: y.copy_(x), alg_bytes=2 * 24 * nr)
