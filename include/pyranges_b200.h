@@ -22,6 +22,9 @@
  *                                + global id offsets                      pyranges/pyranges_main.py:1210-1223
  *   iv_merge_count/_emit      <- sort_values("Start") + find_clusters     pyranges/methods/merge.py:12-14
  *   iv_rle_count/_emit        <- pyrle.methods.coverage                   pyranges/methods/to_rle.py:18
+ *   iv_materialize_pairs      <- scdf.reindex / ocdf.reindex + "Overlap"  pyranges/methods/join.py:95-123,147-151
+ *                                and the clip of intersect                pyranges/methods/intersection.py:39-48
+ *   iv_gather                 <- the same reindex for a payload column    pyranges/methods/join.py:95-123
  *
  * Where the reference loops over (chromosome, strand) keys in Python and calls the native library
  * once per key (pyranges/multithreaded.py:182-303, :306-372), every entry point here is BATCHED over
@@ -51,7 +54,7 @@
 extern "C" {
 #endif
 
-#define IV_ABI_VERSION 3
+#define IV_ABI_VERSION 4
 
 #define IV_OK 0
 #define IV_ERR_INVALID (-1)   /* bad argument */
@@ -236,6 +239,23 @@ int iv_rle_weighted_count(const int64_t* starts, const int64_t* ends, const doub
                           const iv_groups_t* groups, void* ws, size_t ws_bytes, int64_t* out_run_off, void* stream);
 int iv_rle_weighted_emit(int64_t n, const iv_groups_t* groups, const void* ws, int64_t n_runs, const int64_t* run_off,
                          int64_t* out_runs, double* out_values, void* stream);
+
+/* ---- device-side materialisation of the joined frame --------------------- */
+/* For every pair i: qr = pair_q[i] - q_row_offset, sr = pair_s[i] - s_row_offset (rows of the query / subject
+ * columns the pair lists refer to; iv_emit_pairs without labels writes global rows, offsets 0).
+ *   out_q_start/out_q_end = the query row's Start / End   (clip != 0: clipped to the overlap, i.e. intersect)
+ *   out_s_start/out_s_end = the subject row's Start / End (the "_b" columns of join)
+ *   out_overlap           = min(End, End_b) - max(Start, Start_b)           (join(report_overlap=True))
+ * Any output may be NULL. */
+int iv_materialize_pairs(const int64_t* q_start, const int64_t* q_end, const int64_t* s_start,
+                         const int64_t* s_end, const int64_t* pair_q, const int64_t* pair_s, int64_t n_pairs,
+                         int64_t q_row_offset, int64_t s_row_offset, int32_t clip, int64_t* out_q_start,
+                         int64_t* out_q_end, int64_t* out_s_start, int64_t* out_s_end, int64_t* out_overlap,
+                         void* stream);
+/* out[i] = column[rows[i]] for elements of 1, 2, 4 or 8 bytes; rows[i] < 0 (the filler row of outer joins) gives
+ * *fill (host pointer to one element, NULL = zero bytes). */
+int iv_gather(const void* column, int32_t elem_bytes, const int64_t* rows, int64_t n, void* out, const void* fill,
+              void* stream);
 
 #ifdef __cplusplus
 }

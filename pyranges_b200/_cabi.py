@@ -13,7 +13,7 @@ IV_OK = 0
 IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN = 0, 1, 2
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
-IV_ABI_VERSION = 3
+IV_ABI_VERSION = 4
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
 
@@ -66,6 +66,8 @@ PROTOTYPES = {
     "iv_rle_weighted_workspace_bytes": (_sz, [_i64, _i32]),
     "iv_rle_weighted_count": (C.c_int, [_vp, _vp, _vp, _i64, _PG, _vp, _sz, _vp, _vp]),
     "iv_rle_weighted_emit": (C.c_int, [_i64, _PG, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "iv_materialize_pairs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "iv_gather": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -543,34 +543,46 @@ k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ coun
                 pE = (ec >> shift) == b ? rec_rank_s(ix, r, b, (uint32_t)ec & mask) : rank_s_lt<X>(ix, ec);
             }
             // candidates in start order: [pL, pS) started in this bin before s' (class B if still open),
-            // [pS, pE) start inside the query (class A).  Four at a time, loads first: one latency per chunk.
+            // [pS, pE) start inside the query (class A); then the bin's stabbing list (class B, open at the bin
+            // origin).  Four at a time, and the first chunk of every list is requested before any is consumed:
+            // one gather latency per query instead of one per list.
             uint32_t pL = r.w[0];
             if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
                 pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
-            for (uint32_t p = pL; p < pS; p += 4) {  // started before s': open iff its end offset is beyond s'
-                uint32_t so[4];
+            const uint32_t nc = (r.w[3] >> 16) & 0xffu;
+            const uint32_t x0 = r.w[2], x1 = nc < 255 ? x0 + nc : __ldg(&ix.bins[b + 1].co);
+            const uint2* __restrict__ cross = reinterpret_cast<const uint2*>(ix.cross);
+            uint32_t so[4], rw[4];
+            uint2 en[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) so[u] = p + u < pS ? __ldg(ix.seoff + p + u) : 0u;
+            for (int u = 0; u < 4; u++) so[u] = pL + u < pS ? __ldg(ix.seoff + pL + u) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) en[u] = x0 + u < x1 ? __ldg(cross + x0 + u) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) rw[u] = pS + u < pE ? __ldg(ix.row_s + pS + u) : 0u;
+            for (uint32_t p = pL; p < pS; p += 4) {  // started before s': open iff its end offset is beyond s'
+                if (p != pL) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) so[u] = p + u < pS ? __ldg(ix.seoff + p + u) : 0u;
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (so[u] > rel) put(__ldg(ix.row_s + p + u));
             }
             for (uint32_t p = pS; p < pE; p += 4) {  // start inside the query: all hits
-                uint32_t rw[4];
+                if (p != pS) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) rw[u] = p + u < pE ? __ldg(ix.row_s + p + u) : 0u;
+                    for (int u = 0; u < 4; u++) rw[u] = p + u < pE ? __ldg(ix.row_s + p + u) : 0u;
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (p + u < pE) put(rw[u]);
             }
-            // class B, open at the bin origin: the bin's stabbing list
-            const uint32_t nc = (r.w[3] >> 16) & 0xffu;
-            const uint32_t x0 = r.w[2], x1 = nc < 255 ? x0 + nc : __ldg(&ix.bins[b + 1].co);
             for (uint32_t j = x0; j < x1; j += 4) {
-                uint2 en[4];
+                if (j != x0) {
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    en[u] = j + u < x1 ? __ldg(reinterpret_cast<const uint2*>(ix.cross) + j + u) : make_uint2(0u, 0u);
+                    for (int u = 0; u < 4; u++) en[u] = j + u < x1 ? __ldg(cross + j + u) : make_uint2(0u, 0u);
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (en[u].y > rel) put(en[u].x);

@@ -377,3 +377,34 @@ def radix_sort_u64(keys, values=None, begin_bit=0, end_bit=64):
     cabi.check(L.iv_radix_sort_u64(_ptr(keys), _ptr(values), vb, keys.numel(), begin_bit, end_bit, _ptr(ws), ws.numel(),
                                    _stream()), "iv_radix_sort_u64")
     return keys, values
+
+
+def materialize_pairs(q_iv, s_iv, pair_q, pair_s, clip=False, want=("q_start", "q_end", "s_start", "s_end"),
+                      q_row_offset=0, s_row_offset=0):
+    """Coordinate columns of the joined frame for the pair lists of SubjectIndex.pairs, gathered on the device
+    (pyranges/methods/join.py:95-123,147-151; clip=True: intersect, intersection.py:39-48).  `want` names the
+    outputs: q_start, q_end, s_start, s_end, overlap.  -> dict name -> int64 tensor [n_pairs]."""
+    L = cabi.lib()
+    dev = _use(q_iv.device)
+    n = int(pair_q.numel())
+    out = {k: torch.empty(n, dtype=torch.int64, device=dev) for k in want}
+    g = lambda k: _ptr(out[k]) if k in out else None  # noqa: E731
+    cabi.check(L.iv_materialize_pairs(_ptr(q_iv.start), _ptr(q_iv.end), _ptr(s_iv.start), _ptr(s_iv.end),
+                                      _ptr(pair_q), _ptr(pair_s), n, q_row_offset, s_row_offset, 1 if clip else 0,
+                                      g("q_start"), g("q_end"), g("s_start"), g("s_end"), g("overlap"), _stream()),
+               "iv_materialize_pairs")
+    return out
+
+
+def gather(column, rows, fill=None):
+    """out[i] = column[rows[i]] on the device for a 1/2/4/8-byte column (payload columns of the joined frame);
+    rows < 0 give `fill` (a Python scalar of the column's dtype, default 0)."""
+    L = cabi.lib()
+    dev = _use(column.device)
+    out = torch.empty(rows.numel(), dtype=column.dtype, device=dev)
+    fb = None
+    if fill is not None:
+        fb = torch.tensor([fill], dtype=column.dtype).numpy().tobytes()
+    cabi.check(L.iv_gather(_ptr(column), column.element_size(), _ptr(rows), rows.numel(), _ptr(out), fb, _stream()),
+               "iv_gather")
+    return out

@@ -42,7 +42,8 @@ def merge_dfs(df1, df2):
 
 
 def process_results(results, keys):
-    """pyranges/multithreaded.py:77-103: drop None/empty, deep copy, RangeIndex."""
+    """pyranges/multithreaded.py:77-103: drop None/empty, RangeIndex.  (The reference also deep-copies each frame
+    because its per-key callables may return views of the inputs; every frame built in this module is new.)"""
     results_dict = {k: r for k, r in zip(keys, results) if r is not None}
     try:
         first_item = next(iter(results_dict.values()))
@@ -54,8 +55,8 @@ def process_results(results, keys):
     for k, v in results_dict.items():
         if v is None or v.empty:
             continue
-        v = v.copy(deep=True)
-        v.index = range(len(v))
+        if not (isinstance(v.index, pd.RangeIndex) and v.index.start == 0 and v.index.step == 1):
+            v.index = pd.RangeIndex(len(v))
         out[k] = v
     return out
 
@@ -212,6 +213,33 @@ def _take_with_null(df, pos):
     return df.take(pos)
 
 
+def _assemble(scdf, ocdf, self_pos, other_pos, suffix, core_self=None, core_other=None, drop_other=("Chromosome",),
+              extra=None, extra_is_other=False):
+    """The inner-join tail of _write_both (pyranges/methods/join.py:95-154) column by column: rows `self_pos` of scdf
+    next to rows `other_pos` of ocdf, names of ocdf that collide get `suffix`.  `core_self` / `core_other` hold the
+    columns of scdf / ocdf that were already gathered on the device (engine.materialize_pairs), keyed by the SOURCE
+    column name; `extra` is appended last (as columns of ocdf, i.e. suffixed on collision, if `extra_is_other`).  One take per remaining column instead of two DataFrame.take + drop +
+    DataFrame.join."""
+    core_self, core_other = core_self or {}, core_other or {}
+    data = {}
+    for c in scdf.columns:
+        if c in core_self:
+            data[c] = core_self[c].astype(scdf[c].dtype, copy=False)
+        else:
+            data[c] = scdf[c].values.take(self_pos)
+    for c in ocdf.columns:
+        if c in drop_other:
+            continue
+        name = c + suffix if c in data else c
+        if c in core_other:
+            data[name] = core_other[c].astype(ocdf[c].dtype, copy=False)
+        else:
+            data[name] = ocdf[c].values.take(other_pos)
+    for n, v in (extra or {}).items():
+        data[n + suffix if (extra_is_other and n in data) else n] = v
+    return pd.DataFrame(data, copy=False)
+
+
 def _join_frames(scdf, ocdf, self_pos, other_pos, counts_self, kwargs):
     """_both_indexes tail + _both_dfs + _write_both (pyranges/methods/join.py:22-154) given the inner pairs
     as row positions into scdf / ocdf."""
@@ -275,13 +303,31 @@ def _b_write_both(plan, kwargs):
     mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
     ix = plan.index()
     counts, out_q, out_s = ix.pairs(plan.queries(), mode)
+    inner = how not in ["outer", "left", "right"]
+    core = None
+    if inner:
+        # the coordinate columns of the joined frame are gathered on the device, where both
+        # tables already live; the host only gathers the payload columns (by position, one take per column)
+        want = ("q_start", "q_end", "s_start", "s_end") + (("overlap",) if kwargs.get("report_overlap") else ())
+        core = {n: t.cpu().numpy() for n, t in E.materialize_pairs(plan.q.iv, plan.s.iv, out_q, out_s, want=want).items()}
     counts, out_q, out_s = counts.cpu().numpy(), out_q.cpu().numpy(), out_s.cpu().numpy()
     first = np.searchsorted(out_q, plan.q.seg_off)  # pairs are emitted in query-row order
+    suffix = kwargs.get("suffix", "_b") if not kwargs.get("new_pos") else kwargs.get("suffixes", "_a _b".split())[1]
     results = []
     for k, scdf in enumerate(plan.q.dfs):
         ocdf = plan.partner(k)
         scdf, ocdf = _sparse(kwargs, scdf, ocdf)
         a, b = first[k], first[k + 1]
+        if inner:
+            if scdf.empty or ocdf.empty or a == b:
+                results.append(None)
+                continue
+            cq = {"Start": core["q_start"][a:b], "End": core["q_end"][a:b]}
+            co = {"Start": core["s_start"][a:b], "End": core["s_end"][a:b]}
+            extra = {"Overlap": core["overlap"][a:b]} if "overlap" in core else None
+            results.append(_assemble(scdf, ocdf, out_q[a:b] - plan.q.seg_off[k],
+                                     out_s[a:b] - plan.group_row_off[plan.seg_group[k]], suffix, cq, co, extra=extra))
+            continue
         if scdf.empty or ocdf.empty:
             if how in ["left", "outer"] and ocdf.empty:
                 ocdf = null_types(kwargs["example_header_other"])
@@ -310,7 +356,7 @@ def _b_number_overlapping(plan, kwargs):
         if scdf.empty or (ocdf.empty and not keep):
             results.append(None)
             continue
-        df = scdf.copy()
+        df = scdf.copy(deep=False)  # new frame object, columns shared: only a column is added
         df.insert(df.shape[1], col, counts[plan.q.seg_off[k]:plan.q.seg_off[k + 1]])
         results.append(df if keep else df[df[col] != 0])
     return results
@@ -348,7 +394,10 @@ def _b_intersection(plan, kwargs):
         raise NotImplementedError("intersect(how='last') is not part of the B200 hot path")
     mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
     _, out_q, out_s = plan.index().pairs(plan.queries(), mode)
-    out_q, out_s = out_q.cpu().numpy(), out_s.cpu().numpy()
+    # the clip max(Start, Start_b) / min(End, End_b) happens where the columns live (engine.materialize_pairs)
+    core = E.materialize_pairs(plan.q.iv, plan.s.iv, out_q, out_s, clip=True, want=("q_start", "q_end"))
+    cs, ce = core["q_start"].cpu().numpy(), core["q_end"].cpu().numpy()
+    out_q = out_q.cpu().numpy()
     first = np.searchsorted(out_q, plan.q.seg_off)
     results = []
     for k, scdf in enumerate(plan.q.dfs):
@@ -358,14 +407,17 @@ def _b_intersection(plan, kwargs):
         if scdf.empty or ocdf.empty or a == b:
             results.append(None)
             continue
-        sp = out_q[a:b] - plan.q.seg_off[k]
-        op = out_s[a:b] - plan.group_row_off[plan.seg_group[k]]
-        df = scdf.take(sp)
         in_dtype = ocdf.Start.dtype
-        os_, oe = ocdf.Start.values[op], ocdf.End.values[op]
-        df["Start"] = np.maximum(df.Start.values, os_).astype(in_dtype)
-        df["End"] = np.minimum(df.End.values, oe).astype(in_dtype)
-        results.append(df)
+        sp = out_q[a:b] - plan.q.seg_off[k]
+        data = {}
+        for c in scdf.columns:
+            if c == "Start":
+                data[c] = cs[a:b].astype(in_dtype, copy=False)
+            elif c == "End":
+                data[c] = ce[a:b].astype(in_dtype, copy=False)
+            else:
+                data[c] = scdf[c].values.take(sp)
+        results.append(pd.DataFrame(data, copy=False))
     return results
 
 
@@ -403,7 +455,7 @@ def _b_count_overlaps(plan, kwargs):
             results.append(None)
             continue
         c = counts[plan.q.seg_off[k]:plan.q.seg_off[k + 1]] if not plan.partner(k).empty else np.zeros(len(scdf), np.int64)
-        df = scdf.copy()
+        df = scdf.copy(deep=False)  # new frame object, columns shared: only a column is added
         df.insert(df.shape[1], kwargs["name"], c.astype(np.int32))
         results.append(df)
     return results
@@ -419,7 +471,7 @@ def _b_coverage(plan, kwargs):
         if scdf.empty:
             results.append(None)
             continue
-        df = scdf.copy()
+        df = scdf.copy(deep=False)  # new frame object, columns shared: only a column is added
         f = frac[plan.q.seg_off[k]:plan.q.seg_off[k + 1]] if not plan.partner(k).empty else 0.0
         df.insert(df.shape[1], col, f)
         results.append(df)
@@ -456,7 +508,6 @@ def _b_nearest(plan, kwargs):
         if scdf.empty or ocdf.empty:
             results.append(None)
             continue
-        ocdf = ocdf.reset_index(drop=True)
         sl = slice(plan.q.seg_off[k], plan.q.seg_off[k + 1])
         r = row[sl] - plan.group_row_off[plan.seg_group[k]]
         d = dist[sl]
@@ -470,14 +521,8 @@ def _b_nearest(plan, kwargs):
         if not len(sel):
             results.append(None)
             continue
-        o2 = ocdf.take(r[sel])
-        o2.index = pd.RangeIndex(len(sel))
-        o2.insert(o2.shape[1], _distance_name(o2, suffix), d[sel])
-        s2 = scdf.take(sel)
-        s2.index = o2.index
-        df = s2.join(o2, rsuffix=suffix)
-        df = df.drop("Chromosome" + suffix, axis=1)
-        results.append(df)
+        results.append(_assemble(scdf, ocdf, sel, r[sel], suffix, extra={_distance_name(ocdf, suffix): d[sel]},
+                                 extra_is_other=True))
     return results
 
 

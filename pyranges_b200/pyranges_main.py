@@ -58,6 +58,17 @@ def _check_strandedness(df):
     return bool(df["Strand"].astype(str).isin(["+", "-"]).all())
 
 
+def _all_equal(col, value):
+    """(col.astype(str) == value).all() without stringifying a categorical column row by row."""
+    if isinstance(col.dtype, pd.CategoricalDtype):
+        codes = col.cat.codes.to_numpy()
+        if not len(codes):
+            return True
+        c = codes[0]
+        return bool(c >= 0 and (codes == c).all() and str(col.cat.categories[c]) == value)
+    return bool((col.astype(str) == value).all())
+
+
 def concat(pyranges, strand=None):
     """pr.concat (pyranges/methods/concat.py:8-51): per-key concatenation of several PyRanges."""
     pyranges = [gr for gr in pyranges if not gr.empty]
@@ -110,20 +121,28 @@ class PyRanges:
             else:
                 dfs = {}
         else:
-            dfs = {k: v.copy() for k, v in df.items() if not v.empty}
+            dfs = {k: (v.copy() if copy_df else v) for k, v in df.items() if not v.empty}
             ok = True
             for key, d in dfs.items():
                 if isinstance(key, tuple):
                     ok = ok and ("Strand" in d) and key[1] in ("+", "-") and \
-                        (d["Chromosome"].astype(str) == str(key[0])).all() and (d["Strand"].astype(str) == key[1]).all()
+                        _all_equal(d["Chromosome"], str(key[0])) and _all_equal(d["Strand"], key[1])
                 else:
-                    ok = ok and (d["Chromosome"].astype(str) == str(key)).all()
+                    ok = ok and _all_equal(d["Chromosome"], str(key))
             if not ok:
                 alldf = pd.concat(dfs.values()).reset_index(drop=True)
                 stranded = _check_strandedness(alldf)
                 by = ["Chromosome", "Strand"] if stranded else "Chromosome"
                 dfs = {k: v for k, v in alldf.groupby(by, observed=True)}
         self.__dict__["dfs"] = dfs
+
+    @classmethod
+    def _wrap(cls, dfs):
+        """A PyRanges around a dict the dispatcher just produced: every frame is new, non-empty and belongs to its
+        key, so the copy and the key validation of __init__ are skipped."""
+        self = cls.__new__(cls)
+        self.__dict__["dfs"] = dfs
+        return self
 
     # ---- container helpers ---------------------------------------------------------------------------
     def __len__(self):
@@ -292,7 +311,7 @@ class PyRanges:
         if how in ["right", "outer"]:
             kwargs["example_header_self"] = self.head(1).df
         dfs = pyrange_apply("_write_both", self, other, **kwargs)
-        gr = PyRanges(dfs)
+        gr = PyRanges._wrap(dfs)
         if slack and len(gr) > 0:
             gr.Start = gr.Start__slack
             gr.End = gr.End__slack
@@ -319,7 +338,7 @@ class PyRanges:
             self = self.copy()
             self.__ix__ = np.arange(len(self))
         dfs = pyrange_apply("_overlap", self, other, **kwargs)
-        result = PyRanges(dfs)
+        result = PyRanges._wrap(dfs)
         if invert:
             found_idxs = getattr(result, "__ix__", []) if len(result) else []
             result = self[~self.__ix__.isin(found_idxs)]
@@ -335,7 +354,7 @@ class PyRanges:
         if invert:
             self = self.copy()
             self.__ix__ = np.arange(len(self))
-        result = PyRanges(pyrange_apply("_intersection", self, other, **kwargs))
+        result = PyRanges._wrap(pyrange_apply("_intersection", self, other, **kwargs))
         if invert:
             found_idxs = getattr(result, "__ix__", []) if len(result) else []
             result = self[~self.__ix__.isin(found_idxs)]
@@ -348,7 +367,7 @@ class PyRanges:
         strand = True if strandedness else False
         self_clusters = self.merge(strand=strand)
         other_clusters = other.merge(strand=strand)
-        return PyRanges(pyrange_apply("_intersection", self_clusters, other_clusters, **kwargs))
+        return PyRanges._wrap(pyrange_apply("_intersection", self_clusters, other_clusters, **kwargs))
 
     def set_union(self, other, strandedness=None, nb_cpu=1):
         """pyranges/pyranges_main.py:3983-4073: merge of the concatenation"""
@@ -370,13 +389,13 @@ class PyRanges:
         kwargs["sparse"] = {"self": False, "other": True}
         strand = True if strandedness else False
         other_clusters = other.merge(strand=strand)
-        return PyRanges(pyrange_apply("_subtraction", self, other_clusters, **kwargs))
+        return PyRanges._wrap(pyrange_apply("_subtraction", self, other_clusters, **kwargs))
 
     def count_overlaps(self, other, strandedness=None, keep_nonoverlapping=True, overlap_col="NumberOverlaps"):
         """pyranges/pyranges_main.py:1293-1386"""
         kwargs = {"strandedness": strandedness, "keep_nonoverlapping": keep_nonoverlapping, "overlap_col": overlap_col}
         kwargs = fill_kwargs(kwargs)
-        return PyRanges(pyrange_apply("_number_overlapping", self, other, **kwargs))
+        return PyRanges._wrap(pyrange_apply("_number_overlapping", self, other, **kwargs))
 
     def coverage(self, other, strandedness=None, keep_nonoverlapping=True, overlap_col="NumberOverlaps",
                  fraction_col="FractionOverlaps", nb_cpu=1):
@@ -387,7 +406,7 @@ class PyRanges:
         counts = self.count_overlaps(other, keep_nonoverlapping=True, overlap_col=overlap_col, strandedness=strandedness)
         strand = True if kwargs["strandedness"] else False
         other = other.merge(count=True, strand=strand)
-        return PyRanges(pyrange_apply("_coverage", counts, other, **kwargs))
+        return PyRanges._wrap(pyrange_apply("_coverage", counts, other, **kwargs))
 
     def nearest(self, other, strandedness=None, overlap=True, how=None, suffix="_b", nb_cpu=1, apply_strand_suffix=None):
         """pyranges/pyranges_main.py:3192-3339"""
@@ -397,7 +416,7 @@ class PyRanges:
         if kwargs.get("how") in "upstream downstream".split():
             assert other.stranded, "If doing upstream or downstream nearest, other pyranges must be stranded"
         dfs = pyrange_apply("_nearest", self, other, **kwargs)
-        gr = PyRanges(dfs)
+        gr = PyRanges._wrap(dfs)
         if not self.stranded and other.stranded:
             if apply_strand_suffix is None:
                 print("join: Strand data from other will be added as strand data to self.\nIf this is undesired use the "
@@ -419,19 +438,19 @@ class PyRanges:
             self.Strand2 = self.Strand
             self = self.unstrand()
         df = pyrange_apply_single("_cluster", self, **kwargs)
-        gr = PyRanges(df)
+        gr = PyRanges._wrap(df)
         # ids are per key; make them globally unique in natsorted key order (pyranges_main.py:1210-1223)
         new_dfs = {}
         max_id = 0
         for i, (k, v) in enumerate(gr.items()):
             if i:
-                v = v.copy()
-                v.loc[:, "Cluster"] += max_id
+                v = v.copy(deep=False)
+                v["Cluster"] = v["Cluster"].values + max_id
             max_id = v.Cluster.max()
             new_dfs[k] = v
         if not strand and _stranded:
             new_dfs = {k: d.rename(columns={"Strand2": "Strand"}) for k, d in new_dfs.items()}
-        return PyRanges(new_dfs)
+        return PyRanges._wrap(new_dfs)
 
     def merge(self, strand=None, count=False, count_col="Count", by=None, slack=0):
         """pyranges/pyranges_main.py:3005-3146"""
@@ -441,7 +460,7 @@ class PyRanges:
             strand = self.stranded
         kwargs = {"strand": strand, "count": count, "by": by, "count_col": count_col, "slack": slack,
                   "sparse": {"self": True}}
-        return PyRanges(pyrange_apply_single("_merge", self, **kwargs))
+        return PyRanges._wrap(pyrange_apply_single("_merge", self, **kwargs))
 
     def to_rle(self, value_col=None, strand=None, rpm=False, nb_cpu=1):
         """pyranges/pyranges_main.py:5772-5880, pyranges/methods/to_rle.py:4-24"""

@@ -168,3 +168,14 @@ def coverage_rle(iv, seg_ranges=None, weights=None):
         R.append(r), V.append(v)
         off.append(off[-1] + len(r))
     return np.asarray(off, np.int64), _t(np.concatenate(R)), _t(np.concatenate(V))
+
+
+def materialize_pairs(q_iv, s_iv, pair_q, pair_s, clip=False, want=("q_start", "q_end", "s_start", "s_end"),
+                      q_row_offset=0, s_row_offset=0):
+    qr, sr = pair_q.numpy() - q_row_offset, pair_s.numpy() - s_row_offset
+    qs, qe, ss, se = q_iv.s[qr], q_iv.e[qr], s_iv.s[sr], s_iv.e[sr]
+    out = {"overlap": np.minimum(qe, se) - np.maximum(qs, ss)}
+    if clip:
+        qs, qe = np.maximum(qs, ss), np.minimum(qe, se)
+    out.update({"q_start": qs, "q_end": qe, "s_start": ss, "s_end": se})
+    return {k: _t(out[k]) for k in want}

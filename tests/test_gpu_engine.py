@@ -375,3 +375,40 @@ def test_subtract(eng, seed):
         WQ.append(q2[o]), WS.append(s2[o]), WE.append(e2[o])
     assert np.array_equal(oq, np.concatenate(WQ))
     assert np.array_equal(os_, np.concatenate(WS)) and np.array_equal(oe, np.concatenate(WE))
+
+
+@pytest.mark.parametrize("case", CASES[1:4])
+def test_materialize_pairs_and_gather(eng, case):
+    """Device-side join tail: coordinate columns, Overlap, the clip of intersect and payload
+    gathers equal numpy fancy indexing on the same pair lists."""
+    import torch
+
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, case)
+    qiv, siv = _dev(eng, qs, qe, qoff), _dev(eng, ss, se, soff)
+    _, a, b = eng.SubjectIndex(siv).pairs(eng.Queries(qiv, sg), eng.IV_MODE_ALL)
+    an, bn = a.cpu().numpy(), b.cpu().numpy()
+    assert len(an) > 0
+    got = eng.materialize_pairs(qiv, siv, a, b, want=("q_start", "q_end", "s_start", "s_end", "overlap"))
+    got = {k: v.cpu().numpy() for k, v in got.items()}
+    assert np.array_equal(got["q_start"], qs[an]) and np.array_equal(got["q_end"], qe[an])
+    assert np.array_equal(got["s_start"], ss[bn]) and np.array_equal(got["s_end"], se[bn])
+    assert np.array_equal(got["overlap"], np.minimum(qe[an], se[bn]) - np.maximum(qs[an], ss[bn]))
+    assert (got["overlap"] > 0).all()
+    clip = eng.materialize_pairs(qiv, siv, a, b, clip=True, want=("q_start", "q_end"))
+    assert np.array_equal(clip["q_start"].cpu().numpy(), np.maximum(qs[an], ss[bn]))
+    assert np.array_equal(clip["q_end"].cpu().numpy(), np.minimum(qe[an], se[bn]))
+    # payload columns of every element width, with the -1 filler rows of outer joins
+    rng = np.random.default_rng(case[0])
+    rows = bn.copy()
+    rows[rng.random(len(rows)) < 0.1] = -1
+    rt = torch.from_numpy(rows).cuda()
+    for dtype, fill in [(np.int8, -1), (np.int16, -1), (np.int32, -1), (np.int64, -1), (np.float32, -1.0), (np.float64, -1.0)]:
+        col = (rng.integers(-100, 100, len(ss))).astype(dtype)
+        out = eng.gather(torch.from_numpy(col).cuda(), rt, fill=fill).cpu().numpy()
+        want = np.where(rows >= 0, col[np.maximum(rows, 0)], np.asarray(fill, dtype))
+        assert out.dtype == col.dtype and np.array_equal(out, want), dtype
+    out = eng.gather(torch.from_numpy(ss).cuda(), rt).cpu().numpy()  # default filler: zero
+    assert np.array_equal(out, np.where(rows >= 0, ss[np.maximum(rows, 0)], 0))
+    # no pairs at all
+    e = torch.zeros(0, dtype=torch.int64).cuda()
+    assert all(v.numel() == 0 for v in eng.materialize_pairs(qiv, siv, e, e).values())
