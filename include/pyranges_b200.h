@@ -22,6 +22,8 @@
  *                                + global id offsets                      pyranges/pyranges_main.py:1210-1223
  *   iv_merge_count/_emit      <- sort_values("Start") + find_clusters     pyranges/methods/merge.py:12-14
  *   iv_rle_count/_emit        <- pyrle.methods.coverage                   pyranges/methods/to_rle.py:18
+ *   iv_split_count/_emit      <- concat(Start, End).sort_values().drop_duplicates() + consecutive pairs
+ *                                                                        pyranges/methods/split.py:4-24
  *   iv_materialize_pairs      <- scdf.reindex / ocdf.reindex + "Overlap"  pyranges/methods/join.py:95-123,147-151
  *                                and the clip of intersect                pyranges/methods/intersection.py:39-48
  *   iv_gather                 <- the same reindex for a payload column    pyranges/methods/join.py:95-123
@@ -239,6 +241,17 @@ int iv_rle_weighted_count(const int64_t* starts, const int64_t* ends, const doub
                           const iv_groups_t* groups, void* ws, size_t ws_bytes, int64_t* out_run_off, void* stream);
 int iv_rle_weighted_emit(int64_t n, const iv_groups_t* groups, const void* ws, int64_t n_runs, const int64_t* run_off,
                          int64_t* out_runs, double* out_values, void* stream);
+
+/* ---- split (feeds the multi-sample count matrix, pyranges/multioverlap.py:146) ---- */
+/* Every pair of consecutive distinct Start/End points of a group is one feature [point, next point) -- with the gaps
+ * between intervals (split(between=True)); the caller drops those with an overlap pass.  groups->lo / hi = min Start /
+ * max End of the group.  Phase 1 leaves, in out_group_off [n_groups+1] (device), the features before each group and
+ * the total; phase 2 writes them group-major in coordinate order. */
+size_t iv_split_workspace_bytes(int64_t n);
+int iv_split_count(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, void* ws,
+                   size_t ws_bytes, int64_t* out_group_off, void* stream);
+int iv_split_emit(int64_t n, const iv_groups_t* groups, const void* ws, int64_t n_features, int64_t* out_start,
+                  int64_t* out_end, int32_t* out_group, void* stream);
 
 /* ---- device-side materialisation of the joined frame --------------------- */
 /* For every pair i: qr = pair_q[i] - q_row_offset, sr = pair_s[i] - s_row_offset (rows of the query / subject

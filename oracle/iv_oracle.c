@@ -261,6 +261,32 @@ i64 ivo_find_clusters(const i64 *S, const i64 *E, i64 n, i64 slack, i64 *out_s, 
     return k;
 }
 
+/* cluster_by(starts, ends, by_ids, slack)  methods/cluster.py:48 (sorted_nearest, un-vendored): rows sorted by
+ * (by_id, Start); the annotate_clusters scan, except that a change of by_id always opens a new cluster. */
+void ivo_cluster_by(const i64 *S, const i64 *E, const i64 *B, i64 n, i64 slack, i64 *out_id) {
+    if (n == 0) return;
+    i64 id = 1, m = E[0];
+    out_id[0] = 1;
+    for (i64 i = 1; i < n; i++) {
+        if (B[i] == B[i - 1] && S[i] - slack <= m) { if (E[i] > m) m = E[i]; }
+        else { id++; m = E[i]; }
+        out_id[i] = id;
+    }
+}
+
+/* merge_by(starts, ends, by_ids, slack)  methods/merge.py:65 -> per cluster (by_id, start, max end, n_members) */
+i64 ivo_merge_by(const i64 *S, const i64 *E, const i64 *B, i64 n, i64 slack, i64 *out_b, i64 *out_s, i64 *out_e,
+                 i64 *out_n) {
+    if (n == 0) return 0;
+    i64 k = 0, m = E[0], cs = S[0], cnt = 1, cb = B[0];
+    for (i64 i = 1; i < n; i++) {
+        if (B[i] == cb && S[i] - slack <= m) { if (E[i] > m) m = E[i]; cnt++; }
+        else { out_b[k] = cb; out_s[k] = cs; out_e[k] = m; out_n[k] = cnt; k++; cb = B[i]; cs = S[i]; m = E[i]; cnt = 1; }
+    }
+    out_b[k] = cb; out_s[k] = cs; out_e[k] = m; out_n[k] = cnt; k++;
+    return k;
+}
+
 /* nearest_previous_nonoverlapping(l_starts, r_ends - 1, r_idx)  methods/nearest.py:69
  * Ls sorted ascending, Re1 sorted ascending (= End - 1), Ridx aligned with Re1.
  * per left: last j with Re1[j] < Ls[i]; ties among equal Re1 -> FIRST of the equal run

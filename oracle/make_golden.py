@@ -12,7 +12,9 @@ cluster-id offsets ...).  The script also replays the known answers of the refer
 and unit tests for this path and aborts if the oracle misses one.
 
 pandas-3 work-arounds: future.infer_string off; PyRanges rebuilt from a dict
-without the empty (chrom, '.') groups; importlib.metadata.version patched.
+without the empty (chrom, '.') groups; importlib.metadata.version patched; for pr.count_overlaps only,
+Series.value_counts of an int32 Series returns int32 counts (pandas >= 3 refuses the int64 -> int32 setitem of
+pyranges/methods/intersection.py:95; pandas < 3 down-cast silently).
 """
 import importlib.metadata as md
 import json
@@ -154,6 +156,34 @@ def known_answers():
                       "Gene": [1, 2, 3, 3]})
     assert g.cluster().df.Cluster.tolist() == [1, 1, 1, 1]
     assert g.cluster(slack=-1).df.Cluster.tolist() == [1, 1, 2, 2]
+    # cluster(by=) doctests :1139-1184 (cluster_by restatement)
+    gb = pr.from_dict({"Chromosome": [1, 1, 1, 1], "Start": [1, 2, 3, 9], "End": [3, 3, 10, 12], "Gene": [1, 2, 3, 3]})
+    cb = gb.cluster(by="Gene", count=True).df
+    assert cb.Cluster.tolist() == [1, 2, 3, 3] and cb.Count.tolist() == [1, 1, 2, 2]
+    cb2 = fix(pr.data.ensembl_gtf())[["Feature", "Source"]].cluster(by=["Feature", "Source"]).df
+    assert len(cb2) == 2446 and int(cb2.Cluster.max()) == 1145 and cb2.Cluster.tolist()[:4] == [1, 2, 2, 2]
+    # merge(by=) doctests :3087-3125 (merge_by restatement)
+    mb = fix(pr.data.ensembl_gtf()).merge(by="Feature", count=True).df
+    assert len(mb) == 748 and mb.Count.tolist()[:4] == [1, 2, 1, 11] and mb.Start.tolist()[:2] == [65564, 69036]
+    mb2 = fix(pr.data.ensembl_gtf()).merge(by=["Feature", "gene_name"], count=True).df
+    assert len(mb2) == 807 and mb2.gene_name.tolist()[-2:] == ["WASH7P", "WASH9P"] and mb2.Count.tolist()[:4] == [1, 2, 2, 4]
+    # split doctests :4386-4460
+    sg = fix(pr.from_dict({"Chromosome": ["chr1"] * 4, "Start": [3, 5, 5, 11], "End": [6, 9, 7, 12],
+                           "Strand": ["+", "+", "-", "-"]}))
+    assert sg.split().df.Start.tolist() == [3, 5, 6, 5, 11] and sg.split().df.End.tolist() == [5, 6, 9, 7, 12]
+    assert sg.split(between=True).df.Start.tolist() == [3, 5, 6, 5, 7, 11]
+    assert sg.split(strand=False).df.Start.tolist() == [3, 5, 6, 7, 11]
+    assert sg.split(strand=False, between=True).df.End.tolist() == [5, 6, 7, 9, 11, 12]
+    # pr.count_overlaps doctest multioverlap.py:38-134
+    ga = pr.from_dict({"Chromosome": ["chr1"] * 4, "Start": [6, 10, 22, 24], "End": [12, 20, 27, 30]})
+    gb2 = pr.from_dict({"Chromosome": ["chr1"] * 2, "Start": [12, 14], "End": [32, 30]})
+    gc = pr.from_dict({"Chromosome": ["chr1"] * 3, "Start": [8, 10, 32], "End": [15, 14, 34]})
+    feat = pr.PyRanges(chromosomes=["chr1"] * 4, starts=[0, 10, 20, 30], ends=[10, 20, 30, 40])
+    with int32_value_counts():
+        cm = pr.count_overlaps({"a": ga, "b": gb2, "c": gc}, feat).df
+        cm2 = pr.count_overlaps({"a": ga, "b": gb2, "c": gc}).df
+    assert cm.a.tolist() == [1, 2, 2, 0] and cm.b.tolist() == [0, 2, 2, 1] and cm.c.tolist() == [1, 2, 0, 1], cm
+    assert len(cm2) == 12, len(cm2)
     # merge doctest :3069-3086 (ensembl_gtf: 62 merged rows... first 11868-14409 count 12)
     eg = fix(pr.data.ensembl_gtf())
     m = eg.merge(count=True, count_col="Count").df
@@ -215,6 +245,44 @@ def run_case(name, op, kwargs, sdf, odf=None, note=""):
         res = getattr(s, op)(**kw)
     m = save(name, op, kwargs, stag, otag, res, note)
     print("%-44s %-15s rows=%s" % (name, op, m.get("n_rows", "rle")))
+
+
+class int32_value_counts:
+    """pandas >= 3 only: see the module docstring."""
+
+    def __enter__(self):
+        self._vc = vc = pd.Series.value_counts
+
+        def value_counts(series, *a, **k):
+            r = vc(series, *a, **k)
+            return r.astype(np.int32) if series.dtype == np.int32 else r
+
+        pd.Series.value_counts = value_counts
+
+    def __exit__(self, *exc):
+        pd.Series.value_counts = self._vc
+
+
+def run_multi(name, samples, features, kwargs):
+    """pr.count_overlaps(grs, features) (pyranges/multioverlap.py:6-165); samples: {column name: (tag, frame)}"""
+    for tag, df in samples.values():
+        save_input(tag, df)
+    ftag = None
+    if features is not None:
+        ftag, fdf = features
+        save_input(ftag, fdf)
+    grs = {n: mk(df) for n, (tag, df) in samples.items()}
+    with int32_value_counts():
+        res = pr.count_overlaps(grs, mk(features[1]) if features is not None else None, **kwargs)
+    d = {}
+    meta = {"case": name, "op": "count_matrix", "kwargs": kwargs, "note": "", "self": ftag, "other": None,
+            "samples": {n: tag for n, (tag, _) in samples.items()}}
+    rdf = res.df
+    meta["n_rows"] = int(len(rdf))
+    _store_df(d, "result", rdf)
+    d["meta"] = np.asarray(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("%-44s %-15s rows=%s" % (name, "count_matrix", len(rdf)))
 
 
 def main():
@@ -307,6 +375,32 @@ def main():
     uniq = ("Auniq", A[1].drop_duplicates(["Chromosome", "Start"]))
     run_case("cluster_negslack_synth", "cluster", {"slack": -5}, uniq)
     run_case("merge_negslack_synth", "merge", {"slack": -5, "count": True}, uniq)
+    # cluster / merge by=
+    rng = np.random.default_rng(17)
+    Gd = A[1].copy()
+    Gd["Gene"] = rng.integers(0, 40, len(Gd))
+    Gd["Kind"] = rng.choice(["exon", "cds", "utr"], len(Gd))
+    G = ("G", Gd)
+    Gu = ("Gu", Gd.drop("Strand", axis=1))
+    for tag, s in (("G", G), ("Gu", Gu)):
+        for strand in ([None, False] if tag == "G" else [None]):
+            sn = "dflt" if strand is None else "nostrand"
+            kw = {} if strand is None else {"strand": strand}
+            run_case("cluster_by_%s_%s" % (tag, sn), "cluster", dict(kw, by="Gene"), s)
+            run_case("cluster_by2_%s_%s" % (tag, sn), "cluster", dict(kw, by=["Kind", "Gene"], count=True, slack=10), s)
+            run_case("merge_by_%s_%s" % (tag, sn), "merge", dict(kw, by="Gene"), s)
+            run_case("merge_by2_%s_%s" % (tag, sn), "merge", dict(kw, by=["Kind", "Gene"], count=True, slack=3), s)
+    # split and the multi-sample count matrix
+    for tag, s in (("f1", f1), ("synth", A), ("synth_u", Au), ("pile", pile)):
+        run_case("split_%s" % tag, "split", {}, s)
+        run_case("split_between_%s" % tag, "split", {"between": True}, s)
+        if "Strand" in s[1].columns:
+            run_case("split_nostrand_%s" % tag, "split", {"strand": False, "between": True}, s)
+    run_multi("matrix_synth_feat", {"a": A, "b": B, "c": Au}, Bu, {})
+    run_multi("matrix_synth_same", {"a": A, "b": B}, A, {"strandedness": "same"})
+    run_multi("matrix_synth_contain", {"a": A, "b": B}, B, {"how": "containment"})
+    run_multi("matrix_synth_nofeat", {"a": Au, "b": Bu}, None, {})
+    run_multi("matrix_f1f2_nofeat", {"x": f1, "y": f2}, None, {})
     run_case("rle_value_synth", "to_rle", {"value_col": "Score"}, A,
              note="float weights: compared with tolerance, not bit-exact (SURVEY.md section 8(c)(iv))")
     print("fixtures written to", OUT)

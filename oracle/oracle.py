@@ -52,6 +52,9 @@ def lib():
         L.ivo_annotate_clusters.argtypes = [_P64, _P64, C.c_int64, C.c_int64, _P64]
         L.ivo_find_clusters.restype = C.c_int64
         L.ivo_find_clusters.argtypes = [_P64, _P64, C.c_int64, C.c_int64, _P64, _P64, _P64]
+        L.ivo_cluster_by.argtypes = [_P64, _P64, _P64, C.c_int64, C.c_int64, _P64]
+        L.ivo_merge_by.restype = C.c_int64
+        L.ivo_merge_by.argtypes = [_P64, _P64, _P64, C.c_int64, C.c_int64, _P64, _P64, _P64, _P64]
         L.ivo_nearest_previous.argtypes = [_P64, C.c_int64, _P64, _P64, C.c_int64, _P64, _P64]
         L.ivo_nearest_next.argtypes = [_P64, C.c_int64, _P64, _P64, C.c_int64, _P64, _P64]
         L.ivo_nearest_nonoverlapping.argtypes = [_P64, _P64, _P64, _P64, C.c_int64, _P64, _P64]
@@ -152,6 +155,28 @@ def find_clusters(starts, ends, slack):
     os_, oe, on = (np.empty(n, dtype=np.int64) for _ in range(3))
     k = lib().ivo_find_clusters(_p(s), _p(e), n, int(slack), _p(os_), _p(oe), _p(on))
     return os_[:k].copy(), oe[:k].copy(), on[:k].copy()
+
+
+def split_points(starts, ends):
+    """pyranges/methods/split.py:11-20: concat(Start, End).sort_values().drop_duplicates(); consecutive points are the
+    features (points, points.shift(-1))[:-1].  -> (feature starts, feature ends)"""
+    pts = np.unique(np.concatenate([_a64(starts), _a64(ends)]))
+    return pts[:-1].copy(), pts[1:].copy()
+
+
+def cluster_by(starts, ends, ids, slack):
+    s, e, b = _a64(starts), _a64(ends), _a64(ids)
+    out = np.empty(len(s), dtype=np.int64)
+    lib().ivo_cluster_by(_p(s), _p(e), _p(b), len(s), int(slack), _p(out))
+    return out
+
+
+def merge_by(starts, ends, ids, slack):
+    s, e, b = _a64(starts), _a64(ends), _a64(ids)
+    n = len(s)
+    ob, os_, oe, on = (np.empty(n, dtype=np.int64) for _ in range(4))
+    k = lib().ivo_merge_by(_p(s), _p(e), _p(b), n, int(slack), _p(ob), _p(os_), _p(oe), _p(on))
+    return ob[:k].copy(), os_[:k].copy(), oe[:k].copy(), on[:k].copy()
 
 
 def nearest_previous_nonoverlapping(l_starts, r_ends, r_indexes):

@@ -4,7 +4,9 @@ Only the entry points of the hot path are real; the rest
 reference's modules import, and raise when called."""
 from oracle.oracle import (  # noqa: F401
     annotate_clusters,
+    cluster_by,
     find_clusters,
+    merge_by,
     nearest_next_nonoverlapping,
     nearest_nonoverlapping,
     nearest_previous_nonoverlapping,
@@ -20,7 +22,7 @@ def _out_of_scope(name):
 
 
 for _n in (
-    "cluster_by merge_by k_nearest_next_nonoverlapping k_nearest_previous_nonoverlapping "
+    "k_nearest_next_nonoverlapping k_nearest_previous_nonoverlapping "
     "max_disjoint maketiles makewindows get_all_ties get_different_ties"
 ).split():
     globals()[_n] = _out_of_scope(_n)

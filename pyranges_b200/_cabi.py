@@ -66,6 +66,9 @@ PROTOTYPES = {
     "iv_rle_weighted_workspace_bytes": (_sz, [_i64, _i32]),
     "iv_rle_weighted_count": (C.c_int, [_vp, _vp, _vp, _i64, _PG, _vp, _sz, _vp, _vp]),
     "iv_rle_weighted_emit": (C.c_int, [_i64, _PG, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "iv_split_workspace_bytes": (_sz, [_i64]),
+    "iv_split_count": (C.c_int, [_vp, _vp, _i64, _PG, _vp, _sz, _vp, _vp]),
+    "iv_split_emit": (C.c_int, [_i64, _PG, _vp, _i64, _vp, _vp, _vp, _vp]),
     "iv_materialize_pairs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "iv_gather": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp]),
 }

@@ -341,6 +341,24 @@ def merge(iv, seg_ranges=None, slack=0, want_count=True):
     return st, en, cnt, grp
 
 
+def split(iv, seg_ranges=None):
+    """PyRanges.split(between=True) (pyranges/methods/split.py:4-24) for all groups at once: every pair of consecutive
+    distinct Start/End points of a group.  -> (group_off int64[n_groups+1] host, start, end) group-major."""
+    L = cabi.lib()
+    g = iv.groups(seg_ranges, gap=1)
+    dev = iv.device
+    ws = _bytes(L.iv_split_workspace_bytes(iv.n), dev)
+    off = torch.zeros(g.n_groups + 1, dtype=torch.int64, device=dev)
+    cabi.check(L.iv_split_count(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(g.c), _ptr(ws), ws.numel(), _ptr(off),
+                                _stream()), "iv_split_count")
+    off = off.cpu().numpy()
+    m = int(off[-1])
+    st = torch.empty(m, dtype=torch.int64, device=dev)
+    en = torch.empty(m, dtype=torch.int64, device=dev)
+    cabi.check(L.iv_split_emit(iv.n, C.byref(g.c), _ptr(ws), m, _ptr(st), _ptr(en), None, _stream()), "iv_split_emit")
+    return off, st, en
+
+
 def coverage_rle(iv, seg_ranges=None, weights=None):
     """pyrle.methods.coverage (pyranges/methods/to_rle.py:18) for all groups at once; weights = float64 device
     tensor aligned with the rows (value_col), None = unit weights (bit-exact integer levels).

@@ -8,7 +8,7 @@ key (building an NCLS per key), this module recognises the hot-path callables by
 
     _write_both, _number_overlapping, _overlap, _intersection, _subtraction, _count_overlaps, _coverage,
     _nearest                                                                (binary)
-    _cluster, _merge, coverage (pyrle.methods.coverage)                   (unary)
+    _cluster, _cluster_by, _merge, _merge_by, _split, coverage (pyrle.methods.coverage)   (unary)
 
 concatenates the Start/End columns of all keys into device-resident int64 columns and runs ONE batched
 kernel sequence (pyranges_b200.engine) for every key; the pandas glue around the index arrays (row
@@ -79,12 +79,15 @@ def _is_stranded(gr):
 class _Frames:
     """A list of (key, DataFrame) in natsorted key order plus their concatenated device columns."""
 
-    def __init__(self, items, device):
+    def __init__(self, items, device, upload=True):
         self.keys = [k for k, _ in items]
         self.dfs = [d for _, d in items]
         lens = np.asarray([len(d) for d in self.dfs], dtype=np.int64)
         self.seg_off = np.zeros(len(lens) + 1, np.int64)
         np.cumsum(lens, out=self.seg_off[1:])
+        if not upload:  # the caller lays the rows out differently (cluster / merge by=)
+            self.starts = self.ends = self.iv = None
+            return
         if len(self.dfs):
             s = np.concatenate([np.asarray(d["Start"].values, dtype=np.int64) for d in self.dfs])
             e = np.concatenate([np.asarray(d["End"].values, dtype=np.int64) for d in self.dfs])
@@ -108,13 +111,13 @@ def _device_of(kwargs):
 class _Plan:
     """Partner selection of pyrange_apply (pyranges/multithreaded.py:221-294) for all keys at once."""
 
-    def __init__(self, self_gr, other_gr, strandedness, device):
+    def __init__(self, self_gr, other_gr, strandedness, device, q_frames=None):
         assert strandedness in ["same", "opposite", False, None]
         self_stranded, other_stranded = _is_stranded(self_gr), _is_stranded(other_gr)
         if strandedness:
             assert self_stranded and other_stranded, \
                 "Can only do stranded operations when both PyRanges contain strand info"
-        self.q = _Frames(natsorted(self_gr.dfs.items()), device)
+        self.q = q_frames if q_frames is not None else _Frames(natsorted(self_gr.dfs.items()), device)
         o_items = natsorted(other_gr.dfs.items())
         self.s = _Frames(o_items, device)
         okeys = self.s.keys
@@ -558,12 +561,12 @@ def pyrange_apply(function, self, other, **kwargs):
 class _UnaryPlan:
     """Key iteration of pyrange_apply_single (pyranges/multithreaded.py:324-363)."""
 
-    def __init__(self, self_gr, strand, device):
+    def __init__(self, self_gr, strand, device, upload=True):
         stranded = _is_stranded(self_gr)
         if strand:
             assert stranded, "Can only do stranded operation when PyRange contains strand info"
         items = natsorted(self_gr.dfs.items())
-        self.f = _Frames(items, device)
+        self.f = _Frames(items, device, upload=upload)
         keys = self.f.keys
         if strand or not stranded:
             self.group_ranges = [(i, i + 1) for i in range(len(keys))]
@@ -585,7 +588,7 @@ class _UnaryPlan:
                 self.chrom.append(keys[i][0])
                 self.strand.append(None)
                 i = j
-        self.row_off = np.asarray([self.f.seg_off[r[0]] for r in self.group_ranges] + [self.f.iv.n], dtype=np.int64)
+        self.row_off = np.asarray([self.f.seg_off[r[0]] for r in self.group_ranges] + [self.f.seg_off[-1]], dtype=np.int64)
 
 
 def _u_cluster(plan, kwargs):
@@ -661,7 +664,114 @@ def _u_coverage(plan, kwargs):
     return results
 
 
-_UNARY = {"_cluster": _u_cluster, "_merge": _u_merge, "coverage": _u_coverage}
+class _ByPlan:
+    """cluster(by=) / merge(by=) (pyranges/methods/cluster.py:25-58, merge.py:41-92): inside every key the rows are
+    grouped by the `by` column(s); the reference sorts each frame by (by, Start) and lets sorted_nearest.cluster_by /
+    merge_by restart at every change of `by`.  Here every (key, by-value) becomes its own row group of the SAME batched
+    cluster / merge kernels: per frame a stable order by the by-codes, then one device upload of the permuted columns
+    with one segment per (key, by-value)."""
+
+    def __init__(self, self_gr, strand, by, device):
+        base = _UnaryPlan(self_gr, strand, device, upload=False)
+        self.out_keys, self.frames, self.chrom, self.strand = base.out_keys, base.frames, base.chrom, base.strand
+        self.by = [by] if isinstance(by, str) else list(by)
+        self.perm, self.first_rows = [], []
+        starts, ends, seg_len, frame_sub = [], [], [], [0]
+        for df in self.frames:
+            # group numbers in sorted order of the by-values = the order of sort_values(by) (cluster.py:35-38)
+            codes = df.groupby(self.by, sort=True, observed=True).ngroup().to_numpy()
+            if (codes < 0).any():
+                raise NotImplementedError("cluster/merge(by=...): missing values in the `by` columns are out of scope")
+            perm = np.argsort(codes, kind="stable")
+            cnt = np.bincount(codes)
+            cnt = cnt[cnt > 0]
+            self.perm.append(perm)
+            self.first_rows.append(perm[np.concatenate([[0], np.cumsum(cnt)[:-1]])] if len(cnt) else perm[:0])
+            starts.append(np.asarray(df["Start"].values, dtype=np.int64)[perm])
+            ends.append(np.asarray(df["End"].values, dtype=np.int64)[perm])
+            seg_len.append(cnt)
+            frame_sub.append(frame_sub[-1] + len(cnt))
+        self.frame_sub = np.asarray(frame_sub, dtype=np.int64)  # sub-groups of frame g: [frame_sub[g], frame_sub[g+1])
+        seg_off = np.zeros(self.frame_sub[-1] + 1, np.int64)
+        if len(seg_len):
+            np.cumsum(np.concatenate(seg_len), out=seg_off[1:])
+        s = np.concatenate(starts) if starts else np.zeros(0, np.int64)
+        e = np.concatenate(ends) if ends else np.zeros(0, np.int64)
+        self.iv = E.DeviceIntervals.from_numpy(s, e, seg_off, device)
+        self.row_off = seg_off[self.frame_sub]
+
+
+def _u_cluster_by(plan, kwargs):
+    """cluster(by=): pyranges/methods/cluster.py:25-58 per key; rows come back in (by, Start) order, ids local."""
+    slack, count = kwargs.get("slack", 0), kwargs.get("count", False)
+    row, cid, _ = E.cluster(plan.iv, None, slack)
+    row, cid = row.cpu().numpy(), cid.cpu().numpy()
+    results = []
+    for g, df in enumerate(plan.frames):
+        a, b = plan.row_off[g], plan.row_off[g + 1]
+        if a == b:
+            results.append(None)
+            continue
+        cdf = df.take(plan.perm[g][row[a:b] - a])
+        ids = cid[a:b] - cid[a] + 1
+        cdf.insert(cdf.shape[1], "Cluster", ids)
+        if count:
+            cdf.insert(cdf.shape[1], "Count", np.bincount(ids)[ids])
+        results.append(cdf)
+    return results
+
+
+def _u_merge_by(plan, kwargs):
+    """merge(by=): pyranges/methods/merge.py:41-92 per key: Chromosome, Start, End, [Strand], the by column(s) of the
+    cluster's group, [count]."""
+    slack = kwargs.get("slack", 0)
+    st, en, cnt, grp = E.merge(plan.iv, None, slack, want_count=bool(kwargs["count"]))
+    st, en, grp = st.cpu().numpy(), en.cpu().numpy(), grp.cpu().numpy()
+    cnt = cnt.cpu().numpy() if cnt is not None else None
+    first = np.searchsorted(grp, plan.frame_sub)
+    results = []
+    for g, df in enumerate(plan.frames):
+        a, b = first[g], first[g + 1]
+        if a == b:
+            results.append(None)
+            continue
+        nidx = pd.RangeIndex(b - a)
+        d = {"Chromosome": pd.Series(plan.chrom[g], dtype="category", index=nidx), "Start": st[a:b], "End": en[a:b]}
+        if plan.strand[g]:
+            d["Strand"] = pd.Series(plan.strand[g], dtype="category", index=nidx)
+        src = plan.first_rows[g][grp[a:b] - plan.frame_sub[g]]  # a row of the cluster's by-group
+        for c in plan.by:
+            d[c] = df[c].values.take(src)
+        cdf = pd.DataFrame(d, copy=False)
+        if kwargs["count"]:
+            cdf.insert(cdf.shape[1], kwargs["count_col"], cnt[a:b])
+        results.append(cdf)
+    return results
+
+
+def _u_split(plan, kwargs):
+    """split(between=True): pyranges/methods/split.py:4-24 per key -- Chromosome, Start, End[, Strand] of every pair
+    of consecutive distinct Start/End points."""
+    off, st, en = E.split(plan.f.iv, plan.group_ranges or None)
+    st, en = st.cpu().numpy(), en.cpu().numpy()
+    strand = kwargs.get("strand", False)
+    results = []
+    for g, df in enumerate(plan.frames):
+        a, b = off[g], off[g + 1]
+        if a == b:
+            results.append(None)
+            continue
+        dtype = df.Start.dtype
+        d = {"Chromosome": np.full(b - a, df.Chromosome.iloc[0], dtype=object), "Start": st[a:b].astype(dtype, copy=False),
+             "End": en[a:b].astype(dtype, copy=False)}
+        if strand and "Strand" in df:
+            d["Strand"] = np.full(b - a, df["Strand"].iloc[0], dtype=object)
+        results.append(pd.DataFrame(d, copy=False))
+    return results
+
+
+_UNARY = {"_split": _u_split, "_cluster": _u_cluster, "_merge": _u_merge, "coverage": _u_coverage, "_cluster_by": _u_cluster_by,
+          "_merge_by": _u_merge_by}
 
 
 def pyrange_apply_single(function, self, **kwargs):
@@ -671,6 +781,9 @@ def pyrange_apply_single(function, self, **kwargs):
         raise NotImplementedError(
             "pyranges_b200.pyrange_apply_single: %r is not on the B200 hot path (supported: %s); no CPU fallback"
             % (name, ", ".join(sorted(_UNARY))))
-    plan = _UnaryPlan(self, kwargs["strand"], _device_of(kwargs))
+    if name in ("_cluster_by", "_merge_by"):
+        plan = _ByPlan(self, kwargs["strand"], kwargs["by"], _device_of(kwargs))
+    else:
+        plan = _UnaryPlan(self, kwargs["strand"], _device_of(kwargs))
     results = _UNARY[name](plan, kwargs)
     return process_results(results, plan.out_keys)

@@ -179,3 +179,14 @@ def materialize_pairs(q_iv, s_iv, pair_q, pair_s, clip=False, want=("q_start", "
         qs, qe = np.maximum(qs, ss), np.minimum(qe, se)
     out.update({"q_start": qs, "q_end": qe, "s_start": ss, "s_end": se})
     return {k: _t(out[k]) for k in want}
+
+
+def split(iv, seg_ranges=None):
+    off, S, E = [0], [], []
+    for a, b in _ranges(iv, seg_ranges):
+        fs, fe = orc.split_points(iv.s[a:b], iv.e[a:b]) if b > a else (np.zeros(0, np.int64),) * 2
+        S.append(fs)
+        E.append(fe)
+        off.append(off[-1] + len(fs))
+    cat = lambda x: np.concatenate(x) if x else np.zeros(0, np.int64)  # noqa: E731
+    return np.asarray(off, np.int64), _t(cat(S)), _t(cat(E))

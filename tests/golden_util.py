@@ -54,6 +54,12 @@ BINARY_OPS = ("join", "overlap", "count_overlaps", "coverage", "nearest", "inter
 
 
 def run_case(meta, PyRanges):
+    if meta["op"] == "count_matrix":  # pr.count_overlaps(grs, features)
+        from pyranges_b200.multioverlap import count_overlaps
+
+        grs = {n: PyRanges(load_input(tag)) for n, tag in meta["samples"].items()}
+        feats = PyRanges(load_input(meta["self"])) if meta["self"] is not None else None
+        return count_overlaps(grs, feats, **meta["kwargs"]), feats, None
     s = PyRanges(load_input(meta["self"]))
     kw = dict(meta["kwargs"])
     if meta["other"] is not None:

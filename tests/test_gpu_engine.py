@@ -412,3 +412,39 @@ def test_materialize_pairs_and_gather(eng, case):
     # no pairs at all
     e = torch.zeros(0, dtype=torch.int64).cuda()
     assert all(v.numel() == 0 for v in eng.materialize_pairs(qiv, siv, e, e).values())
+
+
+@pytest.mark.parametrize("seed,n_seg,n,maxpos,maxlen,shift", [
+    (1, 1, 5, 30, 10, 0), (2, 5, 3000, 50000, 300, 0), (3, 7, 20000, 3000000, 2000, 0), (4, 2, 5000, 400, 100, 0),
+    (5, 300, 40, 100000, 500, 0),              # many small groups (cluster / merge / split by=)
+    (6, 4, 2000, 10 ** 6, 5000, -(10 ** 12)),  # negative coordinates beyond 32 bits
+    (7, 3, 300000, 2 * 10 ** 8, 1000, 0),      # several radix passes, multi-tile scans
+])
+def test_split(eng, seed, n_seg, n, maxpos, maxlen, shift):
+    """iv_split_count/_emit = consecutive distinct Start/End points per group (pyranges/methods/split.py:4-24), also
+    with segments paired into groups (strand=False on stranded keys)."""
+    from oracle import oracle as orc
+
+    s, e, off = gen_segments(seed, n_seg, n, maxpos, maxlen, empty_every=3)
+    s, e = s + shift, e + shift
+    iv = _dev(eng, s, e, off)
+    pairs = [(i, min(i + 2, n_seg)) for i in range(0, n_seg, 2)]
+    for seg_ranges in (None, pairs):
+        goff, st, en = eng.split(iv, seg_ranges)
+        st, en = st.cpu().numpy(), en.cpu().numpy()
+        ranges = seg_ranges or [(i, i + 1) for i in range(n_seg)]
+        ws, we, woff = [], [], [0]
+        for a, b in ranges:
+            ra, rb = off[a], off[b]
+            fs, fe = orc.split_points(s[ra:rb], e[ra:rb]) if rb > ra else (np.zeros(0, np.int64),) * 2
+            ws.append(fs)
+            we.append(fe)
+            woff.append(woff[-1] + len(fs))
+        assert np.array_equal(goff, np.asarray(woff))
+        assert np.array_equal(st, np.concatenate(ws)) and np.array_equal(en, np.concatenate(we))
+
+
+def test_split_empty(eng):
+    z = np.zeros(0, np.int64)
+    goff, st, en = eng.split(_dev(eng, z, z, np.zeros(3, np.int64)))
+    assert goff.tolist() == [0, 0, 0] and st.numel() == 0 and en.numel() == 0

@@ -43,6 +43,13 @@ def test_cluster_merge_doctests():
     assert orc.annotate_clusters(S, E, -1).tolist() == [1, 1, 2, 2]
     cs, ce, cn = orc.find_clusters(S, E, 0)
     assert (cs.tolist(), ce.tolist(), cn.tolist()) == ([1], [12], [4])
+    # cluster(by="Gene") :1139-1150: Gene 1, 2, 3, 3 -> clusters 1, 2, 3, 3 (counts 1, 1, 2, 2)
+    G = np.array([1, 2, 3, 3])
+    assert orc.cluster_by(S, E, G, 0).tolist() == [1, 2, 3, 3]
+    assert orc.cluster_by(S, E, G, -1).tolist() == [1, 2, 3, 3]
+    assert orc.cluster_by(S, E, np.zeros(4, np.int64), -1).tolist() == [1, 1, 2, 2]
+    mb, ms, me, mn = orc.merge_by(S, E, G, 0)
+    assert (mb.tolist(), ms.tolist(), me.tolist(), mn.tolist()) == ([1, 2, 3], [1, 2, 3], [3, 3, 12], [1, 1, 2])
 
 
 def test_nearest_doctest_distances():
