@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define IV_ABI_VERSION 4
+#define IV_ABI_VERSION 5
 
 #define IV_OK 0
 #define IV_ERR_INVALID (-1)   /* bad argument */
@@ -177,11 +177,15 @@ int iv_index_build(const int64_t* starts, const int64_t* ends, int64_t n, const 
                    int32_t flags, void* ws, size_t ws_bytes, iv_index_t* out, void* stream);
 
 size_t iv_overlap_workspace_bytes(int64_t n_queries);
-/* out_count[i] = number of entries query i emits under `mode`; also leaves the per-tile offsets that
- * iv_emit_pairs needs in ws and the grand total in *out_total (device). */
+/* out_count[i] = number of entries query i emits under `mode`.  With a workspace (ws != NULL, 256-byte aligned,
+ * iv_overlap_workspace_bytes(n) bytes) the call also leaves what iv_emit_pairs works from -- per 1024-row tile the
+ * output offset, per 64-row granule the list of its queries WITH hits (row, count, flattened interval) -- and the
+ * grand total in *out_total (device); out_count may then be NULL (join does not need the per-row counts).
+ * Without a workspace only out_count is written. */
 int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mode, int64_t* out_count,
                       void* ws, size_t ws_bytes, int64_t* out_total, void* stream);
-/* Writes min(sum(out_count), out_capacity) entries.  out_q gets the query label, out_s the subject row (or
+/* Writes min(total, out_capacity) entries from the hit lists iv_count_overlaps left in ws (`counts` is not read
+ * and may be NULL; the parameter is kept for callers of ABI v3).  out_q gets the query label, out_s the subject row (or
  * s_label[row]).  Either may be NULL.  out_capacity = entries the output buffers hold: the exact total read back
  * from iv_count_overlaps, or a guess when the emit is launched speculatively before the total is known (entries
  * beyond the capacity are dropped, never written; the caller compares the total and repeats the call if needed).

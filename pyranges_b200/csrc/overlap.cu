@@ -27,6 +27,38 @@ constexpr int OV_ITEMS = 4;
 constexpr int OV_TILE = OV_THREADS * OV_ITEMS;  // 1024 queries per block
 constexpr int OV_GRAN = 64;                       // rows per emit warp: the count kernels also leave their sums
 constexpr int OV_BATCH = 2;                       // record gathers a thread keeps in flight
+constexpr int OV_GPT = OV_TILE / OV_GRAN;         // 16 granules per tile
+
+// ---- hit lists: what the count pass hands to the emit pass ------------------------------------------------------
+// One entry per query WITH hits (a fraction of the rows of a sparse join), written by the count kernels straight
+// from their registers: the row inside its tile, the hit count and the flattened interval.  The entries of a 64-row
+// granule sit at the front of the granule's 64 slots, in row order; gran_hits[] says how many.  The emit pass then
+// works on dense lists -- every lane owns a hit query -- and never touches the query columns or the counts again.
+template <typename X> struct HitEntry;
+template <> struct __align__(16) HitEntry<uint32_t> { uint32_t row, cnt, sc, ec; };
+template <> struct __align__(16) HitEntry<uint64_t> { uint32_t row, cnt; uint64_t sc, ec, pad; };
+template <typename X> __device__ __forceinline__ void put_entry(HitEntry<X>* p, uint32_t row, uint32_t cnt, X sc, X ec);
+template <> __device__ __forceinline__ void put_entry<uint32_t>(HitEntry<uint32_t>* p, uint32_t row, uint32_t cnt,
+                                                                 uint32_t sc, uint32_t ec) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(row, cnt, sc, ec);
+}
+template <> __device__ __forceinline__ void put_entry<uint64_t>(HitEntry<uint64_t>* p, uint32_t row, uint32_t cnt,
+                                                                 uint64_t sc, uint64_t ec) {
+    uint4* v = reinterpret_cast<uint4*>(p);
+    v[0] = make_uint4(row, cnt, (uint32_t)sc, (uint32_t)(sc >> 32));
+    v[1] = make_uint4((uint32_t)ec, (uint32_t)(ec >> 32), 0u, 0u);
+}
+
+template <typename X> struct Hit { uint32_t row, cnt; X sc, ec; };
+template <typename X> __device__ __forceinline__ Hit<X> get_entry(const HitEntry<X>* p);
+template <> __device__ __forceinline__ Hit<uint32_t> get_entry<uint32_t>(const HitEntry<uint32_t>* p) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    return Hit<uint32_t>{v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Hit<uint64_t> get_entry<uint64_t>(const HitEntry<uint64_t>* p) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    return Hit<uint64_t>{a.x, a.y, (uint64_t)a.z | ((uint64_t)a.w << 32), (uint64_t)b.x | ((uint64_t)b.y << 32)};
+}
 
 // ---- bin records ----------------------------------------------------------------------------------------------
 // w[0]=bs w[1]=be w[2]=co w[3]=ns|ne<<8|nc<<16|flags<<24 w[4..5]=so[0..3] w[6..7]=eo[0..3]
@@ -220,10 +252,9 @@ __device__ __forceinline__ void store_items(int64_t* __restrict__ p, int64_t i0,
 // ---- count ----------------------------------------------------------------------------------------------------------
 template <typename X, int MODE>
 __global__ void __launch_bounds__(OV_THREADS)
-k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count, int64_t* __restrict__ tile_sums,
-        int64_t* __restrict__ gran_sums, int64_t first_tile) {
+k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count, int64_t* __restrict__ gran_sums,
+        uint32_t* __restrict__ gran_hits, HitEntry<X>* __restrict__ list, int64_t first_tile) {
     __shared__ int span[2];
-    __shared__ int64_t red[OV_THREADS / 32];
     const int64_t tile = first_tile + blockIdx.x;
     const int64_t tbase = tile * OV_TILE;
     const int64_t last = tbase + OV_TILE - 1 < q.n - 1 ? tbase + OV_TILE - 1 : q.n - 1;
@@ -235,6 +266,7 @@ k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count
     // two half-batches: flatten, issue one record gather per query (all in flight together), then count;
     // dead rows use a harmless geometry
     int64_t tsum = 0;
+    X fsc[OV_ITEMS], fec[OV_ITEMS];  // flattened intervals, kept for the hit list
 #pragma unroll
     for (int h = 0; h < OV_ITEMS; h += OV_BATCH) {
         X sc[OV_BATCH], ec[OV_BATCH];
@@ -248,6 +280,8 @@ k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count
             apply_slack(q.slack, s[j], e[j]);
             sc[k] = f.at(s[j]);
             ec[k] = f.at(e[j]);
+            fsc[j] = sc[k];
+            fec[j] = ec[k];
             out[k] = MODE == IV_MODE_CONTAIN ? (f.g < 0 || f.outside(s[j]) || f.outside(e[j])) : false;
             r[k] = load_rec(ix, ec[k] >> ix.shift);
         }
@@ -272,23 +306,38 @@ k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count
             tsum += c[j];
         }
     }
-    store_items(out_count, i0, q.n, vec, c);
-    if (gran_sums) {  // 64 rows = 16 consecutive threads
-        int64_t g = tsum;
+    if (out_count) store_items(out_count, i0, q.n, vec, c);
+    if (list) {  // a granule = the 64 rows of 16 consecutive threads: its hit entries, in row order
+        const int nh = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+        int inc = nh;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) g += __shfl_xor_sync(FULL, g, o);
-        if ((lane_id() & 15) == 0 && i0 < q.n) gran_sums[i0 / OV_GRAN] = g;
-    }
-    if (tile_sums) {
-        tsum = warp_sum(tsum);
-        if (lane_id() == 0) red[threadIdx.x >> 5] = tsum;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int64_t x = threadIdx.x < OV_THREADS / 32 ? red[threadIdx.x] : 0;
-            x = warp_sum(x);
-            if (threadIdx.x == 0) tile_sums[tile] = x;
+        for (int o = 1; o < 16; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, inc, o, 16);
+            if ((lane_id() & 15) >= o) inc += t;
+        }
+        const int64_t gran = tile * OV_GPT + (threadIdx.x >> 4);
+        HitEntry<X>* slot = list + gran * OV_GRAN + (inc - nh);
+#pragma unroll
+        for (int j = 0; j < OV_ITEMS; j++)
+            if (c[j] > 0) put_entry<X>(slot++, (uint32_t)(threadIdx.x * OV_ITEMS + j), (uint32_t)c[j], fsc[j], fec[j]);
+        int64_t gs = tsum;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) gs += __shfl_xor_sync(FULL, gs, o);
+        if ((lane_id() & 15) == 15 && gran * OV_GRAN < q.n) {
+            gran_hits[gran] = (uint32_t)inc;
+            gran_sums[gran] = gs;
         }
     }
+}
+
+// tile_sums[t] = sum of the tile's 16 granule sums (granules beyond the last row do not exist: 0)
+__global__ void __launch_bounds__(256)
+k_tile_sums(const int64_t* __restrict__ gran_sums, int64_t n, int64_t ntiles, int64_t* __restrict__ tile_sums) {
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;  // 16 consecutive lanes = one tile
+    int64_t v = (g < ntiles * OV_GPT && g * OV_GRAN < n) ? __ldg(gran_sums + g) : 0;
+#pragma unroll
+    for (int o = 1; o < OV_GPT; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+    if ((threadIdx.x & (OV_GPT - 1)) == 0 && g / OV_GPT < ntiles) tile_sums[g / OV_GPT] = v;
 }
 
 // ---- count, lean: the throughput kernel for full, 16-byte aligned tiles ----------------------------------------------
@@ -314,14 +363,15 @@ __device__ __forceinline__ bool rec_fast(const Rec& r) {
 
 template <typename X, int MODE>
 __global__ void __launch_bounds__(LN_THREADS, 6)
-k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, unsigned long long* __restrict__ tile_sums,
-             unsigned long long* __restrict__ gran_sums) {
+k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, unsigned long long* __restrict__ gran_sums,
+             uint32_t* __restrict__ gran_hits, HitEntry<X>* __restrict__ list) {
     __shared__ X q_sc[LN_THREADS / 32][LN_QCAP], q_ec[LN_THREADS / 32][LN_QCAP];
-    __shared__ uint32_t q_row[LN_THREADS / 32][LN_QCAP];
+    __shared__ uint32_t q_row[LN_THREADS / 32][LN_QCAP], q_ent[LN_THREADS / 32][LN_QCAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t bbase = (int64_t)blockIdx.x * (LN_TILES * OV_TILE);
     const int shift = ix.shift;
     const uint32_t mask = (1u << shift) - 1u;
+    const unsigned lt = (1u << lane) - 1u;
     int q_head = 0, q_tail = 0;  // warp-uniform ring positions of the slow queue
     auto count_slow = [&](int n_valid) {
         if (lane < n_valid) {
@@ -329,10 +379,12 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
             const int64_t row = bbase + q_row[warp][at];
             int64_t c = count_all<X>(ix, q_sc[warp][at], q_ec[warp][at]);
             if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
-            out_count[row] = c;
-            if (c && tile_sums) {
-                atomicAdd(tile_sums + row / OV_TILE, (unsigned long long)c);
+            if (out_count) out_count[row] = c;
+            if (c && list) {
+                // the granule's sum was stored (plain) by lane 0 of this warp when the row was queued
                 atomicAdd(gran_sums + row / OV_GRAN, (unsigned long long)c);
+                // the entry was reserved (count 0) when the row was queued: fill in the count
+                list[(bbase / OV_GRAN) * OV_GRAN + q_ent[warp][at]].cnt = (uint32_t)c;
             }
         }
         q_head += n_valid;
@@ -344,7 +396,6 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
     uint32_t lo32 = 0, hi32 = 0, off32 = 0;
     bool geo32 = false;
     for (int t = 0; t < LN_TILES; t++) {
-        unsigned long long tsum = 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int64_t hbase = bbase + t * OV_TILE + h * (OV_TILE / 2);  // 512 rows: 2 per thread
@@ -403,125 +454,102 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
                 cc[k] = (fast[k] && !dead) ? c : 0;
             }
             // rows i0, i0+1: one 16-byte store; queued rows are rewritten by count_slow (same warp, later)
-            if (i0 + 1 < q.n) *reinterpret_cast<longlong2*>(out_count + i0) = make_longlong2(cc[0], cc[1]);
-            else if (i0 < q.n) out_count[i0] = cc[0];
+            if (out_count) {
+                if (i0 + 1 < q.n) *reinterpret_cast<longlong2*>(out_count + i0) = make_longlong2(cc[0], cc[1]);
+                else if (i0 < q.n) out_count[i0] = cc[0];
+            }
+            // this warp's 64 rows are one granule of the hit list: an entry for every row with hits, and a
+            // reserved one (count 0 for now) for every row that goes to the slow queue
+            const unsigned slow0 = __ballot_sync(FULL, !fast[0]), slow1 = __ballot_sync(FULL, !fast[1]);
+            uint32_t ent[2] = {0, 0};
+            if (list) {
+                const bool in0 = cc[0] > 0 || !fast[0], in1 = cc[1] > 0 || !fast[1];
+                const unsigned m0 = __ballot_sync(FULL, in0), m1 = __ballot_sync(FULL, in1);
+                const int64_t gran = hbase / OV_GRAN + warp;
+                ent[0] = (uint32_t)((gran - bbase / OV_GRAN) * OV_GRAN) + __popc(m0 & lt) + __popc(m1 & lt);
+                ent[1] = ent[0] + (in0 ? 1u : 0u);
+                HitEntry<X>* g0 = list + (bbase / OV_GRAN) * OV_GRAN;
+                const uint32_t r0 = (uint32_t)(i0 - (hbase - h * (OV_TILE / 2)));  // row inside its 1024-row tile
+                if (in0) put_entry<X>(g0 + ent[0], r0, (uint32_t)cc[0], sc[0], ec[0]);
+                if (in1) put_entry<X>(g0 + ent[1], r0 + 1, (uint32_t)cc[1], sc[1], ec[1]);
+                // pair sum of the granule's fast rows (plain store: the warp owns the granule; queued rows add theirs
+                // later, from this same warp, with atomics)
+                const unsigned long long g = warp_sum((unsigned long long)(unsigned)(cc[0] + cc[1]));
+                if (lane == 0) {
+                    gran_hits[gran] = __popc(m0) + __popc(m1);
+                    gran_sums[gran] = g;
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                const unsigned m = __ballot_sync(FULL, !fast[k]);
+                const unsigned m = k ? slow1 : slow0;
                 if (m) {  // queue the others (flattened coordinates + row); the whole warp counts them 32 at a time
                     if (!fast[k]) {
-                        const int at = (q_tail + __popc(m & ((1u << lane) - 1u))) % LN_QCAP;
+                        const int at = (q_tail + __popc(m & lt)) % LN_QCAP;
                         q_sc[warp][at] = sc[k];
                         q_ec[warp][at] = ec[k];
                         q_row[warp][at] = (uint32_t)(i0 + k - bbase);
+                        q_ent[warp][at] = ent[k];
                     }
                     q_tail += __popc(m);
                     __syncwarp();
                     if (q_tail - q_head >= 32) count_slow(32);
                 }
             }
-            // this warp's 64 rows are one emit granule
-            const unsigned long long g = warp_sum((unsigned long long)(unsigned)(cc[0] + cc[1]));
-            if (lane == 0 && g && tile_sums) atomicAdd(gran_sums + hbase / OV_GRAN + warp, g);
-            tsum += g;
         }
-        if (lane == 0 && tsum && tile_sums) atomicAdd(tile_sums + bbase / OV_TILE + t, tsum);
     }
     if (q_tail - q_head > 0) count_slow(q_tail - q_head);
 }
 
 // ---- emit -----------------------------------------------------------------------------------------------------------
-// One WARP per 64-row granule, no block-wide barrier: the warp's output offset is the tile offset (scan of the tile
-// sums) plus the sums of the granules before it in the tile (both left by the count kernel); a shuffle scan of the
-// 64 counts gives every query its offset.  Most queries of a sparse join have no hit and the hit ones differ in how
-// many candidates they walk, so the warp first compacts its hit queries into a small shared-memory queue and then
-// gives every lane one HIT query per round.
-constexpr int EM_THREADS = 256;
-constexpr int EM_WARPS = EM_THREADS / 32;
+// One WARP per quarter tile (four 64-row granules), no block-wide barrier.  The warp reads its granules' hit lists
+// (left by the count pass) as one dense sequence, so every lane owns a query WITH hits; its output offset is the
+// tile offset (scan of the tile sums) + the pair sums of the granules before it in the tile + a shuffle scan of the
+// entry counts.  Granules without hits cost two loads.
+constexpr int EM_GW = 4;                          // granules per warp
+constexpr int EM_WARPS = OV_GPT / EM_GW;          // one block = one tile
+constexpr int EM_THREADS = EM_WARPS * 32;
 
 template <typename X, int MODE>
-__global__ void __launch_bounds__(EM_THREADS)
-k_emit(iv_index_t ix, iv_queries_t q, bool vec, const int64_t* __restrict__ counts,
-       const int64_t* __restrict__ tile_off, const int64_t* __restrict__ gran_sums, int64_t* __restrict__ out_q,
+__global__ void __launch_bounds__(EM_THREADS, MODE == IV_MODE_ALL ? 16 : 1)
+k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, const uint32_t* __restrict__ gran_hits,
+       const int64_t* __restrict__ gran_sums, const int64_t* __restrict__ tile_off, int64_t* __restrict__ out_q,
        int64_t* __restrict__ out_s, const int64_t* __restrict__ s_label, int64_t cap) {
-    __shared__ int64_t h_off[EM_WARPS][OV_GRAN];
-    __shared__ X h_sc[EM_WARPS][OV_GRAN], h_ec[EM_WARPS][OV_GRAN];
-    __shared__ uint8_t h_row[EM_WARPS][OV_GRAN];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t gran = (int64_t)blockIdx.x * EM_WARPS + warp;
-    const int64_t gbase = gran * OV_GRAN;
-    if (gbase >= q.n) return;
-    const int64_t tile = gbase / OV_TILE;
-    constexpr int GPT = OV_TILE / OV_GRAN;  // 16 granules per tile
-    // output offset of the granule
-    int64_t pre = lane < (int)(gran % GPT) ? __ldg(gran_sums + tile * GPT + lane) : 0;
-    pre = warp_sum(pre) + __ldg(tile_off + tile);
-    // the 64 counts: two per lane
-    const int64_t i0 = gbase + 2 * lane;
-    int64_t c0 = 0, c1 = 0;
-    if (vec && i0 + 1 < q.n) {
-        const longlong2 cv = __ldg(reinterpret_cast<const longlong2*>(counts + i0));
-        c0 = cv.x; c1 = cv.y;
-    } else {
-        if (i0 < q.n) c0 = __ldg(counts + i0);
-        if (i0 + 1 < q.n) c1 = __ldg(counts + i0 + 1);
+    const int lane = threadIdx.x & 31, quarter = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t tbase = tile * OV_TILE;
+    // lanes 0..15: the tile's granules
+    const int64_t gi = tile * OV_GPT + (lane & (OV_GPT - 1));
+    const bool gvalid = lane < OV_GPT && gi * OV_GRAN < q.n;
+    const uint32_t gh = gvalid ? __ldg(gran_hits + gi) : 0u;
+    int64_t carry = __ldg(tile_off + tile);
+    uint32_t h[EM_GW], nh = 0;
+#pragma unroll
+    for (int j = 0; j < EM_GW; j++) {
+        h[j] = __shfl_sync(FULL, gh, quarter * EM_GW + j);
+        nh += h[j];
     }
-    const int64_t mine = c0 + c1;
-    const int64_t inc = warp_incl_sum(mine);
-    if (__shfl_sync(FULL, inc, 31) == 0) return;  // no hit in the granule
-    int64_t o = pre + inc - mine;
-    // segment geometry of the granule (usually one segment)
-    const int seg0 = find_seg(q.seg_off, q.n_seg, gbase);
-    const Flat<X> f0 = load_flat<X>(ix, q, seg0);
-    const bool one_seg = __ldg(q.seg_off + seg0 + 1) >= gbase + OV_GRAN;
-    const uint64_t hi0 = (uint64_t)f0.lo + f0.width;
-    const bool tight = sizeof(X) == 4 && one_seg && f0.lo >= 0 && hi0 <= 0xffffffffull;
-    const uint32_t lo32 = (uint32_t)f0.lo, hi32 = (uint32_t)hi0, off32 = (uint32_t)f0.base - lo32;
+    if (nh == 0) return;
+    carry += warp_sum((gvalid && lane < quarter * EM_GW) ? __ldg(gran_sums + gi) : (int64_t)0);
+    const HitEntry<X>* base = list + (tile * OV_GPT + quarter * EM_GW) * OV_GRAN;
     const int shift = ix.shift;
     const uint32_t mask = (1u << shift) - 1u;
-    // the lane's two rows, read coalesced and flattened here: the hit ones travel through the queue, so the
-    // round loop below does no scattered reads of the query columns
-    int64_t s0 = 0, s1 = 0, e0 = 0, e1 = 0;
-    if (vec && i0 + 1 < q.n) {
-        const longlong2 sv = __ldg(reinterpret_cast<const longlong2*>(q.start + i0));
-        const longlong2 ev = __ldg(reinterpret_cast<const longlong2*>(q.end + i0));
-        s0 = sv.x; s1 = sv.y; e0 = ev.x; e1 = ev.y;
-    } else {
-        if (i0 < q.n) { s0 = __ldg(q.start + i0); e0 = __ldg(q.end + i0); }
-        if (i0 + 1 < q.n) { s1 = __ldg(q.start + i0 + 1); e1 = __ldg(q.end + i0 + 1); }
-    }
-    apply_slack(q.slack, s0, e0);
-    apply_slack(q.slack, s1, e1);
-    X sc0, ec0, sc1, ec1;
-    if (tight && (((uint64_t)s0 | (uint64_t)e0 | (uint64_t)s1 | (uint64_t)e1) >> 32) == 0) {
-        sc0 = (X)(min(max((uint32_t)s0, lo32), hi32) + off32);
-        ec0 = (X)(min(max((uint32_t)e0, lo32), hi32) + off32);
-        sc1 = (X)(min(max((uint32_t)s1, lo32), hi32) + off32);
-        ec1 = (X)(min(max((uint32_t)e1, lo32), hi32) + off32);
-    } else {
-        const int64_t ra = i0 < q.n ? i0 : q.n - 1, rb = i0 + 1 < q.n ? i0 + 1 : q.n - 1;
-        const Flat<X> fa = one_seg ? f0 : load_flat<X>(ix, q, find_seg_range(q.seg_off, seg0, q.n_seg - 1, ra));
-        const Flat<X> fb = one_seg ? f0 : load_flat<X>(ix, q, find_seg_range(q.seg_off, seg0, q.n_seg - 1, rb));
-        sc0 = fa.at(s0); ec0 = fa.at(e0);
-        sc1 = fb.at(s1); ec1 = fb.at(e1);
-    }
-    // compact the hit queries
-    const unsigned m0 = __ballot_sync(FULL, c0 > 0), m1 = __ballot_sync(FULL, c1 > 0);
-    const unsigned lt = (1u << lane) - 1u;
-    if (c0 > 0) {
-        const int k = __popc(m0 & lt);
-        h_row[warp][k] = (uint8_t)(2 * lane); h_off[warp][k] = o; h_sc[warp][k] = sc0; h_ec[warp][k] = ec0;
-    }
-    if (c1 > 0) {
-        const int k = __popc(m0) + __popc(m1 & lt);
-        h_row[warp][k] = (uint8_t)(2 * lane + 1); h_off[warp][k] = o + c0; h_sc[warp][k] = sc1; h_ec[warp][k] = ec1;
-    }
-    const int nh = __popc(m0) + __popc(m1);
-    __syncwarp();
-    for (int k = lane; k < nh; k += 32) {
-        const int64_t row = gbase + h_row[warp][k];
-        o = h_off[warp][k];
-        const X sc = h_sc[warp][k], ec = h_ec[warp][k];
+    for (uint32_t kbase = 0; kbase < nh; kbase += 32) {
+        uint32_t k = kbase + lane;
+        Hit<X> hit{0u, 0u, 0, 0};
+        if (k < nh) {
+            int j = 0;  // which of the warp's granule lists holds entry k
+#pragma unroll
+            for (int u = 0; u < EM_GW - 1; u++)
+                if (j == u && k >= h[u]) { k -= h[u]; j = u + 1; }
+            hit = get_entry<X>(base + j * OV_GRAN + k);
+        }
+        const int64_t inc = warp_incl_sum((int64_t)hit.cnt);
+        int64_t o = carry + inc - hit.cnt;
+        carry += __shfl_sync(FULL, inc, 31);
+        if (hit.cnt == 0) continue;
+        const int64_t row = tbase + hit.row;
+        const X sc = hit.sc, ec = hit.ec;
         const uint64_t b = sc >> shift;
         const uint32_t rel = (uint32_t)sc & mask;
         const Rec r = load_rec(ix, b);
@@ -755,46 +783,79 @@ static int check_query(const iv_index_t* ix, const iv_queries_t* q, const char* 
     return IV_OK;
 }
 
-// workspace of count / emit: [tile sums -> tile offsets (n/1024 + 2)] [granule sums (n/64 + 2)] [scan scratch]
+// workspace of count / emit:
+//   [tile sums -> tile offsets, int64 (n/1024 + 2)] [pair sums per granule, int64 (n/64 + 2)]
+//   [hits per granule, uint32 (n/64 + 2)] [scan scratch]
+//   [hit list: one 16-byte (32-bit index) or 32-byte (64-bit index) slot per query row]
 static size_t ws_tiles(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_TILE) + 2; }
 static size_t ws_grans(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_GRAN) + 2; }
-
-template <typename X>
-static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, int64_t* out_count,
-                         int64_t* tile_sums, unsigned ntiles, cudaStream_t st) {
-    int64_t* gran_sums = tile_sums ? tile_sums + ws_tiles(q.n) : nullptr;
-    int64_t first = 0;
-    const int64_t nblk = cdiv(q.n, LN_TILES * OV_TILE);
-    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16) {
-        // large aligned inputs go through the lean kernel (ragged last block included);
-        // its warps add their partial sums with atomics: clear the sums first
-        if (tile_sums) cudaMemsetAsync(tile_sums, 0, (ws_tiles(q.n) + ws_grans(q.n)) * sizeof(int64_t), st);
-        unsigned long long* ts = reinterpret_cast<unsigned long long*>(tile_sums);
-        unsigned long long* gs = reinterpret_cast<unsigned long long*>(gran_sums);
-        if (mode == IV_MODE_ALL) k_count_lean<X, IV_MODE_ALL><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts, gs);
-        else k_count_lean<X, IV_MODE_ANY><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, ts, gs);
-        __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
-        first = nblk * LN_TILES;
-        if (first >= (int64_t)ntiles) return;
-    }
-    const unsigned nb = (unsigned)(ntiles - first);
-    if (mode == IV_MODE_ALL) k_count<X, IV_MODE_ALL><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, gran_sums, first);
-    else if (mode == IV_MODE_ANY) k_count<X, IV_MODE_ANY><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, gran_sums, first);
-    else k_count<X, IV_MODE_CONTAIN><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, tile_sums, gran_sums, first);
+struct OverlapWs {
+    int64_t* tile_sums;
+    int64_t* gran_sums;
+    uint32_t* gran_hits;
+    int64_t* scan;
+    void* list;
+    size_t bytes;
+};
+static OverlapWs plan_overlap_ws(void* ws, int64_t n, size_t entry_bytes) {
+    Bump b(ws, 0);
+    OverlapWs w;
+    w.tile_sums = b.take<int64_t>(ws_tiles(n));
+    w.gran_sums = b.take<int64_t>(ws_grans(n));
+    w.gran_hits = b.take<uint32_t>(ws_grans(n));
+    w.scan = b.take<int64_t>(scan_i64_large_temp_elems((int64_t)ws_tiles(n)));
+    w.list = b.take<char>((size_t)cdiv(n > 0 ? n : 1, OV_TILE) * OV_TILE * entry_bytes);
+    w.bytes = b.off;
+    return w;
 }
 
 template <typename X>
-static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, const int64_t* counts,
-                        const int64_t* tile_off, int64_t* out_q, int64_t* out_s, const int64_t* s_label, int64_t cap,
-                        cudaStream_t st) {
-    const int64_t* gran_sums = tile_off + ws_tiles(q.n);
-    const unsigned nb = (unsigned)cdiv(cdiv(q.n, OV_GRAN), EM_WARPS);
+static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, bool vec, int64_t* out_count, void* ws,
+                         unsigned ntiles, cudaStream_t st) {
+    OverlapWs w = plan_overlap_ws(ws, q.n, sizeof(HitEntry<X>));
+    int64_t* gran_sums = ws ? w.gran_sums : nullptr;
+    uint32_t* gran_hits = ws ? w.gran_hits : nullptr;
+    HitEntry<X>* list = ws ? (HitEntry<X>*)w.list : nullptr;
+    int64_t first = 0;
+    const int64_t nblk = cdiv(q.n, LN_TILES * OV_TILE);
+    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16) {
+        // large aligned inputs go through the lean kernel (ragged last block included)
+        unsigned long long* gs = reinterpret_cast<unsigned long long*>(gran_sums);
+        if (mode == IV_MODE_ALL)
+            k_count_lean<X, IV_MODE_ALL><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
+        else
+            k_count_lean<X, IV_MODE_ANY><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
+        __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
+        first = nblk * LN_TILES;
+    }
+    if (first < (int64_t)ntiles) {
+        const unsigned nb = (unsigned)(ntiles - first);
+        if (mode == IV_MODE_ALL)
+            k_count<X, IV_MODE_ALL><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, gran_sums, gran_hits, list, first);
+        else if (mode == IV_MODE_ANY)
+            k_count<X, IV_MODE_ANY><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, gran_sums, gran_hits, list, first);
+        else
+            k_count<X, IV_MODE_CONTAIN><<<nb, OV_THREADS, 0, st>>>(ix, q, vec, out_count, gran_sums, gran_hits, list, first);
+        __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
+    }
+    if (ws) {
+        k_tile_sums<<<(unsigned)cdiv((int64_t)ntiles * OV_GPT, 256), 256, 0, st>>>(gran_sums, q.n, ntiles, w.tile_sums);
+        __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
+    }
+}
+
+template <typename X>
+static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, const void* ws, int64_t* out_q,
+                        int64_t* out_s, const int64_t* s_label, int64_t cap, cudaStream_t st) {
+    const OverlapWs w = plan_overlap_ws((void*)ws, q.n, sizeof(HitEntry<X>));
+    const HitEntry<X>* list = (const HitEntry<X>*)w.list;
+    const unsigned nb = (unsigned)cdiv(q.n, OV_TILE);
     if (mode == IV_MODE_ALL)
-        k_emit<X, IV_MODE_ALL><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label, cap);
+        k_emit<X, IV_MODE_ALL><<<nb, EM_THREADS, 0, st>>>(ix, q, list, w.gran_hits, w.gran_sums, w.tile_sums, out_q, out_s, s_label, cap);
     else if (mode == IV_MODE_ANY)
-        k_emit<X, IV_MODE_ANY><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label, cap);
+        k_emit<X, IV_MODE_ANY><<<nb, EM_THREADS, 0, st>>>(ix, q, list, w.gran_hits, w.gran_sums, w.tile_sums, out_q, out_s, s_label, cap);
     else
-        k_emit<X, IV_MODE_CONTAIN><<<nb, EM_THREADS, 0, st>>>(ix, q, vec, counts, tile_off, gran_sums, out_q, out_s, s_label, cap);
+        k_emit<X, IV_MODE_CONTAIN><<<nb, EM_THREADS, 0, st>>>(ix, q, list, w.gran_hits, w.gran_sums, w.tile_sums, out_q, out_s, s_label, cap);
 }
 
 }  // namespace iv
@@ -802,8 +863,8 @@ static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, b
 using namespace iv;
 
 extern "C" size_t iv_overlap_workspace_bytes(int64_t n_queries) {
-    return (ws_tiles(n_queries) + ws_grans(n_queries) + scan_i64_large_temp_elems((int64_t)ws_tiles(n_queries))) *
-               sizeof(int64_t) + 256;
+    // sized for the 64-bit index (32-byte list slots); a 32-bit index uses half of the list area
+    return plan_overlap_ws(nullptr, n_queries, sizeof(HitEntry<uint64_t>)).bytes + 256;
 }
 
 extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mode, int64_t* out_count,
@@ -812,20 +873,23 @@ extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q,
     int rc = check_query(index, q, "iv_count_overlaps");
     if (rc != IV_OK) return rc;
     IV_REQUIRE(mode >= IV_MODE_ALL && mode <= IV_MODE_CONTAIN, IV_ERR_INVALID, "iv_count_overlaps: mode");
-    IV_REQUIRE(!ws || ws_bytes >= iv_overlap_workspace_bytes(q->n), IV_ERR_WORKSPACE, "iv_count_overlaps: workspace");
+    const bool nar = narrow(index);
+    const size_t need = plan_overlap_ws(nullptr, q->n, nar ? sizeof(HitEntry<uint32_t>) : sizeof(HitEntry<uint64_t>)).bytes;
+    IV_REQUIRE(!ws || ws_bytes >= need, IV_ERR_WORKSPACE, "iv_count_overlaps: workspace %zu < %zu", ws_bytes, need);
     if (q->n == 0) {
         if (out_total) IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
         return IV_OK;
     }
-    IV_REQUIRE(out_count, IV_ERR_INVALID, "iv_count_overlaps: out_count is null");
+    IV_REQUIRE(out_count || ws, IV_ERR_INVALID, "iv_count_overlaps: neither out_count nor a workspace");
+    IV_REQUIRE(!ws || (((uintptr_t)ws) & 255) == 0, IV_ERR_INVALID, "iv_count_overlaps: workspace not 256-byte aligned");
     int64_t ntiles = cdiv(q->n, OV_TILE);
-    int64_t* tile_sums = (int64_t*)ws;
-    bool vec = aligned16(q->start) && aligned16(q->end) && aligned16(out_count);
-    if (narrow(index)) launch_count<uint32_t>(*index, *q, mode, vec, out_count, tile_sums, (unsigned)ntiles, st);
-    else launch_count<uint64_t>(*index, *q, mode, vec, out_count, tile_sums, (unsigned)ntiles, st);
-    IV_LAUNCH_CHECK();
-    if (tile_sums) {
-        rc = scan_exclusive_i64_large(tile_sums, ntiles, tile_sums + ws_tiles(q->n) + ws_grans(q->n), out_total, st);
+    bool vec = aligned16(q->start) && aligned16(q->end) && (!out_count || aligned16(out_count));
+    if (nar) launch_count<uint32_t>(*index, *q, mode, vec, out_count, ws, (unsigned)ntiles, st);
+    else launch_count<uint64_t>(*index, *q, mode, vec, out_count, ws, (unsigned)ntiles, st);
+    IV_CUDA(cudaGetLastError());  // launch_count tallies its own launches
+    if (ws) {
+        const OverlapWs w = plan_overlap_ws(ws, q->n, nar ? sizeof(HitEntry<uint32_t>) : sizeof(HitEntry<uint64_t>));
+        rc = scan_exclusive_i64_large(w.tile_sums, ntiles, w.scan, out_total, st);
         if (rc != IV_OK) return rc;
     }
     return IV_OK;
@@ -835,17 +899,15 @@ extern "C" int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int
                              const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label,
                              int64_t out_capacity, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    (void)counts;  // the hit lists in the workspace carry the counts
     int rc = check_query(index, q, "iv_emit_pairs");
     if (rc != IV_OK) return rc;
     IV_REQUIRE(mode >= IV_MODE_ALL && mode <= IV_MODE_CONTAIN, IV_ERR_INVALID, "iv_emit_pairs: mode");
     if (q->n == 0) return IV_OK;
-    IV_REQUIRE(counts && ws, IV_ERR_INVALID, "iv_emit_pairs: counts / ws is null");
+    IV_REQUIRE(ws, IV_ERR_INVALID, "iv_emit_pairs: ws is null");
     IV_REQUIRE(out_capacity >= 0, IV_ERR_INVALID, "iv_emit_pairs: negative out_capacity");
-    int64_t ntiles = cdiv(q->n, OV_TILE);
-    const int64_t* tile_off = (const int64_t*)ws;
-    bool vec = aligned16(q->start) && aligned16(q->end) && aligned16(counts);
-    if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, out_capacity, st);
-    else launch_emit<uint64_t>(*index, *q, mode, vec, counts, tile_off, out_q, out_s, s_label, out_capacity, st);
+    if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, ws, out_q, out_s, s_label, out_capacity, st);
+    else launch_emit<uint64_t>(*index, *q, mode, ws, out_q, out_s, s_label, out_capacity, st);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -190,32 +190,39 @@ k_u32_tile_sums(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict
     }
 }
 
-// single block: in-place exclusive scan of m values
-template <typename T>
-__global__ void __launch_bounds__(1024) k_scan_small(T* __restrict__ data, int64_t m, T* __restrict__ out_total) {
+// single block: in-place exclusive scan of m values, ITEMS consecutive values per thread and round (all loads of a
+// round are issued together: one memory round trip per 1024 * ITEMS values)
+template <typename T, int ITEMS>
+__global__ void __launch_bounds__(1024) k_scan_small_t(T* __restrict__ data, int64_t m, T* __restrict__ out_total) {
     __shared__ T sm[1024 / 32 + 1];
     T carry = 0;
-    for (int64_t base = 0; base < m; base += 1024 * 4) {
-        T v[4];
+    for (int64_t base = 0; base < m; base += 1024 * ITEMS) {
+        T v[ITEMS];
         T tsum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int64_t i = base + (int64_t)threadIdx.x * 4 + j;
+        for (int j = 0; j < ITEMS; j++) {
+            int64_t i = base + (int64_t)threadIdx.x * ITEMS + j;
             v[j] = i < m ? data[i] : T(0);
-            tsum += v[j];
         }
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) tsum += v[j];
         T tot;
         T ex = block_excl_sum<T, 1024>(tsum, sm, tot);
         T run = carry + ex;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int64_t i = base + (int64_t)threadIdx.x * 4 + j;
+        for (int j = 0; j < ITEMS; j++) {
+            int64_t i = base + (int64_t)threadIdx.x * ITEMS + j;
             if (i < m) data[i] = run;
             run += v[j];
         }
         carry += tot;
     }
     if (threadIdx.x == 0 && out_total) *out_total = carry;
+}
+template <typename T>
+static void scan_small(T* data, int64_t m, T* out_total, cudaStream_t stream) {
+    if (m > 4096) k_scan_small_t<T, 16><<<1, 1024, 0, stream>>>(data, m, out_total);
+    else k_scan_small_t<T, 4><<<1, 1024, 0, stream>>>(data, m, out_total);
 }
 
 __global__ void __launch_bounds__(SC_THREADS)
@@ -247,13 +254,13 @@ int scan_exclusive_u32_large(uint32_t* data, int64_t n, uint32_t* temp_partials,
     if (n <= 0) return IV_OK;
     int64_t nt = cdiv(n, SC_TILE);
     if (nt == 1) {
-        k_scan_small<uint32_t><<<1, 1024, 0, stream>>>(data, n, nullptr);
+        scan_small<uint32_t>(data, n, nullptr, stream);
         IV_LAUNCH_CHECK();
         return IV_OK;
     }
     k_u32_tile_sums<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, temp_partials);
     IV_LAUNCH_CHECK();
-    k_scan_small<uint32_t><<<1, 1024, 0, stream>>>(temp_partials, nt, nullptr);
+    scan_small<uint32_t>(temp_partials, nt, nullptr, stream);
     IV_LAUNCH_CHECK();
     k_u32_apply<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, temp_partials);
     IV_LAUNCH_CHECK();
@@ -308,7 +315,7 @@ int scan_exclusive_i64_large(int64_t* data, int64_t n, int64_t* partials, int64_
     int64_t nt = cdiv(n, SC_TILE);
     k_i64_tile_sums<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, partials);
     IV_LAUNCH_CHECK();
-    k_scan_small<int64_t><<<1, 1024, 0, stream>>>(partials, nt, out_total);
+    scan_small<int64_t>(partials, nt, out_total, stream);
     IV_LAUNCH_CHECK();
     k_i64_apply<<<(unsigned)nt, SC_THREADS, 0, stream>>>(data, n, partials);
     IV_LAUNCH_CHECK();
@@ -316,7 +323,7 @@ int scan_exclusive_i64_large(int64_t* data, int64_t n, int64_t* partials, int64_
 }
 
 int scan_exclusive_i64_inplace(int64_t* data, int64_t n, int64_t* out_total, cudaStream_t stream) {
-    k_scan_small<int64_t><<<1, 1024, 0, stream>>>(data, n > 0 ? n : 0, out_total);
+    scan_small<int64_t>(data, n > 0 ? n : 0, out_total, stream);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -216,12 +216,15 @@ class SubjectIndex:
         return self
 
     # -- counts ------------------------------------------------------------------------------------
-    def count(self, q, mode=IV_MODE_ALL, for_emit=True):
-        """-> (counts int64[nq], ws, total int64[1] device).  NCLS count / has_overlaps /
-        containment count per query (pyranges/methods/coverage.py:26-40, intersection.py:73-78)."""
+    def count(self, q, mode=IV_MODE_ALL, for_emit=True, want_counts=True):
+        """-> (counts int64[nq] | None, ws, total int64[1] device).  NCLS count / has_overlaps /
+        containment count per query (pyranges/methods/coverage.py:26-40, intersection.py:73-78).  for_emit: also
+        leave the hit lists and tile offsets iv_emit_pairs works from in `ws`; the per-row counts themselves are
+        then optional (want_counts=False saves their 8 bytes per row)."""
         L = cabi.lib()
         dev = self.iv.device
-        counts = torch.empty(q.iv.n, dtype=torch.int64, device=dev)
+        assert for_emit or want_counts
+        counts = torch.empty(q.iv.n, dtype=torch.int64, device=dev) if want_counts else None
         ws = _bytes(L.iv_overlap_workspace_bytes(q.iv.n), dev) if for_emit else None
         total = torch.zeros(1, dtype=torch.int64, device=dev) if for_emit else None
         cabi.check(L.iv_count_overlaps(C.byref(self.c), C.byref(q.c), mode, _ptr(counts), _ptr(ws),
@@ -229,7 +232,7 @@ class SubjectIndex:
                    "iv_count_overlaps")
         return counts, ws, total
 
-    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None, capacity=None):
+    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None, capacity=None, want_counts=True):
         """All (query row | label, subject row | label) pairs in query order: count -> scan -> emit
         (NCLS.all_overlaps_both / all_containments_both / first_overlap_both, join.py:15-23).
 
@@ -237,13 +240,13 @@ class SubjectIndex:
         launched.  `capacity` (e.g. the pair count of a previous, similar join) lets the emit be launched
         speculatively into buffers of that size right behind the count; the total is read afterwards and the
         emit is simply repeated into exact buffers if the guess was too small."""
-        counts, ws, total = self.count(q, mode, for_emit=True)
+        counts, ws, total = self.count(q, mode, for_emit=True, want_counts=want_counts)
         dev = self.iv.device
 
         def emit(n):
             oq = torch.empty(n, dtype=torch.int64, device=dev) if want_q else None
             os_ = torch.empty(n, dtype=torch.int64, device=dev) if want_s else None
-            cabi.check(cabi.lib().iv_emit_pairs(C.byref(self.c), C.byref(q.c), mode, _ptr(counts), _ptr(ws),
+            cabi.check(cabi.lib().iv_emit_pairs(C.byref(self.c), C.byref(q.c), mode, None, _ptr(ws),
                                                 _ptr(oq), _ptr(os_), _ptr(s_label), n, _stream()), "iv_emit_pairs")
             return oq, os_
 

@@ -51,7 +51,7 @@ class SubjectIndex:
                 s, e = np.maximum(s - q.slack, 0), e + q.slack
             yield k, a, b, sa, sb, s, e, orc.NCLS(self.iv.s[sa:sb], self.iv.e[sa:sb], np.arange(sa, sb, dtype=np.int64))
 
-    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None):
+    def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None, capacity=None, want_counts=True):
         A, B = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)]
         for k, a, b, sa, sb, s, e, t in self._per_key(q):
             ids = np.arange(a, b, dtype=np.int64)

@@ -39,11 +39,15 @@ def timeit(name, fn, reps=20, alg_bytes=None):
     torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / reps
     extra = "  %.0f GB/s algorithmic" % (alg_bytes / us / 1e3) if alg_bytes else ""
-    print("%-28s %9.1f us%s" % (name, us, extra))
+    print("%-32s %9.1f us%s" % (name, us, extra))
 
 
 def f_count():
     cabi.check(L.iv_count_overlaps(C.byref(ix.c), C.byref(q.c), 0, E._ptr(counts), E._ptr(ws), ws.numel(), E._ptr(total), st))
+
+
+def f_count_lists():
+    cabi.check(L.iv_count_overlaps(C.byref(ix.c), C.byref(q.c), 0, None, E._ptr(ws), ws.numel(), E._ptr(total), st))
 
 
 def f_count_only():
@@ -51,7 +55,7 @@ def f_count_only():
 
 
 def f_emit():
-    cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), 0, E._ptr(counts), E._ptr(ws), E._ptr(out_q), E._ptr(out_s), None, out_q.numel(), st))
+    cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), 0, None, E._ptr(ws), E._ptr(out_q), E._ptr(out_s), None, out_q.numel(), st))
 
 
 def f_build():
@@ -59,9 +63,10 @@ def f_build():
 
 
 print("reads %d annotations %d pairs %d" % (nr, na, p))
-timeit("iv_count_overlaps (+scan)", f_count, alg_bytes=24 * nr)
+timeit("iv_count_overlaps (+lists)", f_count, alg_bytes=24 * nr)
+timeit("iv_count_overlaps (lists only)", f_count_lists, alg_bytes=16 * nr)
 timeit("iv_count_overlaps (no sums)", f_count_only, alg_bytes=24 * nr)
-timeit("iv_emit_pairs", f_emit, alg_bytes=24 * nr + 16 * p)
+timeit("iv_emit_pairs", f_emit, alg_bytes=16 * p)
 timeit("SubjectIndex() python", f_build, reps=10)
 timeit("iv_index_build (C call)", ix.build, reps=10, alg_bytes=24 * na)
 # subtract against the merged annotations (strand ignored -> chromosome groups)
