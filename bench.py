@@ -232,7 +232,8 @@ def run_b200(args, rank, world, local_rank):
         q = E.Queries(q_iv, seg_group)
         if e:
             e[1].record()
-        counts, ws, total = ix.count(q, E.IV_MODE_ALL)
+        # join needs the pairs, not the per-row counts: the count pass only leaves its hit lists in ws
+        _, ws, total = ix.count(q, E.IV_MODE_ALL, want_counts=False)
         if e:
             e[2].record()
         # speculative emission (engine.SubjectIndex.pairs(capacity=...)): buffers sized from the previous step's
@@ -243,7 +244,7 @@ def run_b200(args, rank, world, local_rank):
         out_s = torch.empty(p, dtype=torch.int64, device=dev)
         if e:
             e[3].record()
-        cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), E.IV_MODE_ALL, E._ptr(counts), E._ptr(ws), E._ptr(out_q),
+        cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), E.IV_MODE_ALL, None, E._ptr(ws), E._ptr(out_q),
                                    E._ptr(out_s), None, out_q.numel(), E._stream()), "iv_emit_pairs")
         if e:
             e[4].record()
@@ -253,7 +254,7 @@ def run_b200(args, rank, world, local_rank):
             if p > cap:
                 out_q = torch.empty(p, dtype=torch.int64, device=dev)
                 out_s = torch.empty(p, dtype=torch.int64, device=dev)
-                cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), E.IV_MODE_ALL, E._ptr(counts), E._ptr(ws),
+                cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), E.IV_MODE_ALL, None, E._ptr(ws),
                                            E._ptr(out_q), E._ptr(out_s), None, p, E._stream()), "iv_emit_pairs")
             else:
                 out_q, out_s = out_q[:p], out_s[:p]
@@ -319,19 +320,26 @@ def run_b200(args, rank, world, local_rank):
     ph = np.asarray([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in timers])
     ph_ms = ph.mean(axis=0)
     peak, peak_src = measured_peak_gbs()
-    # k_emit is the one launch of iv_emit_pairs (events sit directly around the call); the count phase is
-    # memset + k_count_lean + ragged tail + tile-sum scan and includes the host allocation of the counts
-    alg = {"iv_index_build": 24 * ns, "iv_count_overlaps": 16 * nq + 8 * nq, "alloc": 0, "k_emit": 24 * nq + 16 * p}
-    names = ["iv_index_build", "iv_count_overlaps", "alloc", "k_emit"]
-    dom = 3
+    # Phases of the step (events sit directly around the C calls): iv_count_overlaps = k_count_lean (+ the ragged
+    # tail, k_tile_sums and the single-block scan of the 10^4 tile sums: a few us), iv_emit_pairs = the one k_emit
+    # launch.  Algorithmic bytes: the count pass reads Start/End of every query and writes one 16-byte hit-list entry
+    # per query with hits (+ 12 bytes of granule metadata per 64 rows); the emit pass reads those entries and writes
+    # the pairs.  The roofline is quoted on whichever of the two takes longer.
+    hits = int((count_step() > 0).sum().item())
+    alg = {"iv_index_build": 24 * ns, "k_count_lean": 16 * nq + 16 * hits + 12 * (nq // 64), "alloc": 0,
+           "k_emit": 16 * hits + 12 * (nq // 64) + 16 * p}
+    names = ["iv_index_build", "k_count_lean", "alloc", "k_emit"]
+    dom = 1 if ph_ms[1] >= ph_ms[3] else 3
     ach = alg[names[dom]] / (ph_ms[dom] / 1e3) / 1e9
+    pipe = 16 * nq + 16 * ns + 16 * p  # what a join must move at least: both tables in, the pairs out
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[names[dom]],
+                "algorithmic_bytes_per_launch": alg[names[dom]], "hit_queries": hits,
                 "phase_ms": {n: float(m) for n, m in zip(names, ph_ms)},
-                "pipeline_algorithmic_bytes": 24 * nq + 24 * ns + 16 * p,
-                "pipeline_achieved": (24 * nq + 24 * ns + 16 * p) / (join_ms / args.steps / 1e3) / 1e9,
-                "pipeline_frac": (24 * nq + 24 * ns + 16 * p) / (join_ms / args.steps / 1e3) / 1e9 / peak}
+                "phase_achieved_gbs": {n: alg[n] / (m / 1e3) / 1e9 for n, m in zip(names, ph_ms) if alg[n]},
+                "pipeline_algorithmic_bytes": pipe,
+                "pipeline_achieved": pipe / (join_ms / args.steps / 1e3) / 1e9,
+                "pipeline_frac": pipe / (join_ms / args.steps / 1e3) / 1e9 / peak}
 
     # ---- end to end through the host-facing call: pinned host arrays in, host index arrays out ----
     e2e = None

@@ -562,21 +562,39 @@ k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, cons
                 }
                 o++;
             };
-            uint32_t pS, pE;
-            if (rec_inline_s(r)) {
-                pS = r.w[0] + swar_cnt4(r.w[4], r.w[5], rel);
-                pE = (ec >> shift) == b ? r.w[0] + swar_cnt4(r.w[4], r.w[5], (uint32_t)ec & mask) : rank_s_lt<X>(ix, ec);
-            } else {
-                pS = rec_rank_s(ix, r, b, rel);
-                pE = (ec >> shift) == b ? rec_rank_s(ix, r, b, (uint32_t)ec & mask) : rank_s_lt<X>(ix, ec);
-            }
             // candidates in start order: [pL, pS) started in this bin before s' (class B if still open),
             // [pS, pE) start inside the query (class A); then the bin's stabbing list (class B, open at the bin
-            // origin).  Four at a time, and the first chunk of every list is requested before any is consumed:
-            // one gather latency per query instead of one per list.
-            uint32_t pL = r.w[0];
-            if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
-                pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
+            // origin).
+            uint32_t pL = r.w[0], pS, pE;
+            const bool same = (ec >> shift) == b;
+            const uint32_t ns = r.w[3] & 0xffu;
+            if (rec_inline_s(r)) {
+                pS = r.w[0] + swar_cnt4(r.w[4], r.w[5], rel);
+                pE = same ? r.w[0] + swar_cnt4(r.w[4], r.w[5], (uint32_t)ec & mask) : rank_s_lt<X>(ix, ec);
+            } else if (ns <= 32) {
+                // more than four starts in the bin: ONE pass over its (start, end) offsets does both rank searches
+                // and the candidate tests
+                const uint32_t erel = same ? ((uint32_t)ec & mask) : 0xffffffffu, hi = pL + ns;
+                for (uint32_t p = pL; p < hi; p += 4) {
+                    uint32_t so[4], se[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) so[u] = p + u < hi ? __ldg(ix.soff + p + u) : 0xffffffffu;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) se[u] = p + u < hi ? __ldg(ix.seoff + p + u) : 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (so[u] < rel ? se[u] > rel : so[u] < erel) put(__ldg(ix.row_s + p + u));
+                }
+                pL = pS = hi;                                // nothing left in this bin
+                pE = same ? hi : rank_s_lt<X>(ix, ec);       // class A continues in the following bins
+            } else {
+                pS = rec_rank_s(ix, r, b, rel);
+                pE = same ? rec_rank_s(ix, r, b, (uint32_t)ec & mask) : rank_s_lt<X>(ix, ec);
+                if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
+                    pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
+            }
+            // four at a time, and the first chunk of every list is requested before any is consumed: one gather
+            // latency per query instead of one per list
             const uint32_t nc = (r.w[3] >> 16) & 0xffu;
             const uint32_t x0 = r.w[2], x1 = nc < 255 ? x0 + nc : __ldg(&ix.bins[b + 1].co);
             const uint2* __restrict__ cross = reinterpret_cast<const uint2*>(ix.cross);

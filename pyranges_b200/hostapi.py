@@ -59,7 +59,7 @@ class NCLSBatch:
             chunks = 8 if (n >= (1 << 21) and hs.is_pinned() and he.is_pinned() and out is not None) else 1
         if chunks <= 1:
             q = self._queries(hs, he, seg_off, seg_group, slack)
-            _, a, b = self.index.pairs(q, E.IV_MODE_ALL)
+            _, a, b = self.index.pairs(q, E.IV_MODE_ALL, want_counts=False)
             if out is not None:  # pinned staging buffers supplied by the caller
                 p = a.numel()
                 out[0][:p].copy_(a, non_blocking=True)
@@ -94,7 +94,7 @@ class NCLSBatch:
             main.wait_event(ev)
             off = np.clip(seg_off, a, b) - a  # the chunk's own segment offsets (empty segments allowed)
             q = E.Queries(E.DeviceIntervals(ds, de, off), seg_group, slack=slack)
-            _, qa, qb = self.index.pairs(q, E.IV_MODE_ALL, capacity=hint)
+            _, qa, qb = self.index.pairs(q, E.IV_MODE_ALL, capacity=hint, want_counts=False)
             hint = int(qa.numel() * 1.25) + 4096
             if a:
                 qa.add_(a)

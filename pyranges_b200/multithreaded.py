@@ -305,15 +305,16 @@ def _b_write_both(plan, kwargs):
         raise NotImplementedError("join(how='last') is not part of the B200 hot path")
     mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
     ix = plan.index()
-    counts, out_q, out_s = ix.pairs(plan.queries(), mode)
     inner = how not in ["outer", "left", "right"]
+    counts, out_q, out_s = ix.pairs(plan.queries(), mode, want_counts=not inner)  # counts: rows without partner
     core = None
     if inner:
         # the coordinate columns of the joined frame are gathered on the device, where both
         # tables already live; the host only gathers the payload columns (by position, one take per column)
         want = ("q_start", "q_end", "s_start", "s_end") + (("overlap",) if kwargs.get("report_overlap") else ())
         core = {n: t.cpu().numpy() for n, t in E.materialize_pairs(plan.q.iv, plan.s.iv, out_q, out_s, want=want).items()}
-    counts, out_q, out_s = counts.cpu().numpy(), out_q.cpu().numpy(), out_s.cpu().numpy()
+    counts = counts.cpu().numpy() if counts is not None else None
+    out_q, out_s = out_q.cpu().numpy(), out_s.cpu().numpy()
     first = np.searchsorted(out_q, plan.q.seg_off)  # pairs are emitted in query-row order
     suffix = kwargs.get("suffix", "_b") if not kwargs.get("new_pos") else kwargs.get("suffixes", "_a _b".split())[1]
     results = []
@@ -396,7 +397,7 @@ def _b_intersection(plan, kwargs):
     if how == "last":
         raise NotImplementedError("intersect(how='last') is not part of the B200 hot path")
     mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
-    _, out_q, out_s = plan.index().pairs(plan.queries(), mode)
+    _, out_q, out_s = plan.index().pairs(plan.queries(), mode, want_counts=False)
     # the clip max(Start, Start_b) / min(End, End_b) happens where the columns live (engine.materialize_pairs)
     core = E.materialize_pairs(plan.q.iv, plan.s.iv, out_q, out_s, clip=True, want=("q_start", "q_end"))
     cs, ce = core["q_start"].cpu().numpy(), core["q_end"].cpu().numpy()

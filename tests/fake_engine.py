@@ -62,9 +62,9 @@ class SubjectIndex:
             A.append(x[o])
             B.append(y[o])
         A, B = np.concatenate(A), np.concatenate(B)
-        return _t(np.bincount(A, minlength=q.iv.n).astype(np.int64)), _t(A), _t(B)
+        return (_t(np.bincount(A, minlength=q.iv.n).astype(np.int64)) if want_counts else None), _t(A), _t(B)
 
-    def count(self, q, mode=IV_MODE_ALL, for_emit=True):
+    def count(self, q, mode=IV_MODE_ALL, for_emit=True, want_counts=True):
         c, _, _ = self.pairs(q, mode)
         return c, None, _t(np.asarray([int(c.sum())]))
 
