@@ -137,12 +137,34 @@ k_index_arrays(const int64_t* __restrict__ e, int64_t n, iv_groups_t G, const ui
 
 // Stabbing list of bin b = the subjects with S' < origin(b) <= E'.  Its length needs no counting pass:
 // #{S' < o} - #{E' < o} = bsarr[b] - bearr[b].  (A member with E' == o can never be a hit -- its eoff is 0 --
-// and is filtered like every member that ends before the query starts.)
+// and is filtered like every member that ends before the query starts.)  The list offsets are the exclusive scan of
+// those lengths over the bins: per-tile sums here (the same pass clears the fill cursors), a single-block scan of
+// the sums, and the final pass inside k_bins_finalize.
+constexpr int BT_ITEMS = 8;
+constexpr int BT_TILE = IX_THREADS * BT_ITEMS;  // bins per block
+
 __global__ void __launch_bounds__(IX_THREADS)
-k_cross_counts(int64_t n_bins, const uint32_t* __restrict__ bsarr, const uint32_t* __restrict__ bearr,
-               uint32_t* __restrict__ ccnt) {
-    const int64_t b = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
-    if (b <= n_bins + 1) ccnt[b] = b <= n_bins ? bsarr[b] - bearr[b] : 0u;
+k_cross_tile_sums(int64_t n_bins, const uint32_t* __restrict__ bsarr, const uint32_t* __restrict__ bearr,
+                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ partials) {
+    __shared__ uint32_t sm[IX_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * BT_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int it = 0; it < BT_ITEMS; it++) {
+        const int64_t b = base + it * IX_THREADS + threadIdx.x;
+        if (b <= n_bins + 1) {
+            cursor[b] = 0u;
+            if (b <= n_bins) s += bsarr[b] - bearr[b];
+        }
+    }
+    s = warp_sum(s);
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t x = threadIdx.x < IX_THREADS / 32 ? sm[threadIdx.x] : 0u;
+        x = warp_sum(x);
+        if (threadIdx.x == 0) partials[blockIdx.x] = x;
+    }
 }
 
 // Fill: every (subject, crossed bin) pair is one unit of work, spread over the block's threads whatever the
@@ -150,7 +172,7 @@ k_cross_counts(int64_t n_bins, const uint32_t* __restrict__ bsarr, const uint32_
 // (atomic cursor).
 __global__ void __launch_bounds__(IX_THREADS)
 k_cross_fill(int64_t n, const uint64_t* __restrict__ key_s, const uint64_t* __restrict__ end_s,
-             const uint32_t* __restrict__ row_s, int shift, const uint32_t* __restrict__ coff,
+             const uint32_t* __restrict__ row_s, int shift, const iv_binrec_t* __restrict__ bins,
              uint32_t* __restrict__ cursor, int64_t cap, iv_cross_t* __restrict__ cross, uint32_t* __restrict__ cross_p) {
     __shared__ uint32_t pre[IX_THREADS + 1];
     __shared__ uint32_t wsum[IX_THREADS / 32 + 1];
@@ -179,7 +201,7 @@ k_cross_fill(int64_t n, const uint64_t* __restrict__ key_s, const uint64_t* __re
         }
         const int64_t bb = sB[lo] + (u - pre[lo]);
         const uint64_t d = sE[lo] - ((uint64_t)bb << shift);
-        const int64_t at = (int64_t)__ldg(coff + bb) + atomicAdd(cursor + bb, 1u);
+        const int64_t at = (int64_t)__ldg(&bins[bb].co) + atomicAdd(cursor + bb, 1u);
         if (at < cap) {
             iv_cross_t c;
             c.row = sRow[lo];
@@ -190,36 +212,57 @@ k_cross_fill(int64_t n, const uint64_t* __restrict__ key_s, const uint64_t* __re
     }
 }
 
-// assemble the 32-byte bin records from the rank / stabbing-list offsets and the first offsets of each bin
+// assemble the 32-byte bin records: ranks at the bin origin, the stabbing-list offset (block scan of the list lengths
+// on top of the tile's scanned partial) and the first offsets of each bin.  BT_ITEMS consecutive bins per thread.
 __global__ void __launch_bounds__(IX_THREADS)
 k_bins_finalize(int64_t n_bins, int shift, const uint32_t* __restrict__ bsarr, const uint32_t* __restrict__ bearr,
-                const uint32_t* __restrict__ coff, const uint32_t* __restrict__ soff, const uint32_t* __restrict__ eoff,
-                iv_binrec_t* __restrict__ bins) {
-    const int64_t b = (int64_t)blockIdx.x * IX_THREADS + threadIdx.x;
-    if (b > n_bins) return;
-    const uint32_t bs = bsarr[b], be = bearr[b], co = coff[b];
-    const uint32_t ns = bsarr[b + 1] - bs, ne = bearr[b + 1] - be, nc = coff[b + 1] - co;
-    const bool inl = shift <= 15;  // inline offsets are 15-bit (SWAR compares in the count kernel)
-    uint32_t so[4], eo[4];
+                const uint32_t* __restrict__ partials, const uint32_t* __restrict__ soff,
+                const uint32_t* __restrict__ eoff, iv_binrec_t* __restrict__ bins) {
+    __shared__ uint32_t wsum[IX_THREADS / 32 + 1];
+    const int64_t b0 = (int64_t)blockIdx.x * BT_TILE + (int64_t)threadIdx.x * BT_ITEMS;
+    uint32_t bs[BT_ITEMS + 1], be[BT_ITEMS + 1];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        so[i] = (inl && (uint32_t)i < ns) ? __ldg(soff + bs + i) : 0x7fffu;
-        eo[i] = (inl && (uint32_t)i < ne) ? __ldg(eoff + be + i) : 0x7fffu;
+    for (int j = 0; j <= BT_ITEMS; j++) {
+        const int64_t b = b0 + j;
+        bs[j] = b <= n_bins + 1 ? bsarr[b] : 0u;
+        be[j] = b <= n_bins + 1 ? bearr[b] : 0u;
     }
-    uint4 a, c;
-    a.x = bs; a.y = be; a.z = co;
-    a.w = (ns < 255 ? ns : 255u) | ((ne < 255 ? ne : 255u) << 8) | ((nc < 255 ? nc : 255u) << 16) |
-          ((inl ? (uint32_t)IV_BIN_INLINE | ((ns <= 4 && ne <= 4) ? (uint32_t)IV_BIN_FAST : 0u) : 0u) << 24);
-    c.x = so[0] | (so[1] << 16); c.y = so[2] | (so[3] << 16);
-    c.z = eo[0] | (eo[1] << 16); c.w = eo[2] | (eo[3] << 16);
-    uint4* out = reinterpret_cast<uint4*>(bins + b);
-    out[0] = a;
-    out[1] = c;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < BT_ITEMS; j++)
+        if (b0 + j <= n_bins) mine += bs[j] - be[j];
+    uint32_t tot;
+    uint32_t co = __ldg(partials + blockIdx.x) + block_excl_sum<uint32_t, IX_THREADS>(mine, wsum, tot);
+    const bool inl = shift <= 15;  // inline offsets are 15-bit (SWAR compares in the count kernel)
+#pragma unroll
+    for (int j = 0; j < BT_ITEMS; j++) {
+        const int64_t b = b0 + j;
+        if (b > n_bins + 1) break;
+        // bin n_bins + 1 is the sentinel a look-up of "the next bin" may touch: no members, list offset = total
+        const uint32_t ns = b <= n_bins ? bs[j + 1] - bs[j] : 0u, ne = b <= n_bins ? be[j + 1] - be[j] : 0u;
+        const uint32_t nc = b <= n_bins ? bs[j] - be[j] : 0u;
+        uint32_t so[4], eo[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            so[i] = (inl && (uint32_t)i < ns) ? __ldg(soff + bs[j] + i) : 0x7fffu;
+            eo[i] = (inl && (uint32_t)i < ne) ? __ldg(eoff + be[j] + i) : 0x7fffu;
+        }
+        uint4 a, c;
+        a.x = bs[j]; a.y = be[j]; a.z = co;
+        a.w = (ns < 255 ? ns : 255u) | ((ne < 255 ? ne : 255u) << 8) | ((nc < 255 ? nc : 255u) << 16) |
+              ((inl ? (uint32_t)IV_BIN_INLINE | ((ns <= 4 && ne <= 4) ? (uint32_t)IV_BIN_FAST : 0u) : 0u) << 24);
+        c.x = so[0] | (so[1] << 16); c.y = so[2] | (so[3] << 16);
+        c.z = eo[0] | (eo[1] << 16); c.w = eo[2] | (eo[3] << 16);
+        uint4* out = reinterpret_cast<uint4*>(bins + b);
+        out[0] = a;
+        out[1] = c;
+        co += nc;
+    }
 }
 
 struct IndexLayout {
     uint64_t *ks0, *ks1, *ke0, *ke1, *end_s;
-    uint32_t *rs0, *rs1, *re0, *re1, *soff, *seoff, *eoff, *bsarr, *bearr, *ccnt, *cursor, *cross_p, *scan_tmp;
+    uint32_t *rs0, *rs1, *re0, *re1, *soff, *seoff, *eoff, *bsarr, *bearr, *cursor, *cross_p, *scan_tmp;
     iv_binrec_t* bins;
     iv_cross_t* cross;
     void* sort_temp;
@@ -259,9 +302,11 @@ static void plan_index(int64_t n, int64_t span, int64_t sum_len, int flags, Bump
     L.bins = b.take<iv_binrec_t>((size_t)L.n_bins + 2);
     L.bsarr = b.take<uint32_t>((size_t)L.n_bins + 4);
     L.bearr = b.take<uint32_t>((size_t)L.n_bins + 4);
-    L.ccnt = b.take<uint32_t>((size_t)L.n_bins + 4);
     L.cursor = b.take<uint32_t>((size_t)L.n_bins + 4);
-    L.scan_tmp = b.take<uint32_t>(scan_u32_large_temp_elems(L.n_bins + 2) + 64);
+    {
+        const int64_t nbt = cdiv(L.n_bins + 2, BT_TILE);
+        L.scan_tmp = b.take<uint32_t>((size_t)((nbt + 63) & ~(int64_t)63) + scan_u32_large_temp_elems(nbt) + 64);
+    }
     L.cross = b.take<iv_cross_t>((size_t)L.cross_cap);
     L.cross_p = b.take<uint32_t>((size_t)L.cross_cap);
     L.sort_temp = b.take<char>(radix_sort_temp_bytes(n));
@@ -427,19 +472,20 @@ static int index_build_direct(const int64_t* starts, const int64_t* ends, int64_
     if (rc != IV_OK) return rc;
     if (res) { out->key_s = L.ks1; out->row_s = L.rs1; out->key_e = L.ke1; out->row_e = L.re1; }
     if (!(flags & IV_INDEX_ENDS_PERM)) out->row_e = nullptr;
-    IV_CUDA(cudaMemsetAsync(L.cursor, 0, ((size_t)L.n_bins + 4) * sizeof(uint32_t), st));
     k_index_arrays<<<dim3(nb, 2), IX_THREADS, 0, st>>>(ends, n, G, out->key_s, out->row_s, out->key_e, L.shift, L.n_bins,
                                                        L.end_s, L.soff, L.seoff, L.eoff, L.bsarr, L.bearr);
     IV_LAUNCH_CHECK();
-    k_cross_counts<<<(unsigned)cdiv(L.n_bins + 2, IX_THREADS), IX_THREADS, 0, st>>>(L.n_bins, L.bsarr, L.bearr, L.ccnt);
+    // stabbing-list offsets: tile sums of the list lengths -> single-block scan -> finished inside k_bins_finalize
+    const int64_t nbt = cdiv(L.n_bins + 2, BT_TILE);
+    k_cross_tile_sums<<<(unsigned)nbt, IX_THREADS, 0, st>>>(L.n_bins, L.bsarr, L.bearr, L.cursor, L.scan_tmp);
     IV_LAUNCH_CHECK();
-    rc = scan_exclusive_u32_large(L.ccnt, L.n_bins + 2, L.scan_tmp, st);
+    rc = scan_exclusive_u32_large(L.scan_tmp, nbt, L.scan_tmp + ((nbt + 63) & ~(int64_t)63), st);
     if (rc != IV_OK) return rc;
-    k_cross_fill<<<nb, IX_THREADS, 0, st>>>(n, out->key_s, L.end_s, out->row_s, L.shift, L.ccnt, L.cursor, L.cross_cap,
-                                            L.cross, L.cross_p);
+    k_bins_finalize<<<(unsigned)nbt, IX_THREADS, 0, st>>>(L.n_bins, L.shift, L.bsarr, L.bearr, L.scan_tmp, L.soff, L.eoff,
+                                                         L.bins);
     IV_LAUNCH_CHECK();
-    k_bins_finalize<<<(unsigned)cdiv(L.n_bins + 1, IX_THREADS), IX_THREADS, 0, st>>>(L.n_bins, L.shift, L.bsarr, L.bearr,
-                                                                                     L.ccnt, L.soff, L.eoff, L.bins);
+    k_cross_fill<<<nb, IX_THREADS, 0, st>>>(n, out->key_s, L.end_s, out->row_s, L.shift, L.bins, L.cursor, L.cross_cap,
+                                            L.cross, L.cross_p);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -367,138 +367,146 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
              uint32_t* __restrict__ gran_hits, HitEntry<X>* __restrict__ list) {
     __shared__ X q_sc[LN_THREADS / 32][LN_QCAP], q_ec[LN_THREADS / 32][LN_QCAP];
     __shared__ uint32_t q_row[LN_THREADS / 32][LN_QCAP], q_ent[LN_THREADS / 32][LN_QCAP];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t bbase = (int64_t)blockIdx.x * (LN_TILES * OV_TILE);
+    constexpr uint32_t BLOCK_ROWS = LN_TILES * OV_TILE;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t bbase = (int64_t)blockIdx.x * BLOCK_ROWS;
+    // everything below is indexed relative to the block's first row, in 32 bits
+    const uint32_t nrem = (uint32_t)(q.n - bbase < (int64_t)BLOCK_ROWS ? q.n - bbase : (int64_t)BLOCK_ROWS);
+    const int64_t* __restrict__ qs = q.start + bbase;
+    const int64_t* __restrict__ qe = q.end + bbase;
+    int64_t* __restrict__ oc = out_count ? out_count + bbase : nullptr;
+    HitEntry<X>* __restrict__ lb = list ? list + bbase : nullptr;
+    uint32_t* __restrict__ gh = gran_hits + bbase / OV_GRAN;
+    unsigned long long* __restrict__ gs = gran_sums + bbase / OV_GRAN;
     const int shift = ix.shift;
     const uint32_t mask = (1u << shift) - 1u;
     const unsigned lt = (1u << lane) - 1u;
-    int q_head = 0, q_tail = 0;  // warp-uniform ring positions of the slow queue
-    auto count_slow = [&](int n_valid) {
+    uint32_t q_head = 0, q_tail = 0;  // warp-uniform ring positions of the slow queue
+    auto count_slow = [&](uint32_t n_valid) {
         if (lane < n_valid) {
-            const int at = (q_head + lane) % LN_QCAP;
-            const int64_t row = bbase + q_row[warp][at];
+            const uint32_t at = (q_head + lane) % LN_QCAP;
+            const uint32_t row = q_row[warp][at];
             int64_t c = count_all<X>(ix, q_sc[warp][at], q_ec[warp][at]);
             if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
-            if (out_count) out_count[row] = c;
-            if (c && list) {
+            if (oc) oc[row] = c;
+            if (c && lb) {
                 // the granule's sum was stored (plain) by lane 0 of this warp when the row was queued
-                atomicAdd(gran_sums + row / OV_GRAN, (unsigned long long)c);
+                atomicAdd(gs + row / OV_GRAN, (unsigned long long)c);
                 // the entry was reserved (count 0) when the row was queued: fill in the count
-                list[(bbase / OV_GRAN) * OV_GRAN + q_ent[warp][at]].cnt = (uint32_t)c;
+                lb[q_ent[warp][at]].cnt = (uint32_t)c;
             }
         }
         q_head += n_valid;
         __syncwarp();
     };
-    // segment geometry: re-derived only when the block crosses a key boundary (uniform per half-tile otherwise)
+    // segment geometry: most blocks lie inside one key; otherwise it is re-derived per half-tile
     int seg = find_seg(q.seg_off, q.n_seg, bbase), f_seg = -1;
+    const bool blk_uniform = __ldg(q.seg_off + seg + 1) >= bbase + (int64_t)BLOCK_ROWS;
     Flat<X> f0;
     uint32_t lo32 = 0, hi32 = 0, off32 = 0;
     bool geo32 = false;
-    for (int t = 0; t < LN_TILES; t++) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int64_t hbase = bbase + t * OV_TILE + h * (OV_TILE / 2);  // 512 rows: 2 per thread
-            if (hbase >= q.n) break;  // ragged last block
+    for (uint32_t hrel = 0; hrel < BLOCK_ROWS; hrel += OV_TILE / 2) {  // 512 rows: 2 per thread
+        if (hrel >= nrem) break;  // ragged last block
+        bool uniform = true;
+        if (!blk_uniform) {
+            const int64_t hbase = bbase + hrel;
             while (seg + 1 < q.n_seg && __ldg(q.seg_off + seg + 1) <= hbase) seg++;
-            if (seg != f_seg) {
-                f0 = load_flat<X>(ix, q, seg);
-                f_seg = seg;
-                const uint64_t hi = (uint64_t)f0.lo + f0.width;
-                geo32 = sizeof(X) == 4 && f0.lo >= 0 && hi <= 0xffffffffull;
-                lo32 = (uint32_t)f0.lo;
-                hi32 = (uint32_t)hi;
-                off32 = (uint32_t)f0.base - lo32;
-            }
-            const bool uniform = __ldg(q.seg_off + seg + 1) >= hbase + OV_TILE / 2;
-            const int64_t i0 = hbase + 2 * threadIdx.x;
-            int64_t s[2] = {0, 0}, e[2] = {0, 0};
-            if (i0 + 1 < q.n) {
-                const longlong2 s2 = __ldg(reinterpret_cast<const longlong2*>(q.start + i0));
-                const longlong2 e2 = __ldg(reinterpret_cast<const longlong2*>(q.end + i0));
-                s[0] = s2.x; s[1] = s2.y; e[0] = e2.x; e[1] = e2.y;
-            } else if (i0 < q.n) {
-                s[0] = __ldg(q.start + i0); e[0] = __ldg(q.end + i0);
-            }
-            X sc[2], ec[2];
-            Rec r[2];
+            uniform = __ldg(q.seg_off + seg + 1) >= hbase + OV_TILE / 2;
+        }
+        if (seg != f_seg) {
+            f0 = load_flat<X>(ix, q, seg);
+            f_seg = seg;
+            const uint64_t hi = (uint64_t)f0.lo + f0.width;
+            geo32 = sizeof(X) == 4 && f0.lo >= 0 && hi <= 0xffffffffull;
+            lo32 = (uint32_t)f0.lo;
+            hi32 = (uint32_t)hi;
+            off32 = (uint32_t)f0.base - lo32;
+        }
+        const uint32_t r0 = hrel + 2 * threadIdx.x;  // rows r0, r0 + 1 of the block
+        int64_t s[2] = {0, 0}, e[2] = {0, 0};
+        if (r0 + 1 < nrem) {
+            const longlong2 s2 = __ldg(reinterpret_cast<const longlong2*>(qs + r0));
+            const longlong2 e2 = __ldg(reinterpret_cast<const longlong2*>(qe + r0));
+            s[0] = s2.x; s[1] = s2.y; e[0] = e2.x; e[1] = e2.y;
+        } else if (r0 < nrem) {
+            s[0] = __ldg(qs + r0); e[0] = __ldg(qe + r0);
+        }
+        X sc[2], ec[2];
+        Rec r[2];
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                apply_slack(q.slack, s[k], e[k]);
-                if (uniform && geo32 && (((uint64_t)s[k] | (uint64_t)e[k]) >> 32) == 0) {
-                    // x' = clamp(x, lo, hi) + (base - lo), all in 32 bits
-                    sc[k] = (X)(min(max((uint32_t)s[k], lo32), hi32) + off32);
-                    ec[k] = (X)(min(max((uint32_t)e[k], lo32), hi32) + off32);
-                } else {
-                    Flat<X> f = f0;
-                    if (!uniform) {
-                        int sg = find_seg_range(q.seg_off, seg, q.n_seg - 1, i0 + k);
-                        if (sg != seg) f = load_flat<X>(ix, q, sg);
-                    }
-                    sc[k] = f.at(s[k]);
-                    ec[k] = f.at(e[k]);
+        for (int k = 0; k < 2; k++) {
+            if (uniform && geo32 && (((uint64_t)s[k] | (uint64_t)e[k]) >> 32) == 0) {
+                // x' = clamp(x, lo, hi) + (base - lo), all in 32 bits
+                sc[k] = (X)(min(max((uint32_t)s[k], lo32), hi32) + off32);
+                ec[k] = (X)(min(max((uint32_t)e[k], lo32), hi32) + off32);
+            } else {
+                Flat<X> f = f0;
+                if (!uniform) {
+                    int sg = find_seg_range(q.seg_off, seg, q.n_seg - 1, bbase + r0 + k);
+                    if (sg != seg) f = load_flat<X>(ix, q, sg);
                 }
-                r[k] = load_rec(ix, ec[k] >> shift);
+                sc[k] = f.at(s[k]);
+                ec[k] = f.at(e[k]);
             }
-            int cc[2];
-            bool fast[2];
+            r[k] = load_rec(ix, ec[k] >> shift);
+        }
+        int cc[2];
+        bool fast[2];
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const X xs = sc[k] + 1;
-                const bool dead = i0 + k >= q.n;  // beyond the ragged end: count 0, never queued
-                fast[k] = dead || ((xs >> shift) == (ec[k] >> shift) && rec_fast(r[k]));
-                int c = (int)(r[k].w[0] - r[k].w[1]) + (int)swar_cnt4(r[k].w[4], r[k].w[5], (uint32_t)ec[k] & mask) -
-                        (int)swar_cnt4(r[k].w[6], r[k].w[7], (uint32_t)xs & mask);
-                c = c > 0 ? c : 0;
-                if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
-                cc[k] = (fast[k] && !dead) ? c : 0;
+        for (int k = 0; k < 2; k++) {
+            const X xs = sc[k] + 1;
+            const bool dead = r0 + k >= nrem;  // beyond the ragged end: count 0, never queued
+            fast[k] = dead || ((xs >> shift) == (ec[k] >> shift) && rec_fast(r[k]));
+            int c = (int)(r[k].w[0] - r[k].w[1]) + (int)swar_cnt4(r[k].w[4], r[k].w[5], (uint32_t)ec[k] & mask) -
+                    (int)swar_cnt4(r[k].w[6], r[k].w[7], (uint32_t)xs & mask);
+            c = c > 0 ? c : 0;
+            if (MODE == IV_MODE_ANY) c = c > 0 ? 1 : 0;
+            cc[k] = (fast[k] && !dead) ? c : 0;
+        }
+        // rows r0, r0+1: one 16-byte store; queued rows are rewritten by count_slow (same warp, later)
+        if (oc) {
+            if (r0 + 1 < nrem) *reinterpret_cast<longlong2*>(oc + r0) = make_longlong2(cc[0], cc[1]);
+            else if (r0 < nrem) oc[r0] = cc[0];
+        }
+        // this warp's 64 rows are one granule of the hit list: an entry for every row with hits, and a
+        // reserved one (count 0 for now) for every row that goes to the slow queue
+        const unsigned slow0 = __ballot_sync(FULL, !fast[0]), slow1 = __ballot_sync(FULL, !fast[1]);
+        uint32_t ent[2] = {0, 0};
+        if (lb) {
+            const bool in0 = cc[0] > 0 || !fast[0], in1 = cc[1] > 0 || !fast[1];
+            const unsigned m0 = __ballot_sync(FULL, in0), m1 = __ballot_sync(FULL, in1);
+            const uint32_t gran = hrel / OV_GRAN + warp;  // granule of the block
+            ent[0] = gran * OV_GRAN + __popc(m0 & lt) + __popc(m1 & lt);
+            ent[1] = ent[0] + (in0 ? 1u : 0u);
+            const uint32_t trow = r0 & (OV_TILE - 1);  // row inside its 1024-row tile
+            if (in0) put_entry<X>(lb + ent[0], trow, (uint32_t)cc[0], sc[0], ec[0]);
+            if (in1) put_entry<X>(lb + ent[1], trow + 1, (uint32_t)cc[1], sc[1], ec[1]);
+            // pair sum of the granule's fast rows (plain store: the warp owns the granule; queued rows add theirs
+            // later, from this same warp, with atomics)
+            const unsigned long long g = warp_sum((unsigned long long)(unsigned)(cc[0] + cc[1]));
+            if (lane == 0) {
+                gh[gran] = __popc(m0) + __popc(m1);
+                gs[gran] = g;
             }
-            // rows i0, i0+1: one 16-byte store; queued rows are rewritten by count_slow (same warp, later)
-            if (out_count) {
-                if (i0 + 1 < q.n) *reinterpret_cast<longlong2*>(out_count + i0) = make_longlong2(cc[0], cc[1]);
-                else if (i0 < q.n) out_count[i0] = cc[0];
-            }
-            // this warp's 64 rows are one granule of the hit list: an entry for every row with hits, and a
-            // reserved one (count 0 for now) for every row that goes to the slow queue
-            const unsigned slow0 = __ballot_sync(FULL, !fast[0]), slow1 = __ballot_sync(FULL, !fast[1]);
-            uint32_t ent[2] = {0, 0};
-            if (list) {
-                const bool in0 = cc[0] > 0 || !fast[0], in1 = cc[1] > 0 || !fast[1];
-                const unsigned m0 = __ballot_sync(FULL, in0), m1 = __ballot_sync(FULL, in1);
-                const int64_t gran = hbase / OV_GRAN + warp;
-                ent[0] = (uint32_t)((gran - bbase / OV_GRAN) * OV_GRAN) + __popc(m0 & lt) + __popc(m1 & lt);
-                ent[1] = ent[0] + (in0 ? 1u : 0u);
-                HitEntry<X>* g0 = list + (bbase / OV_GRAN) * OV_GRAN;
-                const uint32_t r0 = (uint32_t)(i0 - (hbase - h * (OV_TILE / 2)));  // row inside its 1024-row tile
-                if (in0) put_entry<X>(g0 + ent[0], r0, (uint32_t)cc[0], sc[0], ec[0]);
-                if (in1) put_entry<X>(g0 + ent[1], r0 + 1, (uint32_t)cc[1], sc[1], ec[1]);
-                // pair sum of the granule's fast rows (plain store: the warp owns the granule; queued rows add theirs
-                // later, from this same warp, with atomics)
-                const unsigned long long g = warp_sum((unsigned long long)(unsigned)(cc[0] + cc[1]));
-                if (lane == 0) {
-                    gran_hits[gran] = __popc(m0) + __popc(m1);
-                    gran_sums[gran] = g;
-                }
-            }
+        }
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const unsigned m = k ? slow1 : slow0;
-                if (m) {  // queue the others (flattened coordinates + row); the whole warp counts them 32 at a time
-                    if (!fast[k]) {
-                        const int at = (q_tail + __popc(m & lt)) % LN_QCAP;
-                        q_sc[warp][at] = sc[k];
-                        q_ec[warp][at] = ec[k];
-                        q_row[warp][at] = (uint32_t)(i0 + k - bbase);
-                        q_ent[warp][at] = ent[k];
-                    }
-                    q_tail += __popc(m);
-                    __syncwarp();
-                    if (q_tail - q_head >= 32) count_slow(32);
+        for (int k = 0; k < 2; k++) {
+            const unsigned m = k ? slow1 : slow0;
+            if (m) {  // queue the others (flattened coordinates + row); the whole warp counts them 32 at a time
+                if (!fast[k]) {
+                    const uint32_t at = (q_tail + __popc(m & lt)) % LN_QCAP;
+                    q_sc[warp][at] = sc[k];
+                    q_ec[warp][at] = ec[k];
+                    q_row[warp][at] = r0 + k;
+                    q_ent[warp][at] = ent[k];
                 }
+                q_tail += __popc(m);
+                __syncwarp();
+                if (q_tail - q_head >= 32) count_slow(32);
             }
         }
     }
-    if (q_tail - q_head > 0) count_slow(q_tail - q_head);
+    if (q_tail != q_head) count_slow(q_tail - q_head);
 }
 
 // ---- emit -----------------------------------------------------------------------------------------------------------
@@ -836,8 +844,8 @@ static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, 
     HitEntry<X>* list = ws ? (HitEntry<X>*)w.list : nullptr;
     int64_t first = 0;
     const int64_t nblk = cdiv(q.n, LN_TILES * OV_TILE);
-    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16) {
-        // large aligned inputs go through the lean kernel (ragged last block included)
+    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16 && q.slack == 0) {
+        // large aligned inputs without slack go through the lean kernel (ragged last block included)
         unsigned long long* gs = reinterpret_cast<unsigned long long*>(gran_sums);
         if (mode == IV_MODE_ALL)
             k_count_lean<X, IV_MODE_ALL><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
