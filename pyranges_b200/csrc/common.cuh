@@ -61,6 +61,8 @@ static inline int bits_for(uint64_t v) {  // number of bits needed to represent 
 
 // ---- internal radix sort (sort.cu) ----------------------------------------------------------------
 size_t radix_sort_temp_bytes(int64_t n);
+// number of scatter passes of a sort of n keys on nbits bits; the sorted data ends in buffer (passes & 1)
+int radix_sort_passes(int64_t n, int nbits);
 // Sorts keys (+ optional 4/8-byte values) on bits [begin_bit, end_bit) ping-ponging between
 // (k0,v0) and (k1,v1); input is in (k0,v0).  *result_buf = 0/1 says where the sorted data is.
 // several independent sorts of the same length in one launch sequence (blockIdx.y = job)

@@ -408,7 +408,7 @@ extern "C" int iv_rle_emit(int64_t n, const iv_groups_t* groups, const void* ws,
     plan_rle(n, G.n_groups, b, L);
     const int64_t m = 2 * n;
     int bits = bits_for((uint64_t)(G.total_span > 0 ? G.total_span : 1));
-    int res = ((bits + 7) / 8) & 1;
+    int res = radix_sort_passes(m, bits) & 1;  // the buffer iv_rle*_count's sort ended in
     const uint64_t* keys = res ? L.k1 : L.k0;
     int64_t* run_start = (int64_t*)(res ? L.k0 : L.k1);  // the idle sort buffer holds the run starts
     const unsigned nt = (unsigned)cdiv(m, RL_TILE);
@@ -729,7 +729,7 @@ extern "C" int iv_rle_weighted_emit(int64_t n, const iv_groups_t* groups, const 
     plan_rlew(n, G.n_groups, b, L);
     const int64_t m = 2 * n;
     int bits = bits_for((uint64_t)(G.total_span > 0 ? G.total_span : 1));
-    int res = ((bits + 7) / 8) & 1;
+    int res = radix_sort_passes(m, bits) & 1;  // the buffer iv_rle*_count's sort ended in
     const uint64_t* keys = res ? L.k1 : L.k0;
     int64_t* run_start = (int64_t*)(res ? L.k0 : L.k1);  // the idle sort buffer holds the run starts
     const unsigned nb = (unsigned)cdiv(m, RL_THREADS);

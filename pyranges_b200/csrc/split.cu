@@ -80,8 +80,8 @@ static void plan_split(int64_t n, Bump& b, SplitLayout& L) {
     L.sort_temp = b.take<char>(radix_sort_temp_bytes((int64_t)m));
 }
 
-// which ping-pong buffer the LSD sort of m keys on `bits` bits ends in (one pass per 8 bits, sort.cu)
-static int sorted_buf(int64_t m, int bits) { return m <= 1 ? 0 : ((bits + 7) / 8) & 1; }
+// which ping-pong buffer the LSD sort of m keys on `bits` bits ends in (sort.cu)
+static int sorted_buf(int64_t m, int bits) { return radix_sort_passes(m, bits) & 1; }
 
 }  // namespace iv
 
