@@ -65,7 +65,7 @@ class DeviceIntervals:
     lo, hi, maxlen : per-segment min Start / max End / max length, computed once at ingest.
     """
 
-    def __init__(self, start, end, seg_off, bounds=None):
+    def __init__(self, start, end, seg_off, bounds=None, seg_off_dev=None):
         assert start.dtype == torch.int64 and end.dtype == torch.int64 and start.is_cuda and end.is_cuda
         self.device = _use(start.device)
         self.start, self.end = start.contiguous(), end.contiguous()
@@ -73,7 +73,9 @@ class DeviceIntervals:
         self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
         assert self.seg_off[0] == 0 and self.seg_off[-1] == self.n
         self.n_seg = len(self.seg_off) - 1
-        self.seg_off_dev = _to_dev(self.seg_off, self.device)
+        # (a caller that pipelines uploads passes the device copy: a small pageable copy issued now would queue
+        # behind its bulk transfers on the copy engine)
+        self.seg_off_dev = seg_off_dev if seg_off_dev is not None else _to_dev(self.seg_off, self.device)
         self._b = bounds  # (lo, hi, maxlen, sumlen) per segment; computed on first use (subjects / unary ops)
         self._groups = {}
 
@@ -173,15 +175,17 @@ class Groups:
 class Queries:
     """iv_queries_t over a DeviceIntervals: every segment names its partner group (-1 = none)."""
 
-    def __init__(self, iv, seg_group, seg_mode=None, slack=0, label=None):
+    def __init__(self, iv, seg_group, seg_mode=None, slack=0, label=None, desc_dev=None):
         self.iv = iv
         sg = np.ascontiguousarray(seg_group, dtype=np.int32)
         assert len(sg) == iv.n_seg
         arr = sg if seg_mode is None else np.concatenate([sg, np.ascontiguousarray(seg_mode, dtype=np.int32)])
         # the partner map is a few hundred bytes; its device copy is memoised on the columns (a pageable
-        # host->device copy would otherwise synchronise the stream on every call)
+        # host->device copy would otherwise synchronise the stream on every call) or handed in (desc_dev)
         key = arr.tobytes()
         cache = iv.__dict__.setdefault("_qdesc", {})
+        if desc_dev is not None:
+            cache[key] = desc_dev
         if key not in cache:
             cache[key] = _to_dev(arr, iv.device) if len(arr) else torch.zeros(1, dtype=torch.int32, device=iv.device)
         self.dev = cache[key]

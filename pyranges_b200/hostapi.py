@@ -73,27 +73,36 @@ class NCLSBatch:
         step = -(-n // chunks)
         step = (step + 4095) // 4096 * 4096  # chunk edges on the count kernel's 4096-row blocks
         bounds = [(a, min(a + step, n)) for a in range(0, n, step)]
-        # device columns from the main stream's pool (reused call after call), filled on the copy stream
-        d_s = torch.empty(n, dtype=torch.int64, device=dev)
-        d_e = torch.empty(n, dtype=torch.int64, device=dev)
-        d_s.record_stream(s_copy)
-        d_e.record_stream(s_copy)
-        s_copy.wait_stream(main)
+        # the chunks' small descriptors (segment offsets, partner map) go up first, in one copy: issued later they
+        # would queue behind the bulk uploads on the copy engine and stall the host once per chunk
+        offs = [np.clip(seg_off, a, b) - a for a, b in bounds]
+        sg32 = np.ascontiguousarray(seg_group, dtype=np.int32)
+        k1 = len(seg_off)
+        packed = np.concatenate(offs + [sg32.astype(np.int64)])
+        packed_dev = torch.from_numpy(packed).to(dev)
+        sg_dev = packed_dev[len(bounds) * k1:].to(torch.int32)
+        # device columns from the COPY stream's pool (reused call after call): the uploads start at once, they do not
+        # wait for whatever the main stream is still doing (e.g. the index build queued just before this call)
         landed = []
         with torch.cuda.stream(s_copy):
+            d_s = torch.empty(n, dtype=torch.int64, device=dev)
+            d_e = torch.empty(n, dtype=torch.int64, device=dev)
             for a, b in bounds:
                 d_s[a:b].copy_(hs[a:b], non_blocking=True)
                 d_e[a:b].copy_(he[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(s_copy)
                 landed.append((d_s[a:b], d_e[a:b], ev))
+        d_s.record_stream(main)
+        d_e.record_stream(main)
         pos = 0
         keep = []
         hint = None  # pairs of the previous chunk: the next chunk's emit is launched before its total is known
-        for (a, b), (ds, de, ev) in zip(bounds, landed):
+        for ci, ((a, b), (ds, de, ev)) in enumerate(zip(bounds, landed)):
             main.wait_event(ev)
-            off = np.clip(seg_off, a, b) - a  # the chunk's own segment offsets (empty segments allowed)
-            q = E.Queries(E.DeviceIntervals(ds, de, off), seg_group, slack=slack)
+            # the chunk's own segment offsets (empty segments allowed)
+            civ = E.DeviceIntervals(ds, de, offs[ci], seg_off_dev=packed_dev[ci * k1:(ci + 1) * k1])
+            q = E.Queries(civ, sg32, slack=slack, desc_dev=sg_dev)
             _, qa, qb = self.index.pairs(q, E.IV_MODE_ALL, capacity=hint, want_counts=False)
             hint = int(qa.numel() * 1.25) + 4096
             if a:
@@ -112,7 +121,6 @@ class NCLSBatch:
             keep.append((q, qa, qb))
             pos += p
         s_back.synchronize()
-        main.wait_stream(s_copy)
         return out[0][:pos], out[1][:pos]
 
     def count(self, starts, ends, seg_off, seg_group, slack=0, out=None):
