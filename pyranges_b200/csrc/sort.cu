@@ -338,11 +338,175 @@ int scan_exclusive_i64_inplace(int64_t* data, int64_t n, int64_t* out_total, cud
     return IV_OK;
 }
 
+// ---- small inputs: one partition pass + one bucket pass ------------------------------------------------------
+// A few hundred thousand keys are bound by the NUMBER of dependent launches (three per digit), not by bytes.
+// Such inputs take one stable partition on their top 8 bits (the three kernels above) and then ONE launch in which
+// every block sorts one of the 256 buckets on the remaining bits with the same stable LSD radix, all digits in one
+// go: in shared memory (composite "low bits | position in the bucket" words, 1024-key chunks ranked with
+// __match_any_sync) when the bucket fits, through global memory when it does not (heavily skewed keys: slower,
+// still correct).  5 launches instead of 3 per digit; the sorted data ends in the first buffer.
+constexpr int BK_THREADS = 256;
+constexpr int BK_WARPS = BK_THREADS / 32;
+constexpr int BK_ITEMS = 4;
+constexpr int BK_CHUNK = BK_THREADS * BK_ITEMS;  // keys ranked per round
+constexpr int BK_CAP = 4096;                     // keys a block sorts in shared memory
+constexpr int BK_POS_BITS = 12;                  // log2(BK_CAP)
+constexpr int BK_MAX_LOW_BITS = 64 - BK_POS_BITS;
+constexpr int64_t BK_MAX_N = (int64_t)1 << 18;
+constexpr int64_t BK_MIN_N = 4096;
+
+// One stable counting pass of m keys on digit (key >> shift) & dmask: src -> dst (shared or global memory),
+// payloads moved alongside when given.  base[256], warp_cnt[BK_WARPS][256]: shared scratch.
+template <bool WITH_VALUES>
+__device__ __forceinline__ void bk_pass(const uint64_t* src, uint64_t* dst, uint32_t m, int shift, uint32_t dmask,
+                                        uint32_t* base, uint32_t* warp_cnt, const char* vsrc, char* vdst, int VB) {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    if (tid < RS_RADIX) base[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < m; i += BK_THREADS) atomicAdd(&base[(uint32_t)(src[i] >> shift) & dmask], 1u);
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 256 digit counts
+        uint32_t run = 0;
+        for (int d0 = 0; d0 < RS_RADIX; d0 += 32) {
+            const uint32_t v = base[d0 + tid];
+            const uint32_t inc = warp_incl_sum(v);
+            base[d0 + tid] = run + inc - v;
+            run += __shfl_sync(FULL, inc, 31);
+        }
+    }
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < m; c0 += BK_CHUNK) {
+        for (int i = tid; i < BK_WARPS * RS_RADIX; i += BK_THREADS) warp_cnt[i] = 0;
+        __syncthreads();
+        uint64_t key[BK_ITEMS];
+        uint32_t rank[BK_ITEMS], dig[BK_ITEMS];
+#pragma unroll
+        for (int it = 0; it < BK_ITEMS; it++) {  // warp w owns 128 consecutive keys of the chunk, 32 per item
+            const uint32_t i = c0 + w * (BK_ITEMS * 32) + it * 32 + lane;
+            const bool valid = i < m;
+            key[it] = valid ? src[i] : 0ull;
+            const uint32_t d = valid ? ((uint32_t)(key[it] >> shift) & dmask) : (0x100u | lane);
+            dig[it] = d;
+            const unsigned mm = __match_any_sync(FULL, d);
+            const int leader = __ffs(mm) - 1;
+            uint32_t c = 0;
+            if (valid && lane == leader) {
+                c = warp_cnt[w * RS_RADIX + d];
+                warp_cnt[w * RS_RADIX + d] = c + (uint32_t)__popc(mm);
+            }
+            c = __shfl_sync(FULL, c, leader);
+            rank[it] = c + (uint32_t)__popc(mm & ((1u << lane) - 1u));
+            __syncwarp();
+        }
+        __syncthreads();
+        if (tid < RS_RADIX) {  // digit tid: offsets of the warps, in order; the running total carries into the next chunk
+            uint32_t run = base[tid];
+#pragma unroll
+            for (int ww = 0; ww < BK_WARPS; ww++) {
+                const uint32_t c = warp_cnt[ww * RS_RADIX + tid];
+                warp_cnt[ww * RS_RADIX + tid] = run;
+                run += c;
+            }
+            base[tid] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < BK_ITEMS; it++) {
+            const uint32_t i = c0 + w * (BK_ITEMS * 32) + it * 32 + lane;
+            if (i < m) {
+                const uint32_t pos = warp_cnt[w * RS_RADIX + dig[it]] + rank[it];
+                dst[pos] = key[it];
+                if (WITH_VALUES) {
+                    if (VB == 4) ((uint32_t*)vdst)[pos] = ((const uint32_t*)vsrc)[i];
+                    else if (VB == 8) ((uint64_t*)vdst)[pos] = ((const uint64_t*)vsrc)[i];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_rs_buckets(SortJobs J, int64_t n, int begin_bit, int low_bits, const uint32_t* __restrict__ totals) {
+    extern __shared__ __align__(16) unsigned char bk_smem[];
+    uint64_t* sa = reinterpret_cast<uint64_t*>(bk_smem);                 // [BK_CAP]
+    uint64_t* sb = sa + BK_CAP;                                          // [BK_CAP]
+    uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(sb + BK_CAP);       // [BK_WARPS][256]
+    uint32_t* base = warp_cnt + BK_WARPS * RS_RADIX;                     // [256]
+    __shared__ uint32_t s_b0, s_m;
+    const int tid = threadIdx.x, job = blockIdx.y, bucket = blockIdx.x;
+    // after the partition pass the data is in the second buffer
+    const uint64_t* __restrict__ kin = J.kin[job];
+    uint64_t* __restrict__ kout = J.kout[job];
+    const int VB = J.vb[job];
+    if (tid < 32) {  // bucket range = prefix of the digit totals
+        uint32_t before = 0, mine = 0;
+        for (int d = tid; d < RS_RADIX; d += 32) {
+            const uint32_t t = __ldg(totals + job * RS_RADIX + d);
+            if (d < bucket) before += t;
+            if (d == bucket) mine = t;
+        }
+        before = warp_sum(before);
+        mine = warp_sum(mine);
+        if (tid == 0) { s_b0 = before; s_m = mine; }
+    }
+    __syncthreads();
+    const uint32_t b0 = s_b0, m = s_m;
+    if (m == 0) return;
+    if (m <= BK_CAP) {
+        const uint64_t low_mask = (1ull << low_bits) - 1ull;  // low_bits <= 52
+        for (uint32_t i = tid; i < m; i += BK_THREADS)
+            sa[i] = (((__ldg(kin + b0 + i) >> begin_bit) & low_mask) << BK_POS_BITS) | i;
+        __syncthreads();
+        uint64_t *a = sa, *b = sb;
+        for (int sh = 0; sh < low_bits; sh += 8) {
+            const int bits = low_bits - sh < 8 ? low_bits - sh : 8;
+            bk_pass<false>(a, b, m, BK_POS_BITS + sh, (1u << bits) - 1u, base, warp_cnt, nullptr, nullptr, 0);
+            uint64_t* t = a; a = b; b = t;
+        }
+        for (uint32_t i = tid; i < m; i += BK_THREADS) {
+            const uint32_t src = b0 + (uint32_t)(a[i] & ((1u << BK_POS_BITS) - 1u));
+            kout[b0 + i] = __ldg(kin + src);
+            if (VB == 4) ((uint32_t*)J.vout[job])[b0 + i] = __ldg((const uint32_t*)J.vin[job] + src);
+            else if (VB == 8) ((uint64_t*)J.vout[job])[b0 + i] = __ldg((const uint64_t*)J.vin[job] + src);
+        }
+        return;
+    }
+    // oversize bucket: the same passes through global memory, ping-ponging between the two buffers inside the
+    // bucket's range
+    uint64_t* ka = const_cast<uint64_t*>(kin) + b0;
+    uint64_t* kb = kout + b0;
+    char* va = VB ? (char*)J.vin[job] + (size_t)b0 * VB : nullptr;
+    char* vb = VB ? (char*)J.vout[job] + (size_t)b0 * VB : nullptr;
+    for (int sh = 0; sh < low_bits; sh += 8) {
+        const int bits = low_bits - sh < 8 ? low_bits - sh : 8;
+        bk_pass<true>(ka, kb, m, begin_bit + sh, (1u << bits) - 1u, base, warp_cnt, va, vb, VB);
+        uint64_t* tk = ka; ka = kb; kb = tk;
+        char* tv = va; va = vb; vb = tv;
+    }
+    if (ka != kout + b0) {  // even number of passes: the sorted bucket sits in the input buffer
+        for (uint32_t i = tid; i < m; i += BK_THREADS) {
+            kout[b0 + i] = ka[i];
+            if (VB == 4) ((uint32_t*)J.vout[job])[b0 + i] = ((const uint32_t*)va)[i];
+            else if (VB == 8) ((uint64_t*)J.vout[job])[b0 + i] = ((const uint64_t*)va)[i];
+        }
+    }
+}
+constexpr size_t BK_SMEM = (size_t)BK_CAP * 16 + (size_t)(BK_WARPS + 1) * RS_RADIX * 4;  // 73 KB
+
+static bool bucket_path(int64_t n, int nbits) {
+    return n >= BK_MIN_N && n <= BK_MAX_N && nbits > 8 && nbits - 8 <= BK_MAX_LOW_BITS;
+}
+
 // ---- host driver ---------------------------------------------------------------------------------------------
 static int items_for(int64_t n) { return n <= ((int64_t)1 << 20) ? RS_ITEMS_SMALL : RS_ITEMS_BIG; }
 // (11-bit digits -- 3 passes instead of 4 for 32-bit keys -- were measured for small inputs: the 2048-entry
-// histogram tables made each pass twice as long, 125 us instead of 86 us for the 200k-subject index.)
-int radix_sort_passes(int64_t n, int nbits) { return (n <= 1 || nbits <= 0) ? 0 : (nbits + 7) / 8; }
+// histogram tables made each pass twice as long, 125 us instead of 86 us for the 200k-subject index.  A bitonic
+// network for the buckets of the small-input path took 61 us, the shared-memory LSD passes above 31 us.)
+int radix_sort_passes(int64_t n, int nbits) {
+    if (n <= 1 || nbits <= 0) return 0;
+    return bucket_path(n, nbits) ? 2 : (nbits + 7) / 8;
+}
 
 size_t radix_sort_temp_bytes(int64_t n) {
     int64_t ntiles = cdiv(n > 0 ? n : 1, (int64_t)RS_THREADS * items_for(n));
@@ -354,12 +518,15 @@ template <int ITEMS>
 static int radix_sort_multi_t(const SortJob* jobs, int njobs, int64_t n, int begin_bit, int end_bit, void* temp,
                               cudaStream_t stream, int* result_buf) {
     constexpr int TILE = RS_THREADS * ITEMS;
+    const int orig_begin = begin_bit;
     int64_t ntiles = cdiv(n, TILE);
     uint32_t* hist = (uint32_t*)temp;
     int64_t nh = ntiles * RS_RADIX * njobs;
     uint32_t* totals = hist + ((nh + 63) & ~(int64_t)63);
     const int nrows = RS_RADIX * njobs;
     int cur = 0;
+    const bool buckets = bucket_path(n, end_bit - begin_bit);
+    if (buckets) begin_bit = end_bit - 8;  // the partition pass: top digit only
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         int bits = end_bit - shift < 8 ? end_bit - shift : 8;
         uint32_t mask = (1u << bits) - 1u;
@@ -379,6 +546,23 @@ static int radix_sort_multi_t(const SortJob* jobs, int njobs, int64_t n, int beg
         k_rs_scatter<ITEMS><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, totals, ntiles);
         IV_LAUNCH_CHECK();
         cur ^= 1;
+    }
+    if (buckets) {
+        static bool attr_set = false;  // opt in to 73 KB of dynamic shared memory once per process
+        if (!attr_set) {
+            IV_CUDA(cudaFuncSetAttribute(k_rs_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
+            attr_set = true;
+        }
+        SortJobs J;
+        for (int j = 0; j < njobs; j++) {
+            J.kin[j] = jobs[j].k1; J.kout[j] = jobs[j].k0;
+            J.vin[j] = jobs[j].v1; J.vout[j] = jobs[j].v0;
+            J.vb[j] = jobs[j].vb;
+        }
+        k_rs_buckets<<<dim3(RS_RADIX, (unsigned)njobs), BK_THREADS, BK_SMEM, stream>>>(J, n, orig_begin,
+                                                                                      end_bit - 8 - orig_begin, totals);
+        IV_LAUNCH_CHECK();
+        cur = 0;
     }
     *result_buf = cur;
     return IV_OK;

@@ -63,6 +63,37 @@ def test_radix_sort(eng):
         assert np.array_equal(kt.cpu().numpy(), np.sort(k))
 
 
+def test_radix_sort_small_input_path(eng):
+    """4096 <= n <= 2^18 keys take one partition pass + one bucket pass (sort.cu): uniform keys (bitonic buckets),
+    heavily skewed keys (a bucket beyond the shared-memory capacity: block-local chunked radix), duplicate keys
+    (stability), every payload width, a begin bit."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    cases = []
+    for n, bits in [(4096, 32), (70000, 40), (200000, 32), (262144, 24), (100000, 9), (50000, 59)]:
+        cases.append((rng.integers(0, 2 ** bits, n, dtype=np.int64), 0, bits))
+    skew = rng.integers(0, 2 ** 32, 150000, dtype=np.int64)
+    skew[:140000] = (7 << 24) | rng.integers(0, 2 ** 20, 140000)          # 93 % of the keys in one bucket
+    cases.append((skew, 0, 32))
+    dup = rng.integers(0, 50, 60000, dtype=np.int64) << 20                 # 50 distinct keys: stability
+    cases.append((dup, 0, 32))
+    allsame = np.full(30000, 12345 << 3, dtype=np.int64)
+    cases.append((allsame, 0, 24))
+    cases.append(((rng.integers(0, 2 ** 30, 90000, dtype=np.int64) << 1) | rng.integers(0, 2, 90000), 1, 31))
+    for k, b0, b1 in cases:
+        n = len(k)
+        sk = (k >> b0) & ((1 << (b1 - b0)) - 1)
+        o = np.argsort(sk, kind="stable")
+        for vdtype in (None, torch.int32, torch.int64):
+            kt = torch.from_numpy(k.copy()).cuda()
+            vt = torch.arange(n, dtype=vdtype).cuda() if vdtype is not None else None
+            eng.radix_sort_u64(kt, vt, b0, b1)
+            assert np.array_equal(kt.cpu().numpy(), k[o]), (n, b0, b1, vdtype)
+            if vt is not None:
+                assert np.array_equal(vt.cpu().numpy(), o), (n, b0, b1, vdtype)
+
+
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("slack", [0, 7])
 def test_count_modes(eng, case, slack):
