@@ -184,7 +184,8 @@ size_t iv_overlap_workspace_bytes(int64_t n_queries);
  * Without a workspace only out_count is written. */
 int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mode, int64_t* out_count,
                       void* ws, size_t ws_bytes, int64_t* out_total, void* stream);
-/* Writes min(total, out_capacity) entries from the hit lists iv_count_overlaps left in ws (`counts` is not read
+/* Writes the pairs of every query whose entries all lie below out_capacity (all of them when total <= out_capacity)
+ * from the hit lists iv_count_overlaps left in ws (`counts` is not read
  * and may be NULL; the parameter is kept for callers of ABI v3).  out_q gets the query label, out_s the subject row (or
  * s_label[row]).  Either may be NULL.  out_capacity = entries the output buffers hold: the exact total read back
  * from iv_count_overlaps, or a guess when the emit is launched speculatively before the total is known (entries

@@ -555,7 +555,9 @@ k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, cons
         const int64_t inc = warp_incl_sum((int64_t)hit.cnt);
         int64_t o = carry + inc - hit.cnt;
         carry += __shfl_sync(FULL, inc, 31);
-        if (hit.cnt == 0) continue;
+        // a query whose pairs do not all fit the caller's buffers is dropped as a whole (speculative emission: the
+        // caller compares the total with its capacity and repeats the call)
+        if (hit.cnt == 0 || o + hit.cnt > cap) continue;
         const int64_t row = tbase + hit.row;
         const X sc = hit.sc, ec = hit.ec;
         const uint64_t b = sc >> shift;
@@ -563,12 +565,13 @@ k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, cons
         const Rec r = load_rec(ix, b);
         const int64_t ql = q.label ? __ldg(q.label + row) : row;
         if (MODE == IV_MODE_ALL) {
+            int64_t* __restrict__ qp = out_q ? out_q + o : nullptr;  // this query's slice of the outputs
+            int64_t* __restrict__ sp = out_s ? out_s + o : nullptr;
+            uint32_t j = 0;
             auto put = [&](uint32_t srow) {
-                if (o < cap) {  // cap: entries the caller's buffers hold (speculative emission)
-                    if (out_q) out_q[o] = ql;
-                    if (out_s) out_s[o] = s_label ? __ldg(s_label + srow) : (int64_t)srow;
-                }
-                o++;
+                if (qp) qp[j] = ql;
+                if (sp) sp[j] = s_label ? __ldg(s_label + srow) : (int64_t)srow;
+                j++;
             };
             // candidates in start order: [pL, pS) started in this bin before s' (class B if still open),
             // [pS, pE) start inside the query (class A); then the bin's stabbing list (class B, open at the bin
@@ -642,23 +645,19 @@ k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, cons
                     if (en[u].y > rel) put(en[u].x);
             }
         } else if (MODE == IV_MODE_ANY) {
-            if (o < cap) {
-                if (out_q) out_q[o] = ql;
-                if (out_s) {
-                    FirstHit fh(ix);
-                    for_each_hit_rec<X, true>(ix, sc, ec, r, fh);
-                    const int64_t srow = fh.brow;
-                    out_s[o] = s_label ? __ldg(s_label + srow) : srow;
-                }
+            if (out_q) out_q[o] = ql;
+            if (out_s) {
+                FirstHit fh(ix);
+                for_each_hit_rec<X, true>(ix, sc, ec, r, fh);
+                const int64_t srow = fh.brow;
+                out_s[o] = s_label ? __ldg(s_label + srow) : srow;
             }
         } else {
             const uint64_t qs = sc, qe = ec;
             for_each_hit_rec<X, true>(ix, sc, ec, r, [&](uint32_t p) {
                 if (__ldg(ix.key_s + p) <= qs && qe <= __ldg(ix.end_s + p)) {
-                    if (o < cap) {
-                        if (out_q) out_q[o] = ql;
-                        if (out_s) { int64_t srow = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + srow) : srow; }
-                    }
+                    if (out_q) out_q[o] = ql;
+                    if (out_s) { int64_t srow = __ldg(ix.row_s + p); out_s[o] = s_label ? __ldg(s_label + srow) : srow; }
                     o++;
                 }
             });
