@@ -56,6 +56,25 @@ def _to_dev(a, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
 
 
+_desc_cache = {}
+
+
+def _desc_to_dev(a, device):
+    """Device copy of a SMALL read-only descriptor array (segment offsets, group table, partner map), memoised by
+    content: the same chromosome table comes back call after call, and a pageable host->device copy costs a stream
+    synchronisation each time (and queues behind bulk transfers on the copy engine)."""
+    a = np.ascontiguousarray(a)
+    if a.nbytes > (1 << 16):
+        return _to_dev(a, device)
+    key = (str(device), a.dtype.str, a.tobytes())
+    t = _desc_cache.get(key)
+    if t is None:
+        if len(_desc_cache) >= 4096:
+            _desc_cache.clear()
+        t = _desc_cache[key] = _to_dev(a, device)
+    return t
+
+
 class DeviceIntervals:
     """Key-segmented interval columns on one GPU.
 
@@ -75,7 +94,7 @@ class DeviceIntervals:
         self.n_seg = len(self.seg_off) - 1
         # (a caller that pipelines uploads passes the device copy: a small pageable copy issued now would queue
         # behind its bulk transfers on the copy engine)
-        self.seg_off_dev = seg_off_dev if seg_off_dev is not None else _to_dev(self.seg_off, self.device)
+        self.seg_off_dev = seg_off_dev if seg_off_dev is not None else _desc_to_dev(self.seg_off, self.device)
         self._b = bounds  # (lo, hi, maxlen, sumlen) per segment; computed on first use (subjects / unary ops)
         self._groups = {}
 
@@ -166,7 +185,7 @@ class Groups:
         self.base = base
         self.total_span = int(base[-1])
         packed = np.concatenate([self.row_off, lo, hi, base]).astype(np.int64)
-        self.dev = _to_dev(packed, iv.device)
+        self.dev = _desc_to_dev(packed, iv.device)
         p = self.dev.data_ptr()
         self.c = IvGroups(g, 0, p, p + 8 * (g + 1), p + 8 * (2 * g + 1), p + 8 * (3 * g + 1), self.total_span,
                           self.sumlen, self.maxlen)
@@ -187,7 +206,7 @@ class Queries:
         if desc_dev is not None:
             cache[key] = desc_dev
         if key not in cache:
-            cache[key] = _to_dev(arr, iv.device) if len(arr) else torch.zeros(1, dtype=torch.int32, device=iv.device)
+            cache[key] = _desc_to_dev(arr, iv.device) if len(arr) else torch.zeros(1, dtype=torch.int32, device=iv.device)
         self.dev = cache[key]
         p = self.dev.data_ptr()
         self.label = label

@@ -295,8 +295,21 @@ def test_large_staged_paths(eng):
         want = oracle_counts(qs, qe, qoff, sg, ss, se, soff, name)
         assert np.array_equal(c.cpu().numpy(), want), name
         assert int(total.item()) == int(want.sum())
-    _, a, b = ix.pairs(q, eng.IV_MODE_ALL)
     wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "all"))
+    for want_counts in (True, False):  # join does not need the per-row counts: hit lists only
+        cnt, a, b = ix.pairs(q, eng.IV_MODE_ALL, want_counts=want_counts)
+        assert (cnt is not None) == want_counts
+        ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
+        assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
+    # the same rows far beyond 32 bits (64-bit instantiation of the lean kernel, 32-byte list entries)
+    big = 5_000_000_000_000
+    q64 = eng.Queries(_dev(eng, qs + big, qe + big, qoff), sg)
+    ss64 = ss + big
+    ss64[0] = 0  # one subject at the origin stretches the flattened span of its group beyond 2^32
+    se64 = np.maximum(se + big, ss64 + 1)
+    ix64 = eng.SubjectIndex(_dev(eng, ss64, se64, soff))
+    _, a, b = ix64.pairs(q64, eng.IV_MODE_ALL, want_counts=False)
+    wa, wb = canon_pairs(*oracle_pairs(qs + big, qe + big, qoff, sg, ss64, se64, soff, "all"))
     ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
     assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
 

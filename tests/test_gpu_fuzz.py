@@ -53,7 +53,8 @@ def test_fuzz_binary_ops(seed):
         assert np.array_equal(c.cpu().numpy(), want), (seed, name)
         assert int(total.item()) == int(want.sum())
     for mode, name in [(E.IV_MODE_ALL, "all"), (E.IV_MODE_CONTAIN, "contain")]:
-        _, a, b = ix.pairs(q, mode)
+        cnt, a, b = ix.pairs(q, mode, want_counts=bool(seed % 2))  # with and without the per-row counts
+        assert (cnt is not None) == bool(seed % 2)
         wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, name, slack))
         ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
         assert np.array_equal(ga, wa) and np.array_equal(gb, wb), (seed, name)
