@@ -73,9 +73,13 @@ __device__ __forceinline__ Rec load_rec(const iv_index_t& ix, uint64_t b) {
         : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint32_t cnt4(uint32_t a, uint32_t b, uint32_t rel) {
-    return ((a & 0xffffu) < rel) + ((a >> 16) < rel) + ((b & 0xffffu) < rel) + ((b >> 16) < rel);
+// #{15-bit offsets of (a, b) that are < rel}, rel <= 0x8000: per 16-bit half, bit 15 of (rel + 0x7fff - x) is set iff
+// x < rel (no borrow between the halves: x <= 0x7fff <= rel + 0x7fff)
+__device__ __forceinline__ uint32_t swar_cnt4(uint32_t a, uint32_t b, uint32_t rel) {
+    const uint32_t c = (rel + 0x7fffu) * 0x10001u;
+    return __popc(((c - a) & 0x80008000u) | (((c - b) & 0x80008000u) >> 1));
 }
+__device__ __forceinline__ uint32_t cnt4(uint32_t a, uint32_t b, uint32_t rel) { return swar_cnt4(a, b, rel); }
 // lo + #{off[p] < rel : p in [lo, hi)}   (off ascending inside a bin)
 __device__ __noinline__ uint32_t rank_in(const uint32_t* __restrict__ off, uint32_t lo, uint32_t hi, uint32_t rel) {
     if (hi - lo <= 32) {  // independent loads over at most a few sectors: one round trip, not log2(n) dependent ones
@@ -213,20 +217,56 @@ __device__ __forceinline__ void for_each_hit(const iv_index_t& ix, X sc, X ec, F
     for_each_hit_rec<X, WANT_P>(ix, sc, ec, load_rec(ix, sc >> ix.shift), f);
 }
 
-// first hit in nested-containment-list order: smallest start, then largest end, then smallest row
-struct FirstHit {
-    const iv_index_t& ix;
-    uint64_t bs, be;
-    uint32_t brow;
-    bool any;
-    __device__ FirstHit(const iv_index_t& i) : ix(i), bs(0), be(0), brow(0), any(false) {}
-    __device__ __forceinline__ void operator()(uint32_t j) {
-        uint64_t s = __ldg(ix.key_s + j), e = __ldg(ix.end_s + j);
-        uint32_t r = __ldg(ix.row_s + j);
-        bool better = !any || s < bs || (s == bs && (e > be || (e == be && r < brow)));
-        if (better) { bs = s; be = e; brow = r; any = true; }
+// first hit in nested-containment-list order: smallest start, then largest end, then smallest row --
+// found without visiting every hit: in start order the stabbing-list members (started before the bin)
+// come before the bin's earlier starts, and those before the starts inside the query; inside each class the smallest
+// start-order position has the smallest start (and, among equal starts and ends, the smallest row: the sort is
+// stable).  Only a run of EQUAL starts at the winning position needs the ends compared.  r = record of bin(sc); the
+// query must have at least one hit.  -> subject row.
+template <typename X>
+__device__ __forceinline__ uint32_t first_hit_rec(const iv_index_t& ix, X sc, X ec, const Rec& r) {
+    const uint64_t b = sc >> ix.shift;
+    const uint32_t rel = rel_of(ix, sc);
+    uint32_t lo = 0xffffffffu, hi = 0;  // candidate positions [lo, hi) of the winning class, start order
+    // class B, open at the bin origin
+    const uint32_t nc = (r.w[3] >> 16) & 0xffu;
+    const uint32_t c0 = r.w[2], c1 = nc < 255 ? c0 + nc : __ldg(&ix.bins[b + 1].co);
+    for (uint32_t j = c0; j < c1; j++) {
+        const uint2 en = __ldg(reinterpret_cast<const uint2*>(ix.cross) + j);
+        if (en.y > rel) {
+            const uint32_t p = __ldg(ix.cross_p + j);
+            lo = p < lo ? p : lo;
+        }
     }
-};
+    if (lo != 0xffffffffu) {
+        hi = r.w[0];  // members of the list all start before the bin: positions below the bin's first start
+    } else {
+        const uint32_t pS = rec_rank_s(ix, r, b, rel);
+        uint32_t pL = r.w[0];
+        if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
+            pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
+        for (uint32_t p = pL; p < pS; p++)  // class B, started in this bin
+            if (__ldg(ix.seoff + p) > rel) { lo = p; hi = pS; break; }
+        if (lo == 0xffffffffu) {  // class A: the first start inside the query
+            lo = pS;
+            hi = (ec >> ix.shift) == b ? rec_rank_s(ix, r, b, rel_of(ix, ec)) : rank_s_lt<X>(ix, ec);
+        }
+    }
+    // ties: the run of starts equal to key_s[lo] inside [lo, hi); every member of the run that is a hit competes on
+    // (largest end, smallest position)
+    uint32_t best = lo;
+    if (lo + 1 < hi) {
+        const uint64_t s0 = __ldg(ix.key_s + lo);
+        if (__ldg(ix.key_s + lo + 1) == s0) {
+            uint64_t be = __ldg(ix.end_s + lo);
+            for (uint32_t p = lo + 1; p < hi && __ldg(ix.key_s + p) == s0; p++) {
+                const uint64_t e = __ldg(ix.end_s + p);
+                if (e > (uint64_t)sc && e > be) { be = e; best = p; }  // e > sc: it is a hit (its start is < ec already)
+            }
+        }
+    }
+    return __ldg(ix.row_s + best);
+}
 
 __device__ __forceinline__ void load_items(const int64_t* __restrict__ p, int64_t i0, int64_t n, bool vec, int64_t (&v)[OV_ITEMS]) {
     if (vec && i0 + OV_ITEMS <= n) {
@@ -351,11 +391,6 @@ constexpr int LN_THREADS = 256;
 constexpr int LN_TILES = 4;                        // consecutive 1024-row tiles per block
 constexpr int LN_QCAP = 64;                        // slow queue entries per warp
 
-// #{15-bit offsets of (a, b) that are < rel}: per 16-bit half, bit 15 of (rel + 0x7fff - x) is set iff x < rel
-__device__ __forceinline__ uint32_t swar_cnt4(uint32_t a, uint32_t b, uint32_t rel) {
-    const uint32_t c = (rel + 0x7fffu) * 0x10001u;
-    return __popc(((c - a) & 0x80008000u) | (((c - b) & 0x80008000u) >> 1));
-}
 __device__ __forceinline__ bool rec_fast(const Rec& r) {
     // inline flag set, at most four starts and four ends
     return (r.w[3] & (IV_BIN_INLINE << 24)) && (r.w[3] & 0xffu) <= 4 && ((r.w[3] >> 8) & 0xffu) <= 4;
@@ -647,9 +682,7 @@ k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, cons
         } else if (MODE == IV_MODE_ANY) {
             if (out_q) out_q[o] = ql;
             if (out_s) {
-                FirstHit fh(ix);
-                for_each_hit_rec<X, true>(ix, sc, ec, r, fh);
-                const int64_t srow = fh.brow;
+                const int64_t srow = first_hit_rec<X>(ix, sc, ec, r);
                 out_s[o] = s_label ? __ldg(s_label + srow) : srow;
             }
         } else {
@@ -719,10 +752,8 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
         const Rec r1 = load_rec(ix, b1);
         bool done = false;
         if (overlap && count_rec<X>(ix, sc, ec, r1, b1) > 0) {
-            FirstHit fh(ix);
-            if ((uint64_t)(sc >> ix.shift) == b1) for_each_hit_rec<X, true>(ix, sc, ec, r1, fh);
-            else for_each_hit<X, true>(ix, sc, ec, fh);
-            row = fh.brow; dist = 0; done = true;
+            row = first_hit_rec<X>(ix, sc, ec, (uint64_t)(sc >> ix.shift) == b1 ? r1 : load_rec(ix, sc >> ix.shift));
+            dist = 0; done = true;
         }
         if (!done) {
             const int64_t g_first = __ldg(ix.groups.row_off + f.g), g_end = __ldg(ix.groups.row_off + f.g + 1);
