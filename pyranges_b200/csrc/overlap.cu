@@ -700,7 +700,7 @@ k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, cons
 
 // ---- NCLS.coverage -----------------------------------------------------------------------------------------------
 template <typename X>
-__global__ void __launch_bounds__(OV_THREADS)
+__global__ void __launch_bounds__(OV_THREADS, 6)
 k_coverage(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_bp, double* __restrict__ out_frac) {
     __shared__ int span[2];
     const int64_t tbase = (int64_t)blockIdx.x * OV_THREADS;
@@ -730,7 +730,7 @@ k_coverage(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_bp, double* 
 
 // ---- nearest --------------------------------------------------------------------------------------------------------
 template <typename X>
-__global__ void __launch_bounds__(OV_THREADS)
+__global__ void __launch_bounds__(OV_THREADS, 6)
 k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_row, int64_t* __restrict__ out_dist) {
     __shared__ int span[2];
     const int64_t tbase = (int64_t)blockIdx.x * OV_THREADS;
@@ -791,7 +791,7 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
 // of a query are then the `count` consecutive entries of the start order that follow the #{E' <= s'} subjects lying
 // entirely before it.  A query without hit survives as one piece, a completely covered one yields none.
 template <typename X, bool EMIT>
-__global__ void __launch_bounds__(OV_THREADS)
+__global__ void __launch_bounds__(OV_THREADS, 6)
 k_subtract(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ pieces, const int64_t* __restrict__ offsets,
            int64_t* __restrict__ out_q, int64_t* __restrict__ out_start, int64_t* __restrict__ out_end) {
     __shared__ int span[2];
