@@ -67,7 +67,7 @@ k_rs_prefix(uint32_t* __restrict__ hist, int64_t ntiles, uint32_t* __restrict__ 
 }
 
 template <int RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, RS_ITEMS > 4 ? 4 : 1)  // 16 keys per thread would take 112 registers: cap at 64 for 4 blocks/SM
 k_rs_scatter(SortJobs J, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ hist,
              const uint32_t* __restrict__ totals, int64_t ntiles) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
