@@ -506,21 +506,22 @@ def _b_nearest(plan, kwargs):
         modes.append({"previous": E.IV_NEAREST_PREVIOUS, "next": E.IV_NEAREST_NEXT}.get(h, E.IV_NEAREST_BOTH))
     row, dist = plan.index(ends_perm=True).nearest(plan.queries(seg_mode=np.asarray(modes, np.int32)), overlap=overlap)
     row, dist = row.cpu().numpy(), dist.cpu().numpy()
+    # the reference sorts the rows without overlap by (Start, End) (sort_one_by_one, nearest.py:100): the (key, Start,
+    # End, row) order of all keys comes from the device sort of the cluster kernels
+    by_start = E.cluster(plan.q.iv, None, 0)[0].cpu().numpy() if plan.q.iv.n else np.zeros(0, np.int64)
     results = []
     for k, scdf in enumerate(plan.q.dfs):
         ocdf = plan.partner(k)
         if scdf.empty or ocdf.empty:
             results.append(None)
             continue
-        sl = slice(plan.q.seg_off[k], plan.q.seg_off[k + 1])
+        a, b = plan.q.seg_off[k], plan.q.seg_off[k + 1]
+        sl = slice(a, b)
         r = row[sl] - plan.group_row_off[plan.seg_group[k]]
         d = dist[sl]
         hit = np.flatnonzero(d == 0)  # overlapping rows first, in self order (nearest.py:29-53)
-        rest = np.flatnonzero(d > 0)
-        if len(rest):
-            # the reference sorts the remaining rows by (Start, End) (sort_one_by_one, nearest.py:100)
-            s, e = scdf.Start.values[rest], scdf.End.values[rest]
-            rest = rest[np.lexsort([e, s])]
+        order = by_start[sl] - a
+        rest = order[d[order] > 0]
         sel = np.concatenate([hit, rest])
         if not len(sel):
             results.append(None)
