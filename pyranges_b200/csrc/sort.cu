@@ -548,10 +548,12 @@ static int radix_sort_multi_t(const SortJob* jobs, int njobs, int64_t n, int beg
         cur ^= 1;
     }
     if (buckets) {
-        static bool attr_set = false;  // opt in to 73 KB of dynamic shared memory once per process
-        if (!attr_set) {
+        static bool attr_set[64] = {false};  // opt in to 73 KB of dynamic shared memory once per device
+        int dev = 0;
+        IV_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
             IV_CUDA(cudaFuncSetAttribute(k_rs_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
-            attr_set = true;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
         SortJobs J;
         for (int j = 0; j < njobs; j++) {

@@ -69,7 +69,7 @@ def _desc_to_dev(a, device):
     key = (str(device), a.dtype.str, a.tobytes())
     t = _desc_cache.get(key)
     if t is None:
-        if len(_desc_cache) >= 4096:
+        if len(_desc_cache) >= 512:
             _desc_cache.clear()
         t = _desc_cache[key] = _to_dev(a, device)
     return t
