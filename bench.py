@@ -331,7 +331,7 @@ def run_b200(args, rank, world, local_rank):
     names = ["iv_index_build", "k_count_lean", "alloc", "k_emit"]
     dom = 1 if ph_ms[1] >= ph_ms[3] else 3
     ach = alg[names[dom]] / (ph_ms[dom] / 1e3) / 1e9
-    pipe = 16 * nq + 16 * ns + 16 * p  # what a join must move at least: both tables in, the pairs out
+    pipe = 24 * nq + 24 * ns + 16 * p  # the join's algorithmic bytes (both tables incl. labels in, pairs out)
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[names[dom]], "hit_queries": hits,
