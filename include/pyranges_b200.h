@@ -13,6 +13,7 @@
  *                                NCLS.all_overlaps_self                  pyranges/methods/intersection.py:74
  *                                NCLS.all_containments_both              pyranges/methods/join.py:17, intersection.py:76
  *                                NCLS.first_overlap_both                 pyranges/methods/join.py:19 (via nearest.py:32)
+ *                                NCLS.last_overlap_both                  pyranges/methods/join.py:21, intersection.py:28
  *   iv_coverage_bp            <- NCLS.coverage                           pyranges/methods/coverage.py:64-68
  *   iv_subtract_count/_emit   <- NCLS.set_difference_helper              pyranges/methods/subtraction.py:63-65
  *   iv_nearest                <- first_overlap_both + nearest_previous_nonoverlapping +
@@ -68,6 +69,7 @@ extern "C" {
 #define IV_MODE_ALL 0     /* every overlapping (query, subject) pair            all_overlaps_both      */
 #define IV_MODE_ANY 1     /* one entry per query with >= 1 hit                   has_overlaps / first   */
 #define IV_MODE_CONTAIN 2 /* pairs with subject.start <= q.start && q.end <= subject.end             */
+#define IV_MODE_LAST 3    /* like ANY, the subject is the LAST hit of the nested-list traversal   last_overlap_both */
 
 /* nearest direction per query segment (pyranges/methods/nearest.py:85-90) */
 #define IV_NEAREST_BOTH 0
@@ -191,7 +193,8 @@ int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mo
  * from iv_count_overlaps, or a guess when the emit is launched speculatively before the total is known (entries
  * beyond the capacity are dropped, never written; the caller compares the total and repeats the call if needed).
  * In mode ANY out_s receives the FIRST hit: smallest start, then largest end, then smallest row (the head of the
- * nested-containment-list traversal). */
+ * nested-containment-list traversal); in mode LAST the last one: largest start, then smallest end, then largest
+ * row. */
 int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int32_t mode, const int64_t* counts,
                   const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label, int64_t out_capacity,
                   void* stream);

@@ -333,6 +333,8 @@ def main():
             run_case("join_left_po_%s" % tag, "join", {"how": "left", "preserve_order": True}, s, o)
             run_case("join_slack_%s" % tag, "join", {"slack": 5, "report_overlap": True}, s, o)
             run_case("join_contain_%s" % tag, "join", {"how": "containment"}, s, o)
+            run_case("join_first_%s" % tag, "join", {"how": "first"}, s, o)
+            run_case("join_last_%s" % tag, "join", {"how": "last"}, s, o)
             run_case("overlap_all_%s" % tag, "overlap", {"how": None}, s, o)
             run_case("overlap_contain_%s" % tag, "overlap", {"how": "containment"}, s, o)
             run_case("overlap_invert_%s" % tag, "overlap", {"invert": True}, s, o)
@@ -347,6 +349,7 @@ def main():
             run_case("subtract_%s_%s" % (tag, sn), "subtract", {"strandedness": st}, s, o)
         if tag in ("f1f2", "synth", "synth_uu", "pile"):
             run_case("intersect_first_%s" % tag, "intersect", {"how": "first"}, s, o)
+            run_case("intersect_last_%s" % tag, "intersect", {"how": "last"}, s, o)
             run_case("intersect_contain_%s" % tag, "intersect", {"how": "containment"}, s, o)
             run_case("intersect_invert_%s" % tag, "intersect", {"invert": True}, s, o)
             run_case("set_intersect_contain_%s" % tag, "set_intersect", {"how": "containment"}, s, o)

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpyranges_b200.so")
 
 IV_OK = 0
-IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN = 0, 1, 2
+IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
 IV_ABI_VERSION = 5

@@ -268,6 +268,57 @@ __device__ __forceinline__ uint32_t first_hit_rec(const iv_index_t& ix, X sc, X 
     return __ldg(ix.row_s + best);
 }
 
+// The LAST hit of the same traversal order: largest start, then smallest end, then largest row -- the mirror image:
+// starts inside the query come last, then the bin's earlier starts, then the stabbing list.
+template <typename X>
+__device__ __forceinline__ uint32_t last_hit_rec(const iv_index_t& ix, X sc, X ec, const Rec& r) {
+    const uint64_t b = sc >> ix.shift;
+    const uint32_t rel = rel_of(ix, sc);
+    const uint32_t pS = rec_rank_s(ix, r, b, rel);
+    const uint32_t pE = (ec >> ix.shift) == b ? rec_rank_s(ix, r, b, rel_of(ix, ec)) : rank_s_lt<X>(ix, ec);
+    uint32_t hi = 0xffffffffu, lo = 0;  // the winner is position hi; candidates of its class reach down to lo
+    if (pE > pS) {  // class A: every position is a hit
+        hi = pE - 1;
+        lo = pS;
+    } else {
+        uint32_t pL = r.w[0];
+        if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
+            pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
+        for (uint32_t p = pS; p > pL; p--)  // class B, started in this bin: the latest start still open
+            if (__ldg(ix.seoff + p - 1) > rel) { hi = p - 1; lo = pL; break; }
+        if (hi == 0xffffffffu) {  // class B, open at the bin origin: the latest start of the stabbing list
+            const uint32_t nc = (r.w[3] >> 16) & 0xffu;
+            const uint32_t c0 = r.w[2], c1 = nc < 255 ? c0 + nc : __ldg(&ix.bins[b + 1].co);
+            uint32_t best = 0;
+            bool any = false;
+            for (uint32_t j = c0; j < c1; j++) {
+                const uint2 en = __ldg(reinterpret_cast<const uint2*>(ix.cross) + j);
+                if (en.y > rel) {
+                    const uint32_t p = __ldg(ix.cross_p + j);
+                    best = (!any || p > best) ? p : best;
+                    any = true;
+                }
+            }
+            hi = best;
+            lo = 0;
+        }
+    }
+    // ties: the run of starts equal to key_s[hi] reaching down from hi; every member that is a hit competes on
+    // (smallest end, largest position)
+    uint32_t best = hi;
+    if (hi > lo) {
+        const uint64_t s0 = __ldg(ix.key_s + hi);
+        if (__ldg(ix.key_s + hi - 1) == s0) {
+            uint64_t be = __ldg(ix.end_s + hi);
+            for (uint32_t p = hi; p > lo && __ldg(ix.key_s + p - 1) == s0; p--) {
+                const uint64_t e = __ldg(ix.end_s + p - 1);
+                if (e > (uint64_t)sc && e < be) { be = e; best = p - 1; }
+            }
+        }
+    }
+    return __ldg(ix.row_s + best);
+}
+
 __device__ __forceinline__ void load_items(const int64_t* __restrict__ p, int64_t i0, int64_t n, bool vec, int64_t (&v)[OV_ITEMS]) {
     if (vec && i0 + OV_ITEMS <= n) {
         const longlong2* p2 = reinterpret_cast<const longlong2*>(p + i0);
@@ -330,7 +381,7 @@ k_count(iv_index_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count
             const int j = h + k;
             const int64_t ca = count_rec<X>(ix, sc[k], ec[k], r[k], ec[k] >> ix.shift);
             if (MODE == IV_MODE_ALL) c[j] = ca;
-            else if (MODE == IV_MODE_ANY) c[j] = ca > 0 ? 1 : 0;
+            else if (MODE == IV_MODE_ANY || MODE == IV_MODE_LAST) c[j] = ca > 0 ? 1 : 0;
             else {
                 // containment: subject.start <= q.start && q.end <= subject.end (raw coordinates)
                 int64_t cnt = 0;
@@ -679,10 +730,10 @@ k_emit(iv_index_t ix, iv_queries_t q, const HitEntry<X>* __restrict__ list, cons
                 for (int u = 0; u < 4; u++)
                     if (en[u].y > rel) put(en[u].x);
             }
-        } else if (MODE == IV_MODE_ANY) {
+        } else if (MODE == IV_MODE_ANY || MODE == IV_MODE_LAST) {
             if (out_q) out_q[o] = ql;
             if (out_s) {
-                const int64_t srow = first_hit_rec<X>(ix, sc, ec, r);
+                const int64_t srow = MODE == IV_MODE_ANY ? first_hit_rec<X>(ix, sc, ec, r) : last_hit_rec<X>(ix, sc, ec, r);
                 out_s[o] = s_label ? __ldg(s_label + srow) : srow;
             }
         } else {
@@ -874,6 +925,7 @@ static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, 
     HitEntry<X>* list = ws ? (HitEntry<X>*)w.list : nullptr;
     int64_t first = 0;
     const int64_t nblk = cdiv(q.n, LN_TILES * OV_TILE);
+    if (mode == IV_MODE_LAST) mode = IV_MODE_ANY;  // one entry per query with hits: the count pass is the same
     if (mode != IV_MODE_CONTAIN && vec && nblk >= 16 && q.slack == 0) {
         // large aligned inputs without slack go through the lean kernel (ragged last block included)
         unsigned long long* gs = reinterpret_cast<unsigned long long*>(gran_sums);
@@ -910,6 +962,8 @@ static void launch_emit(const iv_index_t& ix, const iv_queries_t& q, int mode, c
         k_emit<X, IV_MODE_ALL><<<nb, EM_THREADS, 0, st>>>(ix, q, list, w.gran_hits, w.gran_sums, w.tile_sums, out_q, out_s, s_label, cap);
     else if (mode == IV_MODE_ANY)
         k_emit<X, IV_MODE_ANY><<<nb, EM_THREADS, 0, st>>>(ix, q, list, w.gran_hits, w.gran_sums, w.tile_sums, out_q, out_s, s_label, cap);
+    else if (mode == IV_MODE_LAST)
+        k_emit<X, IV_MODE_LAST><<<nb, EM_THREADS, 0, st>>>(ix, q, list, w.gran_hits, w.gran_sums, w.tile_sums, out_q, out_s, s_label, cap);
     else
         k_emit<X, IV_MODE_CONTAIN><<<nb, EM_THREADS, 0, st>>>(ix, q, list, w.gran_hits, w.gran_sums, w.tile_sums, out_q, out_s, s_label, cap);
 }
@@ -928,7 +982,7 @@ extern "C" int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q,
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_query(index, q, "iv_count_overlaps");
     if (rc != IV_OK) return rc;
-    IV_REQUIRE(mode >= IV_MODE_ALL && mode <= IV_MODE_CONTAIN, IV_ERR_INVALID, "iv_count_overlaps: mode");
+    IV_REQUIRE(mode >= IV_MODE_ALL && mode <= IV_MODE_LAST, IV_ERR_INVALID, "iv_count_overlaps: mode");
     const bool nar = narrow(index);
     const size_t need = plan_overlap_ws(nullptr, q->n, nar ? sizeof(HitEntry<uint32_t>) : sizeof(HitEntry<uint64_t>)).bytes;
     IV_REQUIRE(!ws || ws_bytes >= need, IV_ERR_WORKSPACE, "iv_count_overlaps: workspace %zu < %zu", ws_bytes, need);
@@ -958,7 +1012,7 @@ extern "C" int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int
     (void)counts;  // the hit lists in the workspace carry the counts
     int rc = check_query(index, q, "iv_emit_pairs");
     if (rc != IV_OK) return rc;
-    IV_REQUIRE(mode >= IV_MODE_ALL && mode <= IV_MODE_CONTAIN, IV_ERR_INVALID, "iv_emit_pairs: mode");
+    IV_REQUIRE(mode >= IV_MODE_ALL && mode <= IV_MODE_LAST, IV_ERR_INVALID, "iv_emit_pairs: mode");
     if (q->n == 0) return IV_OK;
     IV_REQUIRE(ws, IV_ERR_INVALID, "iv_emit_pairs: ws is null");
     IV_REQUIRE(out_capacity >= 0, IV_ERR_INVALID, "iv_emit_pairs: negative out_capacity");

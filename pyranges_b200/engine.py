@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _cabi as cabi
-from ._cabi import (IV_INDEX_ENDS_PERM, IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_NEAREST_BOTH,  # noqa: F401
+from ._cabi import (IV_INDEX_ENDS_PERM, IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST, IV_NEAREST_BOTH,  # noqa: F401
                     IV_NEAREST_NEXT, IV_NEAREST_PREVIOUS, IvGroups, IvIndex, IvQueries)
 
 I64_MAX = np.iinfo(np.int64).max

@@ -301,9 +301,7 @@ def _b_write_both(plan, kwargs):
     """join: pyranges/methods/join.py:125-154 for all keys."""
     how = kwargs.get("how")
     assert (how in "containment first last outer right left".split() + [False, None]) or isinstance(how, int)
-    if how == "last":
-        raise NotImplementedError("join(how='last') is not part of the B200 hot path")
-    mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
+    mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY, "last": E.IV_MODE_LAST}.get(how, E.IV_MODE_ALL)
     ix = plan.index()
     inner = how not in ["outer", "left", "right"]
     counts, out_q, out_s = ix.pairs(plan.queries(), mode, want_counts=not inner)  # counts: rows without partner
@@ -394,9 +392,7 @@ def _b_intersection(plan, kwargs):
     overlapping pair, clipped to the overlap."""
     how = kwargs["how"]
     assert how in "containment first last".split() + [False, None]
-    if how == "last":
-        raise NotImplementedError("intersect(how='last') is not part of the B200 hot path")
-    mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY}.get(how, E.IV_MODE_ALL)
+    mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY, "last": E.IV_MODE_LAST}.get(how, E.IV_MODE_ALL)
     _, out_q, out_s = plan.index().pairs(plan.queries(), mode, want_counts=False)
     # the clip max(Start, Start_b) / min(End, End_b) happens where the columns live (engine.materialize_pairs)
     core = E.materialize_pairs(plan.q.iv, plan.s.iv, out_q, out_s, clip=True, want=("q_start", "q_end"))

@@ -9,7 +9,7 @@ import torch
 
 from oracle import oracle as orc
 
-IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN = 0, 1, 2
+IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 
 
@@ -56,7 +56,7 @@ class SubjectIndex:
         for k, a, b, sa, sb, s, e, t in self._per_key(q):
             ids = np.arange(a, b, dtype=np.int64)
             fn = {IV_MODE_ALL: t.all_overlaps_both, IV_MODE_CONTAIN: t.all_containments_both,
-                  IV_MODE_ANY: t.first_overlap_both}[mode]
+                  IV_MODE_ANY: t.first_overlap_both, IV_MODE_LAST: t.last_overlap_both}[mode]
             x, y = fn(s, e, ids)
             o = np.argsort(x, kind="stable")
             A.append(x[o])

@@ -124,6 +124,10 @@ def test_pairs(eng, case):
     _, a, b = ix.pairs(q, eng.IV_MODE_ANY)
     wa, wb = oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "first")
     assert np.array_equal(a.cpu().numpy(), wa) and np.array_equal(b.cpu().numpy(), wb)
+    # last_overlap_both: the tail of the same traversal (largest start, smallest end, largest row)
+    _, a, b = ix.pairs(q, eng.IV_MODE_LAST)
+    wa, wb = oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "last")
+    assert np.array_equal(a.cpu().numpy(), wa) and np.array_equal(b.cpu().numpy(), wb)
 
 
 def test_pairs_labels(eng):

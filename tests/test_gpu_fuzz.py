@@ -58,9 +58,10 @@ def test_fuzz_binary_ops(seed):
         wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, name, slack))
         ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
         assert np.array_equal(ga, wa) and np.array_equal(gb, wb), (seed, name)
-    _, a, b = ix.pairs(q, E.IV_MODE_ANY)
-    wa, wb = oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "first", slack)
-    assert np.array_equal(a.cpu().numpy(), wa) and np.array_equal(b.cpu().numpy(), wb), seed
+    for mode, name in [(E.IV_MODE_ANY, "first"), (E.IV_MODE_LAST, "last")]:
+        _, a, b = ix.pairs(q, mode)
+        wa, wb = oracle_pairs(qs, qe, qoff, sg, ss, se, soff, name, slack)
+        assert np.array_equal(a.cpu().numpy(), wa) and np.array_equal(b.cpu().numpy(), wb), (seed, name)
     if slack == 0:
         bp, _ = ix.coverage_bp(q)
         want = np.zeros(len(qs), np.int64)

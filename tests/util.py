@@ -59,6 +59,8 @@ def oracle_pairs(qs, qe, q_off, seg_group, ss, se, s_off, mode="all", slack=0):
             x, y = t.all_overlaps_both(s, e, ids)
         elif mode == "contain":
             x, y = t.all_containments_both(s, e, ids)
+        elif mode == "last":
+            x, y = t.last_overlap_both(s, e, ids)
         else:
             x, y = t.first_overlap_both(s, e, ids)
         A.append(x)
