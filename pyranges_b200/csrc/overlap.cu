@@ -3,7 +3,8 @@
 // Replaces (reference call sites; the native code itself lives in the un-vendored ncls /
 // sorted_nearest packages):
 //   NCLS.all_overlaps_both / all_overlaps_self / has_overlaps / all_containments_both /
-//   first_overlap_both          pyranges/methods/join.py:15-23, intersection.py:73-78, coverage.py:26
+//   first_overlap_both / last_overlap_both   pyranges/methods/join.py:15-23, intersection.py:73-78, coverage.py:26
+//   NCLS.set_difference_helper  pyranges/methods/subtraction.py:63-65
 //   NCLS.coverage               pyranges/methods/coverage.py:64
 //   nearest_previous/next/_nonoverlapping   pyranges/methods/nearest.py:59,69,113
 //
@@ -13,8 +14,9 @@
 // hits    = class A: s' <= S' < e'  (contiguous in start order, all of them overlap)
 //         + class B: S' < s' < E'   (stabbing set) = members of the bin's stabbing list that end after s'
 //                                    + earlier starts of the same bin that end after s'
-// emit    = count -> per-tile sums -> exclusive scan of tile sums -> emit kernel re-scans the counts of
-//           its tile in shared memory (no global offsets array).
+// emit    = the count pass leaves, per 64-row granule, the list of its queries WITH hits (row, count, flattened
+//           interval) and the granule's pair sum; tile sums -> exclusive scan -> the emit pass walks the dense
+//           lists, one warp per quarter tile, and never reads the query columns or the counts again.
 //
 // Kernels are instantiated for 32-bit flattened coordinates (total span < 2^32: any single genome) and for
 // 64-bit ones; the 32-bit instantiation halves the integer work per query.
