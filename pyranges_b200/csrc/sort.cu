@@ -65,6 +65,25 @@ k_rs_prefix(uint32_t* __restrict__ hist, int64_t ntiles, uint32_t* __restrict__ 
     }
     if (lane == 0) totals[row] = run;
 }
+// Long rows (large inputs: tens of thousands of tiles): one BLOCK per row, every thread scans a contiguous piece --
+// 256 x 8 resident warps instead of 256 warps walking 32 entries at a time.
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_prefix_long(uint32_t* __restrict__ hist, int64_t ntiles, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t wsum[RS_WARPS + 1];
+    uint32_t* h = hist + (int64_t)blockIdx.x * ntiles;
+    const int64_t per = (ntiles + RS_THREADS - 1) / RS_THREADS;
+    const int64_t a = (int64_t)threadIdx.x * per, b = a + per < ntiles ? a + per : ntiles;
+    uint32_t sum = 0;
+    for (int64_t t = a; t < b; t++) sum += h[t];
+    uint32_t tot;
+    uint32_t run = block_excl_sum<uint32_t, RS_THREADS>(sum, wsum, tot);
+    for (int64_t t = a; t < b; t++) {
+        const uint32_t v = h[t];
+        h[t] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = tot;
+}
 
 template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS > 4 ? 4 : 1)  // 16 keys per thread would take 112 registers: cap at 64 for 4 blocks/SM
@@ -541,7 +560,8 @@ static int radix_sort_multi_t(const SortJob* jobs, int njobs, int64_t n, int beg
         dim3 grid((unsigned)ntiles, (unsigned)njobs);
         k_rs_hist<ITEMS><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, ntiles);
         IV_LAUNCH_CHECK();
-        k_rs_prefix<<<(unsigned)cdiv(nrows, RS_WARPS), RS_THREADS, 0, stream>>>(hist, ntiles, totals, nrows);
+        if (ntiles >= 2048) k_rs_prefix_long<<<(unsigned)nrows, RS_THREADS, 0, stream>>>(hist, ntiles, totals);
+        else k_rs_prefix<<<(unsigned)cdiv(nrows, RS_WARPS), RS_THREADS, 0, stream>>>(hist, ntiles, totals, nrows);
         IV_LAUNCH_CHECK();
         k_rs_scatter<ITEMS><<<grid, RS_THREADS, 0, stream>>>(J, n, shift, mask, hist, totals, ntiles);
         IV_LAUNCH_CHECK();
