@@ -91,3 +91,44 @@ def test_cluster_merge_rle_properties_full_size(c2):
         a, b = reads.seg_off[k], reads.seg_off[k + 1]
         assert float((runs[sl].double() * vals[sl]).sum().item()) == float((reads.ends[a:b] - reads.starts[a:b]).sum())
         assert bool((vals[sl][1:] != vals[sl][:-1]).all())  # equal neighbours are coalesced
+
+
+def test_c3_count_overlap_join_100m_x_1m():
+    """BASELINE.json config 3 / the north-star size: 100 M reads x 1 M annotations.  count_overlaps against the oracle
+    on sampled keys, overlap (ANY) = counts > 0, and the join's pair list: total = sum of counts, query order, every
+    pair a true overlap of the right chromosome, no duplicates, per-query multiplicity = counts."""
+    import torch
+
+    from oracle import oracle as orc
+    from pyranges_b200 import engine as E
+    from pyranges_b200 import synthetic as S
+
+    reads, annot = S.reads(100_000_000, seed=1), S.annotations(1_000_000, seed=2)
+    sg = (np.arange(reads.n_keys) // 2).astype(np.int32)
+    q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off)
+    s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off)
+    ix = E.SubjectIndex(s_iv, annot.chrom_ranges())
+    q = E.Queries(q_iv, sg)
+    counts, a, b = ix.pairs(q, E.IV_MODE_ALL)
+    p = a.numel()
+    assert int(counts.sum().item()) == p and p > 100_000_000
+    assert bool((a[1:] >= a[:-1]).all())
+    assert bool(((s_iv.start[b] < q_iv.end[a]) & (q_iv.start[a] < s_iv.end[b])).all())
+    grp_off = torch.from_numpy(annot.seg_off[::2].copy()).cuda()
+    key_of_q = torch.searchsorted(q_iv.seg_off_dev, a, right=True) - 1
+    assert bool(((torch.searchsorted(grp_off, b, right=True) - 1) == key_of_q // 2).all())
+    del key_of_q
+    assert bool((torch.bincount(a, minlength=reads.n) == counts).all())
+    # no pair twice: inside a query (pairs are grouped by query) the subject rows are distinct
+    o = torch.argsort(a * annot.n + b)
+    assert bool(((a[o][1:] != a[o][:-1]) | (b[o][1:] != b[o][:-1])).all())
+    del o, a, b
+    any_c, _, _ = ix.count(q, E.IV_MODE_ANY, for_emit=False)
+    assert bool((any_c == (counts > 0).long()).all())
+    hc = counts.cpu().numpy()
+    for k in (46, 47, 42):  # chrY +, chrY -, chr22 +
+        g = k // 2
+        sa, sb = annot.seg_off[2 * g], annot.seg_off[2 * g + 2]
+        t = orc.NCLS(annot.starts[sa:sb], annot.ends[sa:sb], np.arange(sa, sb))
+        sl = slice(reads.seg_off[k], reads.seg_off[k + 1])
+        assert np.array_equal(hc[sl], t.count(reads.starts[sl], reads.ends[sl])), k
