@@ -132,3 +132,49 @@ def test_c3_count_overlap_join_100m_x_1m():
         t = orc.NCLS(annot.starts[sa:sb], annot.ends[sa:sb], np.arange(sa, sb))
         sl = slice(reads.seg_off[k], reads.seg_off[k + 1])
         assert np.array_equal(hc[sl], t.count(reads.starts[sl], reads.ends[sl])), k
+
+
+def test_c4_nearest_cluster_merge_50m():
+    """BASELINE.json config 4: nearest (strandedness='same', how='upstream') of 50 M intervals against 1 M annotations
+    and cluster / merge of the 50 M intervals, unsorted and sorted input."""
+    import torch
+
+    from pyranges_b200 import engine as E
+    from pyranges_b200 import synthetic as S
+
+    iv, ann = S.reads(50_000_000, seed=3, min_len=50, max_len=500), S.annotations(1_000_000, seed=2)
+    q_iv = E.DeviceIntervals.from_numpy(iv.starts, iv.ends, iv.seg_off)
+    s_iv = E.DeviceIntervals.from_numpy(ann.starts, ann.ends, ann.seg_off)
+    sg = np.arange(iv.n_keys, dtype=np.int32)  # same strand: every key against its own key
+    modes = np.asarray([E.IV_NEAREST_PREVIOUS if k % 2 == 0 else E.IV_NEAREST_NEXT for k in range(iv.n_keys)], np.int32)
+    ix = E.SubjectIndex(s_iv, None, ends_perm=True)
+    q = E.Queries(q_iv, sg, seg_mode=modes)
+    row, dist = ix.nearest(q, overlap=True)
+    counts, _, _ = ix.count(E.Queries(q_iv, sg), E.IV_MODE_ALL, for_emit=False)
+    assert bool(((dist == 0) == (counts > 0)).all())
+    found = row >= 0
+    S_, E_ = s_iv.start[row.clamp(min=0)], s_iv.end[row.clamp(min=0)]
+    s, e = q_iv.start, q_iv.end
+    gap = torch.where(E_ <= s, s - E_ + 1, torch.where(S_ >= e, S_ - e + 1, torch.zeros_like(s)))
+    assert bool((gap[found] == dist[found]).all())
+    # direction: '+' keys look upstream = towards smaller coordinates, '-' keys towards larger ones
+    plus = (torch.searchsorted(q_iv.seg_off_dev, torch.arange(iv.n, device=row.device), right=True) - 1) % 2 == 0
+    far = found & (dist > 0)
+    assert bool((E_[far & plus] <= s[far & plus]).all()) and bool((S_[far & ~plus] >= e[far & ~plus]).all())
+    # the partner sits in the query's own key
+    key_q = torch.searchsorted(q_iv.seg_off_dev, torch.arange(iv.n, device=row.device), right=True) - 1
+    key_s = torch.searchsorted(s_iv.seg_off_dev, row.clamp(min=0), right=True) - 1
+    assert bool((key_q[found] == key_s[found]).all())
+    del S_, E_, gap, plus, far, key_q, key_s, row, dist, counts
+    # cluster / merge: unsorted input, then the same rows sorted (the sort is skipped: same result)
+    r1, c1, n1 = E.cluster(q_iv)
+    ms, me, mc, mg = E.merge(q_iv)
+    m = int(n1.item())
+    assert ms.numel() == m and int(mc.sum().item()) == iv.n
+    assert bool((c1[1:] >= c1[:-1]).all()) and int(c1[-1].item()) == m
+    o = np.lexsort([iv.ends, iv.starts, np.repeat(np.arange(iv.n_keys), np.diff(iv.seg_off))])
+    qs_iv = E.DeviceIntervals.from_numpy(iv.starts[o], iv.ends[o], iv.seg_off)
+    ms2, me2, mc2, mg2 = E.merge(qs_iv)
+    assert bool((ms2 == ms).all()) and bool((me2 == me).all()) and bool((mc2 == mc).all()) and bool((mg2 == mg).all())
+    r2, c2_, n2 = E.cluster(qs_iv)
+    assert int(n2.item()) == m and bool((c2_ == c1).all())
