@@ -254,27 +254,43 @@ static void scan_small(T* data, int64_t m, T* out_total, cudaStream_t stream) {
     else k_scan_small_t<T, 4><<<1, 1024, 0, stream>>>(data, m, out_total);
 }
 
+// Tile-local exclusive scan with coalesced accesses: warp w of the block owns values [w * 32 * SC_ITEMS, ...) of the
+// tile, lane l reads / writes elements j * 32 + l of that chunk; shuffle scans inside the chunk, one pass over the
+// warp totals.  `first` = exclusive prefix of the tile (its scanned partial).
+template <typename T>
+__device__ __forceinline__ void tile_scan_apply(T* __restrict__ data, int64_t n, T first, T* sm /* [SC_THREADS/32] */) {
+    constexpr int W = SC_THREADS / 32;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wbase = (int64_t)blockIdx.x * SC_TILE + (int64_t)w * (32 * SC_ITEMS);
+    T v[SC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        const int64_t i = wbase + j * 32 + lane;
+        v[j] = i < n ? data[i] : T(0);
+    }
+    T run = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        const T inc = warp_incl_sum(v[j]);
+        v[j] = run + inc - v[j];
+        run += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) sm[w] = run;
+    __syncthreads();
+    T x = lane < W ? sm[lane] : T(0);
+    const T xi = warp_incl_sum(x);
+    const T before = first + __shfl_sync(FULL, xi - x, w);
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        const int64_t i = wbase + j * 32 + lane;
+        if (i < n) data[i] = before + v[j];
+    }
+}
+
 __global__ void __launch_bounds__(SC_THREADS)
 k_u32_apply(uint32_t* __restrict__ data, int64_t n, const uint32_t* __restrict__ partials) {
-    __shared__ uint32_t sm[SC_THREADS / 32 + 1];
-    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
-    uint32_t v[SC_ITEMS];
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < SC_ITEMS; j++) {
-        int64_t i = base + j;
-        v[j] = i < n ? data[i] : 0;
-        s += v[j];
-    }
-    uint32_t tot;
-    uint32_t ex = block_excl_sum<uint32_t, SC_THREADS>(s, sm, tot);
-    uint32_t run = __ldg(partials + blockIdx.x) + ex;
-#pragma unroll
-    for (int j = 0; j < SC_ITEMS; j++) {
-        int64_t i = base + j;
-        if (i < n) data[i] = run;
-        run += v[j];
-    }
+    __shared__ uint32_t sm[SC_THREADS / 32];
+    tile_scan_apply<uint32_t>(data, n, __ldg(partials + blockIdx.x), sm);
 }
 
 size_t scan_u32_large_temp_elems(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, SC_TILE) + 1; }
@@ -318,25 +334,8 @@ k_i64_tile_sums(const int64_t* __restrict__ in, int64_t n, int64_t* __restrict__
 }
 __global__ void __launch_bounds__(SC_THREADS)
 k_i64_apply(int64_t* __restrict__ data, int64_t n, const int64_t* __restrict__ partials) {
-    __shared__ int64_t sm[SC_THREADS / 32 + 1];
-    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
-    int64_t v[SC_ITEMS];
-    int64_t s = 0;
-#pragma unroll
-    for (int j = 0; j < SC_ITEMS; j++) {
-        int64_t i = base + j;
-        v[j] = i < n ? data[i] : 0;
-        s += v[j];
-    }
-    int64_t tot;
-    int64_t ex = block_excl_sum<int64_t, SC_THREADS>(s, sm, tot);
-    int64_t run = __ldg(partials + blockIdx.x) + ex;
-#pragma unroll
-    for (int j = 0; j < SC_ITEMS; j++) {
-        int64_t i = base + j;
-        if (i < n) data[i] = run;
-        run += v[j];
-    }
+    __shared__ int64_t sm[SC_THREADS / 32];
+    tile_scan_apply<int64_t>(data, n, __ldg(partials + blockIdx.x), sm);
 }
 size_t scan_i64_large_temp_elems(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, SC_TILE) + 2; }
 int scan_exclusive_i64_large(int64_t* data, int64_t n, int64_t* partials, int64_t* out_total, cudaStream_t stream) {

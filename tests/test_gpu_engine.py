@@ -385,15 +385,19 @@ def test_coverage_rle_weighted(eng, seed, n_seg, n, maxpos, maxlen, integer_weig
             assert np.allclose(expand(runs[sl], vals[sl]), expand(wr, wv), rtol=1e-9, atol=1e-9), k
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
 def test_subtract(eng, seed):
-    """iv_subtract_count/_emit vs the oracle's set_difference_helper on merged (disjoint) subjects."""
+    """iv_subtract_count/_emit vs the oracle's set_difference_helper on merged (disjoint) subjects; seeds 5 and 6 are
+    large enough for the lean count kernel (most rows untouched / most rows cut)."""
     from oracle import oracle as orc
 
     rng = np.random.default_rng(seed)
     maxpos = int(rng.choice([500, 100_000, 8_000_000_000]))
-    qs, qe, qoff = gen_segments(seed, 4, 2000, min(maxpos, 10**9), 300)
-    ss, se, soff = gen_segments(seed + 9, 3, 800, min(maxpos, 10**9), 300)
+    nq, ns = (2000, 800) if seed < 5 else (90_000, 3000 if seed == 5 else 60_000)
+    if seed >= 5:
+        maxpos = 30_000_000
+    qs, qe, qoff = gen_segments(seed, 4, nq, min(maxpos, 10**9), 300)
+    ss, se, soff = gen_segments(seed + 9, 3, ns, min(maxpos, 10**9), 300)
     if maxpos > 2**32:
         qs, qe, ss, se = qs * 9, qe * 9, ss * 9, se * 9
     # merge the subjects per key on the device first (PyRanges.subtract does the same)
