@@ -449,7 +449,7 @@ __device__ __forceinline__ bool rec_fast(const Rec& r) {
     return (r.w[3] & (IV_BIN_INLINE << 24)) && (r.w[3] & 0xffu) <= 4 && ((r.w[3] >> 8) & 0xffu) <= 4;
 }
 
-template <typename X, int MODE>
+template <typename X, int MODE, bool SLACK>
 __global__ void __launch_bounds__(LN_THREADS, 6)
 k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, unsigned long long* __restrict__ gran_sums,
              uint32_t* __restrict__ gran_hits, HitEntry<X>* __restrict__ list) {
@@ -523,6 +523,7 @@ k_count_lean(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ out_count, uns
         Rec r[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
+            if (SLACK) apply_slack(q.slack, s[k], e[k]);  // join(slack=k): its own instantiation
             if (uniform && geo32 && (((uint64_t)s[k] | (uint64_t)e[k]) >> 32) == 0) {
                 // x' = clamp(x, lo, hi) + (base - lo), all in 32 bits
                 sc[k] = (X)(min(max((uint32_t)s[k], lo32), hi32) + off32);
@@ -928,13 +929,18 @@ static void launch_count(const iv_index_t& ix, const iv_queries_t& q, int mode, 
     int64_t first = 0;
     const int64_t nblk = cdiv(q.n, LN_TILES * OV_TILE);
     if (mode == IV_MODE_LAST) mode = IV_MODE_ANY;  // one entry per query with hits: the count pass is the same
-    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16 && q.slack == 0) {
-        // large aligned inputs without slack go through the lean kernel (ragged last block included)
+    if (mode != IV_MODE_CONTAIN && vec && nblk >= 16) {
+        // large aligned inputs go through the lean kernel (ragged last block included)
         unsigned long long* gs = reinterpret_cast<unsigned long long*>(gran_sums);
-        if (mode == IV_MODE_ALL)
-            k_count_lean<X, IV_MODE_ALL><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
+        const unsigned nbk = (unsigned)nblk;
+        if (mode == IV_MODE_ALL && q.slack == 0)
+            k_count_lean<X, IV_MODE_ALL, false><<<nbk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
+        else if (mode == IV_MODE_ALL)
+            k_count_lean<X, IV_MODE_ALL, true><<<nbk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
+        else if (q.slack == 0)
+            k_count_lean<X, IV_MODE_ANY, false><<<nbk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
         else
-            k_count_lean<X, IV_MODE_ANY><<<(unsigned)nblk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
+            k_count_lean<X, IV_MODE_ANY, true><<<nbk, LN_THREADS, 0, st>>>(ix, q, out_count, gs, gran_hits, list);
         __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
         first = nblk * LN_TILES;
     }

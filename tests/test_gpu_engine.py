@@ -305,6 +305,14 @@ def test_large_staged_paths(eng):
         assert (cnt is not None) == want_counts
         ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
         assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
+    # join(slack=k) on the lean kernel's slack instantiation
+    qk = eng.Queries(_dev(eng, qs, qe, qoff), sg, slack=25)
+    c, _, _ = ix.count(qk, eng.IV_MODE_ALL)
+    assert np.array_equal(c.cpu().numpy(), oracle_counts(qs, qe, qoff, sg, ss, se, soff, "all", 25))
+    _, a, b = ix.pairs(qk, eng.IV_MODE_ALL, want_counts=False)
+    wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "all", 25))
+    ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
+    assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
     # the same rows far beyond 32 bits (64-bit instantiation of the lean kernel, 32-byte list entries)
     big = 5_000_000_000_000
     q64 = eng.Queries(_dev(eng, qs + big, qe + big, qoff), sg)
