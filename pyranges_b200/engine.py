@@ -57,6 +57,7 @@ def _to_dev(a, device):
 
 
 _desc_cache = {}
+_groups_cache = {}
 
 
 def _desc_to_dev(a, device):
@@ -103,7 +104,19 @@ class DeviceIntervals:
         key = (None if seg_ranges is None else tuple(map(tuple, seg_ranges)), int(gap), bool(zero_lo))
         g = self._groups.get(key)
         if g is None:
-            g = self._groups[key] = Groups(self, seg_ranges, gap=gap, zero_lo=zero_lo)
+            # the descriptor only depends on the segment table and its bounds, not on the rows: the same chromosome
+            # table comes back with every new upload of the same frame (content-keyed, small)
+            ckey = None
+            if self.n_seg <= 4096:
+                ckey = (key, str(self.device), self.seg_off.tobytes()) + tuple(np.ascontiguousarray(b).tobytes() for b in self.bounds)
+                g = _groups_cache.get(ckey)
+            if g is None:
+                g = Groups(self, seg_ranges, gap=gap, zero_lo=zero_lo)
+                if ckey is not None:
+                    if len(_groups_cache) >= 128:
+                        _groups_cache.clear()
+                    _groups_cache[ckey] = g
+            self._groups[key] = g
         return g
 
     @property
