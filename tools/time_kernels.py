@@ -11,9 +11,14 @@ from pyranges_b200 import _cabi as cabi
 from pyranges_b200 import engine as E
 from pyranges_b200 import synthetic as S
 
-nr = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-na = int(sys.argv[2]) if len(sys.argv) > 2 else 200_000
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+nr = int(_pos[0]) if len(_pos) > 0 else 10_000_000
+na = int(_pos[1]) if len(_pos) > 1 else 200_000
 reads, annot = S.reads(nr), S.annotations(na)
+if "--sorted" in sys.argv:  # position-sorted reads inside every key (the natural order of an aligned BAM)
+    key = np.repeat(np.arange(reads.n_keys), np.diff(reads.seg_off))
+    o = np.lexsort([reads.starts, key])
+    reads.starts[:], reads.ends[:] = reads.starts[o], reads.ends[o]
 sg = (np.arange(reads.n_keys) // 2).astype(np.int32)
 q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off)
 s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off)
