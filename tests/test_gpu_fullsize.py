@@ -178,3 +178,28 @@ def test_c4_nearest_cluster_merge_50m():
     assert bool((ms2 == ms).all()) and bool((me2 == me).all()) and bool((mc2 == mc).all()) and bool((mg2 == mg).all())
     r2, c2_, n2 = E.cluster(qs_iv)
     assert int(n2.item()) == m and bool((c2_ == c1).all())
+
+
+@pytest.mark.parametrize("n,bits,vdtype", [(10_000_000, 40, "int32"), (20_000_000, 33, None), (9_000_000, 64, "int64")])
+def test_radix_sort_large_vs_torch(n, bits, vdtype):
+    """large-input path of the radix sort (4096-key tiles, block-per-row histogram prefix) against torch's stable sort"""
+    import torch
+
+    from pyranges_b200 import engine as E
+
+    g = torch.Generator(device="cuda").manual_seed(n % 1000)
+    hi = 2 ** min(bits, 62)
+    k = torch.randint(0, hi, (n,), dtype=torch.int64, device="cuda", generator=g)
+    if bits == 64:
+        k = k | (torch.randint(0, 2, (n,), dtype=torch.int64, device="cuda", generator=g) << 63)  # top bit: unsigned order
+    m = k[3::7].numel()
+    k[::7][:m] = k[3::7]  # duplicates: stability matters
+    want_k, want_o = torch.sort(k if bits < 64 else (k ^ (1 << 63)), stable=True)
+    if bits == 64:
+        want_k = want_k ^ (1 << 63)
+    v = None if vdtype is None else torch.arange(n, dtype=getattr(torch, vdtype), device="cuda")
+    kk = k.clone()
+    E.radix_sort_u64(kk, v, 0, bits)
+    assert bool((kk == want_k).all())
+    if v is not None:
+        assert bool((v.long() == want_o).all())
