@@ -220,9 +220,9 @@ def run_b200(args, rank, world, local_rank):
     s_iv.bounds  # ingest-time metadata (per-key min Start / max End), like the chromosome table
     nq, ns = reads.n, annot.n
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    seg_off_dev = q_iv.seg_off_dev
 
     state = {}
+    side = torch.cuda.Stream(dev) if world > 1 else None  # carries the per-key count exchange of the multi-GPU step
 
     def join_step(timers=None):
         e = [ev() for _ in range(5)] if timers is not None else None
@@ -234,6 +234,15 @@ def run_b200(args, rank, world, local_rank):
             e[1].record()
         # join needs the pairs, not the per-row counts: the count pass only leaves its hit lists in ws
         _, ws, total = ix.count(q, E.IV_MODE_ALL, want_counts=False)
+        if world > 1:
+            # per-key pair counts -> every rank can derive the global output offsets (the only collective; keys are
+            # disjoint across ranks, so the sum over ranks is the gathered vector).  They are known right after the
+            # count pass: the all-reduce runs on a side stream while the emit pass writes the pairs.
+            per_key = ix.segment_pair_counts(q, ws, total)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dist.all_reduce(per_key)
+            per_key.record_stream(side)
         if e:
             e[2].record()
         # speculative emission (engine.SubjectIndex.pairs(capacity=...)): buffers sized from the previous step's
@@ -260,11 +269,7 @@ def run_b200(args, rank, world, local_rank):
                 out_q, out_s = out_q[:p], out_s[:p]
         state["cap"] = int(p * 1.02) + 4096
         if world > 1:
-            # per-key pair counts -> every rank can derive the global output offsets (the only collective;
-            # keys are disjoint across ranks, so the sum over ranks is the gathered vector)
-            key_first = torch.searchsorted(out_q, seg_off_dev)
-            per_key = key_first[1:] - key_first[:-1]
-            dist.all_reduce(per_key)
+            torch.cuda.current_stream().wait_stream(side)
         return p, out_q, out_s
 
     def count_step():

@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define IV_ABI_VERSION 5
+#define IV_ABI_VERSION 6
 
 #define IV_OK 0
 #define IV_ERR_INVALID (-1)   /* bad argument */
@@ -198,6 +198,12 @@ int iv_count_overlaps(const iv_index_t* index, const iv_queries_t* q, int32_t mo
 int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int32_t mode, const int64_t* counts,
                   const void* ws, int64_t* out_q, int64_t* out_s, const int64_t* s_label, int64_t out_capacity,
                   void* stream);
+/* out_seg_pairs[k] = number of entries the query rows of segment k emit, read off the workspace and the total that
+ * iv_count_overlaps (same index, queries, mode) left: the per-key result counts of pyrange_apply
+ * (pyranges/multithreaded.py:77-103) are known BEFORE the pairs exist, so a multi-GPU caller can exchange them
+ * (global offsets of the concatenated result) while iv_emit_pairs runs. */
+int iv_segment_pair_counts(const iv_index_t* index, const iv_queries_t* q, const void* ws, const int64_t* total,
+                           int64_t* out_seg_pairs, void* stream);
 /* out_bp[i] = sum over hits of min(e,E)-max(s,S); out_fraction[i] = out_bp / (end-start), NaN -> 0 */
 int iv_coverage_bp(const iv_index_t* index, const iv_queries_t* q, int64_t* out_bp, double* out_fraction,
                    void* stream);

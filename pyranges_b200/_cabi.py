@@ -13,7 +13,7 @@ IV_OK = 0
 IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
-IV_ABI_VERSION = 5
+IV_ABI_VERSION = 6
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
 
@@ -51,6 +51,7 @@ PROTOTYPES = {
     "iv_overlap_workspace_bytes": (_sz, [_i64]),
     "iv_count_overlaps": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _sz, _vp, _vp]),
     "iv_emit_pairs": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "iv_segment_pair_counts": (C.c_int, [_PI, _PQ, _vp, _vp, _vp, _vp]),
     "iv_coverage_bp": (C.c_int, [_PI, _PQ, _vp, _vp, _vp]),
     "iv_subtract_workspace_bytes": (_sz, [_i64]),
     "iv_subtract_count": (C.c_int, [_PI, _PQ, _vp, _vp, _sz, _vp, _vp]),

@@ -883,6 +883,43 @@ k_subtract(iv_index_t ix, iv_queries_t q, int64_t* __restrict__ pieces, const in
     if (!EMIT) pieces[i] = np;
 }
 
+// ---- pairs per query segment, straight from the count pass ----------------------------------------------------------
+// pairs of the rows before row r = tile offset + pair sums of the tile's granules before r's granule + counts of the
+// granule's hit-list entries whose row lies before r.  One warp per segment: out[k] = prefix(seg_off[k+1]) -
+// prefix(seg_off[k]).  Lets a multi-GPU caller start exchanging the per-key result counts while the emit pass runs.
+template <typename X>
+__device__ __forceinline__ int64_t pairs_before(const iv_queries_t& q, const HitEntry<X>* __restrict__ list,
+                                                const uint32_t* __restrict__ gran_hits,
+                                                const int64_t* __restrict__ gran_sums,
+                                                const int64_t* __restrict__ tile_off, const int64_t* __restrict__ total,
+                                                int64_t r) {
+    const int lane = lane_id();
+    if (r >= q.n) return __ldg(total);
+    const int64_t t = r / OV_TILE, g = r / OV_GRAN;
+    const int gin = (int)(g - t * OV_GPT);
+    const uint32_t trow = (uint32_t)(r - t * OV_TILE);
+    int64_t v = lane < gin ? __ldg(gran_sums + t * OV_GPT + lane) : 0;
+    const uint32_t nh = __ldg(gran_hits + g);
+    for (uint32_t k = lane; k < nh; k += 32) {
+        const Hit<X> h = get_entry<X>(list + g * OV_GRAN + k);
+        if (h.row < trow) v += h.cnt;
+    }
+    return warp_sum(v) + __ldg(tile_off + t);
+}
+template <typename X>
+__global__ void __launch_bounds__(256)
+k_seg_pairs(iv_queries_t q, const HitEntry<X>* __restrict__ list, const uint32_t* __restrict__ gran_hits,
+            const int64_t* __restrict__ gran_sums, const int64_t* __restrict__ tile_off,
+            const int64_t* __restrict__ total, int64_t* __restrict__ out) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= q.n_seg) return;
+    const int64_t a = __ldg(q.seg_off + k), b = __ldg(q.seg_off + k + 1);
+    int64_t v = 0;
+    if (b > a) v = pairs_before<X>(q, list, gran_hits, gran_sums, tile_off, total, b) -
+                   pairs_before<X>(q, list, gran_hits, gran_sums, tile_off, total, a);
+    if (lane_id() == 0) out[k] = v;
+}
+
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 static bool narrow(const iv_index_t* ix) { return ix->total_span < (int64_t)0xfffffff0ll; }
 
@@ -1026,6 +1063,31 @@ extern "C" int iv_emit_pairs(const iv_index_t* index, const iv_queries_t* q, int
     IV_REQUIRE(out_capacity >= 0, IV_ERR_INVALID, "iv_emit_pairs: negative out_capacity");
     if (narrow(index)) launch_emit<uint32_t>(*index, *q, mode, ws, out_q, out_s, s_label, out_capacity, st);
     else launch_emit<uint64_t>(*index, *q, mode, ws, out_q, out_s, s_label, out_capacity, st);
+    IV_LAUNCH_CHECK();
+    return IV_OK;
+}
+
+extern "C" int iv_segment_pair_counts(const iv_index_t* index, const iv_queries_t* q, const void* ws,
+                                      const int64_t* total, int64_t* out_seg_pairs, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_query(index, q, "iv_segment_pair_counts");
+    if (rc != IV_OK) return rc;
+    if (q->n_seg <= 0) return IV_OK;
+    IV_REQUIRE(out_seg_pairs, IV_ERR_INVALID, "iv_segment_pair_counts: null output");
+    if (q->n == 0) {
+        IV_CUDA(cudaMemsetAsync(out_seg_pairs, 0, (size_t)q->n_seg * 8, st));
+        return IV_OK;
+    }
+    IV_REQUIRE(ws && total, IV_ERR_INVALID, "iv_segment_pair_counts: ws / total is null");
+    const bool nar = narrow(index);
+    const OverlapWs w = plan_overlap_ws((void*)ws, q->n, nar ? sizeof(HitEntry<uint32_t>) : sizeof(HitEntry<uint64_t>));
+    const unsigned nb = (unsigned)cdiv(q->n_seg, 8);
+    if (nar)
+        k_seg_pairs<uint32_t><<<nb, 256, 0, st>>>(*q, (const HitEntry<uint32_t>*)w.list, w.gran_hits, w.gran_sums, w.tile_sums,
+                                                  total, out_seg_pairs);
+    else
+        k_seg_pairs<uint64_t><<<nb, 256, 0, st>>>(*q, (const HitEntry<uint64_t>*)w.list, w.gran_hits, w.gran_sums, w.tile_sums,
+                                                  total, out_seg_pairs);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

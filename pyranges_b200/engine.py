@@ -268,6 +268,14 @@ class SubjectIndex:
                    "iv_count_overlaps")
         return counts, ws, total
 
+    def segment_pair_counts(self, q, ws, total):
+        """Pairs per query segment (key), from what count(for_emit=True) left in `ws`: available before the emit, so
+        that the per-key result counts can be exchanged between GPUs while the pairs are written."""
+        out = torch.empty(max(q.iv.n_seg, 1), dtype=torch.int64, device=self.iv.device)
+        cabi.check(cabi.lib().iv_segment_pair_counts(C.byref(self.c), C.byref(q.c), _ptr(ws), _ptr(total), _ptr(out),
+                                                     _stream()), "iv_segment_pair_counts")
+        return out[:q.iv.n_seg]
+
     def pairs(self, q, mode=IV_MODE_ALL, want_q=True, want_s=True, s_label=None, capacity=None, want_counts=True):
         """All (query row | label, subject row | label) pairs in query order: count -> scan -> emit
         (NCLS.all_overlaps_both / all_containments_both / first_overlap_both, join.py:15-23).

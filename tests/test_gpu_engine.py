@@ -120,6 +120,10 @@ def test_pairs(eng, case):
         assert np.all(np.diff(a) >= 0), "pairs must come out in query order"
         ga, gb = canon_pairs(a, b)
         assert np.array_equal(ga, wa) and np.array_equal(gb, wb), name
+        # pairs per key, known right after the count pass (before any pair is written)
+        _, ws, total = ix.count(q, mode, want_counts=False)
+        per_key = ix.segment_pair_counts(q, ws, total).cpu().numpy()
+        assert np.array_equal(per_key, np.diff(np.searchsorted(a, qoff))), name
     # first_overlap_both: one pair per hit query, subject = head of the nested-list traversal
     _, a, b = ix.pairs(q, eng.IV_MODE_ANY)
     wa, wb = oracle_pairs(qs, qe, qoff, sg, ss, se, soff, "first")
@@ -305,6 +309,9 @@ def test_large_staged_paths(eng):
         assert (cnt is not None) == want_counts
         ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
         assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
+    _, ws, total = ix.count(q, eng.IV_MODE_ALL, want_counts=False)
+    per_key = ix.segment_pair_counts(q, ws, total).cpu().numpy()
+    assert np.array_equal(per_key, np.diff(np.searchsorted(np.sort(wa), qoff)))
     # join(slack=k) on the lean kernel's slack instantiation
     qk = eng.Queries(_dev(eng, qs, qe, qoff), sg, slack=25)
     c, _, _ = ix.count(qk, eng.IV_MODE_ALL)
