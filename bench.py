@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- join overlap pairs/s and count_overlaps queries/s on synthetic hg38-shaped intervals.
+"""bench.py -- join overlap pairs/s and count_overlaps queries/s on synthetic hg38-shaped intervals, 1/2/4/8 B200.
 
-Workload (BASELINE.json configs[1]): 10 M reads (100 bp) x 200 k gene/exon annotations, strandedness=None
-(reads are keyed by (chromosome, strand), every key is joined against both strands of its chromosome).
-One "step" = one full join pass: subject index build (the reference rebuilds its NCLS on every call,
-pyranges/methods/join.py:12) -> count -> scan -> emit of all (query row, subject row) int64 pairs.
+Headline workload (BASELINE.json configs[2], the one the metric's "1/2/4/8 B200" is quoted on): 100 M reads (100 bp) x
+1 M gene/exon annotations, strandedness=None (reads keyed by (chromosome, strand), every key joined against both strands
+of its chromosome).  `--workload c2` selects configs[1] (10 M x 200 k).  One "step" = one full join pass: subject index
+build (the reference rebuilds its NCLS on every call, pyranges/methods/join.py:12) -> all (query row, subject row)
+int64 pairs in query order.  Extra keys of the same JSON line: count_overlaps and overlap(how="first") on the same
+inputs, the C4 operations (nearest upstream/same, cluster, merge on 50 M intervals, unsorted and sorted) and C5 (to_rle
+of 200 M reads), each with its own roofline entry (SURVEY.md section 8(d) bytes).
 
   python bench.py [--gpus N --steps K --warmup W]             this repo's CUDA path
   python bench.py --impl reference [...]                       CPU restatement of ncls on the host cores
 
-N > 1 (torchrun): the read set grows with N (N x 10 M reads against the same 200 k annotations: reads and pairs
-per GPU stay fixed = weak scaling); chromosomes are assigned to ranks by a size-balanced (LPT) rule, every rank joins its own
-chromosomes with no data-path collective, and the ranks exchange only their per-key pair counts (one small NCCL
-all-reduce per step) from which every rank knows the global output offsets.
+N > 1 (torchrun): STRONG scaling of the fixed genome-wide set: chromosomes are assigned to ranks by a size-balanced
+(LPT) rule, every rank generates and processes exactly the rows a single-GPU run holds for its chromosomes, no
+data-path collective; the ranks exchange only per-key result counts (global offsets of the concatenated result /
+cluster-id offsets / run counts).  Order-invariant 64-bit checksums of the results are printed: they must agree
+between N = 1, 2, 4 and 8.
 """
 import argparse
 import json
@@ -27,6 +31,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOADS = {"c2": (10_000_000, 200_000), "c3": (100_000_000, 1_000_000)}
+C4_ROWS, C5_ROWS = 50_000_000, 200_000_000
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -34,12 +41,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000)
-    ap.add_argument("--annot", type=int, default=200_000)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="override the read count of the workload")
+    ap.add_argument("--annot", type=int, default=0, help="override the annotation count of the workload")
+    ap.add_argument("--ops", default="all", help="all | none | comma list of count,overlap,sorted,nearest,cluster,merge,rle,api")
+    ap.add_argument("--ops-scale", type=float, default=1.0, help="scale of the C4 / C5 row counts (tests)")
+    ap.add_argument("--ops-steps", type=int, default=5)
+    ap.add_argument("--path", default="auto", choices=["auto", "fused", "twopass"], help="join kernels (auto: fused)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    r, s = WORKLOADS[a.workload]
+    a.reads = a.reads or r
+    a.annot = a.annot or s
+    want = {"count", "overlap", "sorted", "nearest", "cluster", "merge", "rle", "api"}
+    a.ops = want if a.ops == "all" else (set() if a.ops == "none" else set(a.ops.split(",")))
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -87,23 +105,65 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full summary, if any."""
+def ncu_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` on `workload` from a committed `ncu --set full` capture of this command
+    (profiles/traffic.json: {"<workload>/<kernel>": {"bytes": ..., "source": "profiles/<file>"}}), else None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            e = json.load(f).get("%s/%s" % (workload, kernel))
+        return (e["bytes"], e["source"]) if e else (None, None)
     except Exception:
-        return None
+        return None, None
+
+
+def shard(world, rank):
+    from pyranges_b200 import synthetic as S
+
+    return None if world == 1 else S.shard_chromosomes(world, rank)
 
 
 def make_workload(args, rank, world=1):
     from pyranges_b200 import synthetic as S
 
-    chroms = None if world == 1 else S.shard_chromosomes(world, rank)
-    reads = S.reads(args.reads * world, seed=1, chroms=chroms)
-    annot = S.annotations(args.annot, seed=2, chroms=chroms)  # the genome annotation does not grow with N
+    chroms = shard(world, rank)
+    reads = S.reads_by_chrom(args.reads, seed=1, chroms=chroms)
+    annot = S.annotations_by_chrom(args.annot, seed=2, chroms=chroms)
     seg_group = (np.arange(reads.n_keys) // 2).astype(np.int32)  # strandedness=None: partner = whole chromosome
     return reads, annot, seg_group
+
+
+# ---- order-invariant checksums (identical for every sharding of the same genome-wide set) ------------------------
+_M1, _M2, _M3 = -7046029254386353131, -4417276706812531889, -4658895280553007687  # odd 64-bit constants, as int64
+
+
+def _mix(x):
+    x = x ^ (x >> 29)
+    x = x * _M3
+    return x ^ (x >> 32)
+
+
+def key_local(torch, rows, seg_off_dev, global_key_dev):
+    """row of the concatenated local layout -> (global key id << 32) | row inside its key"""
+    k = torch.searchsorted(seg_off_dev, rows, right=True) - 1
+    return (global_key_dev[k] << 32) | (rows - seg_off_dev[k])
+
+
+def checksum_pairs(torch, a, b, q_meta, s_meta, chunk=1 << 26):
+    tot = torch.zeros((), dtype=torch.int64, device=a.device)
+    for i in range(0, a.numel(), chunk):
+        qa = key_local(torch, a[i:i + chunk], *q_meta)
+        sb = key_local(torch, b[i:i + chunk], *s_meta)
+        tot += _mix(qa * _M1 + sb * _M2).sum()
+    return tot
+
+
+def checksum_rows(torch, values, meta, chunk=1 << 26):
+    """checksum of one int64 value per row (counts, flags, cluster ids ...)"""
+    tot = torch.zeros((), dtype=torch.int64, device=values.device)
+    for i in range(0, values.numel(), chunk):
+        rows = torch.arange(i, min(i + chunk, values.numel()), device=values.device)
+        tot += _mix(key_local(torch, rows, *meta) * _M1 + values[i:i + chunk] * _M2).sum()
+    return tot
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -160,8 +220,10 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     threads = min(cores, len(annot.chrom_ranges()))
     # calibrate the per-step sample so that the whole run stays within a few minutes
-    p, q, dt, _ = oracle_join(reads, annot, seg_group, frac=0.05, threads=threads)
-    frac = float(min(1.0, 0.05 * 6.0 / max(dt, 1e-3)))  # ~6 s per step at most
+    f0 = min(1.0, 500_000.0 / max(reads.n, 1))
+    p, q, dt, _ = oracle_join(reads, annot, seg_group, frac=f0, threads=threads)
+    budget = 120.0 / max(args.steps + args.warmup, 1)  # seconds per step
+    frac = float(min(1.0, f0 * min(budget, 6.0) / max(dt, 1e-3)))
     for _ in range(args.warmup):
         oracle_join(reads, annot, seg_group, frac=frac, threads=threads)
     t0 = time.perf_counter()
@@ -172,12 +234,12 @@ def run_reference(args, rank, world):
         queries += q
     dt = time.perf_counter() - t0
     val = pairs / dt
-    sample = "first %.1f%% of the rows of every read key (%d queries/step) x all %d annotations, %d threads over chromosomes" % (
-        100 * frac, queries // max(args.steps, 1), annot.n, threads)
+    sample = ("first %.2f%% of the rows of every read key (%d queries/step) x all %d annotations (NCLS rebuilt per step), "
+              "%d threads over chromosomes" % (100 * frac, queries // max(args.steps, 1), annot.n, threads))
     line = {
         "impl": "reference", "metric": "join overlap pairs/s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "count_overlaps_queries_per_s": queries / dt,
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
@@ -187,103 +249,53 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, n_gpus):
-    return {"workload": "synthetic hg38-shaped %d reads (100 bp) x %d gene/exon annotations: join (+ count_overlaps), "
-                        "strandedness=None, per GPU" % (args.reads, args.annot),
-            "reads_per_gpu": args.reads, "annotations_genome_wide": args.annot, "keys": 48,
-            "l2": "inputs (%.0f MB of int64 query columns) exceed the 126 MB L2; no flush" % (16 * args.reads / 1e6),
+    return {"workload": "%s: synthetic hg38-shaped %d reads (100 bp) x %d gene/exon annotations, join (+ count_overlaps, "
+                        "overlap), strandedness=None, genome-wide set fixed for every N" % (args.workload, args.reads, args.annot),
+            "reads": args.reads, "annotations": args.annot, "keys": 48,
+            "l2": "inputs (%.0f MB of int64 query columns over %d GPU(s)) exceed the 126 MB L2; no flush" % (
+                16 * args.reads / 1e6, n_gpus),
             "index_build": "inside the timed region",
-            "parallelism": "chromosomes sharded over %d GPU(s) by size (LPT); %d x %d reads genome-wide against the "
-                           "same %d annotations" % (n_gpus, n_gpus, args.reads, args.annot)}
+            "parallelism": "chromosomes sharded over %d GPU(s) by size (LPT), strong scaling" % n_gpus}
 
 
 # ---------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
-    import ctypes as C
-
     import torch
     import torch.distributed as dist
 
     from pyranges_b200 import _cabi as cabi
     from pyranges_b200 import engine as E
     from pyranges_b200 import hostapi
+    from pyranges_b200 import synthetic as S
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = cabi.lib()
-
-    reads, annot, seg_group = make_workload(args, rank, world)
-    groups = annot.chrom_ranges()
-    q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off, dev)
-    s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off, dev)
-    s_iv.bounds  # ingest-time metadata (per-key min Start / max End), like the chromosome table
-    nq, ns = reads.n, annot.n
+    peak, peak_src = measured_peak_gbs()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-
-    state = {}
-    side = torch.cuda.Stream(dev) if world > 1 else None  # carries the per-key count exchange of the multi-GPU step
-
-    def join_step(timers=None):
-        e = [ev() for _ in range(5)] if timers is not None else None
-        if e:
-            e[0].record()
-        ix = E.SubjectIndex(s_iv, groups)
-        q = E.Queries(q_iv, seg_group)
-        if e:
-            e[1].record()
-        # join needs the pairs, not the per-row counts: the count pass only leaves its hit lists in ws
-        _, ws, total = ix.count(q, E.IV_MODE_ALL, want_counts=False)
-        if world > 1:
-            # per-key pair counts -> every rank can derive the global output offsets (the only collective; keys are
-            # disjoint across ranks, so the sum over ranks is the gathered vector).  They are known right after the
-            # count pass: the all-reduce runs on a side stream while the emit pass writes the pairs.
-            per_key = ix.segment_pair_counts(q, ws, total)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                dist.all_reduce(per_key)
-            per_key.record_stream(side)
-        if e:
-            e[2].record()
-        # speculative emission (engine.SubjectIndex.pairs(capacity=...)): buffers sized from the previous step's
-        # pair count, emit launched right behind the count, total read afterwards; exact redo if it was too small
-        cap = state.get("cap", 0)
-        p = cap if cap else int(total.item())
-        out_q = torch.empty(p, dtype=torch.int64, device=dev)
-        out_s = torch.empty(p, dtype=torch.int64, device=dev)
-        if e:
-            e[3].record()
-        cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), E.IV_MODE_ALL, None, E._ptr(ws), E._ptr(out_q),
-                                   E._ptr(out_s), None, out_q.numel(), E._stream()), "iv_emit_pairs")
-        if e:
-            e[4].record()
-            timers.append(e)
-        if cap:
-            p = int(total.item())
-            if p > cap:
-                out_q = torch.empty(p, dtype=torch.int64, device=dev)
-                out_s = torch.empty(p, dtype=torch.int64, device=dev)
-                cabi.check(L.iv_emit_pairs(C.byref(ix.c), C.byref(q.c), E.IV_MODE_ALL, None, E._ptr(ws),
-                                           E._ptr(out_q), E._ptr(out_s), None, p, E._stream()), "iv_emit_pairs")
-            else:
-                out_q, out_s = out_q[:p], out_s[:p]
-        state["cap"] = int(p * 1.02) + 4096
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(side)
-        return p, out_q, out_s
-
-    def count_step():
-        ix = E.SubjectIndex(s_iv, groups)
-        q = E.Queries(q_iv, seg_group)
-        c, _, _ = ix.count(q, E.IV_MODE_ALL, for_emit=False)
-        return c
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, collect=None):
+    def reduce_max(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum_i64(x):
+        t = x.clone().reshape(-1) if isinstance(x, torch.Tensor) else torch.tensor([int(x)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return int(t[0].item()) if t.numel() == 1 else t
+
+    def timed(fn, steps, warmup):
+        """W untimed + K timed steps between barriers; device time (CUDA events), max over ranks; -> (ms total, launches)"""
         for _ in range(warmup):
             fn()
         barrier()
@@ -291,93 +303,138 @@ def run_b200(args, rank, world, local_rank):
         n0 = L.iv_launch_count()
         a.record()
         for _ in range(steps):
-            fn() if collect is None else fn(collect)
+            fn()
         b.record()
         barrier()
-        ms = a.elapsed_time(b)
-        launches = L.iv_launch_count() - n0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches
+        return reduce_max(a.elapsed_time(b)), L.iv_launch_count() - n0
 
-    # ---- device-resident join (the headline `value`) ---------------------------------------------
-    p, _, _ = join_step()
+    def meta(ka, iv):
+        return iv.seg_off_dev, torch.from_numpy(ka.global_key).to(dev)
+
+    def roof(alg_bytes, ms):
+        ach = alg_bytes / (ms / 1e3) / 1e9
+        return {"algorithmic_bytes": int(alg_bytes), "achieved": ach, "frac": ach / peak}
+
+    # ---- the headline workload ------------------------------------------------------------------
+    reads, annot, seg_group = make_workload(args, rank, world)
+    groups = annot.chrom_ranges()
+    q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off, dev)
+    s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off, dev)
+    s_iv.bounds  # ingest-time metadata (per-key min Start / max End), like the chromosome table
+    nq, ns = reads.n, annot.n
+    nq_all, ns_all = args.reads, args.annot
+    q_meta, s_meta = meta(reads, q_iv), meta(annot, s_iv)
+
+    join = E.JoinStep(s_iv, groups, q_iv, seg_group, path=args.path)
+    # one untimed pass sizes the output buffers (the step launches its emit into buffers of the previous step's size and
+    # checks the device-side total afterwards: no host synchronisation inside a step)
+    a, b, p_local = join.run_sync()
+    pairs_all = reduce_sum_i64(p_local)
+    ck_pairs = reduce_sum_i64(checksum_pairs(torch, a, b, q_meta, s_meta))
+    del a, b
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.3)
     t0 = time.perf_counter()
-    timers = []
-    join_ms, launches = timed(join_step, args.steps, args.warmup, collect=timers)
-    count_ms, _ = timed(count_step, args.steps, args.warmup)
+    join.phase_events = []
+    join_ms, launches = timed(join.step, args.steps, args.warmup)
+    join.check()  # every step's device-side total fitted its buffers (else the run is invalid: raises)
     t1 = time.perf_counter()
     clocks = sampler.summary(t0, t1) if sampler else None
-    pairs_all = p
-    if world > 1:
-        t = torch.tensor([p], dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        pairs_all = int(t.item())
     value = pairs_all * args.steps / (join_ms / 1e3)
-    count_qps = nq * world * args.steps / (count_ms / 1e3)
-
-    # per-phase device times (same timed region): index build | count+scan | emit
     torch.cuda.synchronize()
-    ph = np.asarray([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in timers])
-    ph_ms = ph.mean(axis=0)
-    peak, peak_src = measured_peak_gbs()
-    # Phases of the step (events sit directly around the C calls): iv_count_overlaps = k_count_lean (+ the ragged
-    # tail, k_tile_sums and the single-block scan of the 10^4 tile sums: a few us), iv_emit_pairs = the one k_emit
-    # launch.  Algorithmic bytes: the count pass reads Start/End of every query and writes one 16-byte hit-list entry
-    # per query with hits (+ 12 bytes of granule metadata per 64 rows); the emit pass reads those entries and writes
-    # the pairs.  The roofline is quoted on whichever of the two takes longer.
-    hits = int((count_step() > 0).sum().item())
-    alg = {"iv_index_build": 24 * ns, "k_count_lean": 16 * nq + 16 * hits + 12 * (nq // 64), "alloc": 0,
-           "k_emit": 16 * hits + 12 * (nq // 64) + 16 * p}
-    names = ["iv_index_build", "k_count_lean", "alloc", "k_emit"]
-    dom = 1 if ph_ms[1] >= ph_ms[3] else 3
-    ach = alg[names[dom]] / (ph_ms[dom] / 1e3) / 1e9
-    pipe = 24 * nq + 24 * ns + 16 * p  # the join's algorithmic bytes (both tables incl. labels in, pairs out)
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[names[dom]], "hit_queries": hits,
-                "phase_ms": {n: float(m) for n, m in zip(names, ph_ms)},
-                "phase_achieved_gbs": {n: alg[n] / (m / 1e3) / 1e9 for n, m in zip(names, ph_ms) if alg[n]},
-                "pipeline_algorithmic_bytes": pipe,
-                "pipeline_achieved": pipe / (join_ms / args.steps / 1e3) / 1e9,
-                "pipeline_frac": pipe / (join_ms / args.steps / 1e3) / 1e9 / peak}
+    phases = join.phase_summary(args.steps)  # per-phase device times of the timed steps (events around the C calls)
+    join.phase_events = None
+
+    # roofline of the dominant phase.  Algorithmic bytes (no credit for temporaries): every input
+    # column the phase must read once + every output it must write once.
+    alg = {"index_build": 24 * ns, "join": 16 * nq + 16 * p_local, "count": 16 * nq, "emit": 16 * p_local}
+    dom = max(phases, key=lambda k: phases[k])
+    dom_ms = phases[dom]
+    traffic, traffic_src = ncu_traffic(join.kernel_of(dom), args.workload)
+    pipe = 24 * nq + 24 * ns + 16 * p_local  # the join's algorithmic bytes (labels included)
+    pipe_req = 16 * nq + 16 * ns + 16 * p_local  # what this implementation has to move (labels = row numbers)
+    step_ms_local = join_ms / args.steps
+    roofline = {"bound": "hbm", "kernel": join.kernel_of(dom), "phase": dom,
+                "achieved": alg[dom] / (dom_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg[dom] / (dom_ms / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg[dom]),
+                "rank0_phase_ms": phases,
+                "rank0_phase_achieved_gbs": {k: alg[k] / (m / 1e3) / 1e9 for k, m in phases.items() if m > 0},
+                "pipeline": {"bytes_8d": int(pipe), "bytes_no_labels": int(pipe_req), "ms": step_ms_local,
+                             "achieved_8d": pipe / (step_ms_local / 1e3) / 1e9, "frac_8d": pipe / (step_ms_local / 1e3) / 1e9 / peak,
+                             "frac_no_labels": pipe_req / (step_ms_local / 1e3) / 1e9 / peak,
+                             "note": "rank 0's bytes over the max-over-ranks step time, index build included"}}
+
+    ops = {}
+    # ---- count_overlaps / overlap(how="first") on the same inputs -------------------------------------
+    if "count" in args.ops:
+        cnt = E.CountStep(s_iv, groups, q_iv, seg_group, E.IV_MODE_ALL)
+        c = cnt.step()
+        ck = reduce_sum_i64(checksum_rows(torch, c, q_meta))
+        ms, _ = timed(cnt.step, args.steps, args.warmup)
+        ms /= args.steps
+        ops["count_overlaps"] = dict(roof(16 * nq + 16 * ns + 8 * nq, ms), ms=ms, queries_per_s=nq_all / (ms / 1e3),
+                                     checksum=ck, note="index build + counts, int64 NumberOverlaps column")
+        del c
+    if "overlap" in args.ops:
+        ov = E.OverlapFirstStep(s_iv, groups, q_iv, seg_group)
+        rows = ov.run_sync()
+        k_all = reduce_sum_i64(rows.numel())
+        ck = reduce_sum_i64(_mix(key_local(torch, rows, *q_meta) * _M1).sum())
+        ms, _ = timed(ov.step, args.steps, args.warmup)
+        ov.check()
+        ms /= args.steps
+        ops["overlap_first"] = dict(roof(16 * nq + 16 * ns + 8 * rows.numel(), ms), ms=ms, queries_per_s=nq_all / (ms / 1e3),
+                                    rows_out=k_all, checksum=ck, note="index build + surviving self rows (how='first')")
+        del rows
+    if "sorted" in args.ops:
+        # the same reads in position order inside every key (BAM order): the record gathers coalesce
+        o1 = torch.argsort(q_iv.end, stable=True)
+        key = torch.repeat_interleave(torch.arange(reads.n_keys, device=dev), torch.from_numpy(np.diff(reads.seg_off)).to(dev))
+        o2 = torch.argsort(((key << 32) | q_iv.start)[o1], stable=True)
+        o = o1[o2]
+        qs_iv = E.DeviceIntervals(q_iv.start[o], q_iv.end[o], reads.seg_off, seg_off_dev=q_iv.seg_off_dev)
+        del o, o1, o2, key
+        js = E.JoinStep(s_iv, groups, qs_iv, seg_group, path=args.path)
+        _, _, ps = js.run_sync()
+        assert reduce_sum_i64(ps) == pairs_all
+        ms, _ = timed(js.step, args.steps, args.warmup)
+        js.check()
+        ms /= args.steps
+        ops["join_position_sorted"] = dict(roof(24 * nq + 24 * ns + 16 * p_local, ms), ms=ms,
+                                           pairs_per_s=pairs_all / (ms / 1e3), note="8(d) join bytes over the whole step")
+        del js, qs_iv
 
     # ---- end to end through the host-facing call: pinned host arrays in, host index arrays out ----
     e2e = None
     if not args.no_e2e:
         hq_s, hq_e = torch.from_numpy(reads.starts).pin_memory(), torch.from_numpy(reads.ends).pin_memory()
         hs_s, hs_e = torch.from_numpy(annot.starts).pin_memory(), torch.from_numpy(annot.ends).pin_memory()
-        cap = int(p * 1.1) + 1024
+        cap = int(p_local * 1.05) + 4096
         out = (torch.empty(cap, dtype=torch.int64).pin_memory(), torch.empty(cap, dtype=torch.int64).pin_memory())
-        bounds = s_iv.bounds
 
         def e2e_step():
-            nb = hostapi.NCLSBatch(hs_s, hs_e, annot.seg_off, groups, device=dev, bounds=bounds)
-            a, _ = nb.all_overlaps_both(hq_s, hq_e, reads.seg_off, seg_group, out=out)
-            return a.numel()
+            nb = hostapi.NCLSBatch(hs_s, hs_e, annot.seg_off, groups, device=dev)
+            x, _ = nb.all_overlaps_both(hq_s, hq_e, reads.seg_off, seg_group, out=out)
+            return x.numel()
 
-        for _ in range(max(1, args.warmup)):
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(max(1, min(args.warmup, 3))):
             e2e_step()
         barrier()
         te = time.perf_counter()
         pe = 0
-        for _ in range(args.steps):
+        for _ in range(e_steps):
             pe += e2e_step()
         barrier()
-        dt = time.perf_counter() - te
-        if world > 1:
-            t = torch.tensor([dt, float(pe)], dtype=torch.float64, device=dev)
-            tm = t.clone()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t)
-            dt, pe = float(tm[0].item()), float(t[1].item())
+        dt = reduce_max(time.perf_counter() - te)
+        pe = reduce_sum_i64(pe)
         e2e = {"value": pe / dt, "unit": "pairs/s", "h2d_bytes_per_step": 16 * nq + 16 * ns,
-               "d2h_bytes_per_step": 16 * p, "ms_per_step": 1e3 * dt / args.steps,
-               "call": "pyranges_b200.hostapi.NCLSBatch(...).all_overlaps_both(...) on pinned host int64 arrays"}
+               "d2h_bytes_per_step": 16 * p_local, "ms_per_step": 1e3 * dt / e_steps, "steps": e_steps,
+               "call": "pyranges_b200.hostapi.NCLSBatch(starts, ends, ...).all_overlaps_both(...) on pinned host int64 "
+                       "arrays (bytes are rank 0's)"}
+        del hq_s, hq_e, hs_s, hs_e, out
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------
     cpu = None
@@ -389,25 +446,164 @@ def run_b200(args, rank, world, local_rank):
         cdt = 0.0
         passes = 0
         while cdt < args.cpu_seconds and passes < 50:
-            a, b, d, done = oracle_join(reads, annot, seg_group, frac=1.0, threads=1, budget_s=args.cpu_seconds)
-            cp, cq, cdt, passes = cp + a, cq + b, cdt + d, passes + 1
+            x, y, d, done = oracle_join(reads, annot, seg_group, frac=1.0, threads=1, budget_s=args.cpu_seconds - cdt)
+            cp, cq, cdt, passes = cp + x, cq + y, cdt + d, passes + 1
         cpu = {"value": cp / cdt, "unit": "pairs/s", "cores": 1, "kind": "port",
                "queries_per_s": cq / cdt,
-               "sample": "%d pass(es) over %d chromosomes (%d reads x their annotations each): NCLS build + "
-                         "all_overlaps_both per chromosome, %.1f s on 1 core" % (passes, done, cq // max(passes, 1), cdt)}
+               "sample": "%d pass(es), the last over the first %d chromosomes (%d reads x their annotations in all): NCLS "
+                         "build + all_overlaps_both per chromosome, %.1f s on 1 core" % (passes, done, cq, cdt)}
+
+    join_path = join.path
+    del join, q_iv, s_iv
+    torch.cuda.empty_cache()
+
+    # ---- C4: nearest (strandedness="same", how="upstream"), cluster, merge on 50 M intervals ----------
+    chroms = shard(world, rank)
+    if args.ops & {"nearest", "cluster", "merge"}:
+        n4 = int(C4_ROWS * args.ops_scale)
+        iv4 = S.reads_by_chrom(n4, seed=3, min_len=50, max_len=500, chroms=chroms)
+        ann = S.annotations_by_chrom(int(1_000_000 * args.ops_scale), seed=2, chroms=chroms)
+        q4 = E.DeviceIntervals.from_numpy(iv4.starts, iv4.ends, iv4.seg_off, dev)
+        s4 = E.DeviceIntervals.from_numpy(ann.starts, ann.ends, ann.seg_off, dev)
+        s4.bounds
+        q4.bounds
+        m4 = meta(iv4, q4)
+        if "nearest" in args.ops:
+            # partner = same key; '+' keys look upstream = previous, '-' keys = next (pyranges/methods/nearest.py:85-90)
+            sg = np.arange(iv4.n_keys, dtype=np.int32)
+            modes = np.asarray([E.IV_NEAREST_PREVIOUS if k % 2 == 0 else E.IV_NEAREST_NEXT for k in range(iv4.n_keys)], np.int32)
+            qq = E.Queries(q4, sg, seg_mode=modes)
+
+            def nearest_step():
+                return E.SubjectIndex(s4, None, ends_perm=True).nearest(qq, overlap=True)
+
+            row, dist_ = nearest_step()
+            ck = reduce_sum_i64(checksum_rows(torch, dist_, m4))
+            ms, _ = timed(nearest_step, args.ops_steps, 2)
+            ms /= args.ops_steps
+            ops["nearest_upstream_same"] = dict(roof(24 * iv4.n + 24 * ann.n + 16 * iv4.n, ms), ms=ms, rows=n4,
+                                                rows_per_s=n4 / (ms / 1e3), checksum=ck,
+                                                note="index build (with end permutation) + iv_nearest; checksum over Distance")
+            del row, dist_, qq
+        variants = [("unsorted", q4)]
+        if args.ops & {"cluster", "merge"}:
+            o1 = torch.argsort(q4.end, stable=True)
+            key = torch.repeat_interleave(torch.arange(iv4.n_keys, device=dev), torch.from_numpy(np.diff(iv4.seg_off)).to(dev))
+            o = o1[torch.argsort(((key << 32) | q4.start)[o1], stable=True)]
+            q4s = E.DeviceIntervals(q4.start[o], q4.end[o], iv4.seg_off, bounds=q4.bounds, seg_off_dev=q4.seg_off_dev)
+            del o, o1, key
+            variants.append(("sorted", q4s))
+        key_counts = torch.zeros(48, dtype=torch.int64, device=dev)
+        gk = torch.from_numpy(iv4.global_key).to(dev)
+        for name, ivx in variants:
+            if "cluster" in args.ops:
+                def cluster_step():
+                    row, cid, nc = E.cluster(ivx)
+                    if world > 1:
+                        # cluster ids are made globally unique in natsorted key order (pyranges_main.py:1210-1223): the
+                        # ranks exchange their per-key cluster counts (keys are disjoint: the sum is the gather)
+                        key_counts.zero_()
+                        last = cid[ivx.seg_off_dev[1:] - 1] if ivx.n else cid
+                        key_counts[gk] = last - torch.cat([last.new_zeros(1), last[:-1]])
+                        dist.all_reduce(key_counts)
+                    return row, cid, nc
+
+                row, cid, nc = cluster_step()
+                ncl = reduce_sum_i64(nc)
+                ms, _ = timed(cluster_step, args.ops_steps, 2)
+                ms /= args.ops_steps
+                ops["cluster_" + name] = dict(roof(24 * ivx.n, ms), ms=ms, rows=n4, rows_per_s=n4 / (ms / 1e3), clusters=ncl)
+                del row, cid
+            if "merge" in args.ops:
+                def merge_step():
+                    return E.merge(ivx)
+
+                st, en, cnt_, grp = merge_step()
+                m_loc = st.numel()
+                ck = reduce_sum_i64(_mix(st * _M1 + en * _M2 + cnt_ * _M3).sum())
+                ms, _ = timed(merge_step, args.ops_steps, 2)
+                ms /= args.ops_steps
+                ops["merge_" + name] = dict(roof(16 * ivx.n + 24 * m_loc, ms), ms=ms, rows=n4, rows_per_s=n4 / (ms / 1e3),
+                                            merged=reduce_sum_i64(m_loc), checksum=ck)
+                del st, en, cnt_, grp
+        del variants, q4, s4
+        torch.cuda.empty_cache()
+
+    # ---- C5: per-chromosome coverage RLE (to_rle) of 200 M reads -------------------------------------------
+    if "rle" in args.ops:
+        n5 = int(C5_ROWS * args.ops_scale)
+        iv5 = S.reads_by_chrom(n5, seed=4, chroms=chroms)
+        r5 = E.DeviceIntervals.from_numpy(iv5.starts, iv5.ends, iv5.seg_off, dev)
+        r5.bounds
+        gk5 = torch.from_numpy(iv5.global_key).to(dev)
+        run_counts = torch.zeros(48, dtype=torch.int64, device=dev)
+
+        def rle_step():
+            off, runs, vals = E.coverage_rle(r5)
+            if world > 1:  # per-key run counts -> offsets of the concatenated PyRles on every rank
+                run_counts.zero_()
+                run_counts[gk5] = torch.from_numpy(np.diff(off)).to(dev)
+                dist.all_reduce(run_counts)
+            return off, runs, vals
+
+        off, runs, vals = rle_step()
+        r_loc = runs.numel()
+        ck = reduce_sum_i64(_mix(runs * _M1 + vals.to(torch.int64) * _M2).sum())
+        ms, _ = timed(rle_step, max(2, args.ops_steps // 2), 1)
+        ms /= max(2, args.ops_steps // 2)
+        ops["to_rle"] = dict(roof(16 * iv5.n + 16 * r_loc, ms), ms=ms, reads=n5, reads_per_s=n5 / (ms / 1e3),
+                             runs=reduce_sum_i64(r_loc), checksum=ck)
+        del off, runs, vals, r5
+        torch.cuda.empty_cache()
+
+    # ---- the public API (PyRanges.join on DataFrames), builder-sized: 2 M x 40 k rows ---------------------------
+    if "api" in args.ops and rank == 0:
+        try:
+            ops["api_join"] = api_join_bench(dev)
+        except Exception as ex:  # the API leg must not take the headline down
+            ops["api_join"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {
             "metric": "join overlap pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": join_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": join_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args, world),
-            "pairs_per_step": pairs_all, "count_overlaps_queries_per_s": count_qps,
-            "count_overlaps_ms_per_step": count_ms / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "pairs_per_step": pairs_all, "pairs_checksum": ck_pairs, "join_path": join_path,
+            "count_overlaps_queries_per_s": ops.get("count_overlaps", {}).get("queries_per_s"),
+            "roofline": roofline, "ops": ops, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def api_join_bench(dev, n_reads=2_000_000, n_annot=40_000, reps=5):
+    """gr.join(other) through the drop-in PyRanges class (DataFrames in, DataFrames out)."""
+    import pandas as pd
+    import torch
+
+    import pyranges_b200 as pr
+    from pyranges_b200 import synthetic as S
+
+    def frame(ka):
+        key = np.repeat(np.arange(ka.n_keys), np.diff(ka.seg_off))
+        names = np.asarray([c for c, _ in S.HG38])
+        return pd.DataFrame({"Chromosome": names[ka.chrom_ids[key // 2]], "Start": ka.starts, "End": ka.ends,
+                             "Strand": np.where(key % 2 == 0, "+", "-")})
+
+    gr = pr.PyRanges(frame(S.reads_by_chrom(n_reads, seed=1)))
+    other = pr.PyRanges(frame(S.annotations_by_chrom(n_annot, seed=2)))
+    res = gr.join(other)
+    rows = len(res)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        gr.join(other)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    return {"ms": 1e3 * dt, "rows_out": rows, "pairs_per_s": rows / dt,
+            "workload": "PyRanges.join, %d x %d rows, strandedness=None, DataFrames in / out" % (n_reads, n_annot)}
 
 
 def main():

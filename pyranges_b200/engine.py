@@ -473,3 +473,174 @@ def gather(column, rows, fill=None):
     cabi.check(L.iv_gather(_ptr(column), column.element_size(), _ptr(rows), rows.numel(), _ptr(out), fb, _stream()),
                "iv_gather")
     return out
+
+
+# ---- repeated operations on resident columns ------------------------------------------------------------------------
+class _Totals:
+    """Device-side result sizes of asynchronous steps: every step copies its total into a pinned host slot without
+    synchronising; check() waits once and validates all of them against the capacity the step emitted into."""
+
+    def __init__(self):
+        self.slots = []
+
+    def push(self, total_dev, cap):
+        h = torch.empty(1, dtype=torch.int64).pin_memory()
+        h.copy_(total_dev, non_blocking=True)
+        self.slots.append((h, cap))
+
+    def check(self, what):
+        torch.cuda.current_stream().synchronize()
+        worst = 0
+        for h, cap in self.slots:
+            p = int(h.item())
+            if p > cap:
+                raise cabi.CabiError("%s: a step produced %d entries for buffers of %d" % (what, p, cap))
+            worst = max(worst, p)
+        self.slots = []
+        return worst
+
+
+class JoinStep:
+    """gr.join(other) over and over on the same resident columns, the way a pipeline (or a benchmark) calls it: every
+    step REBUILDS the subject index (the reference builds a new NCLS per call, pyranges/methods/join.py:12) and writes
+    all (query row, subject row) pairs in query order.  Output buffers are sized by the first, synchronous pass
+    (run_sync); later steps launch everything without a host synchronisation and leave their pair total in a pinned
+    slot that check() validates afterwards (a step whose pairs did not fit raises there).
+
+    path = "twopass": iv_index_build -> iv_count_overlaps (hit lists) -> iv_emit_pairs
+    path = "fused"  : iv_lists_build -> iv_join_pairs (one kernel: count, look-back offsets, staged emission)"""
+
+    def __init__(self, s_iv, group_ranges, q_iv, seg_group, path="auto", slack=0):
+        self.s_iv, self.q_iv, self.group_ranges = s_iv, q_iv, group_ranges
+        self.q = Queries(q_iv, seg_group, slack=slack)
+        if path == "auto":
+            path = "fused" if ListIndex.supported(s_iv, group_ranges, q_iv) else "twopass"
+        self.path = path
+        self.cap = 0
+        self.totals = _Totals()
+        self.phase_events = None
+        self.out = None
+
+    def _ev(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _run(self, cap):
+        dev = self.q_iv.device
+        ev = [self._ev()] if self.phase_events is not None else None
+        out_q = torch.empty(cap, dtype=torch.int64, device=dev)
+        out_s = torch.empty(cap, dtype=torch.int64, device=dev)
+        if self.path == "fused":
+            ix = ListIndex(self.s_iv, self.group_ranges)
+            if ev:
+                ev.append(self._ev())
+            total = ix.join_pairs(self.q, out_q, out_s, cap)
+            if ev:
+                ev.append(self._ev())
+        else:
+            ix = SubjectIndex(self.s_iv, self.group_ranges)
+            if ev:
+                ev.append(self._ev())
+            _, ws, total = ix.count(self.q, IV_MODE_ALL, want_counts=False)
+            if ev:
+                ev.append(self._ev())
+            cabi.check(cabi.lib().iv_emit_pairs(C.byref(ix.c), C.byref(self.q.c), IV_MODE_ALL, None, _ptr(ws), _ptr(out_q),
+                                                _ptr(out_s), None, cap, _stream()), "iv_emit_pairs")
+            if ev:
+                ev.append(self._ev())
+        if ev:
+            self.phase_events.append(ev)
+        return out_q, out_s, total
+
+    def run_sync(self):
+        """-> (query rows, subject rows, number of pairs); sizes the buffers of the following step() calls"""
+        cap = self.cap or max(2 * self.q_iv.n, 1 << 20)
+        while True:
+            out_q, out_s, total = self._run(cap)
+            p = int(total.item())
+            if p <= cap:
+                break
+            cap = p + 4096
+        self.cap = int(p * 1.02) + 4096
+        return out_q[:p], out_s[:p], p
+
+    def step(self):
+        if not self.cap:
+            return self.run_sync()
+        out_q, out_s, total = self._run(self.cap)
+        self.totals.push(total, self.cap)
+        self.out = (out_q, out_s, total)
+        return self.out
+
+    def check(self):
+        return self.totals.check("JoinStep")
+
+    def kernel_of(self, phase):
+        names = {"index_build": "iv_lists_build" if self.path == "fused" else "iv_index_build",
+                 "join": "k_join", "count": "k_count_lean", "emit": "k_emit"}
+        return names.get(phase, phase)
+
+    def phase_summary(self, last_n):
+        """mean device milliseconds per phase over the last `last_n` recorded steps"""
+        names = ["index_build", "join"] if self.path == "fused" else ["index_build", "count", "emit"]
+        evs = self.phase_events[-last_n:]
+        return {n: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in evs])) for i, n in enumerate(names)}
+
+
+class CountStep:
+    """gr.count_overlaps(other) on resident columns: index rebuild + one int64 count per query row, asynchronous."""
+
+    def __init__(self, s_iv, group_ranges, q_iv, seg_group, mode=IV_MODE_ALL, path="auto"):
+        self.s_iv, self.q_iv, self.group_ranges, self.mode = s_iv, q_iv, group_ranges, mode
+        self.q = Queries(q_iv, seg_group)
+        if path == "auto":
+            path = "lists" if ListIndex.supported(s_iv, group_ranges, q_iv) else "ranks"
+        self.path = path
+
+    def step(self):
+        if self.path == "lists":
+            return ListIndex(self.s_iv, self.group_ranges).count(self.q, self.mode)
+        c, _, _ = SubjectIndex(self.s_iv, self.group_ranges).count(self.q, self.mode, for_emit=False)
+        return c
+
+
+class OverlapFirstStep:
+    """gr.overlap(other, how="first") on resident columns: the self rows with at least one hit, in row order
+    (NCLS.has_overlaps, pyranges/methods/intersection.py:78).  Same asynchronous protocol as JoinStep."""
+
+    def __init__(self, s_iv, group_ranges, q_iv, seg_group):
+        self.s_iv, self.q_iv, self.group_ranges = s_iv, q_iv, group_ranges
+        self.q = Queries(q_iv, seg_group)
+        self.cap = 0
+        self.totals = _Totals()
+
+    def _run(self, cap):
+        ix = SubjectIndex(self.s_iv, self.group_ranges)
+        _, ws, total = ix.count(self.q, IV_MODE_ANY, want_counts=False)
+        rows = torch.empty(cap, dtype=torch.int64, device=self.q_iv.device)
+        cabi.check(cabi.lib().iv_emit_pairs(C.byref(ix.c), C.byref(self.q.c), IV_MODE_ANY, None, _ptr(ws), _ptr(rows), None,
+                                            None, cap, _stream()), "iv_emit_pairs")
+        return rows, total
+
+    def run_sync(self):
+        rows, total = self._run(self.q_iv.n)
+        p = int(total.item())
+        self.cap = min(self.q_iv.n, int(p * 1.02) + 4096)
+        return rows[:p]
+
+    def step(self):
+        rows, total = self._run(self.cap)
+        self.totals.push(total, self.cap)
+        return rows, total
+
+    def check(self):
+        return self.totals.check("OverlapFirstStep")
+
+
+class ListIndex:
+    """placeholder until csrc/lists.cu lands"""
+
+    @staticmethod
+    def supported(s_iv, group_ranges, q_iv):
+        return False

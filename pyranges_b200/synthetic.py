@@ -97,3 +97,77 @@ def annotations(n, seed=2, chroms=None):
     key = np.concatenate([gc * 2 + gstrand, gc[parent] * 2 + gstrand[parent]])
     perm = rng.permutation(n)  # interleave genes and exons: rows are unsorted
     return KeyedArrays(s[perm], e[perm], key[perm], 2 * len(SIZES))
+
+
+# ---- per-chromosome generators (bench.py) ---------------------------------------------------------------------------
+# The same distributions as reads() / annotations() above, but every chromosome draws from its own seeded stream and
+# holds an exact size-proportional share of the rows.  A rank that owns a subset of the chromosomes therefore generates
+# exactly the rows a single-GPU run holds for them: the genome-wide set is FIXED whatever the number of GPUs (strong
+# scaling), and order-invariant checksums of the results must agree between N = 1, 2, 4 and 8.
+def _keyed_from_chroms(parts, chroms):
+    """parts: per chromosome (starts, ends, strand); -> KeyedArrays whose key k = (chroms[k // 2], strand k % 2)"""
+    S, E, off = [], [], [0]
+    for s, e, strand in parts:
+        plus = strand == 0
+        for m in (plus, ~plus):
+            S.append(s[m])
+            E.append(e[m])
+            off.append(off[-1] + int(m.sum()))
+    ka = KeyedArrays.__new__(KeyedArrays)
+    ka.starts = np.ascontiguousarray(np.concatenate(S)) if S else np.zeros(0, np.int64)
+    ka.ends = np.ascontiguousarray(np.concatenate(E)) if E else np.zeros(0, np.int64)
+    ka.seg_off = np.asarray(off, np.int64)
+    ka.n = int(off[-1])
+    ka.n_keys = 2 * len(chroms)
+    ka.chrom_ids = np.asarray(chroms, np.int64)
+    ka.global_key = (np.repeat(ka.chrom_ids, 2) * 2 + np.tile(np.arange(2), len(chroms))).astype(np.int64)
+    return ka
+
+
+def reads_by_chrom(n_total, seed=1, length=100, min_len=None, max_len=None, chroms=None):
+    """the rows of chromosomes `chroms` (default: all) of an n_total-row genome-wide read set"""
+    chroms = list(range(len(SIZES))) if chroms is None else list(chroms)
+    per = _split_counts(n_total)
+    parts = []
+    for c in chroms:
+        rng = np.random.default_rng([seed, c])
+        n = int(per[c])
+        strand = rng.integers(0, 2, n)
+        ln = np.full(n, length, np.int64) if min_len is None else rng.integers(min_len, max_len + 1, n)
+        s = np.floor(rng.random(n) * (SIZES[c] - ln)).astype(np.int64)
+        parts.append((s, s + ln, strand))
+    return _keyed_from_chroms(parts, chroms)
+
+
+def annotations_by_chrom(n_total, seed=2, chroms=None):
+    """the rows of chromosomes `chroms` of an n_total-row genome-wide gene/exon annotation (10 % genes)"""
+    chroms = list(range(len(SIZES))) if chroms is None else list(chroms)
+    ng_all, ne_all = _split_counts(max(1, n_total // 10)), _split_counts(n_total - max(1, n_total // 10))
+    parts = []
+    for c in chroms:
+        rng = np.random.default_rng([seed, c])
+        ng, ne = max(1, int(ng_all[c])), int(ne_all[c])
+        gstrand = rng.integers(0, 2, ng)
+        glen = np.clip(np.floor(rng.lognormal(np.log(25000.0), 1.2, ng)), 500, 2000000).astype(np.int64)
+        glen = np.minimum(glen, SIZES[c] - 1)
+        gs = np.floor(rng.random(ng) * (SIZES[c] - glen)).astype(np.int64)
+        parent = rng.integers(0, ng, ne)
+        elen = np.clip(np.floor(rng.lognormal(np.log(150.0), 0.8, ne)), 20, 10000).astype(np.int64)
+        elen = np.minimum(elen, glen[parent])
+        es = gs[parent] + np.floor(rng.random(ne) * (glen[parent] - elen + 1)).astype(np.int64)
+        s = np.concatenate([gs, es])
+        e = np.concatenate([gs + glen, es + elen])
+        strand = np.concatenate([gstrand, gstrand[parent]])
+        perm = rng.permutation(ng + ne)  # interleave genes and exons: rows are unsorted
+        parts.append((s[perm], e[perm], strand[perm]))
+    return _keyed_from_chroms(parts, chroms)
+
+
+def sorted_within_keys(ka):
+    """the same rows, every key sorted by (Start, End): position-sorted input (BAM order)"""
+    key = np.repeat(np.arange(ka.n_keys), np.diff(ka.seg_off))
+    o = np.lexsort([ka.ends, ka.starts, key])
+    out = KeyedArrays.__new__(KeyedArrays)
+    out.__dict__.update(ka.__dict__)
+    out.starts, out.ends = np.ascontiguousarray(ka.starts[o]), np.ascontiguousarray(ka.ends[o])
+    return out
