@@ -7,7 +7,7 @@ LIB = pyranges_b200/libpyranges_b200.so
 
 all: $(LIB) oracle/libiv_oracle.so
 
-build/%.o: pyranges_b200/csrc/%.cu pyranges_b200/csrc/common.cuh include/pyranges_b200.h
+build/%.o: pyranges_b200/csrc/%.cu pyranges_b200/csrc/common.cuh pyranges_b200/csrc/query.cuh include/pyranges_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

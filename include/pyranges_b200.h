@@ -14,6 +14,10 @@
  *                                NCLS.all_containments_both              pyranges/methods/join.py:17, intersection.py:76
  *                                NCLS.first_overlap_both                 pyranges/methods/join.py:19 (via nearest.py:32)
  *                                NCLS.last_overlap_both                  pyranges/methods/join.py:21, intersection.py:28
+ *   iv_lists_build            <- NCLS(starts, ends, ids)                 pyranges/methods/join.py:12, coverage.py:20
+ *   iv_join_pairs             <- NCLS.all_overlaps_both                  pyranges/methods/join.py:15,23 (one kernel)
+ *   iv_join_count             <- NCLS.all_overlaps_both + value_counts   pyranges/methods/coverage.py:26-40
+ *                                NCLS.has_overlaps                       pyranges/methods/intersection.py:78
  *   iv_coverage_bp            <- NCLS.coverage                           pyranges/methods/coverage.py:64-68
  *   iv_subtract_count/_emit   <- NCLS.set_difference_helper              pyranges/methods/subtraction.py:63-65
  *   iv_nearest                <- first_overlap_both + nearest_previous_nonoverlapping +
@@ -57,7 +61,7 @@
 extern "C" {
 #endif
 
-#define IV_ABI_VERSION 6
+#define IV_ABI_VERSION 7
 
 #define IV_OK 0
 #define IV_ERR_INVALID (-1)   /* bad argument */
@@ -167,10 +171,12 @@ size_t iv_sort_workspace_bytes(int64_t n, int32_t value_bytes);
 int iv_radix_sort_u64(uint64_t* keys, void* values, int32_t value_bytes, int64_t n, int32_t begin_bit,
                       int32_t end_bit, void* ws, size_t ws_bytes, void* stream);
 
-/* out_lo[k] = min start, out_hi[k] = max end, out_maxlen[k] = max(end-start), out_sumlen[k] = sum(end-start)
- * of segment k (INT64_MAX / INT64_MIN / 0 / 0 for an empty segment). */
+/* out_lo[k] = min start, out_hi[k] = max end, out_maxlen[k] = max(end-start), out_sumlen[k] = sum(end-start),
+ * out_minlen[k] = min(end-start) of segment k (INT64_MAX / INT64_MIN / 0 / 0 / INT64_MAX for an empty segment).
+ * out_minlen may be NULL. */
 int iv_segment_bounds(const int64_t* starts, const int64_t* ends, const int64_t* seg_off, int32_t n_seg,
-                      int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, int64_t* out_sumlen, void* stream);
+                      int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, int64_t* out_sumlen, int64_t* out_minlen,
+                      void* stream);
 
 /* ---- binary operations ------------------------------------------------------------------------ */
 
@@ -220,6 +226,66 @@ int iv_subtract_emit(const iv_index_t* index, const iv_queries_t* q, const int64
 /* out_row[i] = subject row of the nearest interval or -1, out_dist[i] = 0 (overlap), gap+1, or -1 */
 int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_t overlap, int64_t* out_row,
                int64_t* out_dist, void* stream);
+
+/* ---- list index + fused join: the join / count_overlaps / overlap fast path ------------------------------------ */
+/* Every coordinate bin (bin = flattened coordinate >> shift, shift <= 15) owns its TOUCH LIST: the subjects that
+ * intersect the bin, i.e. those that start before it and are still open at its origin ("crossing") followed by those
+ * that start inside it, each as an 8-byte entry.  A query whose start falls into bin b overlaps exactly
+ *      the entries of list b with  (crossing or so < e' - origin)  and  eo > s' - origin
+ *    + for every later bin the query reaches: its NON-crossing entries with  so < e' - origin(bin),
+ * every subject once.  No sort is needed to build the lists (difference array -> offsets -> fill -> per-bin ordering),
+ * and one 32-byte record (= one L2 sector, one 256-bit load) holds a bin's list offset, length and first three entries:
+ * most queries are answered -- counted AND emitted -- from that single gather.  Zero-length subjects (start == end) are
+ * handled exactly (hit iff s < start < e) as long as the group window is one coordinate wider than its rows on both
+ * sides (lo <= min start - 1, hi >= max end + 1). */
+typedef struct iv_lentry {
+    uint32_t row; /* subject row */
+    uint16_t so;  /* start - bin origin (15 bits); IV_L_CROSS set: the subject starts before the bin */
+    uint16_t eo;  /* min(end - bin origin, 0xFFFF) */
+} iv_lentry_t;
+#define IV_L_CROSS 0x8000u
+typedef struct iv_lrec {
+    uint32_t co;     /* the bin's list is cand[co, co + n) */
+    uint32_t n8;     /* min(n, 255) in the low byte; n = co of the next record - co when it says 255 */
+    iv_lentry_t e[3]; /* the first three entries of the list (crossing entries by row, then starts by (start, row)) */
+} iv_lrec_t;
+typedef struct iv_lists {
+    int64_t n;          /* subjects */
+    int64_t total_span;
+    int32_t shift;
+    int32_t flags;
+    int64_t n_bins;     /* rec[] holds n_bins + 2 records (the last two are sentinels) */
+    int64_t cand_cap;   /* capacity of cand[] */
+    const iv_lrec_t* rec;
+    const iv_lentry_t* cand;
+    iv_groups_t groups;
+} iv_lists_t;
+
+/* 0 = these subjects cannot be indexed this way (flattened span beyond 2^41, or so many long subjects that the lists
+ * would exceed 2^31 entries): use iv_index_build */
+size_t iv_lists_workspace_bytes(int64_t n, int64_t total_span, int64_t sum_len);
+/* bin width (log2) iv_lists_build will use for these subjects; < 0 = unsupported.  Callers route queries that are
+ * much longer than a bin to the rank index (a query costs one gather per bin it reaches). */
+int32_t iv_lists_shift(int64_t n, int64_t total_span, int64_t sum_len);
+int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, void* ws,
+                   size_t ws_bytes, iv_lists_t* out, void* stream);
+
+size_t iv_join_workspace_bytes(int64_t n_queries);
+/* All (query label | row, subject row | s_label[row]) pairs in query order, ONE kernel: every 2048-row tile counts its
+ * hits, stages its pairs in shared memory, obtains its output offset by a decoupled look-back over the tiles before
+ * it and writes its pairs with coalesced stores.  out_capacity = entries the output buffers hold; pairs beyond it are
+ * dropped (never written) and *out_total (device) receives the true total, so the caller can repeat the call with
+ * larger buffers.  ws: iv_join_workspace_bytes(q->n) bytes, 256-byte aligned. */
+int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int64_t* out_q, int64_t* out_s,
+                  const int64_t* s_label, int64_t out_capacity, void* ws, size_t ws_bytes, int64_t* out_total,
+                  void* stream);
+/* out_count[i] = number of overlapping subjects (IV_MODE_ALL) or 0/1 (IV_MODE_ANY) of query i */
+int iv_join_count(const iv_lists_t* lists, const iv_queries_t* q, int32_t mode, int64_t* out_count, void* stream);
+/* out_seg_pairs[k] = number of pairs of query segment k in a pair list written in query order WITHOUT labels
+ * (pair_q ascending rows): binary searches of the segment boundaries over the first min(*total, capacity) pairs
+ * (total: device). */
+int iv_sorted_pair_segments(const int64_t* pair_q, const int64_t* total, int64_t capacity, const int64_t* seg_off,
+                            int32_t n_seg, int64_t* out_seg_pairs, void* stream);
 
 /* ---- unary operations ------------------------------------------------------------------------- */
 /* groups->base must leave a gap of max(slack,0)+1 between consecutive groups. `len_bits` = number of

@@ -13,7 +13,7 @@ IV_OK = 0
 IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
-IV_ABI_VERSION = 6
+IV_ABI_VERSION = 7
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
 
@@ -30,12 +30,17 @@ class IvIndex(C.Structure):
                 ("groups", IvGroups)]
 
 
+class IvLists(C.Structure):
+    _fields_ = [("n", _i64), ("total_span", _i64), ("shift", _i32), ("flags", _i32), ("n_bins", _i64),
+                ("cand_cap", _i64), ("rec", _vp), ("cand", _vp), ("groups", IvGroups)]
+
+
 class IvQueries(C.Structure):
     _fields_ = [("n", _i64), ("start", _vp), ("end", _vp), ("label", _vp), ("n_seg", _i32), ("_pad", _i32),
                 ("seg_off", _vp), ("seg_group", _vp), ("seg_mode", _vp), ("slack", _i64)]
 
 
-_PG, _PI, _PQ = C.POINTER(IvGroups), C.POINTER(IvIndex), C.POINTER(IvQueries)
+_PG, _PI, _PQ, _PL = C.POINTER(IvGroups), C.POINTER(IvIndex), C.POINTER(IvQueries), C.POINTER(IvLists)
 
 # name -> (restype, argtypes); mirrors include/pyranges_b200.h one to one
 PROTOTYPES = {
@@ -45,7 +50,14 @@ PROTOTYPES = {
     "iv_launch_count": (C.c_uint64, []),
     "iv_sort_workspace_bytes": (_sz, [_i64, _i32]),
     "iv_radix_sort_u64": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
-    "iv_segment_bounds": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "iv_segment_bounds": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "iv_lists_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "iv_lists_shift": (_i32, [_i64, _i64, _i64]),
+    "iv_lists_build": (C.c_int, [_vp, _vp, _i64, _PG, _vp, _sz, _PL, _vp]),
+    "iv_join_workspace_bytes": (_sz, [_i64]),
+    "iv_join_pairs": (C.c_int, [_PL, _PQ, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    "iv_join_count": (C.c_int, [_PL, _PQ, _i32, _vp, _vp]),
+    "iv_sorted_pair_segments": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
     "iv_index_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "iv_index_build": (C.c_int, [_vp, _vp, _i64, _PG, _i32, _vp, _sz, _PI, _vp]),
     "iv_overlap_workspace_bytes": (_sz, [_i64]),

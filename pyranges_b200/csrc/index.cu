@@ -24,46 +24,50 @@ namespace iv {
 constexpr int IX_THREADS = 256;
 
 // ---- per-segment bounds (ingest-time metadata) ------------------------------------------------------------------
-__global__ void k_bounds_init(int64_t* lo, int64_t* hi, int64_t* ml, int64_t* sl, int n) {
+__global__ void k_bounds_init(int64_t* lo, int64_t* hi, int64_t* ml, int64_t* sl, int64_t* mn, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         lo[i] = INT64_MAX;
         hi[i] = INT64_MIN;
         ml[i] = 0;
         sl[i] = 0;
+        if (mn) mn[i] = INT64_MAX;
     }
 }
 
 constexpr int BD_SPLIT = 64;
 __global__ void __launch_bounds__(IX_THREADS)
 k_bounds(const int64_t* __restrict__ s, const int64_t* __restrict__ e, const int64_t* __restrict__ seg_off,
-         int64_t* lo, int64_t* hi, int64_t* ml, int64_t* sl) {
-    __shared__ long long sm[4][IX_THREADS / 32];
+         int64_t* lo, int64_t* hi, int64_t* ml, int64_t* sl, int64_t* minl) {
+    __shared__ long long sm[5][IX_THREADS / 32];
     int seg = blockIdx.x;
     int64_t a = seg_off[seg], b = seg_off[seg + 1];
     int64_t len = b - a;
     int64_t chunk = (len + BD_SPLIT - 1) / BD_SPLIT;
     int64_t ca = a + chunk * blockIdx.y, cb = ca + chunk < b ? ca + chunk : b;
-    long long mn = INT64_MAX, mx = INT64_MIN, m = 0, sum = 0;
+    long long mn = INT64_MAX, mx = INT64_MIN, m = 0, sum = 0, sh = INT64_MAX;
     for (int64_t i = ca + threadIdx.x; i < cb; i += IX_THREADS) {
         long long x = s[i], y = e[i];
         mn = x < mn ? x : mn;
         mx = y > mx ? y : mx;
         m = (y - x) > m ? (y - x) : m;
+        sh = (y - x) < sh ? (y - x) : sh;
         sum += y > x ? y - x : 0;
     }
     mn = warp_min(mn);
     mx = warp_max(mx);
     m = warp_max(m);
+    sh = warp_min(sh);
     sum = warp_sum(sum);
     int w = threadIdx.x >> 5;
-    if (lane_id() == 0) { sm[0][w] = mn; sm[1][w] = mx; sm[2][w] = m; sm[3][w] = sum; }
+    if (lane_id() == 0) { sm[0][w] = mn; sm[1][w] = mx; sm[2][w] = m; sm[3][w] = sum; sm[4][w] = sh; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < IX_THREADS / 32; k++) {
             mn = sm[0][k] < mn ? sm[0][k] : mn;
             mx = sm[1][k] > mx ? sm[1][k] : mx;
             m = sm[2][k] > m ? sm[2][k] : m;
+            sh = sm[4][k] < sh ? sm[4][k] : sh;
             sum += sm[3][k];
         }
         if (ca < cb) {
@@ -71,6 +75,7 @@ k_bounds(const int64_t* __restrict__ s, const int64_t* __restrict__ e, const int
             atomicMax((long long*)hi + seg, mx);
             atomicMax((long long*)ml + seg, m);
             atomicAdd((unsigned long long*)sl + seg, (unsigned long long)sum);
+            if (minl) atomicMin((long long*)minl + seg, sh);
         }
     }
 }
@@ -318,15 +323,15 @@ using namespace iv;
 
 extern "C" int iv_segment_bounds(const int64_t* starts, const int64_t* ends, const int64_t* seg_off, int32_t n_seg,
                                  int64_t* out_lo, int64_t* out_hi, int64_t* out_maxlen, int64_t* out_sumlen,
-                                 void* stream) {
+                                 int64_t* out_minlen, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     IV_REQUIRE(n_seg >= 0, IV_ERR_INVALID, "iv_segment_bounds: n_seg < 0");
     if (n_seg == 0) return IV_OK;
     IV_REQUIRE(out_lo && out_hi && out_maxlen && out_sumlen, IV_ERR_INVALID, "iv_segment_bounds: null output");
-    k_bounds_init<<<(n_seg + 255) / 256, 256, 0, st>>>(out_lo, out_hi, out_maxlen, out_sumlen, n_seg);
+    k_bounds_init<<<(n_seg + 255) / 256, 256, 0, st>>>(out_lo, out_hi, out_maxlen, out_sumlen, out_minlen, n_seg);
     IV_LAUNCH_CHECK();
     k_bounds<<<dim3((unsigned)n_seg, BD_SPLIT), IX_THREADS, 0, st>>>(starts, ends, seg_off, out_lo, out_hi, out_maxlen,
-                                                                      out_sumlen);
+                                                                      out_sumlen, out_minlen);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

@@ -21,6 +21,7 @@
 // Kernels are instantiated for 32-bit flattened coordinates (total span < 2^32: any single genome) and for
 // 64-bit ones; the 32-bit instantiation halves the integer work per query.
 #include "common.cuh"
+#include "query.cuh"
 
 namespace iv {
 
@@ -124,34 +125,9 @@ template <typename X> __device__ __forceinline__ uint32_t rank_e_lt(const iv_ind
     return rec_rank_e(ix, load_rec(ix, b), b, rel_of(ix, x));
 }
 
-// ---- query geometry ---------------------------------------------------------------------------------------------
-// x' = base + clamp(x - lo, 0, width): the partner group's window of the flattened axis
-template <typename X> struct Flat {
-    int64_t lo;
-    uint64_t width;
-    X base;
-    int g;  // partner group, -1 = none (lo = width = base = 0: every count comes out 0)
-    __device__ __forceinline__ X at(int64_t x) const {
-        uint64_t d = (uint64_t)(x - lo);
-        d = x < lo ? 0ull : d;
-        d = d > width ? width : d;
-        return base + (X)d;
-    }
-    __device__ __forceinline__ bool outside(int64_t x) const { return x < lo || (uint64_t)(x - lo) > width; }
-    __device__ __forceinline__ int64_t raw(uint64_t xf) const { return (int64_t)(xf - (uint64_t)base) + lo; }
-};
+// ---- query geometry (query.cuh) -------------------------------------------------------------------------------------
 template <typename X> __device__ __forceinline__ Flat<X> load_flat(const iv_index_t& ix, const iv_queries_t& q, int seg) {
-    Flat<X> f;
-    f.g = __ldg(q.seg_group + seg);
-    f.lo = 0; f.width = 0; f.base = 0;
-    if (f.g >= 0 && ix.n > 0) {
-        f.lo = __ldg(ix.groups.lo + f.g);
-        f.width = (uint64_t)(__ldg(ix.groups.hi + f.g) - f.lo);
-        f.base = (X)__ldg(ix.groups.base + f.g);
-    } else {
-        f.g = -1;
-    }
-    return f;
+    return load_flat_groups<X>(ix.groups, ix.n, q, seg);
 }
 // per-thread cache: most blocks sit inside one query segment
 template <typename X> struct FlatCache {
@@ -167,14 +143,6 @@ template <typename X> struct FlatCache {
         return seg == sp.klo ? f0 : load_flat<X>(ix, q, seg);
     }
 };
-__device__ __forceinline__ void apply_slack(int64_t slack, int64_t& s, int64_t& e) {
-    if (slack != 0) {  // join(slack=k): pyranges/multithreaded.py:420-423
-        s -= slack;
-        if (s < 0) s = 0;
-        e += slack;
-    }
-}
-
 // count from the record of bin(ec); general fallback when s'+1 sits in another bin or a bin overflows
 template <typename X>
 __device__ __forceinline__ int64_t count_rec(const iv_index_t& ix, X sc, X ec, const Rec& r, uint64_t b1) {

@@ -96,12 +96,14 @@ class DeviceIntervals:
         # (a caller that pipelines uploads passes the device copy: a small pageable copy issued now would queue
         # behind its bulk transfers on the copy engine)
         self.seg_off_dev = seg_off_dev if seg_off_dev is not None else _desc_to_dev(self.seg_off, self.device)
-        self._b = bounds  # (lo, hi, maxlen, sumlen) per segment; computed on first use (subjects / unary ops)
+        # (lo, hi, maxlen, sumlen[, minlen]) per segment; computed on first use (subjects / unary ops)
+        self._b = bounds if bounds is None or len(bounds) == 5 else tuple(bounds) + (np.ones(self.n_seg, np.int64),)
         self._groups = {}
 
-    def groups(self, seg_ranges=None, gap=1, zero_lo=False):
-        """iv_groups_t descriptor of these rows (ingest-time metadata: memoised per grouping)."""
-        key = (None if seg_ranges is None else tuple(map(tuple, seg_ranges)), int(gap), bool(zero_lo))
+    def groups(self, seg_ranges=None, gap=1, zero_lo=False, widen=False):
+        """iv_groups_t descriptor of these rows (ingest-time metadata: memoised per grouping).  widen: windows reach
+        one coordinate beyond the rows on both sides (list index over zero-length subjects)."""
+        key = (None if seg_ranges is None else tuple(map(tuple, seg_ranges)), int(gap), bool(zero_lo), bool(widen))
         g = self._groups.get(key)
         if g is None:
             # the descriptor only depends on the segment table and its bounds, not on the rows: the same chromosome
@@ -111,7 +113,7 @@ class DeviceIntervals:
                 ckey = (key, str(self.device), self.seg_off.tobytes()) + tuple(np.ascontiguousarray(b).tobytes() for b in self.bounds)
                 g = _groups_cache.get(ckey)
             if g is None:
-                g = Groups(self, seg_ranges, gap=gap, zero_lo=zero_lo)
+                g = Groups(self, seg_ranges, gap=gap, zero_lo=zero_lo, widen=widen)
                 if ckey is not None:
                     if len(_groups_cache) >= 128:
                         _groups_cache.clear()
@@ -141,6 +143,16 @@ class DeviceIntervals:
     def sumlen(self):
         return self.bounds[3]
 
+    @property
+    def minlen(self):
+        return self.bounds[4]
+
+    @property
+    def has_zero_length(self):
+        """any row with Start == End"""
+        m = self.minlen
+        return bool(len(m)) and bool((m[np.diff(self.seg_off) > 0] <= 0).any())
+
     @classmethod
     def from_numpy(cls, starts, ends, seg_off, device="cuda", pinned=False):
         dev = _use(device)
@@ -152,20 +164,21 @@ class DeviceIntervals:
         k = self.n_seg
         if k == 0:
             z = np.zeros(0, np.int64)
-            return z, z.copy(), z.copy(), z.copy()
-        out = torch.empty(4 * k, dtype=torch.int64, device=self.device)
+            return z, z.copy(), z.copy(), z.copy(), z.copy()
+        out = torch.empty(5 * k, dtype=torch.int64, device=self.device)
         p = out.data_ptr()
         cabi.check(cabi.lib().iv_segment_bounds(_ptr(self.start), _ptr(self.end), _ptr(self.seg_off_dev), k,
                                                 C.c_void_p(p), C.c_void_p(p + 8 * k), C.c_void_p(p + 16 * k),
-                                                C.c_void_p(p + 24 * k), _stream()), "iv_segment_bounds")
+                                                C.c_void_p(p + 24 * k), C.c_void_p(p + 32 * k), _stream()),
+                   "iv_segment_bounds")
         h = out.cpu().numpy()
-        return h[:k].copy(), h[k:2 * k].copy(), h[2 * k:3 * k].copy(), h[3 * k:].copy()
+        return tuple(h[i * k:(i + 1) * k].copy() for i in range(5))
 
 
 class Groups:
     """iv_groups_t: contiguous row groups (partner frames) with their flattened-coordinate origins."""
 
-    def __init__(self, iv, seg_ranges=None, gap=1, zero_lo=False):
+    def __init__(self, iv, seg_ranges=None, gap=1, zero_lo=False, widen=False):
         k = iv.n_seg
         if seg_ranges is None:
             seg_ranges = [(i, i + 1) for i in range(k)]
@@ -187,6 +200,8 @@ class Groups:
         empty = lo > hi
         lo = np.where(empty, 0, lo)
         hi = np.where(empty, 0, hi)
+        if widen:
+            lo, hi = lo - 1, hi + 1
         if zero_lo:
             if g and lo.min() < 0:
                 raise ValueError("coverage needs non-negative coordinates")
@@ -235,6 +250,10 @@ class SubjectIndex:
 
     def __init__(self, iv, seg_ranges=None, ends_perm=False):
         self.iv = iv
+        if iv.has_zero_length:
+            # the rank index counts with #{S < e} - #{E <= s}, which needs S < E; join / count_overlaps / overlap go
+            # through ListIndex, which handles such rows exactly
+            raise ValueError("zero-length intervals (Start == End) in `other` are not supported by this operation")
         self.groups = iv.groups(seg_ranges, gap=1)
         self.flags = IV_INDEX_ENDS_PERM if ends_perm else 0
         L = cabi.lib()
@@ -475,6 +494,28 @@ def gather(column, rows, fill=None):
     return out
 
 
+# ---- path selection: list index (fused join) where it applies, rank index otherwise --------------------------------------
+def _mean_len(q_iv):
+    return float(q_iv.sumlen.sum()) / q_iv.n if q_iv.n else 0.0
+
+
+def overlap_pairs(s_iv, group_ranges, q, want_counts=False, capacity=None):
+    """NCLS.all_overlaps_both for all keys (pyranges/methods/join.py:15,23): -> (counts | None, query rows, subject
+    rows), pairs in query order."""
+    if ListIndex.supported(s_iv, group_ranges, _mean_len(q.iv)):
+        ix = ListIndex(s_iv, group_ranges)
+        a, b = ix.pairs(q, capacity=capacity)
+        return (ix.count(q, IV_MODE_ALL) if want_counts else None), a, b
+    return SubjectIndex(s_iv, group_ranges).pairs(q, IV_MODE_ALL, want_counts=want_counts, capacity=capacity)
+
+
+def overlap_counts(s_iv, group_ranges, q, mode=IV_MODE_ALL):
+    """overlaps per query row: all (IV_MODE_ALL), 0/1 (IV_MODE_ANY) or containments (IV_MODE_CONTAIN)"""
+    if mode in (IV_MODE_ALL, IV_MODE_ANY) and ListIndex.supported(s_iv, group_ranges, _mean_len(q.iv)):
+        return ListIndex(s_iv, group_ranges).count(q, mode)
+    return SubjectIndex(s_iv, group_ranges).count(q, mode, for_emit=False)[0]
+
+
 # ---- repeated operations on resident columns ------------------------------------------------------------------------
 class _Totals:
     """Device-side result sizes of asynchronous steps: every step copies its total into a pinned host slot without
@@ -514,7 +555,7 @@ class JoinStep:
         self.s_iv, self.q_iv, self.group_ranges = s_iv, q_iv, group_ranges
         self.q = Queries(q_iv, seg_group, slack=slack)
         if path == "auto":
-            path = "fused" if ListIndex.supported(s_iv, group_ranges, q_iv) else "twopass"
+            path = "fused" if ListIndex.supported(s_iv, group_ranges, _mean_len(q_iv)) else "twopass"
         self.path = path
         self.cap = 0
         self.totals = _Totals()
@@ -595,7 +636,7 @@ class CountStep:
         self.s_iv, self.q_iv, self.group_ranges, self.mode = s_iv, q_iv, group_ranges, mode
         self.q = Queries(q_iv, seg_group)
         if path == "auto":
-            path = "lists" if ListIndex.supported(s_iv, group_ranges, q_iv) else "ranks"
+            path = "lists" if ListIndex.supported(s_iv, group_ranges, _mean_len(q_iv)) else "ranks"
         self.path = path
 
     def step(self):
@@ -639,8 +680,73 @@ class OverlapFirstStep:
 
 
 class ListIndex:
-    """placeholder until csrc/lists.cu lands"""
+    """Device index of the join / count_overlaps / overlap fast path -- the NCLS replacement of
+    pyranges/methods/join.py:12 for all keys at once, built without a sort (csrc/lists.cu): per coordinate bin the list
+    of subjects touching it, 32-byte bin records with the first three entries inline.  iv_join_pairs / iv_join_count
+    (csrc/join.cu) answer a query from one record gather in the common case."""
+
+    LONG_QUERY_BINS = 4  # queries longer than this many bins on average go to the rank index (one gather per bin)
 
     @staticmethod
-    def supported(s_iv, group_ranges, q_iv):
-        return False
+    def supported(s_iv, group_ranges, q_mean_len=None):
+        """can (and should) these subjects / queries of this mean length use the list index?"""
+        g = s_iv.groups(group_ranges, gap=1, widen=s_iv.has_zero_length)
+        shift = cabi.lib().iv_lists_shift(s_iv.n, g.total_span, g.sumlen)
+        if shift < 0:
+            return False
+        if s_iv.has_zero_length:
+            return True  # the only index that handles zero-length subjects
+        return q_mean_len is None or q_mean_len <= ListIndex.LONG_QUERY_BINS * (1 << shift)
+
+    def __init__(self, iv, seg_ranges=None):
+        self.iv = iv
+        self.groups = iv.groups(seg_ranges, gap=1, widen=iv.has_zero_length)
+        L = cabi.lib()
+        nbytes = L.iv_lists_workspace_bytes(iv.n, self.groups.total_span, self.groups.sumlen)
+        if nbytes == 0:
+            raise cabi.CabiError("ListIndex: span / subject lengths beyond the list index (use SubjectIndex)")
+        self.ws = _bytes(nbytes, iv.device)
+        self.c = cabi.IvLists()
+        self.build()
+
+    def build(self):
+        iv = self.iv
+        cabi.check(cabi.lib().iv_lists_build(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(self.groups.c), _ptr(self.ws),
+                                             self.ws.numel(), C.byref(self.c), _stream()), "iv_lists_build")
+        return self
+
+    def join_pairs(self, q, out_q, out_s, capacity, s_label=None):
+        """launch the fused join into caller buffers of `capacity` entries; -> total (device int64[1]); pairs beyond
+        the capacity are dropped: compare the total and repeat with larger buffers"""
+        L = cabi.lib()
+        dev = self.iv.device
+        ws = _bytes(L.iv_join_workspace_bytes(q.iv.n), dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        cabi.check(L.iv_join_pairs(C.byref(self.c), C.byref(q.c), _ptr(out_q), _ptr(out_s), _ptr(s_label), int(capacity),
+                                   _ptr(ws), ws.numel(), _ptr(total), _stream()), "iv_join_pairs")
+        return total
+
+    def pairs(self, q, want_q=True, want_s=True, s_label=None, capacity=None):
+        """all (query row | label, subject row | label) pairs in query order (NCLS.all_overlaps_both) -> (out_q, out_s)"""
+        dev = self.iv.device
+        cap = int(capacity) if capacity else max(2 * q.iv.n, 1 << 16)
+        while True:
+            oq = torch.empty(cap, dtype=torch.int64, device=dev) if want_q else None
+            os_ = torch.empty(cap, dtype=torch.int64, device=dev) if want_s else None
+            p = int(self.join_pairs(q, oq, os_, cap, s_label).item())
+            if p <= cap:
+                return (oq[:p] if want_q else None), (os_[:p] if want_s else None)
+            cap = p
+
+    def count(self, q, mode=IV_MODE_ALL):
+        """overlaps per query (IV_MODE_ALL) or 0/1 (IV_MODE_ANY), int64[nq]"""
+        counts = torch.empty(q.iv.n, dtype=torch.int64, device=self.iv.device)
+        cabi.check(cabi.lib().iv_join_count(C.byref(self.c), C.byref(q.c), mode, _ptr(counts), _stream()), "iv_join_count")
+        return counts
+
+    def segment_pair_counts(self, q, out_q, total, capacity):
+        """pairs per query segment (key) of a pair list written WITHOUT query labels (query rows ascending)"""
+        out = torch.empty(max(q.iv.n_seg, 1), dtype=torch.int64, device=self.iv.device)
+        cabi.check(cabi.lib().iv_sorted_pair_segments(_ptr(out_q), _ptr(total), int(capacity), _ptr(q.iv.seg_off_dev),
+                                                      q.iv.n_seg, _ptr(out), _stream()), "iv_sorted_pair_segments")
+        return out[:q.iv.n_seg]

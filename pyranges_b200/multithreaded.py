@@ -302,9 +302,11 @@ def _b_write_both(plan, kwargs):
     how = kwargs.get("how")
     assert (how in "containment first last outer right left".split() + [False, None]) or isinstance(how, int)
     mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY, "last": E.IV_MODE_LAST}.get(how, E.IV_MODE_ALL)
-    ix = plan.index()
     inner = how not in ["outer", "left", "right"]
-    counts, out_q, out_s = ix.pairs(plan.queries(), mode, want_counts=not inner)  # counts: rows without partner
+    if mode == E.IV_MODE_ALL:  # counts: rows without partner (outer joins)
+        counts, out_q, out_s = E.overlap_pairs(plan.s.iv, plan.group_ranges or None, plan.queries(), want_counts=not inner)
+    else:
+        counts, out_q, out_s = plan.index().pairs(plan.queries(), mode, want_counts=not inner)
     core = None
     if inner:
         # the coordinate columns of the joined frame are gathered on the device, where both
@@ -350,8 +352,7 @@ def _b_number_overlapping(plan, kwargs):
     """count_overlaps: pyranges/methods/coverage.py:6-45 for all keys (no pair materialisation)."""
     keep = kwargs.get("keep_nonoverlapping", True)
     col = kwargs.get("overlap_col", True)
-    counts, _, _ = plan.index().count(plan.queries(), E.IV_MODE_ALL, for_emit=False)
-    counts = counts.cpu().numpy()
+    counts = E.overlap_counts(plan.s.iv, plan.group_ranges or None, plan.queries(), E.IV_MODE_ALL).cpu().numpy()
     results = []
     for k, scdf in enumerate(plan.q.dfs):
         ocdf = plan.partner(k)
@@ -369,8 +370,7 @@ def _b_overlap(plan, kwargs):
     how = kwargs["how"]
     assert how in "containment first".split() + [False, None]
     mode = E.IV_MODE_ALL if not how else (E.IV_MODE_CONTAIN if how == "containment" else E.IV_MODE_ANY)
-    counts, _, _ = plan.index().count(plan.queries(), mode, for_emit=False)
-    counts = counts.cpu().numpy()
+    counts = E.overlap_counts(plan.s.iv, plan.group_ranges or None, plan.queries(), mode).cpu().numpy()
     results = []
     for k, scdf in enumerate(plan.q.dfs):
         ocdf = plan.partner(k)
@@ -393,7 +393,10 @@ def _b_intersection(plan, kwargs):
     how = kwargs["how"]
     assert how in "containment first last".split() + [False, None]
     mode = {"containment": E.IV_MODE_CONTAIN, "first": E.IV_MODE_ANY, "last": E.IV_MODE_LAST}.get(how, E.IV_MODE_ALL)
-    _, out_q, out_s = plan.index().pairs(plan.queries(), mode, want_counts=False)
+    if mode == E.IV_MODE_ALL:
+        _, out_q, out_s = E.overlap_pairs(plan.s.iv, plan.group_ranges or None, plan.queries())
+    else:
+        _, out_q, out_s = plan.index().pairs(plan.queries(), mode, want_counts=False)
     # the clip max(Start, Start_b) / min(End, End_b) happens where the columns live (engine.materialize_pairs)
     core = E.materialize_pairs(plan.q.iv, plan.s.iv, out_q, out_s, clip=True, want=("q_start", "q_end"))
     cs, ce = core["q_start"].cpu().numpy(), core["q_end"].cpu().numpy()
@@ -447,8 +450,7 @@ def _b_count_overlaps(plan, kwargs):
     frame is copied (Appendix B quirk 6 consciously not kept)."""
     how = kwargs.get("how")
     mode = E.IV_MODE_ALL if not how else (E.IV_MODE_CONTAIN if how == "containment" else E.IV_MODE_ANY)
-    counts, _, _ = plan.index().count(plan.queries(), mode, for_emit=False)
-    counts = counts.cpu().numpy()
+    counts = E.overlap_counts(plan.s.iv, plan.group_ranges or None, plan.queries(), mode).cpu().numpy()
     results = []
     for k, scdf in enumerate(plan.q.dfs):
         if scdf.empty:

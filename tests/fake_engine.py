@@ -190,3 +190,11 @@ def split(iv, seg_ranges=None):
         off.append(off[-1] + len(fs))
     cat = lambda x: np.concatenate(x) if x else np.zeros(0, np.int64)  # noqa: E731
     return np.asarray(off, np.int64), _t(cat(S)), _t(cat(E))
+
+
+def overlap_pairs(s_iv, group_ranges, q, want_counts=False, capacity=None):
+    return SubjectIndex(s_iv, group_ranges).pairs(q, IV_MODE_ALL, want_counts=want_counts)
+
+
+def overlap_counts(s_iv, group_ranges, q, mode=IV_MODE_ALL):
+    return SubjectIndex(s_iv, group_ranges).count(q, mode, for_emit=False)[0]
