@@ -2,8 +2,8 @@
 // index (lists.cu).  Replaces NCLS.all_overlaps_both (pyranges/methods/join.py:15,23) and, in its count-only form,
 // all_overlaps_both + value_counts / has_overlaps (pyranges/methods/coverage.py:26-40, intersection.py:78).
 //
-// A block owns a tile of 2048 consecutive query rows (tiles are handed out by an atomic ticket, so a tile only ever
-// waits for tiles that are already running), a warp 256 consecutive rows of it, a lane two rows per iteration:
+// A block takes a ticket for 2048 consecutive query rows (so a tile only ever waits for tiles that are already running),
+// a WARP is its own tile of 256 consecutive rows, a lane owns two rows per iteration:
 //   1. 16-byte streaming loads of Start / End, 32-bit clamp into the partner group's window of the flattened axis,
 //      ONE 256-bit gather of the record of the bin the query starts in (list offset, length, first three entries);
 //   2. count sweep: two 16-bit compares per entry (inline entries from registers; longer lists and the later bins of a
@@ -15,6 +15,8 @@
 //   5. every warp copies its staged pairs to out_q / out_s with fully coalesced 8-byte streaming stores.
 // A warp whose pairs do not fit its staging area repeats its rows once the offset is known and writes directly.
 // DRAM sees the query columns once and the pair columns once; the index stays in L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "query.cuh"
 
@@ -25,9 +27,10 @@ constexpr int JN_WARPS = JN_THREADS / 32;
 constexpr int JN_ITERS = 4;                       // iterations of 64 rows per warp
 constexpr int JN_WROWS = 64 * JN_ITERS;           // 256 rows per warp
 constexpr int JN_TILE = JN_WROWS * JN_WARPS;      // 2048 rows per block
-constexpr int JN_WCAP = 768;                      // staged pairs per warp (3 per row; the rest goes the direct way)
+constexpr int JN_WCAP = 768;                      // staged pairs per warp (3 per row; the rest is repeated later)
 
-constexpr int JM_STAGE = 0, JM_DIRECT = 1, JM_COUNT = 2, JM_ANY = 3;
+constexpr int JM_COUNT = 2, JM_ANY = 3;
+
 
 struct LRec { uint32_t w[8]; };  // w0 = co, w1 = n8, (w2, w3) (w4, w5) (w6, w7) = entries {row, so | eo << 16}
 
@@ -119,192 +122,233 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* state
 }
 
 // ---- the rows of one warp ----------------------------------------------------------------------------------------------------
-struct WarpOut {
-    unsigned long long total;  // pairs of the warp's rows
-    bool overflow;             // they did not fit the staging area (JM_STAGE)
+// segment geometry of the rows a warp walks over (monotone: re-derived only when the key changes)
+template <typename X> struct Geo {
+    int seg, f_seg;
+    Flat<X> f0;
+    uint32_t lo32, hi32, off32;
+    bool geo32;
+    __device__ __forceinline__ Geo(const iv_queries_t& q, int64_t row) : f_seg(-1), lo32(0), hi32(0), off32(0), geo32(false) {
+        seg = find_seg(q.seg_off, q.n_seg, row);
+    }
 };
 
-template <typename X, int MODE, bool SLACK>
-__device__ __forceinline__ WarpOut warp_rows(const iv_lists_t& ix, const iv_queries_t& q, int64_t wbase, bool vec,
-                                             uint32_t* __restrict__ st_s, uint16_t* __restrict__ st_q, uint32_t qloc0,
-                                             int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
-                                             const int64_t* __restrict__ s_label, int64_t cap, unsigned long long obase,
-                                             int64_t* __restrict__ out_count) {
+// the two rows (ibase + 2 * lane, + 1) of a lane: flattened interval, liveness, record of the bin the query starts in
+template <typename X> struct Rows2 {
+    X sc[2], ec[2];
+    LRec r[2];
+    bool live[2];
+};
+
+template <typename X, bool SLACK>
+__device__ __forceinline__ void load_rows(const iv_lists_t& ix, const iv_queries_t& q, bool vec, int64_t ibase, Geo<X>& G,
+                                          Rows2<X>& R) {
     const int lane = lane_id();
     const int shift = ix.shift;
-    WarpOut wo{0ull, false};
-    if (wbase >= q.n) return wo;
-    int seg = find_seg(q.seg_off, q.n_seg, wbase), f_seg = -1;
-    Flat<X> f0;
-    uint32_t lo32 = 0, hi32 = 0, off32 = 0;
-    bool geo32 = false;
+    while (G.seg + 1 < q.n_seg && __ldg(q.seg_off + G.seg + 1) <= ibase) G.seg++;
+    const bool uniform = __ldg(q.seg_off + G.seg + 1) >= ibase + 64;
+    if (G.seg != G.f_seg) {
+        G.f0 = load_flat_groups<X>(ix.groups, ix.n, q, G.seg);
+        G.f_seg = G.seg;
+        const uint64_t hi = (uint64_t)G.f0.lo + G.f0.width;
+        G.geo32 = sizeof(X) == 4 && G.f0.lo >= 0 && hi <= 0xffffffffull;
+        G.lo32 = (uint32_t)G.f0.lo;
+        G.hi32 = (uint32_t)hi;
+        G.off32 = (uint32_t)G.f0.base - G.lo32;
+    }
+    const int64_t r0 = ibase + 2 * lane;
+    int64_t s[2] = {0, 0}, e[2] = {0, 0};
+    if (vec && r0 + 1 < q.n) {
+        const longlong2 s2 = __ldcs(reinterpret_cast<const longlong2*>(q.start + r0));
+        const longlong2 e2 = __ldcs(reinterpret_cast<const longlong2*>(q.end + r0));
+        s[0] = s2.x; s[1] = s2.y; e[0] = e2.x; e[1] = e2.y;
+    } else {
+        if (r0 < q.n) { s[0] = __ldcs(q.start + r0); e[0] = __ldcs(q.end + r0); }
+        if (r0 + 1 < q.n) { s[1] = __ldcs(q.start + r0 + 1); e[1] = __ldcs(q.end + r0 + 1); }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (SLACK) apply_slack(q.slack, s[k], e[k]);
+        bool partner;
+        if (uniform && G.geo32 && (((uint64_t)s[k] | (uint64_t)e[k]) >> 32) == 0) {
+            R.sc[k] = (X)(min(max((uint32_t)s[k], G.lo32), G.hi32) + G.off32);
+            R.ec[k] = (X)(min(max((uint32_t)e[k], G.lo32), G.hi32) + G.off32);
+            partner = G.f0.g >= 0;
+        } else {
+            Flat<X> f = G.f0;
+            if (!uniform) {
+                const int sg = find_seg_range(q.seg_off, G.seg, q.n_seg - 1, r0 + k < q.n ? r0 + k : q.n - 1);
+                if (sg != G.seg) f = load_flat_groups<X>(ix.groups, ix.n, q, sg);
+            }
+            R.sc[k] = f.at(s[k]);
+            R.ec[k] = f.at(e[k]);
+            partner = f.g >= 0;
+        }
+        // rows beyond the end, keys without a partner and malformed rows (end < start) have no hits
+        R.live[k] = r0 + k < q.n && partner && R.ec[k] >= R.sc[k];
+        if (!R.live[k]) { R.sc[k] = 0; R.ec[k] = 0; }
+        R.r[k] = load_lrec(ix.rec, (uint64_t)R.sc[k] >> shift);
+    }
+}
+
+template <typename X>
+__device__ __forceinline__ void count_rows(const iv_lists_t& ix, const Rows2<X>& R, uint32_t (&c)[2]) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        uint32_t n = 0;
+        if (R.live[k]) walk_query<X>(ix, R.sc[k], R.ec[k], R.r[k], [&](uint32_t) { n++; });
+        c[k] = n;
+    }
+}
+
+// count-only kernels: out_count[row] = hits (JM_COUNT) or 0 / 1 (JM_ANY)
+template <typename X, int MODE, bool SLACK>
+__global__ void __launch_bounds__(JN_THREADS, 4)
+k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wbase = (int64_t)blockIdx.x * JN_TILE + (int64_t)warp * JN_WROWS;
+    if (wbase >= q.n) return;
+    Geo<X> G(q, wbase);
 #pragma unroll 1
     for (int it = 0; it < JN_ITERS; it++) {
         const int64_t ibase = wbase + it * 64;
         if (ibase >= q.n) break;
-        while (seg + 1 < q.n_seg && __ldg(q.seg_off + seg + 1) <= ibase) seg++;
-        const bool uniform = __ldg(q.seg_off + seg + 1) >= ibase + 64;
-        if (seg != f_seg) {
-            f0 = load_flat_groups<X>(ix.groups, ix.n, q, seg);
-            f_seg = seg;
-            const uint64_t hi = (uint64_t)f0.lo + f0.width;
-            geo32 = sizeof(X) == 4 && f0.lo >= 0 && hi <= 0xffffffffull;
-            lo32 = (uint32_t)f0.lo;
-            hi32 = (uint32_t)hi;
-            off32 = (uint32_t)f0.base - lo32;
-        }
-        const int64_t r0 = ibase + 2 * lane;  // rows r0, r0 + 1
-        int64_t s[2] = {0, 0}, e[2] = {0, 0};
-        if (vec && r0 + 1 < q.n) {
-            const longlong2 s2 = __ldcs(reinterpret_cast<const longlong2*>(q.start + r0));
-            const longlong2 e2 = __ldcs(reinterpret_cast<const longlong2*>(q.end + r0));
-            s[0] = s2.x; s[1] = s2.y; e[0] = e2.x; e[1] = e2.y;
-        } else {
-            if (r0 < q.n) { s[0] = __ldcs(q.start + r0); e[0] = __ldcs(q.end + r0); }
-            if (r0 + 1 < q.n) { s[1] = __ldcs(q.start + r0 + 1); e[1] = __ldcs(q.end + r0 + 1); }
-        }
-        X sc[2], ec[2];
-        LRec r[2];
-        bool live[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (SLACK) apply_slack(q.slack, s[k], e[k]);
-            bool partner;
-            if (uniform && geo32 && (((uint64_t)s[k] | (uint64_t)e[k]) >> 32) == 0) {
-                sc[k] = (X)(min(max((uint32_t)s[k], lo32), hi32) + off32);
-                ec[k] = (X)(min(max((uint32_t)e[k], lo32), hi32) + off32);
-                partner = f0.g >= 0;
-            } else {
-                Flat<X> f = f0;
-                if (!uniform) {
-                    const int sg = find_seg_range(q.seg_off, seg, q.n_seg - 1, r0 + k < q.n ? r0 + k : q.n - 1);
-                    if (sg != seg) f = load_flat_groups<X>(ix.groups, ix.n, q, sg);
-                }
-                sc[k] = f.at(s[k]);
-                ec[k] = f.at(e[k]);
-                partner = f.g >= 0;
-            }
-            // rows beyond the end, keys without a partner and malformed rows (end < start) have no hits
-            live[k] = r0 + k < q.n && partner && ec[k] >= sc[k];
-            if (!live[k]) { sc[k] = 0; ec[k] = 0; }
-            r[k] = load_lrec(ix.rec, (uint64_t)sc[k] >> shift);
-        }
-        // count sweep
+        Rows2<X> R;
+        load_rows<X, SLACK>(ix, q, vec, ibase, G, R);
         uint32_t c[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            uint32_t n = 0;
-            if (live[k]) walk_query<X>(ix, sc[k], ec[k], r[k], [&](uint32_t) { n++; });
-            c[k] = MODE == JM_ANY ? (n > 0 ? 1u : 0u) : n;
+        count_rows<X>(ix, R, c);
+        if (MODE == JM_ANY) { c[0] = c[0] ? 1u : 0u; c[1] = c[1] ? 1u : 0u; }
+        const int64_t r0 = ibase + 2 * lane;
+        if (vec && r0 + 1 < q.n) {
+            __stcs(reinterpret_cast<longlong2*>(out_count + r0), make_longlong2((long long)c[0], (long long)c[1]));
+        } else {
+            if (r0 < q.n) out_count[r0] = c[0];
+            if (r0 + 1 < q.n) out_count[r0 + 1] = c[1];
         }
-        if (MODE == JM_COUNT || MODE == JM_ANY) {
-            if (vec && r0 + 1 < q.n) {
-                __stcs(reinterpret_cast<longlong2*>(out_count + r0), make_longlong2((long long)c[0], (long long)c[1]));
-            } else {
-                if (r0 < q.n) out_count[r0] = c[0];
-                if (r0 + 1 < q.n) out_count[r0 + 1] = c[1];
-            }
-            continue;
-        }
-        // position of the lane's pairs among the warp's
-        const uint32_t mine = c[0] + c[1];
-        const uint32_t inc = warp_incl_sum(mine);
-        const uint32_t itot = __shfl_sync(FULL, inc, 31);
-        if (itot == 0) continue;
-        if (MODE == JM_STAGE) {
-            if (!wo.overflow && wo.total + itot <= (unsigned long long)JN_WCAP) {
-                uint32_t pos = (uint32_t)wo.total + inc - mine;
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    if (c[k]) {
-                        const uint16_t ql = (uint16_t)(qloc0 + it * 64 + 2 * lane + k);
-                        walk_query<X>(ix, sc[k], ec[k], r[k], [&](uint32_t row) {
-                            st_s[pos] = row;
-                            st_q[pos] = ql;
-                            pos++;
-                        });
-                    }
-                }
-            } else {
-                wo.overflow = true;
-            }
-        } else {  // JM_DIRECT: the output offset of the warp is known
-            unsigned long long o = obase + wo.total + inc - mine;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                if (c[k]) {
-                    const int64_t row_q = r0 + k;
-                    const int64_t ql = q.label ? __ldg(q.label + row_q) : row_q;
-                    walk_query<X>(ix, sc[k], ec[k], r[k], [&](uint32_t row) {
-                        if ((int64_t)o < cap) {
-                            if (out_q) out_q[o] = ql;
-                            if (out_s) out_s[o] = s_label ? __ldg(s_label + row) : (int64_t)row;
-                        }
-                        o++;
-                    });
-                }
-            }
-        }
-        wo.total += itot;
     }
-    return wo;
 }
 
-template <typename X, bool SLACK>
-__global__ void __launch_bounds__(JN_THREADS, 4)
+// ---- the fused join ---------------------------------------------------------------------------------------------------------------
+// Every WARP is its own tile of 256 rows (tile id = block ticket * 8 + warp: the warps of a block are co-resident and
+// blocks with smaller tickets started earlier, so a tile only waits for tiles that are running or done); no block-wide
+// barrier after the ticket.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
+// pair total, looks back for its output offset and copies the staged pairs out with coalesced stores; iterations that
+// did not fit are repeated afterwards -- the offset is known by then -- through the same staging area, one at a time.
+template <typename X, bool SLACK, int OCC>
+__global__ void __launch_bounds__(JN_THREADS, OCC)
 k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
        const int64_t* __restrict__ s_label, int64_t cap, unsigned long long* __restrict__ state,
-       unsigned int* __restrict__ ticket, int64_t n_tiles, int64_t* __restrict__ out_total) {
-    __shared__ uint32_t st_s[JN_WARPS][JN_WCAP];
-    __shared__ uint16_t st_q[JN_WARPS][JN_WCAP];
-    __shared__ unsigned long long s_wtot[JN_WARPS];
-    __shared__ unsigned long long s_base;
+       unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total) {
+    __shared__ uint32_t st_s_all[JN_WARPS][JN_WCAP];
+    __shared__ uint8_t st_q_all[JN_WARPS][JN_WCAP];
+    __shared__ uint32_t s_cnt[JN_WARPS][JN_ITERS];
     __shared__ unsigned int s_tile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
-    const int64_t tile = s_tile;
-    const int64_t tbase = tile * JN_TILE;
-    const int64_t wbase = tbase + (int64_t)warp * JN_WROWS;
-    const WarpOut wo = warp_rows<X, JM_STAGE, SLACK>(ix, q, wbase, vec, st_s[warp], st_q[warp], (uint32_t)(warp * JN_WROWS),
-                                                     nullptr, nullptr, nullptr, 0, 0ull, nullptr);
-    if (lane == 0) s_wtot[warp] = wo.total;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long agg = 0;
-#pragma unroll
-        for (int w = 0; w < JN_WARPS; w++) agg += s_wtot[w];
-        const unsigned long long excl = lookback(state, tile, agg);
-        if (lane == 0) {
-            s_base = excl;
-            if (tile == n_tiles - 1) *out_total = (int64_t)(excl + agg);
-        }
-    }
-    __syncthreads();
-    unsigned long long obase = s_base;
-    for (int w = 0; w < warp; w++) obase += s_wtot[w];
-    if (!wo.overflow) {
-        const uint32_t n = (uint32_t)wo.total;
+    const int64_t wtile = (int64_t)s_tile * JN_WARPS + warp;
+    if (wtile >= n_wtiles) return;
+    const int64_t wbase = wtile * JN_WROWS;
+    uint32_t* __restrict__ st_s = st_s_all[warp];
+    uint8_t* __restrict__ st_q = st_q_all[warp];
+
+    // coalesced copy of `n` staged pairs to the outputs at offset o0; rows are relative to rbase
+    auto copy_out = [&](uint32_t n, unsigned long long o0, int64_t rbase) {
         for (uint32_t k = lane; k < n; k += 32) {
-            const int64_t o = (int64_t)(obase + k);
+            const int64_t o = (int64_t)(o0 + k);
             if (o < cap) {
-                const int64_t row_q = tbase + st_q[warp][k];
-                const uint32_t row_s = st_s[warp][k];
+                const int64_t row_q = rbase + st_q[k];
+                const uint32_t row_s = st_s[k];
                 if (out_q) __stcs(out_q + o, q.label ? __ldg(q.label + row_q) : row_q);
                 if (out_s) __stcs(out_s + o, s_label ? __ldg(s_label + row_s) : (int64_t)row_s);
             }
         }
-    } else {
-        warp_rows<X, JM_DIRECT, SLACK>(ix, q, wbase, vec, nullptr, nullptr, 0u, out_q, out_s, s_label, cap, obase, nullptr);
-    }
-}
+    };
+    // emit sweep of one iteration into the staging area, the lane's first pair at `pos`
+    auto stage_rows = [&](const Rows2<X>& R, const uint32_t (&c)[2], uint32_t pos, uint32_t qloc) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (c[k]) {
+                const uint8_t ql = (uint8_t)(qloc + k);
+                walk_query<X>(ix, R.sc[k], R.ec[k], R.r[k], [&](uint32_t row) {
+                    st_s[pos] = row;
+                    st_q[pos] = ql;
+                    pos++;
+                });
+            }
+        }
+    };
 
-template <typename X, int MODE, bool SLACK>
-__global__ void __launch_bounds__(JN_THREADS, 4)
-k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_count) {
-    const int warp = threadIdx.x >> 5;
-    const int64_t wbase = (int64_t)blockIdx.x * JN_TILE + (int64_t)warp * JN_WROWS;
-    warp_rows<X, MODE, SLACK>(ix, q, wbase, vec, nullptr, nullptr, 0u, nullptr, nullptr, nullptr, 0, 0ull, out_count);
+    Geo<X> G(q, wbase);
+    unsigned long long total = 0;
+    uint32_t staged = 0;
+    int staged_iters = 0;
+    bool open = true;
+#pragma unroll 1
+    for (int it = 0; it < JN_ITERS; it++) {
+        const int64_t ibase = wbase + it * 64;
+        uint32_t itot = 0;
+        if (ibase < q.n) {
+            Rows2<X> R;
+            load_rows<X, SLACK>(ix, q, vec, ibase, G, R);
+            uint32_t c[2];
+            count_rows<X>(ix, R, c);
+            const uint32_t mine = c[0] + c[1];
+            const uint32_t inc = warp_incl_sum(mine);
+            itot = __shfl_sync(FULL, inc, 31);
+            if (open && staged + itot <= (uint32_t)JN_WCAP) {
+                if (itot) stage_rows(R, c, staged + inc - mine, (uint32_t)(it * 64 + 2 * lane));
+                staged += itot;
+                staged_iters = it + 1;
+            } else {
+                open = false;
+            }
+        }
+        if (lane == 0) s_cnt[warp][it] = itot;
+        total += itot;
+    }
+    __syncwarp();
+    unsigned long long o = lookback(state, wtile, total);
+    if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);
+    copy_out(staged, o, wbase);
+    o += staged;
+    // iterations that did not fit: once more, through the staging area (or straight to memory when a single iteration
+    // exceeds it)
+    for (int it = staged_iters; it < JN_ITERS; it++) {
+        const uint32_t itot = s_cnt[warp][it];
+        if (itot == 0) continue;
+        const int64_t ibase = wbase + it * 64;
+        __syncwarp();
+        Geo<X> G2(q, ibase);
+        Rows2<X> R;
+        load_rows<X, SLACK>(ix, q, vec, ibase, G2, R);
+        uint32_t c[2];
+        count_rows<X>(ix, R, c);
+        const uint32_t mine = c[0] + c[1];
+        const uint32_t inc = warp_incl_sum(mine);
+        if (itot <= (uint32_t)JN_WCAP) {
+            stage_rows(R, c, inc - mine, (uint32_t)(2 * lane));
+            __syncwarp();
+            copy_out(itot, o, ibase);
+        } else {
+            unsigned long long oo = o + inc - mine;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (c[k]) {
+                    const int64_t row_q = ibase + 2 * lane + k;
+                    const int64_t ql = q.label ? __ldg(q.label + row_q) : row_q;
+                    walk_query<X>(ix, R.sc[k], R.ec[k], R.r[k], [&](uint32_t row) {
+                        if ((int64_t)oo < cap) {
+                            if (out_q) out_q[oo] = ql;
+                            if (out_s) out_s[oo] = s_label ? __ldg(s_label + row) : (int64_t)row;
+                        }
+                        oo++;
+                    });
+                }
+            }
+        }
+        o += itot;
+    }
 }
 
 // pairs per query segment of a pair list in query order (ascending query rows): lower bounds of the segment boundaries
@@ -341,7 +385,7 @@ static int check_join(const iv_lists_t* ix, const iv_queries_t* q, const char* w
 using namespace iv;
 
 extern "C" size_t iv_join_workspace_bytes(int64_t n_queries) {
-    return ((size_t)cdiv(n_queries > 0 ? n_queries : 1, JN_TILE) + 2) * sizeof(unsigned long long) + 256;
+    return ((size_t)cdiv(n_queries > 0 ? n_queries : 1, JN_WROWS) + 2) * sizeof(unsigned long long) + 256;
 }
 
 extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int64_t* out_q, int64_t* out_s,
@@ -358,21 +402,26 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     }
     IV_REQUIRE(ws && (((uintptr_t)ws) & 255) == 0 && ws_bytes >= iv_join_workspace_bytes(q->n), IV_ERR_WORKSPACE,
                "iv_join_pairs: workspace missing, misaligned or too small");
-    const int64_t n_tiles = cdiv(q->n, JN_TILE);
+    const int64_t n_tiles = cdiv(q->n, JN_WROWS);  // one tile per warp
     IV_REQUIRE(n_tiles < ((int64_t)1 << 31), IV_ERR_RANGE, "iv_join_pairs: too many rows");
     unsigned long long* state = (unsigned long long*)ws;
     unsigned int* ticket = (unsigned int*)(state + n_tiles);
     IV_CUDA(cudaMemsetAsync(ws, 0, (size_t)(n_tiles + 1) * sizeof(unsigned long long), st));
     const bool vec = aligned16(q->start) && aligned16(q->end);
     const bool slack = q->slack != 0;
-    const unsigned nb = (unsigned)n_tiles;
+    const unsigned nb = (unsigned)cdiv(q->n, JN_TILE);
+    // resident blocks per SM the kernel is compiled for: 4 (62 registers, no spills; default) or 5 (48 registers);
+    // IV_JOIN_OCC is a tuning switch for measurements
+    static const int occ = getenv("IV_JOIN_OCC") ? atoi(getenv("IV_JOIN_OCC")) : 4;
+#define IV_JK(X, SL, OC) k_join<X, SL, OC><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total)
+#define IV_JK2(X, SL) do { if (occ == 5) IV_JK(X, SL, 5); else if (occ == 6) IV_JK(X, SL, 6); else IV_JK(X, SL, 4); } while (0)
     if (narrow_span(lists)) {
-        if (slack) k_join<uint32_t, true><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total);
-        else k_join<uint32_t, false><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total);
+        if (slack) IV_JK2(uint32_t, true); else IV_JK2(uint32_t, false);
     } else {
-        if (slack) k_join<uint64_t, true><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total);
-        else k_join<uint64_t, false><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total);
+        if (slack) IV_JK2(uint64_t, true); else IV_JK2(uint64_t, false);
     }
+#undef IV_JK2
+#undef IV_JK
     IV_LAUNCH_CHECK();
     return IV_OK;
 }
