@@ -583,7 +583,7 @@ def api_join_bench(dev, n_reads=2_000_000, n_annot=40_000, reps=5):
     import pandas as pd
     import torch
 
-    import pyranges_b200 as pr
+    from pyranges_b200 import pyranges_main as pr
     from pyranges_b200 import synthetic as S
 
     def frame(ka):

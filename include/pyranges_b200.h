@@ -245,7 +245,7 @@ typedef struct iv_lentry {
 } iv_lentry_t;
 #define IV_L_CROSS 0x8000u
 typedef struct iv_lrec {
-    uint32_t co;     /* the bin's list is cand[co, co + n) */
+    uint32_t co;     /* the bin's list is cand_se / cand_row [co, co + n) */
     uint32_t n8;     /* min(n, 255) in the low byte; n = co of the next record - co when it says 255 */
     iv_lentry_t e[3]; /* the first three entries of the list (crossing entries by row, then starts by (start, row)) */
 } iv_lrec_t;
@@ -255,9 +255,10 @@ typedef struct iv_lists {
     int32_t shift;
     int32_t flags;
     int64_t n_bins;     /* rec[] holds n_bins + 2 records (the last two are sentinels) */
-    int64_t cand_cap;   /* capacity of cand[] */
+    int64_t cand_cap;   /* capacity of cand_se[] / cand_row[] */
     const iv_lrec_t* rec;
-    const iv_lentry_t* cand;
+    const uint32_t* cand_se;  /* so | eo << 16 of every list entry (all lists back to back, bin order) */
+    const uint32_t* cand_row; /* subject row of the same entries */
     iv_groups_t groups;
 } iv_lists_t;
 

@@ -32,7 +32,7 @@ class IvIndex(C.Structure):
 
 class IvLists(C.Structure):
     _fields_ = [("n", _i64), ("total_span", _i64), ("shift", _i32), ("flags", _i32), ("n_bins", _i64),
-                ("cand_cap", _i64), ("rec", _vp), ("cand", _vp), ("groups", IvGroups)]
+                ("cand_cap", _i64), ("rec", _vp), ("cand_se", _vp), ("cand_row", _vp), ("groups", IvGroups)]
 
 
 class IvQueries(C.Structure):

@@ -37,7 +37,8 @@ k_cluster_keys(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int
     // already in (group, Start, End) order?  then the stable sort is the identity and is skipped
     if (i > 0) {
         int64_t pa = s[i - 1], pb = e[i - 1];
-        int pg = sp.of(G.row_off, i - 1);
+        // (the row before the block's first one may belong to the previous group)
+        int pg = i - 1 >= first ? sp.of(G.row_off, i - 1) : find_seg(G.row_off, G.n_groups, i - 1);
         uint64_t plen = pb > pa ? (uint64_t)(pb - pa) : 0;
         uint64_t pkey = ((uint64_t)(pa - __ldg(G.lo + pg) + __ldg(G.base + pg)) << lbits) | plen;
         if (pkey > key && *unsorted == 0) *unsorted = 1;

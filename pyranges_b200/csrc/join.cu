@@ -48,44 +48,105 @@ template <bool FIRST>
 __device__ __forceinline__ bool entry_hit(uint32_t se, uint32_t rel_s, uint32_t rel_e) {
     const uint32_t so = se & 0xffffu, eo = se >> 16;
     if (FIRST) return ((so & IV_L_CROSS) || so < rel_e) && eo > rel_s;
-    return so < rel_e;  // a crossing entry has so >= 0x8000 > any rel_e of a later bin (<= 2^15); an open-ended
-                        // rel_e (0xffffffff) is never used for later bins
+    return so < rel_e;  // a crossing entry has so >= 0x8000 >= any rel_e of a later bin
 }
 
-// visit the hits of one bin's list
-template <bool FIRST, typename F>
-__device__ __forceinline__ void walk_bin(const iv_lists_t& ix, uint64_t b, const LRec& r, uint32_t rel_s, uint32_t rel_e, F&& f) {
-    uint32_t n = r.w[1] & 0xffu;
-    if (n == 255u) n = __ldg(&ix.rec[b + 1].co) - r.w[0];
-    if (n > 0 && entry_hit<FIRST>(r.w[3], rel_s, rel_e)) f(r.w[2]);
-    if (n > 1 && entry_hit<FIRST>(r.w[5], rel_s, rel_e)) f(r.w[4]);
-    if (n > 2 && entry_hit<FIRST>(r.w[7], rel_s, rel_e)) f(r.w[6]);
-    if (n > 3) {
-        const uint2* __restrict__ c = reinterpret_cast<const uint2*>(ix.cand) + r.w[0];
-#pragma unroll 4
-        for (uint32_t j = 3; j < n; j++) {
-            const uint2 en = __ldg(c + j);
-            if (entry_hit<FIRST>(en.y, rel_s, rel_e)) f(en.x);
+// ---- what the count sweep learns about a query ------------------------------------------------------------------------------
+// The first JN_MASKED entries of the list of the bin the query starts in are tested from registers: three from the bin
+// record, eight from ONE batch of loads (all in flight together -- a short list costs one round trip, not one per
+// entry).  mask = which of them are hits; extra = hits beyond: entries past the first eleven of a long list and the
+// starts inside the later bins of a query that reaches beyond its first bin (both walked entry by entry: rare).
+constexpr int JN_MASKED = 11;
+
+template <typename X> struct QPlan {
+    uint32_t mask, extra;
+    __device__ __forceinline__ uint32_t count() const { return __popc(mask) + extra; }
+};
+
+template <typename X> struct QGeom {
+    uint64_t b;
+    uint32_t rel_s, rel_e, n;
+    bool single;
+    __device__ __forceinline__ QGeom(const iv_lists_t& ix, X sc, X ec, const LRec& r) {
+        const int shift = ix.shift;
+        b = (uint64_t)sc >> shift;
+        rel_s = (uint32_t)(sc - (X)(b << shift));
+        const uint64_t d = (uint64_t)(ec - (X)(b << shift));  // ec >= sc: no wrap
+        single = d <= (1ull << shift);
+        rel_e = single ? (uint32_t)d : 0x7fffffffu;
+        n = r.w[1] & 0xffu;
+        if (n == 255u) n = __ldg(&ix.rec[b + 1].co) - r.w[0];
+    }
+};
+
+// hits beyond the masked entries: f(subject row)
+template <typename X, typename F>
+__device__ __forceinline__ void walk_extra(const iv_lists_t& ix, X ec, const LRec& r, const QGeom<X>& g, F&& f) {
+    const int shift = ix.shift;
+    for (uint32_t j = JN_MASKED; j < g.n; j++)
+        if (entry_hit<true>(__ldg(ix.cand_se + r.w[0] + j), g.rel_s, g.rel_e)) f(__ldg(ix.cand_row + r.w[0] + j));
+    if (!g.single) {
+        const uint64_t bl = (uint64_t)(ec - 1) >> shift;
+        for (uint64_t bb = g.b + 1; bb <= bl; bb++) {
+            const uint32_t c0 = __ldg(&ix.rec[bb].co), c1 = __ldg(&ix.rec[bb + 1].co);
+            const uint32_t re = bb < bl ? 0x8000u : (uint32_t)(ec - (X)(bl << shift));
+            for (uint32_t j = c0; j < c1; j++)
+                if (entry_hit<false>(__ldg(ix.cand_se + j), 0u, re)) f(__ldg(ix.cand_row + j));
         }
     }
 }
 
-// all hits of a flattened query [sc, ec): r = record of bin(sc)
-template <typename X, typename F>
-__device__ __forceinline__ void walk_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, F&& f) {
-    const int shift = ix.shift;
-    const uint64_t b = (uint64_t)sc >> shift;
-    const uint32_t rel_s = (uint32_t)(sc - (X)(b << shift));
-    const uint64_t d = (uint64_t)(ec - (X)(b << shift));  // ec >= sc: no wrap
-    const bool single = d <= (1ull << shift);
-    walk_bin<true>(ix, b, r, rel_s, single ? (uint32_t)d : 0x7fffffffu, f);
-    if (!single) {
-        const uint64_t bl = (uint64_t)(ec - 1) >> shift;
-        for (uint64_t bb = b + 1; bb <= bl; bb++) {
-            const LRec rr = load_lrec(ix.rec, bb);
-            const uint32_t re = bb < bl ? 0x8000u : (uint32_t)(ec - (X)(bl << shift));
-            walk_bin<false>(ix, bb, rr, 0u, re, f);
+template <typename X>
+__device__ __forceinline__ QPlan<X> plan_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, bool live) {
+    QPlan<X> p{0u, 0u};
+    if (!live) return p;
+    const QGeom<X> g(ix, sc, ec, r);
+    uint32_t m = 0;
+    if (g.n > 0 && entry_hit<true>(r.w[3], g.rel_s, g.rel_e)) m |= 1u;
+    if (g.n > 1 && entry_hit<true>(r.w[5], g.rel_s, g.rel_e)) m |= 2u;
+    if (g.n > 2 && entry_hit<true>(r.w[7], g.rel_s, g.rel_e)) m |= 4u;
+    if (g.n > 3) {
+        // entries 3 .. 10: five aligned 8-byte loads cover them whatever the parity of the list offset
+        const uint32_t first = r.w[0] + 3u, base = first & ~1u, par = first & 1u;
+        const uint2* __restrict__ c = reinterpret_cast<const uint2*>(ix.cand_se + base);
+        uint32_t w[10];
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            const uint2 v = __ldg(c + t);
+            w[2 * t] = v.x;
+            w[2 * t + 1] = v.y;
         }
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const uint32_t se = par ? w[t + 1] : w[t];
+            if (3u + t < g.n && entry_hit<true>(se, g.rel_s, g.rel_e)) m |= 8u << t;
+        }
+    }
+    p.mask = m;
+    if (g.n > (uint32_t)JN_MASKED || !g.single) {
+        uint32_t x = 0;
+        walk_extra<X>(ix, ec, r, g, [&](uint32_t) { x++; });
+        p.extra = x;
+    }
+    return p;
+}
+
+// every hit of a planned query, in list order: f(subject row)
+template <typename X, typename F>
+__device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, const QPlan<X>& p, F&& f) {
+    uint32_t m = p.mask;
+    if (m & 1u) f(r.w[2]);
+    if (m & 2u) f(r.w[4]);
+    if (m & 4u) f(r.w[6]);
+    m >>= 3;
+    while (m) {
+        const int t = __ffs(m) - 1;
+        m &= m - 1;
+        f(__ldg(ix.cand_row + r.w[0] + 3 + t));
+    }
+    if (p.extra) {
+        const QGeom<X> g(ix, sc, ec, r);
+        walk_extra<X>(ix, ec, r, g, f);
     }
 }
 
@@ -109,7 +170,7 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* state
         unsigned long long v = 2ull;  // before the first tile: an inclusive prefix of 0
         if (idx >= 0) {
             v = ld_relaxed(state + idx);
-            while ((v & 3ull) == 0ull) { __nanosleep(20); v = ld_relaxed(state + idx); }
+            while ((v & 3ull) == 0ull) { __nanosleep(100); v = ld_relaxed(state + idx); }
         }
         const unsigned incl = __ballot_sync(FULL, (v & 3ull) == 2ull);
         const int first = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
@@ -133,7 +194,24 @@ template <typename X> struct Geo {
     }
 };
 
-// the two rows (ibase + 2 * lane, + 1) of a lane: flattened interval, liveness, record of the bin the query starts in
+// raw Start / End of the two rows (ibase + 2 * lane, + 1) of a lane: issued one iteration ahead
+struct Raw2 { int64_t s[2], e[2]; };
+__device__ __forceinline__ Raw2 load_raw(const iv_queries_t& q, bool vec, int64_t ibase) {
+    Raw2 w;
+    w.s[0] = w.s[1] = w.e[0] = w.e[1] = 0;
+    const int64_t r0 = ibase + 2 * lane_id();
+    if (vec && r0 + 1 < q.n) {
+        const longlong2 s2 = __ldcs(reinterpret_cast<const longlong2*>(q.start + r0));
+        const longlong2 e2 = __ldcs(reinterpret_cast<const longlong2*>(q.end + r0));
+        w.s[0] = s2.x; w.s[1] = s2.y; w.e[0] = e2.x; w.e[1] = e2.y;
+    } else {
+        if (r0 < q.n) { w.s[0] = __ldcs(q.start + r0); w.e[0] = __ldcs(q.end + r0); }
+        if (r0 + 1 < q.n) { w.s[1] = __ldcs(q.start + r0 + 1); w.e[1] = __ldcs(q.end + r0 + 1); }
+    }
+    return w;
+}
+
+// flattened interval, liveness and the record of the bin the query starts in, for the lane's two rows
 template <typename X> struct Rows2 {
     X sc[2], ec[2];
     LRec r[2];
@@ -141,9 +219,8 @@ template <typename X> struct Rows2 {
 };
 
 template <typename X, bool SLACK>
-__device__ __forceinline__ void load_rows(const iv_lists_t& ix, const iv_queries_t& q, bool vec, int64_t ibase, Geo<X>& G,
-                                          Rows2<X>& R) {
-    const int lane = lane_id();
+__device__ __forceinline__ void flatten_rows(const iv_lists_t& ix, const iv_queries_t& q, int64_t ibase, Raw2 w, Geo<X>& G,
+                                             Rows2<X>& R) {
     const int shift = ix.shift;
     while (G.seg + 1 < q.n_seg && __ldg(q.seg_off + G.seg + 1) <= ibase) G.seg++;
     const bool uniform = __ldg(q.seg_off + G.seg + 1) >= ibase + 64;
@@ -156,23 +233,15 @@ __device__ __forceinline__ void load_rows(const iv_lists_t& ix, const iv_queries
         G.hi32 = (uint32_t)hi;
         G.off32 = (uint32_t)G.f0.base - G.lo32;
     }
-    const int64_t r0 = ibase + 2 * lane;
-    int64_t s[2] = {0, 0}, e[2] = {0, 0};
-    if (vec && r0 + 1 < q.n) {
-        const longlong2 s2 = __ldcs(reinterpret_cast<const longlong2*>(q.start + r0));
-        const longlong2 e2 = __ldcs(reinterpret_cast<const longlong2*>(q.end + r0));
-        s[0] = s2.x; s[1] = s2.y; e[0] = e2.x; e[1] = e2.y;
-    } else {
-        if (r0 < q.n) { s[0] = __ldcs(q.start + r0); e[0] = __ldcs(q.end + r0); }
-        if (r0 + 1 < q.n) { s[1] = __ldcs(q.start + r0 + 1); e[1] = __ldcs(q.end + r0 + 1); }
-    }
+    const int64_t r0 = ibase + 2 * lane_id();
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        if (SLACK) apply_slack(q.slack, s[k], e[k]);
+        int64_t s = w.s[k], e = w.e[k];
+        if (SLACK) apply_slack(q.slack, s, e);
         bool partner;
-        if (uniform && G.geo32 && (((uint64_t)s[k] | (uint64_t)e[k]) >> 32) == 0) {
-            R.sc[k] = (X)(min(max((uint32_t)s[k], G.lo32), G.hi32) + G.off32);
-            R.ec[k] = (X)(min(max((uint32_t)e[k], G.lo32), G.hi32) + G.off32);
+        if (uniform && G.geo32 && (((uint64_t)s | (uint64_t)e) >> 32) == 0) {
+            R.sc[k] = (X)(min(max((uint32_t)s, G.lo32), G.hi32) + G.off32);
+            R.ec[k] = (X)(min(max((uint32_t)e, G.lo32), G.hi32) + G.off32);
             partner = G.f0.g >= 0;
         } else {
             Flat<X> f = G.f0;
@@ -180,24 +249,14 @@ __device__ __forceinline__ void load_rows(const iv_lists_t& ix, const iv_queries
                 const int sg = find_seg_range(q.seg_off, G.seg, q.n_seg - 1, r0 + k < q.n ? r0 + k : q.n - 1);
                 if (sg != G.seg) f = load_flat_groups<X>(ix.groups, ix.n, q, sg);
             }
-            R.sc[k] = f.at(s[k]);
-            R.ec[k] = f.at(e[k]);
+            R.sc[k] = f.at(s);
+            R.ec[k] = f.at(e);
             partner = f.g >= 0;
         }
         // rows beyond the end, keys without a partner and malformed rows (end < start) have no hits
         R.live[k] = r0 + k < q.n && partner && R.ec[k] >= R.sc[k];
         if (!R.live[k]) { R.sc[k] = 0; R.ec[k] = 0; }
         R.r[k] = load_lrec(ix.rec, (uint64_t)R.sc[k] >> shift);
-    }
-}
-
-template <typename X>
-__device__ __forceinline__ void count_rows(const iv_lists_t& ix, const Rows2<X>& R, uint32_t (&c)[2]) {
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        uint32_t n = 0;
-        if (R.live[k]) walk_query<X>(ix, R.sc[k], R.ec[k], R.r[k], [&](uint32_t) { n++; });
-        c[k] = n;
     }
 }
 
@@ -209,15 +268,21 @@ k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_
     const int64_t wbase = (int64_t)blockIdx.x * JN_TILE + (int64_t)warp * JN_WROWS;
     if (wbase >= q.n) return;
     Geo<X> G(q, wbase);
+    Raw2 next = load_raw(q, vec, wbase);
 #pragma unroll 1
     for (int it = 0; it < JN_ITERS; it++) {
         const int64_t ibase = wbase + it * 64;
         if (ibase >= q.n) break;
+        const Raw2 cur = next;
+        if (it + 1 < JN_ITERS && ibase + 64 < q.n) next = load_raw(q, vec, ibase + 64);
         Rows2<X> R;
-        load_rows<X, SLACK>(ix, q, vec, ibase, G, R);
+        flatten_rows<X, SLACK>(ix, q, ibase, cur, G, R);
         uint32_t c[2];
-        count_rows<X>(ix, R, c);
-        if (MODE == JM_ANY) { c[0] = c[0] ? 1u : 0u; c[1] = c[1] ? 1u : 0u; }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            c[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]).count();
+            if (MODE == JM_ANY) c[k] = c[k] ? 1u : 0u;
+        }
         const int64_t r0 = ibase + 2 * lane;
         if (vec && r0 + 1 < q.n) {
             __stcs(reinterpret_cast<longlong2*>(out_count + r0), make_longlong2((long long)c[0], (long long)c[1]));
@@ -238,7 +303,7 @@ template <typename X, bool SLACK, int OCC>
 __global__ void __launch_bounds__(JN_THREADS, OCC)
 k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
        const int64_t* __restrict__ s_label, int64_t cap, unsigned long long* __restrict__ state,
-       unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total) {
+       unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total, int variant) {
     __shared__ uint32_t st_s_all[JN_WARPS][JN_WCAP];
     __shared__ uint8_t st_q_all[JN_WARPS][JN_WCAP];
     __shared__ uint32_t s_cnt[JN_WARPS][JN_ITERS];
@@ -265,17 +330,15 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         }
     };
     // emit sweep of one iteration into the staging area, the lane's first pair at `pos`
-    auto stage_rows = [&](const Rows2<X>& R, const uint32_t (&c)[2], uint32_t pos, uint32_t qloc) {
+    auto stage_rows = [&](const Rows2<X>& R, const QPlan<X> (&p)[2], uint32_t pos, uint32_t qloc) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            if (c[k]) {
-                const uint8_t ql = (uint8_t)(qloc + k);
-                walk_query<X>(ix, R.sc[k], R.ec[k], R.r[k], [&](uint32_t row) {
-                    st_s[pos] = row;
-                    st_q[pos] = ql;
-                    pos++;
-                });
-            }
+            const uint8_t ql = (uint8_t)(qloc + k);
+            emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
+                st_s[pos] = row;
+                st_q[pos] = ql;
+                pos++;
+            });
         }
     };
 
@@ -284,20 +347,24 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     uint32_t staged = 0;
     int staged_iters = 0;
     bool open = true;
+    Raw2 next = load_raw(q, vec, wbase);
 #pragma unroll 1
     for (int it = 0; it < JN_ITERS; it++) {
         const int64_t ibase = wbase + it * 64;
         uint32_t itot = 0;
         if (ibase < q.n) {
+            const Raw2 cur = next;
+            if (it + 1 < JN_ITERS && ibase + 64 < q.n) next = load_raw(q, vec, ibase + 64);
             Rows2<X> R;
-            load_rows<X, SLACK>(ix, q, vec, ibase, G, R);
-            uint32_t c[2];
-            count_rows<X>(ix, R, c);
-            const uint32_t mine = c[0] + c[1];
+            flatten_rows<X, SLACK>(ix, q, ibase, cur, G, R);
+            QPlan<X> p[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
+            const uint32_t mine = p[0].count() + p[1].count();
             const uint32_t inc = warp_incl_sum(mine);
             itot = __shfl_sync(FULL, inc, 31);
             if (open && staged + itot <= (uint32_t)JN_WCAP) {
-                if (itot) stage_rows(R, c, staged + inc - mine, (uint32_t)(it * 64 + 2 * lane));
+                if (itot) stage_rows(R, p, staged + inc - mine, (uint32_t)(it * 64 + 2 * lane));
                 staged += itot;
                 staged_iters = it + 1;
             } else {
@@ -308,8 +375,14 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         total += itot;
     }
     __syncwarp();
-    unsigned long long o = lookback(state, wtile, total);
-    if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);
+    unsigned long long o;
+    if (variant == 1) {  // EXPERIMENT: unordered output regions from an atomic cursor (no waiting)
+        if (lane == 0) o = atomicAdd(reinterpret_cast<unsigned long long*>(out_total), total);
+        o = __shfl_sync(FULL, o, 0);
+    } else {
+        o = lookback(state, wtile, total);
+        if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);
+    }
     copy_out(staged, o, wbase);
     o += staged;
     // iterations that did not fit: once more, through the staging area (or straight to memory when a single iteration
@@ -321,30 +394,29 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         __syncwarp();
         Geo<X> G2(q, ibase);
         Rows2<X> R;
-        load_rows<X, SLACK>(ix, q, vec, ibase, G2, R);
-        uint32_t c[2];
-        count_rows<X>(ix, R, c);
-        const uint32_t mine = c[0] + c[1];
+        flatten_rows<X, SLACK>(ix, q, ibase, load_raw(q, vec, ibase), G2, R);
+        QPlan<X> p[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
+        const uint32_t mine = p[0].count() + p[1].count();
         const uint32_t inc = warp_incl_sum(mine);
         if (itot <= (uint32_t)JN_WCAP) {
-            stage_rows(R, c, inc - mine, (uint32_t)(2 * lane));
+            stage_rows(R, p, inc - mine, (uint32_t)(2 * lane));
             __syncwarp();
             copy_out(itot, o, ibase);
         } else {
             unsigned long long oo = o + inc - mine;
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                if (c[k]) {
-                    const int64_t row_q = ibase + 2 * lane + k;
-                    const int64_t ql = q.label ? __ldg(q.label + row_q) : row_q;
-                    walk_query<X>(ix, R.sc[k], R.ec[k], R.r[k], [&](uint32_t row) {
-                        if ((int64_t)oo < cap) {
-                            if (out_q) out_q[oo] = ql;
-                            if (out_s) out_s[oo] = s_label ? __ldg(s_label + row) : (int64_t)row;
-                        }
-                        oo++;
-                    });
-                }
+                const int64_t row_q = ibase + 2 * lane + k;
+                const int64_t ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
+                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
+                    if ((int64_t)oo < cap) {
+                        if (out_q) out_q[oo] = ql;
+                        if (out_s) out_s[oo] = s_label ? __ldg(s_label + row) : (int64_t)row;
+                    }
+                    oo++;
+                });
             }
         }
         o += itot;
@@ -413,7 +485,9 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     // resident blocks per SM the kernel is compiled for: 4 (62 registers, no spills; default) or 5 (48 registers);
     // IV_JOIN_OCC is a tuning switch for measurements
     static const int occ = getenv("IV_JOIN_OCC") ? atoi(getenv("IV_JOIN_OCC")) : 4;
-#define IV_JK(X, SL, OC) k_join<X, SL, OC><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total)
+    static const int variant = getenv("IV_JOIN_VARIANT") ? atoi(getenv("IV_JOIN_VARIANT")) : 0;
+    if (variant == 1) IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
+#define IV_JK(X, SL, OC) k_join<X, SL, OC><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total, variant)
 #define IV_JK2(X, SL) do { if (occ == 5) IV_JK(X, SL, 5); else if (occ == 6) IV_JK(X, SL, 6); else IV_JK(X, SL, 4); } while (0)
     if (narrow_span(lists)) {
         if (slack) IV_JK2(uint32_t, true); else IV_JK2(uint32_t, false);

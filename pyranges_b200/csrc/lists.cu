@@ -3,7 +3,7 @@
 //
 // bin = flattened coordinate >> shift.  Every bin owns its TOUCH LIST: the subjects intersecting the bin -- those
 // that started before it and are still open at its origin ("crossing"), then those that start inside it -- as 8-byte
-// entries {row, start offset | crossing flag, saturated end offset}.  A query starting in bin b overlaps the entries
+// entries {row; start offset | crossing flag, saturated end offset} (two parallel 32-bit arrays).  A query starting in bin b overlaps the entries
 // of list b that pass two 16-bit compares, plus the non-crossing entries of the later bins it reaches (join.cu).
 //
 // No sort: the list lengths are the running sum of a difference array (+1 at the subject's first bin, -1 behind its
@@ -165,7 +165,8 @@ k_lists_apply(uint32_t* __restrict__ diff, int64_t nb, const long long* __restri
 // (a 2 Mb gene touches a thousand bins, an exon one).
 __global__ void __launch_bounds__(LS_THREADS)
 k_lists_fill(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, iv_groups_t G, int shift,
-             const uint32_t* __restrict__ co, uint32_t* __restrict__ cursor, int64_t cap, uint2* __restrict__ cand) {
+             const uint32_t* __restrict__ co, uint32_t* __restrict__ cursor, int64_t cap, uint32_t* __restrict__ cand_se,
+             uint32_t* __restrict__ cand_row) {
     __shared__ int span[2];
     __shared__ uint32_t pre[LS_THREADS + 1];
     __shared__ uint32_t wsum[LS_THREADS / 32 + 1];
@@ -201,7 +202,10 @@ k_lists_fill(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64
         const uint64_t d = E - origin;
         const uint32_t eo = d > 0xffffull ? 0xffffu : (uint32_t)d;
         const int64_t at = (int64_t)__ldg(co + bb) + atomicAdd(cursor + bb, 1u);
-        if (at < cap) cand[at] = make_uint2((uint32_t)(first + lo), so | (eo << 16));
+        if (at < cap) {
+            cand_row[at] = (uint32_t)(first + lo);
+            cand_se[at] = so | (eo << 16);
+        }
     }
 }
 
@@ -220,8 +224,9 @@ __device__ __forceinline__ void write_rec(iv_lrec_t* __restrict__ rec, int64_t b
 }
 
 __global__ void __launch_bounds__(LS_THREADS)
-k_lists_finalize(int64_t n_bins, const uint32_t* __restrict__ co, uint2* __restrict__ cand, iv_lrec_t* __restrict__ rec,
-                 uint32_t* __restrict__ big, uint32_t* __restrict__ nbig) {
+k_lists_finalize(int64_t n_bins, const uint32_t* __restrict__ co, uint32_t* __restrict__ cand_se,
+                 uint32_t* __restrict__ cand_row, iv_lrec_t* __restrict__ rec, uint32_t* __restrict__ big,
+                 uint32_t* __restrict__ nbig) {
     const int64_t b = (int64_t)blockIdx.x * LS_THREADS + threadIdx.x;
     if (b > n_bins + 1) return;
     const uint32_t c0 = __ldg(co + b);
@@ -232,33 +237,32 @@ k_lists_finalize(int64_t n_bins, const uint32_t* __restrict__ co, uint2* __restr
         return;
     }
     for (uint32_t j = 0; j < n; j++) {  // insertion sort: the lists are a handful of entries long
-        const uint2 x = cand[c0 + j];
+        const uint2 x = make_uint2(cand_row[c0 + j], cand_se[c0 + j]);
         const unsigned long long kx = entry_key(x);
         uint32_t p = j;
         while (p > 0 && entry_key(a[p - 1]) > kx) { a[p] = a[p - 1]; p--; }
         a[p] = x;
     }
     if (n > 1)
-        for (uint32_t j = 0; j < n; j++) cand[c0 + j] = a[j];
+        for (uint32_t j = 0; j < n; j++) { cand_row[c0 + j] = a[j].x; cand_se[c0 + j] = a[j].y; }
     write_rec(rec, b, c0, n, a);
 }
 
 // long lists (pile-ups): one block per list, normalised bitonic network (every compare-exchange ascending, so the
 // virtual padding to a power of two needs no sentinels), in shared memory when the list fits
 __global__ void __launch_bounds__(LS_THREADS)
-k_lists_big(const uint32_t* __restrict__ co, uint2* __restrict__ cand, iv_lrec_t* __restrict__ rec,
-            const uint32_t* __restrict__ big, const uint32_t* __restrict__ nbig) {
+k_lists_big(const uint32_t* __restrict__ co, uint32_t* __restrict__ cand_se, uint32_t* __restrict__ cand_row,
+            iv_lrec_t* __restrict__ rec, const uint32_t* __restrict__ big, const uint32_t* __restrict__ nbig) {
     __shared__ uint2 sh[LS_BIG_SMEM];
     const uint32_t total = *nbig;
     for (uint32_t k = blockIdx.x; k < total; k += gridDim.x) {
         const int64_t b = big[k];
         const uint32_t c0 = co[b], n = co[b + 1] - c0;
-        uint2* a = cand + c0;
+        uint32_t* gr = cand_row + c0;
+        uint32_t* gs = cand_se + c0;
         const bool in_smem = n <= (uint32_t)LS_BIG_SMEM;
-        if (in_smem) {
-            for (uint32_t i = threadIdx.x; i < n; i += LS_THREADS) sh[i] = a[i];
-            a = sh;
-        }
+        if (in_smem)
+            for (uint32_t i = threadIdx.x; i < n; i += LS_THREADS) sh[i] = make_uint2(gr[i], gs[i]);
         __syncthreads();
         uint32_t P = 1;
         while (P < n) P <<= 1;
@@ -266,8 +270,13 @@ k_lists_big(const uint32_t* __restrict__ co, uint2* __restrict__ cand, iv_lrec_t
             for (uint32_t i = threadIdx.x; i < n; i += LS_THREADS) {
                 const uint32_t p = i ^ mask;
                 if (p > i && p < n) {
-                    const uint2 x = a[i], y = a[p];
-                    if (entry_key(x) > entry_key(y)) { a[i] = y; a[p] = x; }
+                    if (in_smem) {
+                        const uint2 x = sh[i], y = sh[p];
+                        if (entry_key(x) > entry_key(y)) { sh[i] = y; sh[p] = x; }
+                    } else {
+                        const uint2 x = make_uint2(gr[i], gs[i]), y = make_uint2(gr[p], gs[p]);
+                        if (entry_key(x) > entry_key(y)) { gr[i] = y.x; gs[i] = y.y; gr[p] = x.x; gs[p] = x.y; }
+                    }
                 }
             }
             __syncthreads();
@@ -276,12 +285,14 @@ k_lists_big(const uint32_t* __restrict__ co, uint2* __restrict__ cand, iv_lrec_t
             step(kk - 1);  // first step of a merge: the partner is the mirror position inside the block of kk
             for (uint32_t j = kk >> 2; j > 0; j >>= 1) step(j);
         }
-        if (in_smem) {
-            uint2* g = cand + c0;
-            for (uint32_t i = threadIdx.x; i < n; i += LS_THREADS) g[i] = sh[i];
-        }
+        if (in_smem)
+            for (uint32_t i = threadIdx.x; i < n; i += LS_THREADS) { gr[i] = sh[i].x; gs[i] = sh[i].y; }
         __syncthreads();
-        if (threadIdx.x == 0) write_rec(rec, b, c0, n, a);
+        if (threadIdx.x == 0) {
+            uint2 f3[3];
+            for (uint32_t j = 0; j < 3 && j < n; j++) f3[j] = make_uint2(gr[j], gs[j]);
+            write_rec(rec, b, c0, n, f3);
+        }
         __syncthreads();
     }
 }
@@ -292,7 +303,7 @@ struct ListsLayout {
     iv_lrec_t* rec;
     uint32_t *diff, *nbig, *co, *big;
     long long *tD, *tO, *tC, *tOin;
-    uint2* cand;
+    uint32_t *cand_se, *cand_row;
 };
 
 // ~2 bins per subject, at most 2^15 coordinates wide (entry offsets are 15-bit), coarser when long subjects would blow
@@ -324,7 +335,8 @@ static bool plan_lists(int64_t n, int64_t span, int64_t sum_len, Bump& b, ListsL
     L.tC = b.take<long long>((size_t)L.ntiles);
     L.tOin = b.take<long long>((size_t)L.ntiles);
     L.big = b.take<uint32_t>((size_t)(L.cand_cap / (LS_SORT_MAX + 1) + 1));
-    L.cand = b.take<uint2>((size_t)L.cand_cap);
+    L.cand_se = b.take<uint32_t>((size_t)L.cand_cap + 16);  // + slack: the join reads whole 8-entry chunks
+    L.cand_row = b.take<uint32_t>((size_t)L.cand_cap + 16);
     return true;
 }
 
@@ -364,7 +376,8 @@ extern "C" int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_
     out->n_bins = L.n_bins;
     out->cand_cap = L.cand_cap;
     out->rec = L.rec;
-    out->cand = reinterpret_cast<const iv_lentry_t*>(L.cand);
+    out->cand_se = L.cand_se;
+    out->cand_row = L.cand_row;
     out->groups = G;
     if (n == 0) {
         IV_CUDA(cudaMemsetAsync(L.rec, 0, (size_t)L.nb * sizeof(iv_lrec_t), st));
@@ -381,11 +394,12 @@ extern "C" int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_
     IV_LAUNCH_CHECK();
     k_lists_apply<<<(unsigned)L.ntiles, LS_THREADS, 0, st>>>(L.diff, L.nb, L.tC, L.tOin, L.co);
     IV_LAUNCH_CHECK();
-    k_lists_fill<<<nbk, LS_THREADS, 0, st>>>(starts, ends, n, G, L.shift, L.co, L.diff, L.cand_cap, L.cand);
+    k_lists_fill<<<nbk, LS_THREADS, 0, st>>>(starts, ends, n, G, L.shift, L.co, L.diff, L.cand_cap, L.cand_se, L.cand_row);
     IV_LAUNCH_CHECK();
-    k_lists_finalize<<<(unsigned)cdiv(L.nb, LS_THREADS), LS_THREADS, 0, st>>>(L.n_bins, L.co, L.cand, L.rec, L.big, L.nbig);
+    k_lists_finalize<<<(unsigned)cdiv(L.nb, LS_THREADS), LS_THREADS, 0, st>>>(L.n_bins, L.co, L.cand_se, L.cand_row, L.rec, L.big,
+                                                                          L.nbig);
     IV_LAUNCH_CHECK();
-    k_lists_big<<<64, LS_THREADS, 0, st>>>(L.co, L.cand, L.rec, L.big, L.nbig);
+    k_lists_big<<<64, LS_THREADS, 0, st>>>(L.co, L.cand_se, L.cand_row, L.rec, L.big, L.nbig);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

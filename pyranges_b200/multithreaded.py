@@ -96,6 +96,63 @@ class _Frames:
         self.starts, self.ends = s, e
         self.iv = E.DeviceIntervals.from_numpy(s, e, self.seg_off, device)
 
+    def with_frames(self, items):
+        """the same device columns under other (key, DataFrame) items holding the same coordinates"""
+        f = _Frames.__new__(_Frames)
+        f.__dict__.update(self.__dict__)
+        f.keys = [k for k, _ in items]
+        f.dfs = [d for _, d in items]
+        return f
+
+
+# Device copies of the coordinate columns persist across calls (north-star subsystem 1: "device-resident int64
+# Start/End/index columns grouped by (Chromosome, Strand)"): a PyRanges keeps its _Frames on the object, and a small
+# table keyed by the identity of the Start / End buffers serves the derived objects the API creates per call (sparse
+# copies, unstranded views) -- pandas >= 3 column subsets share their buffers.  An entry holds references to those
+# buffers, so an address can never come back with other contents while it is cached; replacing a column (PyRanges
+# attribute assignment, any pandas operation: copy-on-write) changes the buffer and misses.  Writing INTO a buffer
+# behind pandas' back (ndarray views) is not detected.
+_FRAME_CACHE = {}
+_FRAME_CACHE_MAX = 8
+
+
+def _col_ptr(df, col):
+    v = df[col].values
+    if not isinstance(v, np.ndarray) or v.dtype != np.int64:
+        return None, None
+    return v.__array_interface__["data"][0], v
+
+
+def _frames_of(gr, device):
+    """the (cached) device ingest of a PyRanges-like object"""
+    items = natsorted(gr.dfs.items())
+    sig, held = [str(device), id(E)], []
+    for k, d in items:
+        ps, vs = _col_ptr(d, "Start")
+        pe, ve = _col_ptr(d, "End")
+        if ps is None or pe is None:
+            return _Frames(items, device)
+        sig.append((k, len(d), ps, pe, vs.strides[0], ve.strides[0]))
+        held.append((vs, ve))
+    sig = tuple(sig)
+    hit = _FRAME_CACHE.get(sig)
+    if hit is not None:
+        f = hit[0]
+        if [id(d) for d in f.dfs] != [id(d) for _, d in items]:
+            # same coordinates, other frame objects (payload columns may differ): share the device columns only
+            f = f.with_frames(items)
+        return f
+    f = _Frames(items, device)
+    if len(_FRAME_CACHE) >= _FRAME_CACHE_MAX:
+        _FRAME_CACHE.pop(next(iter(_FRAME_CACHE)))
+    _FRAME_CACHE[sig] = (f, held)
+    return f
+
+
+def clear_device_cache():
+    """drop every cached device copy of coordinate columns"""
+    _FRAME_CACHE.clear()
+
 
 def _device_of(kwargs):
     import torch
@@ -117,9 +174,8 @@ class _Plan:
         if strandedness:
             assert self_stranded and other_stranded, \
                 "Can only do stranded operations when both PyRanges contain strand info"
-        self.q = q_frames if q_frames is not None else _Frames(natsorted(self_gr.dfs.items()), device)
-        o_items = natsorted(other_gr.dfs.items())
-        self.s = _Frames(o_items, device)
+        self.q = q_frames if q_frames is not None else _frames_of(self_gr, device)
+        self.s = _frames_of(other_gr, device)
         okeys = self.s.keys
         if strandedness or not other_stranded:
             # every key of other is one partner frame
@@ -565,8 +621,7 @@ class _UnaryPlan:
         stranded = _is_stranded(self_gr)
         if strand:
             assert stranded, "Can only do stranded operation when PyRange contains strand info"
-        items = natsorted(self_gr.dfs.items())
-        self.f = _Frames(items, device, upload=upload)
+        self.f = _frames_of(self_gr, device) if upload else _Frames(natsorted(self_gr.dfs.items()), device, upload=False)
         keys = self.f.keys
         if strand or not stranded:
             self.group_ranges = [(i, i + 1) for i in range(len(keys))]
