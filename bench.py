@@ -325,7 +325,7 @@ def run_b200(args, rank, world, local_rank):
     nq_all, ns_all = args.reads, args.annot
     q_meta, s_meta = meta(reads, q_iv), meta(annot, s_iv)
 
-    join = E.JoinStep(s_iv, groups, q_iv, seg_group, path=args.path)
+    join = E.JoinStep(s_iv, groups, q_iv, seg_group, path=args.path, seg_counts=world > 1)
     # one untimed pass sizes the output buffers (the step launches its emit into buffers of the previous step's size and
     # checks the device-side total afterwards: no host synchronisation inside a step)
     a, b, p_local = join.run_sync()
@@ -337,8 +337,27 @@ def run_b200(args, rank, world, local_rank):
     time.sleep(0.3)
     t0 = time.perf_counter()
     join.phase_events = []
-    join_ms, launches = timed(join.step, args.steps, args.warmup)
+    if world > 1:
+        # the only communication of the path: per-key pair counts (global offsets of the concatenated result, keys are
+        # disjoint over ranks so the sum is the gather).  Every step leaves its counts in a row of a device table;
+        # ONE all-reduce of the table closes the timed region -- no collective and no host wait inside a step.
+        gkq = torch.from_numpy(reads.global_key).to(dev)
+        rows = args.steps + args.warmup
+        key_pairs = torch.zeros(rows, 48, dtype=torch.int64, device=dev)
+        it = [0]
+
+        def join_step():
+            join.step()
+            key_pairs[it[0] % rows].index_copy_(0, gkq, join.seg_counts)
+            it[0] += 1
+            if it[0] == rows:
+                dist.all_reduce(key_pairs)
+    else:
+        join_step = join.step
+    join_ms, launches = timed(join_step, args.steps, args.warmup)
     join.check()  # every step's device-side total fitted its buffers (else the run is invalid: raises)
+    if world > 1:  # the exchanged per-key counts of the last step add up to the global pair count
+        assert int(key_pairs[-1].sum().item()) == pairs_all, "per-key pair counts do not add up"
     t1 = time.perf_counter()
     clocks = sampler.summary(t0, t1) if sampler else None
     value = pairs_all * args.steps / (join_ms / 1e3)

@@ -228,26 +228,36 @@ int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_t overlap, 
                int64_t* out_dist, void* stream);
 
 /* ---- list index + fused join: the join / count_overlaps / overlap fast path ------------------------------------ */
-/* Every coordinate bin (bin = flattened coordinate >> shift, shift <= 15) owns its TOUCH LIST: the subjects that
+/* Every coordinate bin (bin = flattened coordinate >> shift, shift <= 14) owns its TOUCH LIST: the subjects that
  * intersect the bin, i.e. those that start before it and are still open at its origin ("crossing") followed by those
- * that start inside it, each as an 8-byte entry.  A query whose start falls into bin b overlaps exactly
- *      the entries of list b with  (crossing or so < e' - origin)  and  eo > s' - origin
- *    + for every later bin the query reaches: its NON-crossing entries with  so < e' - origin(bin),
+ * that start inside it.  A query whose start falls into bin b overlaps exactly
+ *      the entries of list b with  (crossing or S' < e')  and  E' > s'
+ *    + for every later bin the query reaches: its NON-crossing entries with  S' < e',
  * every subject once.  No sort is needed to build the lists (difference array -> offsets -> fill -> per-bin ordering),
  * and one 32-byte record (= one L2 sector, one 256-bit load) holds a bin's list offset, length and first three entries:
- * most queries are answered -- counted AND emitted -- from that single gather.  Zero-length subjects (start == end) are
- * handled exactly (hit iff s < start < e) as long as the group window is one coordinate wider than its rows on both
- * sides (lo <= min start - 1, hi >= max end + 1). */
+ * most queries are answered -- counted AND emitted -- from that single gather.
+ *
+ * Entry test word (se): with sp = 0 for a crossing subject, else S' - origin + 1 (1 .. 2^14), and eo = min(E' - origin,
+ * 0x7fff):      se = 0x80008000 | (0x4000 - sp) | eo << 16.
+ * Query word:   qw = (0x4000 - min(e' - origin, 0x4000)) | (s' - origin + 1) << 16   (a query that reaches beyond the
+ * bin: low half 0).  Then   hit  <=>  ((se - qw) & 0x80008000) == 0x80008000:   the low half keeps its guard bit iff
+ * sp <= e' - origin (the subject starts before the query ends), the high half iff eo >= s' - origin + 1 (it ends after
+ * the query starts); no borrow crosses the halves.
+ * Zero-length subjects (start == end) are handled exactly (hit iff s < start < e) as long as the group window is one
+ * coordinate wider than its rows on both sides (lo <= min start - 1, hi >= max end + 1). */
+#define IV_L_MAX_SHIFT 14
+#define IV_L_GUARD 0x80008000u
+#define IV_L_SMAX 0x4000u /* low half = IV_L_SMAX - sp */
+#define IV_L_EMAX 0x7fffu /* saturated end offset */
 typedef struct iv_lentry {
     uint32_t row; /* subject row */
-    uint16_t so;  /* start - bin origin (15 bits); IV_L_CROSS set: the subject starts before the bin */
-    uint16_t eo;  /* min(end - bin origin, 0xFFFF) */
+    uint32_t se;  /* test word */
 } iv_lentry_t;
-#define IV_L_CROSS 0x8000u
 typedef struct iv_lrec {
     uint32_t co;     /* the bin's list is cand_se / cand_row [co, co + n) */
     uint32_t n8;     /* min(n, 255) in the low byte; n = co of the next record - co when it says 255 */
-    iv_lentry_t e[3]; /* the first three entries of the list (crossing entries by row, then starts by (start, row)) */
+    iv_lentry_t e[3]; /* the first three entries of the list (crossing entries by row, then starts by (start, row));
+                         unused ones carry se = IV_L_GUARD (end offset 0: never a hit) */
 } iv_lrec_t;
 typedef struct iv_lists {
     int64_t n;          /* subjects */
@@ -257,7 +267,7 @@ typedef struct iv_lists {
     int64_t n_bins;     /* rec[] holds n_bins + 2 records (the last two are sentinels) */
     int64_t cand_cap;   /* capacity of cand_se[] / cand_row[] */
     const iv_lrec_t* rec;
-    const uint32_t* cand_se;  /* so | eo << 16 of every list entry (all lists back to back, bin order) */
+    const uint32_t* cand_se;  /* test word of every list entry (all lists back to back, bin order) */
     const uint32_t* cand_row; /* subject row of the same entries */
     iv_groups_t groups;
 } iv_lists_t;

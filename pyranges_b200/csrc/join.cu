@@ -42,40 +42,44 @@ __device__ __forceinline__ LRec load_lrec(const iv_lrec_t* __restrict__ rec, uin
     return r;
 }
 
-// FIRST bin of a query (the one its start falls into): hit <=> (crossing or so < rel_e) and eo > rel_s
-// later bins: only subjects that START there: hit <=> not crossing and so < rel_e
-template <bool FIRST>
-__device__ __forceinline__ bool entry_hit(uint32_t se, uint32_t rel_s, uint32_t rel_e) {
-    const uint32_t so = se & 0xffffu, eo = se >> 16;
-    if (FIRST) return ((so & IV_L_CROSS) || so < rel_e) && eo > rel_s;
-    return so < rel_e;  // a crossing entry has so >= 0x8000 >= any rel_e of a later bin
+// ---- entry tests (encoding: pyranges_b200.h) ------------------------------------------------------------------------------
+// first bin of a query (the one its start falls into): one subtraction decides both compares of the overlap predicate
+__device__ __forceinline__ uint32_t hit_bit(uint32_t se, uint32_t qw) {  // bit 31 = hit
+    const uint32_t t = se - qw;
+    return t & (t << 16) & 0x80000000u;
+}
+// later bins: only subjects that START there, before the query's end: sp in [1, rel_e]
+__device__ __forceinline__ bool later_hit(uint32_t se, uint32_t rel_e) {
+    const uint32_t sp = IV_L_SMAX - (se & 0x7fffu);
+    return sp >= 1u && sp <= rel_e;
 }
 
 // ---- what the count sweep learns about a query ------------------------------------------------------------------------------
 // The first JN_MASKED entries of the list of the bin the query starts in are tested from registers: three from the bin
 // record, eight from ONE batch of loads (all in flight together -- a short list costs one round trip, not one per
-// entry).  mask = which of them are hits; extra = hits beyond: entries past the first eleven of a long list and the
-// starts inside the later bins of a query that reaches beyond its first bin (both walked entry by entry: rare).
+// entry).  mask = which of them are hits (bit j = entry j); extra = hits beyond: entries past the first eleven of a long
+// list and the starts inside the later bins of a query that reaches beyond its first bin (walked entry by entry: rare).
 constexpr int JN_MASKED = 11;
 
-template <typename X> struct QPlan {
+struct QPlan {
     uint32_t mask, extra;
     __device__ __forceinline__ uint32_t count() const { return __popc(mask) + extra; }
 };
 
 template <typename X> struct QGeom {
-    uint64_t b;
-    uint32_t rel_s, rel_e, n;
+    X b;
+    uint32_t qw, n;
     bool single;
     __device__ __forceinline__ QGeom(const iv_lists_t& ix, X sc, X ec, const LRec& r) {
         const int shift = ix.shift;
-        b = (uint64_t)sc >> shift;
-        rel_s = (uint32_t)(sc - (X)(b << shift));
-        const uint64_t d = (uint64_t)(ec - (X)(b << shift));  // ec >= sc: no wrap
-        single = d <= (1ull << shift);
-        rel_e = single ? (uint32_t)d : 0x7fffffffu;
+        b = sc >> shift;
+        const X origin = b << shift;
+        const uint32_t rel_s = (uint32_t)(sc - origin);
+        const X d = ec - origin;  // ec >= sc: no wrap
+        single = d <= ((X)1 << shift);
+        qw = (single ? IV_L_SMAX - (uint32_t)d : 0u) | ((rel_s + 1u) << 16);
         n = r.w[1] & 0xffu;
-        if (n == 255u) n = __ldg(&ix.rec[b + 1].co) - r.w[0];
+        if (n == 255u) n = __ldg(&ix.rec[(uint64_t)b + 1].co) - r.w[0];
     }
 };
 
@@ -84,45 +88,36 @@ template <typename X, typename F>
 __device__ __forceinline__ void walk_extra(const iv_lists_t& ix, X ec, const LRec& r, const QGeom<X>& g, F&& f) {
     const int shift = ix.shift;
     for (uint32_t j = JN_MASKED; j < g.n; j++)
-        if (entry_hit<true>(__ldg(ix.cand_se + r.w[0] + j), g.rel_s, g.rel_e)) f(__ldg(ix.cand_row + r.w[0] + j));
+        if (hit_bit(__ldg(ix.cand_se + r.w[0] + j), g.qw)) f(__ldg(ix.cand_row + r.w[0] + j));
     if (!g.single) {
         const uint64_t bl = (uint64_t)(ec - 1) >> shift;
-        for (uint64_t bb = g.b + 1; bb <= bl; bb++) {
+        for (uint64_t bb = (uint64_t)g.b + 1; bb <= bl; bb++) {
             const uint32_t c0 = __ldg(&ix.rec[bb].co), c1 = __ldg(&ix.rec[bb + 1].co);
-            const uint32_t re = bb < bl ? 0x8000u : (uint32_t)(ec - (X)(bl << shift));
+            const uint32_t re = bb < bl ? IV_L_SMAX : (uint32_t)(ec - (X)(bl << shift));
             for (uint32_t j = c0; j < c1; j++)
-                if (entry_hit<false>(__ldg(ix.cand_se + j), 0u, re)) f(__ldg(ix.cand_row + j));
+                if (later_hit(__ldg(ix.cand_se + j), re)) f(__ldg(ix.cand_row + j));
         }
     }
 }
 
 template <typename X>
-__device__ __forceinline__ QPlan<X> plan_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, bool live) {
-    QPlan<X> p{0u, 0u};
+__device__ __forceinline__ QPlan plan_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, bool live) {
+    QPlan p{0u, 0u};
     if (!live) return p;
     const QGeom<X> g(ix, sc, ec, r);
     uint32_t m = 0;
-    if (g.n > 0 && entry_hit<true>(r.w[3], g.rel_s, g.rel_e)) m |= 1u;
-    if (g.n > 1 && entry_hit<true>(r.w[5], g.rel_s, g.rel_e)) m |= 2u;
-    if (g.n > 2 && entry_hit<true>(r.w[7], g.rel_s, g.rel_e)) m |= 4u;
-    if (g.n > 3) {
-        // entries 3 .. 10: five aligned 8-byte loads cover them whatever the parity of the list offset
-        const uint32_t first = r.w[0] + 3u, base = first & ~1u, par = first & 1u;
-        const uint2* __restrict__ c = reinterpret_cast<const uint2*>(ix.cand_se + base);
-        uint32_t w[10];
+    if (g.n > 3) {  // entries 3 .. 10: eight loads in flight together; processed last to first so that entry j lands on bit j
+        const uint32_t* __restrict__ c = ix.cand_se + r.w[0] + 3u;
+        uint32_t w[8];
 #pragma unroll
-        for (int t = 0; t < 5; t++) {
-            const uint2 v = __ldg(c + t);
-            w[2 * t] = v.x;
-            w[2 * t + 1] = v.y;
-        }
+        for (int t = 0; t < 8; t++) w[t] = __ldg(c + t);
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-            const uint32_t se = par ? w[t + 1] : w[t];
-            if (3u + t < g.n && entry_hit<true>(se, g.rel_s, g.rel_e)) m |= 8u << t;
-        }
+        for (int t = 7; t >= 0; t--) m = __funnelshift_l(hit_bit(w[t], g.qw), m, 1);
     }
-    p.mask = m;
+    m = __funnelshift_l(hit_bit(r.w[7], g.qw), m, 1);
+    m = __funnelshift_l(hit_bit(r.w[5], g.qw), m, 1);
+    m = __funnelshift_l(hit_bit(r.w[3], g.qw), m, 1);
+    p.mask = m & (g.n >= (uint32_t)JN_MASKED ? (1u << JN_MASKED) - 1u : (1u << g.n) - 1u);
     if (g.n > (uint32_t)JN_MASKED || !g.single) {
         uint32_t x = 0;
         walk_extra<X>(ix, ec, r, g, [&](uint32_t) { x++; });
@@ -133,7 +128,7 @@ __device__ __forceinline__ QPlan<X> plan_query(const iv_lists_t& ix, X sc, X ec,
 
 // every hit of a planned query, in list order: f(subject row)
 template <typename X, typename F>
-__device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, const QPlan<X>& p, F&& f) {
+__device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, const QPlan& p, F&& f) {
     uint32_t m = p.mask;
     if (m & 1u) f(r.w[2]);
     if (m & 2u) f(r.w[4]);
@@ -170,7 +165,7 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* state
         unsigned long long v = 2ull;  // before the first tile: an inclusive prefix of 0
         if (idx >= 0) {
             v = ld_relaxed(state + idx);
-            while ((v & 3ull) == 0ull) { __nanosleep(100); v = ld_relaxed(state + idx); }
+            for (unsigned ns = 64; (v & 3ull) == 0ull; ns = ns < 1024 ? ns * 2 : ns) { __nanosleep(ns); v = ld_relaxed(state + idx); }
         }
         const unsigned incl = __ballot_sync(FULL, (v & 3ull) == 2ull);
         const int first = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
@@ -256,7 +251,7 @@ __device__ __forceinline__ void flatten_rows(const iv_lists_t& ix, const iv_quer
         // rows beyond the end, keys without a partner and malformed rows (end < start) have no hits
         R.live[k] = r0 + k < q.n && partner && R.ec[k] >= R.sc[k];
         if (!R.live[k]) { R.sc[k] = 0; R.ec[k] = 0; }
-        R.r[k] = load_lrec(ix.rec, (uint64_t)R.sc[k] >> shift);
+        R.r[k] = load_lrec(ix.rec, (uint64_t)(R.sc[k] >> shift));
     }
 }
 
@@ -330,7 +325,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         }
     };
     // emit sweep of one iteration into the staging area, the lane's first pair at `pos`
-    auto stage_rows = [&](const Rows2<X>& R, const QPlan<X> (&p)[2], uint32_t pos, uint32_t qloc) {
+    auto stage_rows = [&](const Rows2<X>& R, const QPlan (&p)[2], uint32_t pos, uint32_t qloc) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const uint8_t ql = (uint8_t)(qloc + k);
@@ -357,7 +352,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
             if (it + 1 < JN_ITERS && ibase + 64 < q.n) next = load_raw(q, vec, ibase + 64);
             Rows2<X> R;
             flatten_rows<X, SLACK>(ix, q, ibase, cur, G, R);
-            QPlan<X> p[2];
+            QPlan p[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
             const uint32_t mine = p[0].count() + p[1].count();
@@ -395,7 +390,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         Geo<X> G2(q, ibase);
         Rows2<X> R;
         flatten_rows<X, SLACK>(ix, q, ibase, load_raw(q, vec, ibase), G2, R);
-        QPlan<X> p[2];
+        QPlan p[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
         const uint32_t mine = p[0].count() + p[1].count();
@@ -448,7 +443,7 @@ static int check_join(const iv_lists_t* ix, const iv_queries_t* q, const char* w
     IV_REQUIRE(ix && q, IV_ERR_INVALID, "%s: null argument", who);
     IV_REQUIRE(q->n >= 0 && (q->n == 0 || (q->start && q->end && q->seg_off && q->seg_group && q->n_seg > 0)),
                IV_ERR_INVALID, "%s: bad query descriptor", who);
-    IV_REQUIRE(ix->rec && ix->shift >= 0 && ix->shift <= 15, IV_ERR_INVALID, "%s: not a list index", who);
+    IV_REQUIRE(ix->rec && ix->shift >= 0 && ix->shift <= IV_L_MAX_SHIFT, IV_ERR_INVALID, "%s: not a list index", who);
     return IV_OK;
 }
 

@@ -2,9 +2,11 @@
 // sites pyranges/methods/join.py:12, coverage.py:20, intersection.py:71).
 //
 // bin = flattened coordinate >> shift.  Every bin owns its TOUCH LIST: the subjects intersecting the bin -- those
-// that started before it and are still open at its origin ("crossing"), then those that start inside it -- as 8-byte
-// entries {row; start offset | crossing flag, saturated end offset} (two parallel 32-bit arrays).  A query starting in bin b overlaps the entries
-// of list b that pass two 16-bit compares, plus the non-crossing entries of the later bins it reaches (join.cu).
+// that started before it and are still open at its origin ("crossing"), then those that start inside it -- as entries
+// {subject row; test word} in two parallel 32-bit arrays.  The test word holds the start and end offsets from the bin
+// origin as two 15-bit fields under guard bits, laid out so that ONE 32-bit subtraction of the query's word decides
+// both compares of the overlap predicate (pyranges_b200.h).  A query starting in bin b overlaps the entries of list b
+// that pass, plus the non-crossing entries of the later bins it reaches (join.cu).
 //
 // No sort: the list lengths are the running sum of a difference array (+1 at the subject's first bin, -1 behind its
 // last one: two atomics per subject), the list offsets the running sum of the lengths (both in one second-order scan
@@ -198,13 +200,13 @@ k_lists_fill(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64
         const uint64_t S = sS[lo], E = sE[lo];
         const uint64_t b0 = S >> shift, bb = b0 + (u - pre[lo]);
         const uint64_t origin = bb << shift;
-        const uint32_t so = bb > b0 ? IV_L_CROSS : (uint32_t)(S - origin);
+        const uint32_t sp = bb > b0 ? 0u : (uint32_t)(S - origin) + 1u;  // 0 = starts before the bin
         const uint64_t d = E - origin;
-        const uint32_t eo = d > 0xffffull ? 0xffffu : (uint32_t)d;
+        const uint32_t eo = d > (uint64_t)IV_L_EMAX ? IV_L_EMAX : (uint32_t)d;
         const int64_t at = (int64_t)__ldg(co + bb) + atomicAdd(cursor + bb, 1u);
         if (at < cap) {
             cand_row[at] = (uint32_t)(first + lo);
-            cand_se[at] = so | (eo << 16);
+            cand_se[at] = IV_L_GUARD | (IV_L_SMAX - sp) | (eo << 16);
         }
     }
 }
@@ -212,11 +214,10 @@ k_lists_fill(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64
 // ---- K4: canonical order inside every list + the bin records -------------------------------------------------------------
 // crossing entries by row, then starts by (start offset, row)
 __device__ __forceinline__ unsigned long long entry_key(const uint2& en) {
-    const uint32_t so = en.y & 0xffffu;
-    return ((unsigned long long)((so & IV_L_CROSS) ? 0u : so + 1u) << 32) | en.x;
+    return ((unsigned long long)(IV_L_SMAX - (en.y & 0x7fffu)) << 32) | en.x;  // (start offset + 1, 0 = crossing; row)
 }
 __device__ __forceinline__ void write_rec(iv_lrec_t* __restrict__ rec, int64_t b, uint32_t c0, uint32_t n, const uint2* first3) {
-    uint2 z = make_uint2(0u, 0u);
+    const uint2 z = make_uint2(0u, IV_L_GUARD);  // an entry no query hits (end offset 0)
     const uint2 a = n > 0 ? first3[0] : z, bq = n > 1 ? first3[1] : z, c = n > 2 ? first3[2] : z;
     uint4* out = reinterpret_cast<uint4*>(rec + b);
     out[0] = make_uint4(c0, n < 255u ? n : 255u, a.x, a.y);
@@ -306,15 +307,15 @@ struct ListsLayout {
     uint32_t *cand_se, *cand_row;
 };
 
-// ~2 bins per subject, at most 2^15 coordinates wide (entry offsets are 15-bit), coarser when long subjects would blow
+// ~2 bins per subject, at most 2^14 coordinates wide (entry offsets are 14-bit + a guard bit), coarser when long subjects would blow
 // the lists up.  false = cannot be indexed this way.
 static bool choose_lists(int64_t n, int64_t span, int64_t sum_len, int* shift, int64_t* n_bins, int64_t* cand_cap) {
     if (span < 1) span = 1;
     if (sum_len < 0) sum_len = 0;
     const int64_t target = 2 * n > 4096 ? 2 * n : 4096;
     int s = 0;
-    while (s < 15 && (span >> s) > target) s++;
-    while (s < 15 && (sum_len >> s) > 8 * (n > 1024 ? n : 1024)) s++;
+    while (s < IV_L_MAX_SHIFT && (span >> s) > target) s++;
+    while (s < IV_L_MAX_SHIFT && (sum_len >> s) > 8 * (n > 1024 ? n : 1024)) s++;
     *shift = s;
     *n_bins = (span >> s) + 1;
     *cand_cap = (sum_len >> s) + 2 * n + 16;  // a subject touches at most len / binwidth + 2 bins

@@ -551,9 +551,11 @@ class JoinStep:
     path = "twopass": iv_index_build -> iv_count_overlaps (hit lists) -> iv_emit_pairs
     path = "fused"  : iv_lists_build -> iv_join_pairs (one kernel: count, look-back offsets, staged emission)"""
 
-    def __init__(self, s_iv, group_ranges, q_iv, seg_group, path="auto", slack=0):
+    def __init__(self, s_iv, group_ranges, q_iv, seg_group, path="auto", slack=0, seg_counts=False):
         self.s_iv, self.q_iv, self.group_ranges = s_iv, q_iv, group_ranges
         self.q = Queries(q_iv, seg_group, slack=slack)
+        self.want_seg_counts = seg_counts  # also leave the pairs per query key (device) in self.seg_counts
+        self.seg_counts = None
         if path == "auto":
             path = "fused" if ListIndex.supported(s_iv, group_ranges, _mean_len(q_iv)) else "twopass"
         self.path = path
@@ -577,6 +579,8 @@ class JoinStep:
             if ev:
                 ev.append(self._ev())
             total = ix.join_pairs(self.q, out_q, out_s, cap)
+            if self.want_seg_counts:
+                self.seg_counts = ix.segment_pair_counts(self.q, out_q, total, cap)
             if ev:
                 ev.append(self._ev())
         else:
@@ -584,6 +588,8 @@ class JoinStep:
             if ev:
                 ev.append(self._ev())
             _, ws, total = ix.count(self.q, IV_MODE_ALL, want_counts=False)
+            if self.want_seg_counts:
+                self.seg_counts = ix.segment_pair_counts(self.q, ws, total)
             if ev:
                 ev.append(self._ev())
             cabi.check(cabi.lib().iv_emit_pairs(C.byref(ix.c), C.byref(self.q.c), IV_MODE_ALL, None, _ptr(ws), _ptr(out_q),
