@@ -237,10 +237,11 @@ int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_t overlap, 
  * and one 32-byte record (= one L2 sector, one 256-bit load) holds a bin's list offset, length and first three entries:
  * most queries are answered -- counted AND emitted -- from that single gather.
  *
- * Entry test word (se): with sp = 0 for a crossing subject, else S' - origin + 1 (1 .. 2^14), and eo = min(E' - origin,
+ * Entry test word (se): with sp = 0 for a crossing subject, else S' - origin + 1 (< 2^14), and eo = min(E' - origin,
  * 0x7fff):      se = 0x80008000 | (0x4000 - sp) | eo << 16.
- * Query word:   qw = (0x4000 - min(e' - origin, 0x4000)) | (s' - origin + 1) << 16   (a query that reaches beyond the
- * bin: low half 0).  Then   hit  <=>  ((se - qw) & 0x80008000) == 0x80008000:   the low half keeps its guard bit iff
+ * Query word:   qw = (0x4000 - (e' - origin)) | (s' - origin + 1) << 16   for a query that ends within bin width + reach
+ * of the origin, else (0x4000 - bin width) | ...: only the subjects of this bin, the later bins are walked.
+ * Then   hit  <=>  ((se - qw) & 0x80008000) == 0x80008000:   the low half keeps its guard bit iff
  * sp <= e' - origin (the subject starts before the query ends), the high half iff eo >= s' - origin + 1 (it ends after
  * the query starts); no borrow crosses the halves.
  * Zero-length subjects (start == end) are handled exactly (hit iff s < start < e) as long as the group window is one
@@ -263,7 +264,7 @@ typedef struct iv_lists {
     int64_t n;          /* subjects */
     int64_t total_span;
     int32_t shift;
-    int32_t flags;
+    int32_t reach;      /* queries up to this long are answered from the list of their first bin alone (see below) */
     int64_t n_bins;     /* rec[] holds n_bins + 2 records (the last two are sentinels) */
     int64_t cand_cap;   /* capacity of cand_se[] / cand_row[] */
     const iv_lrec_t* rec;
@@ -278,11 +279,14 @@ size_t iv_lists_workspace_bytes(int64_t n, int64_t total_span, int64_t sum_len);
 /* bin width (log2) iv_lists_build will use for these subjects; < 0 = unsupported.  Callers route queries that are
  * much longer than a bin to the rank index (a query costs one gather per bin it reaches). */
 int32_t iv_lists_shift(int64_t n, int64_t total_span, int64_t sum_len);
-int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, void* ws,
-                   size_t ws_bytes, iv_lists_t* out, void* stream);
+/* reach (>= 0, a hint: e.g. the longest query that will be asked; clipped to one bin width): subjects that start within
+ * `reach` of a bin's origin are ALSO listed in the bin before (sp > bin width), so that a query of at most that length
+ * never has to look at a second bin.  Longer queries stay exact: they ignore those entries and walk the later bins. */
+int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, int64_t reach,
+                   void* ws, size_t ws_bytes, iv_lists_t* out, void* stream);
 
 size_t iv_join_workspace_bytes(int64_t n_queries);
-/* All (query label | row, subject row | s_label[row]) pairs in query order, ONE kernel: every 2048-row tile counts its
+/* All (query label | row, subject row | s_label[row]) pairs in query order, ONE kernel: every 512-row tile (a warp) counts its
  * hits, stages its pairs in shared memory, obtains its output offset by a decoupled look-back over the tiles before
  * it and writes its pairs with coalesced stores.  out_capacity = entries the output buffers hold; pairs beyond it are
  * dropped (never written) and *out_total (device) receives the true total, so the caller can repeat the call with

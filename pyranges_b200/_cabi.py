@@ -31,7 +31,7 @@ class IvIndex(C.Structure):
 
 
 class IvLists(C.Structure):
-    _fields_ = [("n", _i64), ("total_span", _i64), ("shift", _i32), ("flags", _i32), ("n_bins", _i64),
+    _fields_ = [("n", _i64), ("total_span", _i64), ("shift", _i32), ("reach", _i32), ("n_bins", _i64),
                 ("cand_cap", _i64), ("rec", _vp), ("cand_se", _vp), ("cand_row", _vp), ("groups", IvGroups)]
 
 
@@ -53,7 +53,7 @@ PROTOTYPES = {
     "iv_segment_bounds": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "iv_lists_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "iv_lists_shift": (_i32, [_i64, _i64, _i64]),
-    "iv_lists_build": (C.c_int, [_vp, _vp, _i64, _PG, _vp, _sz, _PL, _vp]),
+    "iv_lists_build": (C.c_int, [_vp, _vp, _i64, _PG, _i64, _vp, _sz, _PL, _vp]),
     "iv_join_workspace_bytes": (_sz, [_i64]),
     "iv_join_pairs": (C.c_int, [_PL, _PQ, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),
     "iv_join_count": (C.c_int, [_PL, _PQ, _i32, _vp, _vp]),

@@ -2,8 +2,8 @@
 // index (lists.cu).  Replaces NCLS.all_overlaps_both (pyranges/methods/join.py:15,23) and, in its count-only form,
 // all_overlaps_both + value_counts / has_overlaps (pyranges/methods/coverage.py:26-40, intersection.py:78).
 //
-// A block takes a ticket for 2048 consecutive query rows (so a tile only ever waits for tiles that are already running),
-// a WARP is its own tile of 256 consecutive rows, a lane owns two rows per iteration:
+// A block takes a ticket for 4096 consecutive query rows (so a tile only ever waits for tiles that are already running),
+// a WARP is its own tile of 512 consecutive rows, a lane owns two rows per iteration:
 //   1. 16-byte streaming loads of Start / End, 32-bit clamp into the partner group's window of the flattened axis,
 //      ONE 256-bit gather of the record of the bin the query starts in (list offset, length, first three entries);
 //   2. count sweep: two 16-bit compares per entry (inline entries from registers; longer lists and the later bins of a
@@ -24,10 +24,11 @@ namespace iv {
 
 constexpr int JN_THREADS = 256;
 constexpr int JN_WARPS = JN_THREADS / 32;
-constexpr int JN_ITERS = 4;                       // iterations of 64 rows per warp
-constexpr int JN_WROWS = 64 * JN_ITERS;           // 256 rows per warp
-constexpr int JN_TILE = JN_WROWS * JN_WARPS;      // 2048 rows per block
-constexpr int JN_WCAP = 768;                      // staged pairs per warp (3 per row; the rest is repeated later)
+constexpr int JN_ITERS = 8;                       // iterations of 64 rows per warp
+constexpr int JN_WROWS = 64 * JN_ITERS;           // 512 rows per warp
+constexpr int JN_TILE = JN_WROWS * JN_WARPS;      // 4096 rows per block
+constexpr int JN_WCAP = 1088;                     // staged pairs per warp (2.1 per row; the rest is repeated later)
+constexpr size_t JN_SMEM = (size_t)JN_WARPS * JN_WCAP * 6;  // dynamic shared memory of k_join: staging areas
 
 constexpr int JM_COUNT = 2, JM_ANY = 3;
 
@@ -76,8 +77,11 @@ template <typename X> struct QGeom {
         const X origin = b << shift;
         const uint32_t rel_s = (uint32_t)(sc - origin);
         const X d = ec - origin;  // ec >= sc: no wrap
-        single = d <= ((X)1 << shift);
-        qw = (single ? IV_L_SMAX - (uint32_t)d : 0u) | ((rel_s + 1u) << 16);
+        const uint32_t width = 1u << shift;
+        // ends within bin width + reach: the list of this bin holds every candidate; else only this bin's own subjects
+        // are taken from it (sp <= width) and the later bins are walked
+        single = d <= (X)(width + (uint32_t)ix.reach);
+        qw = (IV_L_SMAX - (single ? (uint32_t)d : width)) | ((rel_s + 1u) << 16);
         n = r.w[1] & 0xffu;
         if (n == 255u) n = __ldg(&ix.rec[(uint64_t)b + 1].co) - r.w[0];
     }
@@ -93,7 +97,7 @@ __device__ __forceinline__ void walk_extra(const iv_lists_t& ix, X ec, const LRe
         const uint64_t bl = (uint64_t)(ec - 1) >> shift;
         for (uint64_t bb = (uint64_t)g.b + 1; bb <= bl; bb++) {
             const uint32_t c0 = __ldg(&ix.rec[bb].co), c1 = __ldg(&ix.rec[bb + 1].co);
-            const uint32_t re = bb < bl ? IV_L_SMAX : (uint32_t)(ec - (X)(bl << shift));
+            const uint32_t re = bb < bl ? (1u << shift) : (uint32_t)(ec - (X)(bl << shift));
             for (uint32_t j = c0; j < c1; j++)
                 if (later_hit(__ldg(ix.cand_se + j), re)) f(__ldg(ix.cand_row + j));
         }
@@ -289,7 +293,7 @@ k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_
 }
 
 // ---- the fused join ---------------------------------------------------------------------------------------------------------------
-// Every WARP is its own tile of 256 rows (tile id = block ticket * 8 + warp: the warps of a block are co-resident and
+// Every WARP is its own tile of 512 rows (tile id = block ticket * 8 + warp: the warps of a block are co-resident and
 // blocks with smaller tickets started earlier, so a tile only waits for tiles that are running or done); no block-wide
 // barrier after the ticket.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
 // pair total, looks back for its output offset and copies the staged pairs out with coalesced stores; iterations that
@@ -299,8 +303,7 @@ __global__ void __launch_bounds__(JN_THREADS, OCC)
 k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
        const int64_t* __restrict__ s_label, int64_t cap, unsigned long long* __restrict__ state,
        unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total, int variant) {
-    __shared__ uint32_t st_s_all[JN_WARPS][JN_WCAP];
-    __shared__ uint8_t st_q_all[JN_WARPS][JN_WCAP];
+    extern __shared__ __align__(16) unsigned char jn_smem[];  // [JN_WARPS][JN_WCAP] subject rows, then query rows
     __shared__ uint32_t s_cnt[JN_WARPS][JN_ITERS];
     __shared__ unsigned int s_tile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,8 +312,8 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     const int64_t wtile = (int64_t)s_tile * JN_WARPS + warp;
     if (wtile >= n_wtiles) return;
     const int64_t wbase = wtile * JN_WROWS;
-    uint32_t* __restrict__ st_s = st_s_all[warp];
-    uint8_t* __restrict__ st_q = st_q_all[warp];
+    uint32_t* __restrict__ st_s = reinterpret_cast<uint32_t*>(jn_smem) + warp * JN_WCAP;
+    uint16_t* __restrict__ st_q = reinterpret_cast<uint16_t*>(jn_smem + (size_t)JN_WARPS * JN_WCAP * 4) + warp * JN_WCAP;
 
     // coalesced copy of `n` staged pairs to the outputs at offset o0; rows are relative to rbase
     auto copy_out = [&](uint32_t n, unsigned long long o0, int64_t rbase) {
@@ -328,7 +331,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     auto stage_rows = [&](const Rows2<X>& R, const QPlan (&p)[2], uint32_t pos, uint32_t qloc) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const uint8_t ql = (uint8_t)(qloc + k);
+            const uint16_t ql = (uint16_t)(qloc + k);
             emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
                 st_s[pos] = row;
                 st_q[pos] = ql;
@@ -482,7 +485,18 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     static const int occ = getenv("IV_JOIN_OCC") ? atoi(getenv("IV_JOIN_OCC")) : 4;
     static const int variant = getenv("IV_JOIN_VARIANT") ? atoi(getenv("IV_JOIN_VARIANT")) : 0;
     if (variant == 1) IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
-#define IV_JK(X, SL, OC) k_join<X, SL, OC><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total, variant)
+#define IV_JK(X, SL, OC)                                                                                                \
+    do {                                                                                                               \
+        static bool attr_done[64] = {false};                                                                           \
+        int dev = 0;                                                                                                   \
+        IV_CUDA(cudaGetDevice(&dev));                                                                                  \
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                                 \
+            IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;                                                           \
+        }                                                                                                              \
+        k_join<X, SL, OC><<<nb, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state,  \
+                                                          ticket, n_tiles, out_total, variant);                        \
+    } while (0)
 #define IV_JK2(X, SL) do { if (occ == 5) IV_JK(X, SL, 5); else if (occ == 6) IV_JK(X, SL, 6); else IV_JK(X, SL, 4); } while (0)
     if (narrow_span(lists)) {
         if (slack) IV_JK2(uint32_t, true); else IV_JK2(uint32_t, false);

@@ -26,7 +26,7 @@ constexpr int LS_BIG_SMEM = 2048;               // longer ones by a block: in sh
 // ---- K1: difference array of the list lengths -------------------------------------------------------------------------
 __global__ void __launch_bounds__(LS_THREADS)
 k_lists_hist(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, iv_groups_t G, int shift,
-             uint32_t* __restrict__ diff) {
+             uint32_t reach, uint32_t* __restrict__ diff) {
     __shared__ int span[2];
     const int64_t first = (int64_t)blockIdx.x * LS_THREADS;
     const int64_t last = first + LS_THREADS - 1 < n - 1 ? first + LS_THREADS - 1 : n - 1;
@@ -37,7 +37,9 @@ k_lists_hist(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64
     const int64_t off = __ldg(G.base + g) - __ldg(G.lo + g);
     const uint64_t S = (uint64_t)(__ldg(s + i) + off), E = (uint64_t)(__ldg(e + i) + off);
     const uint64_t b0 = S >> shift, b1 = E > S ? (E - 1) >> shift : b0;
-    atomicAdd(diff + b0, 1u);
+    // a subject that starts within `reach` of its bin's origin is also listed in the bin before
+    const uint64_t bf = (b0 > 0 && (uint32_t)(S - (b0 << shift)) < reach) ? b0 - 1 : b0;
+    atomicAdd(diff + bf, 1u);
     atomicAdd(diff + b1 + 1, 0xffffffffu);
 }
 
@@ -167,7 +169,7 @@ k_lists_apply(uint32_t* __restrict__ diff, int64_t nb, const long long* __restri
 // (a 2 Mb gene touches a thousand bins, an exon one).
 __global__ void __launch_bounds__(LS_THREADS)
 k_lists_fill(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, iv_groups_t G, int shift,
-             const uint32_t* __restrict__ co, uint32_t* __restrict__ cursor, int64_t cap, uint32_t* __restrict__ cand_se,
+             uint32_t reach, const uint32_t* __restrict__ co, uint32_t* __restrict__ cursor, int64_t cap, uint32_t* __restrict__ cand_se,
              uint32_t* __restrict__ cand_row) {
     __shared__ int span[2];
     __shared__ uint32_t pre[LS_THREADS + 1];
@@ -185,7 +187,8 @@ k_lists_fill(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64
         sS[threadIdx.x] = S;
         sE[threadIdx.x] = E;
         const uint64_t b0 = S >> shift, b1 = E > S ? (E - 1) >> shift : b0;
-        cnt = (uint32_t)(b1 - b0 + 1);
+        const uint64_t bf = (b0 > 0 && (uint32_t)(S - (b0 << shift)) < reach) ? b0 - 1 : b0;
+        cnt = (uint32_t)(b1 - bf + 1);
     }
     uint32_t tot;
     pre[threadIdx.x] = block_excl_sum<uint32_t, LS_THREADS>(cnt, wsum, tot);
@@ -198,9 +201,12 @@ k_lists_fill(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64
             if (pre[mid] <= u) lo = mid; else hi = mid;
         }
         const uint64_t S = sS[lo], E = sE[lo];
-        const uint64_t b0 = S >> shift, bb = b0 + (u - pre[lo]);
+        const uint64_t b0 = S >> shift;
+        const uint64_t bf = (b0 > 0 && (uint32_t)(S - (b0 << shift)) < reach) ? b0 - 1 : b0;
+        const uint64_t bb = bf + (u - pre[lo]);
         const uint64_t origin = bb << shift;
-        const uint32_t sp = bb > b0 ? 0u : (uint32_t)(S - origin) + 1u;  // 0 = starts before the bin
+        // 0 = starts before the bin; 1 .. width: starts inside; beyond: starts in the next bin, within reach
+        const uint32_t sp = bb > b0 ? 0u : (uint32_t)(S - origin) + 1u;
         const uint64_t d = E - origin;
         const uint32_t eo = d > (uint64_t)IV_L_EMAX ? IV_L_EMAX : (uint32_t)d;
         const int64_t at = (int64_t)__ldg(co + bb) + atomicAdd(cursor + bb, 1u);
@@ -300,6 +306,7 @@ k_lists_big(const uint32_t* __restrict__ co, uint32_t* __restrict__ cand_se, uin
 
 struct ListsLayout {
     int shift;
+    uint32_t reach;
     int64_t n_bins, cand_cap, nb, ntiles;
     iv_lrec_t* rec;
     uint32_t *diff, *nbig, *co, *big;
@@ -309,21 +316,29 @@ struct ListsLayout {
 
 // ~2 bins per subject, at most 2^14 coordinates wide (entry offsets are 14-bit + a guard bit), coarser when long subjects would blow
 // the lists up.  false = cannot be indexed this way.
-static bool choose_lists(int64_t n, int64_t span, int64_t sum_len, int* shift, int64_t* n_bins, int64_t* cand_cap) {
+static bool choose_lists(int64_t n, int64_t span, int64_t sum_len, int64_t reach_in, int* shift, int64_t* n_bins,
+                         int64_t* cand_cap, uint32_t* reach) {
     if (span < 1) span = 1;
     if (sum_len < 0) sum_len = 0;
     const int64_t target = 2 * n > 4096 ? 2 * n : 4096;
     int s = 0;
     while (s < IV_L_MAX_SHIFT && (span >> s) > target) s++;
     while (s < IV_L_MAX_SHIFT && (sum_len >> s) > 8 * (n > 1024 ? n : 1024)) s++;
+    // queries up to `reach` long are answered from the list of their first bin alone: subjects starting within reach of
+    // a bin's origin are listed in the bin before as well.  At most one bin wide, and start offsets must stay below 2^14.
+    int64_t r = reach_in > 0 ? reach_in : 0;
+    if (r > ((int64_t)1 << s)) r = (int64_t)1 << s;
+    if (r > (int64_t)IV_L_SMAX - 1 - ((int64_t)1 << s)) r = (int64_t)IV_L_SMAX - 1 - ((int64_t)1 << s);
+    if (r < 0) r = 0;
+    *reach = (uint32_t)r;
     *shift = s;
     *n_bins = (span >> s) + 1;
-    *cand_cap = (sum_len >> s) + 2 * n + 16;  // a subject touches at most len / binwidth + 2 bins
+    *cand_cap = (sum_len >> s) + 3 * n + 16;  // a subject touches at most len / binwidth + 2 bins (+ 1 within reach)
     return *n_bins <= ((int64_t)1 << 26) && *cand_cap < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
 }
 
-static bool plan_lists(int64_t n, int64_t span, int64_t sum_len, Bump& b, ListsLayout& L) {
-    if (!choose_lists(n, span, sum_len, &L.shift, &L.n_bins, &L.cand_cap)) return false;
+static bool plan_lists(int64_t n, int64_t span, int64_t sum_len, int64_t reach, Bump& b, ListsLayout& L) {
+    if (!choose_lists(n, span, sum_len, reach, &L.shift, &L.n_bins, &L.cand_cap, &L.reach)) return false;
     L.nb = L.n_bins + 2;  // bins 0 .. n_bins - 1, the bin behind the last one, a sentinel
     L.ntiles = cdiv(L.nb, LS_TILE);
     const size_t padded = (size_t)L.ntiles * LS_TILE;
@@ -348,18 +363,19 @@ using namespace iv;
 extern "C" size_t iv_lists_workspace_bytes(int64_t n, int64_t total_span, int64_t sum_len) {
     Bump b(nullptr, 0);
     ListsLayout L;
-    if (!plan_lists(n > 0 ? n : 0, total_span, sum_len, b, L)) return 0;
+    if (!plan_lists(n > 0 ? n : 0, total_span, sum_len, 0, b, L)) return 0;  // the layout does not depend on the reach
     return b.off + 256;
 }
 
 extern "C" int32_t iv_lists_shift(int64_t n, int64_t total_span, int64_t sum_len) {
     int s;
     int64_t nb, cc;
-    return choose_lists(n > 0 ? n : 0, total_span, sum_len, &s, &nb, &cc) ? s : -1;
+    uint32_t r;
+    return choose_lists(n > 0 ? n : 0, total_span, sum_len, 0, &s, &nb, &cc, &r) ? s : -1;
 }
 
-extern "C" int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, void* ws,
-                              size_t ws_bytes, iv_lists_t* out, void* stream) {
+extern "C" int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups,
+                              int64_t reach, void* ws, size_t ws_bytes, iv_lists_t* out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     IV_REQUIRE(groups && out && n >= 0, IV_ERR_INVALID, "iv_lists_build: null argument");
     IV_REQUIRE(ws && (((uintptr_t)ws) & 255) == 0, IV_ERR_INVALID, "iv_lists_build: workspace null or not 256-byte aligned");
@@ -367,13 +383,14 @@ extern "C" int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_
     const int64_t span = G.total_span > 0 ? G.total_span : 1;
     Bump b(ws, ws_bytes);
     ListsLayout L;
-    IV_REQUIRE(plan_lists(n, span, G.sum_len, b, L), IV_ERR_RANGE,
+    IV_REQUIRE(plan_lists(n, span, G.sum_len, reach, b, L), IV_ERR_RANGE,
                "iv_lists_build: span / subject lengths beyond the list index (use iv_index_build)");
     IV_REQUIRE(b.fits(), IV_ERR_WORKSPACE, "iv_lists_build: workspace %zu < %zu", ws_bytes, b.off);
     memset(out, 0, sizeof(*out));
     out->n = n;
     out->total_span = span;
     out->shift = L.shift;
+    out->reach = (int32_t)L.reach;
     out->n_bins = L.n_bins;
     out->cand_cap = L.cand_cap;
     out->rec = L.rec;
@@ -387,7 +404,7 @@ extern "C" int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_
     const size_t padded = (size_t)L.ntiles * LS_TILE;
     IV_CUDA(cudaMemsetAsync(L.diff, 0, (padded + 64) * sizeof(uint32_t), st));
     const unsigned nbk = (unsigned)cdiv(n, LS_THREADS);
-    k_lists_hist<<<nbk, LS_THREADS, 0, st>>>(starts, ends, n, G, L.shift, L.diff);
+    k_lists_hist<<<nbk, LS_THREADS, 0, st>>>(starts, ends, n, G, L.shift, L.reach, L.diff);
     IV_LAUNCH_CHECK();
     k_lists_reduce<<<(unsigned)L.ntiles, LS_THREADS, 0, st>>>(L.diff, L.nb, L.tD, L.tO);
     IV_LAUNCH_CHECK();
@@ -395,7 +412,7 @@ extern "C" int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_
     IV_LAUNCH_CHECK();
     k_lists_apply<<<(unsigned)L.ntiles, LS_THREADS, 0, st>>>(L.diff, L.nb, L.tC, L.tOin, L.co);
     IV_LAUNCH_CHECK();
-    k_lists_fill<<<nbk, LS_THREADS, 0, st>>>(starts, ends, n, G, L.shift, L.co, L.diff, L.cand_cap, L.cand_se, L.cand_row);
+    k_lists_fill<<<nbk, LS_THREADS, 0, st>>>(starts, ends, n, G, L.shift, L.reach, L.co, L.diff, L.cand_cap, L.cand_se, L.cand_row);
     IV_LAUNCH_CHECK();
     k_lists_finalize<<<(unsigned)cdiv(L.nb, LS_THREADS), LS_THREADS, 0, st>>>(L.n_bins, L.co, L.cand_se, L.cand_row, L.rec, L.big,
                                                                           L.nbig);

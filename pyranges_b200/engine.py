@@ -243,6 +243,12 @@ class Queries:
                            (p + 4 * iv.n_seg) if seg_mode is not None else None, int(slack))
 
 
+def _max_len(q):
+    """longest query of a Queries object, slack included (ingest-time metadata of its columns)"""
+    ml = q.iv.maxlen
+    return (int(ml.max()) if len(ml) else 0) + 2 * int(q.c.slack)
+
+
 class SubjectIndex:
     """Device index over the subject ("other") intervals of ALL groups -- the NCLS replacement
     (pyranges/methods/join.py:12).  Built by iv_index_build: radix sort of flattened starts and of
@@ -503,7 +509,7 @@ def overlap_pairs(s_iv, group_ranges, q, want_counts=False, capacity=None):
     """NCLS.all_overlaps_both for all keys (pyranges/methods/join.py:15,23): -> (counts | None, query rows, subject
     rows), pairs in query order."""
     if ListIndex.supported(s_iv, group_ranges, _mean_len(q.iv)):
-        ix = ListIndex(s_iv, group_ranges)
+        ix = ListIndex(s_iv, group_ranges, reach=_max_len(q))
         a, b = ix.pairs(q, capacity=capacity)
         return (ix.count(q, IV_MODE_ALL) if want_counts else None), a, b
     return SubjectIndex(s_iv, group_ranges).pairs(q, IV_MODE_ALL, want_counts=want_counts, capacity=capacity)
@@ -512,7 +518,7 @@ def overlap_pairs(s_iv, group_ranges, q, want_counts=False, capacity=None):
 def overlap_counts(s_iv, group_ranges, q, mode=IV_MODE_ALL):
     """overlaps per query row: all (IV_MODE_ALL), 0/1 (IV_MODE_ANY) or containments (IV_MODE_CONTAIN)"""
     if mode in (IV_MODE_ALL, IV_MODE_ANY) and ListIndex.supported(s_iv, group_ranges, _mean_len(q.iv)):
-        return ListIndex(s_iv, group_ranges).count(q, mode)
+        return ListIndex(s_iv, group_ranges, reach=_max_len(q)).count(q, mode)
     return SubjectIndex(s_iv, group_ranges).count(q, mode, for_emit=False)[0]
 
 
@@ -554,6 +560,7 @@ class JoinStep:
     def __init__(self, s_iv, group_ranges, q_iv, seg_group, path="auto", slack=0, seg_counts=False):
         self.s_iv, self.q_iv, self.group_ranges = s_iv, q_iv, group_ranges
         self.q = Queries(q_iv, seg_group, slack=slack)
+        self.reach = _max_len(self.q)  # ingest-time metadata of the query columns
         self.want_seg_counts = seg_counts  # also leave the pairs per query key (device) in self.seg_counts
         self.seg_counts = None
         if path == "auto":
@@ -575,7 +582,7 @@ class JoinStep:
         out_q = torch.empty(cap, dtype=torch.int64, device=dev)
         out_s = torch.empty(cap, dtype=torch.int64, device=dev)
         if self.path == "fused":
-            ix = ListIndex(self.s_iv, self.group_ranges)
+            ix = ListIndex(self.s_iv, self.group_ranges, reach=self.reach)
             if ev:
                 ev.append(self._ev())
             total = ix.join_pairs(self.q, out_q, out_s, cap)
@@ -644,10 +651,11 @@ class CountStep:
         if path == "auto":
             path = "lists" if ListIndex.supported(s_iv, group_ranges, _mean_len(q_iv)) else "ranks"
         self.path = path
+        self.reach = _max_len(self.q)
 
     def step(self):
         if self.path == "lists":
-            return ListIndex(self.s_iv, self.group_ranges).count(self.q, self.mode)
+            return ListIndex(self.s_iv, self.group_ranges, reach=self.reach).count(self.q, self.mode)
         c, _, _ = SubjectIndex(self.s_iv, self.group_ranges).count(self.q, self.mode, for_emit=False)
         return c
 
@@ -704,8 +712,11 @@ class ListIndex:
             return True  # the only index that handles zero-length subjects
         return q_mean_len is None or q_mean_len <= ListIndex.LONG_QUERY_BINS * (1 << shift)
 
-    def __init__(self, iv, seg_ranges=None):
+    def __init__(self, iv, seg_ranges=None, reach=0):
+        """reach: the longest query that will be asked (a hint, see iv_lists_build): such queries never look at a second
+        bin.  Queries.max_len() gives it for resident query columns."""
         self.iv = iv
+        self.reach = int(reach)
         self.groups = iv.groups(seg_ranges, gap=1, widen=iv.has_zero_length)
         L = cabi.lib()
         nbytes = L.iv_lists_workspace_bytes(iv.n, self.groups.total_span, self.groups.sumlen)
@@ -717,8 +728,8 @@ class ListIndex:
 
     def build(self):
         iv = self.iv
-        cabi.check(cabi.lib().iv_lists_build(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(self.groups.c), _ptr(self.ws),
-                                             self.ws.numel(), C.byref(self.c), _stream()), "iv_lists_build")
+        cabi.check(cabi.lib().iv_lists_build(_ptr(iv.start), _ptr(iv.end), iv.n, C.byref(self.groups.c), self.reach,
+                                             _ptr(self.ws), self.ws.numel(), C.byref(self.c), _stream()), "iv_lists_build")
         return self
 
     def join_pairs(self, q, out_q, out_s, capacity, s_label=None):

@@ -65,10 +65,14 @@ def _setup(case, empty_every=0):
 
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("slack", [0, 7])
-def test_join_pairs_vs_oracle(eng, case, slack):
+@pytest.mark.parametrize("reach", ["none", "max", "half"])
+def test_join_pairs_vs_oracle(eng, case, slack, reach):
+    """reach: the index also lists subjects that start just behind a bin, so that queries up to that length stay inside
+    their first bin; queries longer than the hint (reach = half the longest) must stay exact"""
     qs, qe, qoff, ss, se, soff, sg = _setup(case, empty_every=3 if case[0] == 3 else 0)
-    ix = eng.ListIndex(_dev(eng, ss, se, soff))
     q = eng.Queries(_dev(eng, qs, qe, qoff), sg, slack=slack)
+    r = {"none": 0, "max": eng._max_len(q), "half": eng._max_len(q) // 2}[reach]
+    ix = eng.ListIndex(_dev(eng, ss, se, soff), reach=r)
     a, b = ix.pairs(q)
     a, b = a.cpu().numpy(), b.cpu().numpy()
     assert np.all(a[1:] >= a[:-1]), "pairs come out in query order"
@@ -76,7 +80,7 @@ def test_join_pairs_vs_oracle(eng, case, slack):
     ga, gb = canon_pairs(a, b)
     assert np.array_equal(ga, wa) and np.array_equal(gb, wb)
     # deterministic: a second build + join gives the identical (not just set-equal) pair list
-    a2, b2 = eng.ListIndex(_dev(eng, ss, se, soff)).pairs(q)
+    a2, b2 = eng.ListIndex(_dev(eng, ss, se, soff), reach=r).pairs(q)
     assert np.array_equal(a2.cpu().numpy(), a) and np.array_equal(b2.cpu().numpy(), b)
     # counts, all / any
     c = ix.count(q, eng.IV_MODE_ALL).cpu().numpy()
@@ -235,8 +239,8 @@ def test_join_zero_length_intervals(eng):
         sg = np.asarray([0, 1], np.int32)
         s_iv = _dev(eng, ss, se, off_s)
         assert s_iv.has_zero_length
-        ix = eng.ListIndex(s_iv)
         q = eng.Queries(_dev(eng, qs, qe, off_q), sg)
+        ix = eng.ListIndex(s_iv, reach=eng._max_len(q) if maxpos != 5000 else 0)
         a, b = ix.pairs(q)
         wa, wb = brute_pairs(qs, qe, off_q, sg, ss, se, off_s)
         ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())

@@ -39,8 +39,9 @@ def timeit(name, fn, alg_bytes=None):
     return ms
 
 
-lx = E.ListIndex(s_iv, groups)
-print("shift", lx.c.shift, "bins", lx.c.n_bins, "cand_cap", lx.c.cand_cap)
+reach = E._max_len(q)
+lx = E.ListIndex(s_iv, groups, reach=reach)
+print("shift", lx.c.shift, "reach", lx.c.reach, "bins", lx.c.n_bins, "cand_cap", lx.c.cand_cap)
 a, b = lx.pairs(q)
 p = a.numel()
 print("pairs", p)
@@ -48,7 +49,7 @@ cap = p + 4096
 oq = torch.empty(cap, dtype=torch.int64, device="cuda")
 os_ = torch.empty(cap, dtype=torch.int64, device="cuda")
 del a, b
-timeit("lists build", lambda: E.ListIndex(s_iv, groups), 24 * annot.n)
+timeit("lists build", lambda: E.ListIndex(s_iv, groups, reach=reach), 24 * annot.n)
 timeit("fused join kernel (+ memset)", lambda: lx.join_pairs(q, oq, os_, cap), 16 * reads.n + 16 * p)
 timeit("fused join, out_q only", lambda: lx.join_pairs(q, oq, None, cap), 16 * reads.n + 8 * p)
 timeit("list count ALL", lambda: lx.count(q, E.IV_MODE_ALL), 24 * reads.n)
