@@ -290,8 +290,10 @@ size_t iv_join_workspace_bytes(int64_t n_queries);
  * hits, stages its pairs in shared memory, obtains its output offset by a decoupled look-back over the tiles before
  * it and writes its pairs with coalesced stores.  out_capacity = entries the output buffers hold; pairs beyond it are
  * dropped (never written) and *out_total (device) receives the true total, so the caller can repeat the call with
- * larger buffers.  ws: iv_join_workspace_bytes(q->n) bytes, 256-byte aligned. */
-int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int64_t* out_q, int64_t* out_s,
+ * larger buffers.  ws: iv_join_workspace_bytes(q->n) bytes, 256-byte aligned.
+ * mode IV_MODE_ANY: one entry per query WITH hits -- out_q only (has_overlaps / overlap(how="first"),
+ * pyranges/methods/intersection.py:78), out_s is not written. */
+int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int32_t mode, int64_t* out_q, int64_t* out_s,
                   const int64_t* s_label, int64_t out_capacity, void* ws, size_t ws_bytes, int64_t* out_total,
                   void* stream);
 /* out_count[i] = number of overlapping subjects (IV_MODE_ALL) or 0/1 (IV_MODE_ANY) of query i */

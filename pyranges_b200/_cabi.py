@@ -55,7 +55,7 @@ PROTOTYPES = {
     "iv_lists_shift": (_i32, [_i64, _i64, _i64]),
     "iv_lists_build": (C.c_int, [_vp, _vp, _i64, _PG, _i64, _vp, _sz, _PL, _vp]),
     "iv_join_workspace_bytes": (_sz, [_i64]),
-    "iv_join_pairs": (C.c_int, [_PL, _PQ, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    "iv_join_pairs": (C.c_int, [_PL, _PQ, _i32, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),
     "iv_join_count": (C.c_int, [_PL, _PQ, _i32, _vp, _vp]),
     "iv_sorted_pair_segments": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
     "iv_index_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),

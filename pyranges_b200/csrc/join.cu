@@ -91,8 +91,16 @@ template <typename X> struct QGeom {
 template <typename X, typename F>
 __device__ __forceinline__ void walk_extra(const iv_lists_t& ix, X ec, const LRec& r, const QGeom<X>& g, F&& f) {
     const int shift = ix.shift;
-    for (uint32_t j = JN_MASKED; j < g.n; j++)
-        if (hit_bit(__ldg(ix.cand_se + r.w[0] + j), g.qw)) f(__ldg(ix.cand_row + r.w[0] + j));
+    // the rest of a long list, eight entries per round trip
+    for (uint32_t j0 = JN_MASKED; j0 < g.n; j0 += 8) {
+        const uint32_t* __restrict__ c = ix.cand_se + r.w[0] + j0;
+        uint32_t w[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) w[t] = __ldg(c + t);  // (the arrays end in slack: reading past the list is safe)
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            if (j0 + t < g.n && hit_bit(w[t], g.qw)) f(__ldg(ix.cand_row + r.w[0] + j0 + t));
+    }
     if (!g.single) {
         const uint64_t bl = (uint64_t)(ec - 1) >> shift;
         for (uint64_t bb = (uint64_t)g.b + 1; bb <= bl; bb++) {
@@ -166,10 +174,11 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* state
     int64_t look = tile - 1;
     while (look >= 0) {
         const int64_t idx = look - lane;
-        unsigned long long v = 2ull;  // before the first tile: an inclusive prefix of 0
-        if (idx >= 0) {
-            v = ld_relaxed(state + idx);
-            for (unsigned ns = 64; (v & 3ull) == 0ull; ns = ns < 1024 ? ns * 2 : ns) { __nanosleep(ns); v = ld_relaxed(state + idx); }
+        unsigned long long v = idx >= 0 ? ld_relaxed(state + idx) : 2ull;  // before the first tile: inclusive prefix 0
+        // poll as a warp (one uniform loop, not 32 divergent ones), backing off while predecessors are still counting
+        for (unsigned ns = 32; __any_sync(FULL, (v & 3ull) == 0ull); ns = ns < 512 ? ns * 2 : ns) {
+            __nanosleep(ns);
+            if ((v & 3ull) == 0ull) v = ld_relaxed(state + idx);
         }
         const unsigned incl = __ballot_sync(FULL, (v & 3ull) == 2ull);
         const int first = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
@@ -298,8 +307,8 @@ k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_
 // barrier after the ticket.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
 // pair total, looks back for its output offset and copies the staged pairs out with coalesced stores; iterations that
 // did not fit are repeated afterwards -- the offset is known by then -- through the same staging area, one at a time.
-template <typename X, bool SLACK, int OCC>
-__global__ void __launch_bounds__(JN_THREADS, OCC)
+template <typename X, bool SLACK, bool ANY>
+__global__ void __launch_bounds__(JN_THREADS, 4)
 k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
        const int64_t* __restrict__ s_label, int64_t cap, unsigned long long* __restrict__ state,
        unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total, int variant) {
@@ -321,9 +330,11 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
             const int64_t o = (int64_t)(o0 + k);
             if (o < cap) {
                 const int64_t row_q = rbase + st_q[k];
-                const uint32_t row_s = st_s[k];
                 if (out_q) __stcs(out_q + o, q.label ? __ldg(q.label + row_q) : row_q);
-                if (out_s) __stcs(out_s + o, s_label ? __ldg(s_label + row_s) : (int64_t)row_s);
+                if (!ANY && out_s) {
+                    const uint32_t row_s = st_s[k];
+                    __stcs(out_s + o, s_label ? __ldg(s_label + row_s) : (int64_t)row_s);
+                }
             }
         }
     };
@@ -332,12 +343,19 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const uint16_t ql = (uint16_t)(qloc + k);
-            emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
-                st_s[pos] = row;
-                st_q[pos] = ql;
-                pos++;
-            });
+            if (ANY) {  // one entry per query with hits: the query row only
+                if (p[k].count()) st_q[pos++] = ql;
+            } else {
+                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
+                    st_s[pos] = row;
+                    st_q[pos] = ql;
+                    pos++;
+                });
+            }
         }
+    };
+    auto pairs_of = [&](const QPlan (&p)[2]) -> uint32_t {
+        return ANY ? (p[0].count() ? 1u : 0u) + (p[1].count() ? 1u : 0u) : p[0].count() + p[1].count();
     };
 
     Geo<X> G(q, wbase);
@@ -358,7 +376,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
             QPlan p[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
-            const uint32_t mine = p[0].count() + p[1].count();
+            const uint32_t mine = pairs_of(p);
             const uint32_t inc = warp_incl_sum(mine);
             itot = __shfl_sync(FULL, inc, 31);
             if (open && staged + itot <= (uint32_t)JN_WCAP) {
@@ -396,7 +414,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         QPlan p[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
-        const uint32_t mine = p[0].count() + p[1].count();
+        const uint32_t mine = pairs_of(p);
         const uint32_t inc = warp_incl_sum(mine);
         if (itot <= (uint32_t)JN_WCAP) {
             stage_rows(R, p, inc - mine, (uint32_t)(2 * lane));
@@ -408,6 +426,13 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
             for (int k = 0; k < 2; k++) {
                 const int64_t row_q = ibase + 2 * lane + k;
                 const int64_t ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
+                if (ANY) {
+                    if (p[k].count()) {
+                        if ((int64_t)oo < cap && out_q) out_q[oo] = ql;
+                        oo++;
+                    }
+                    continue;
+                }
                 emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
                     if ((int64_t)oo < cap) {
                         if (out_q) out_q[oo] = ql;
@@ -458,13 +483,14 @@ extern "C" size_t iv_join_workspace_bytes(int64_t n_queries) {
     return ((size_t)cdiv(n_queries > 0 ? n_queries : 1, JN_WROWS) + 2) * sizeof(unsigned long long) + 256;
 }
 
-extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int64_t* out_q, int64_t* out_s,
+extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int32_t mode, int64_t* out_q, int64_t* out_s,
                              const int64_t* s_label, int64_t out_capacity, void* ws, size_t ws_bytes, int64_t* out_total,
                              void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_join(lists, q, "iv_join_pairs");
     if (rc != IV_OK) return rc;
     IV_REQUIRE(out_total, IV_ERR_INVALID, "iv_join_pairs: out_total is null");
+    IV_REQUIRE(mode == IV_MODE_ALL || mode == IV_MODE_ANY, IV_ERR_INVALID, "iv_join_pairs: mode must be ALL or ANY");
     IV_REQUIRE(out_capacity >= 0, IV_ERR_INVALID, "iv_join_pairs: negative out_capacity");
     if (q->n == 0) {
         IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
@@ -480,24 +506,22 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     const bool vec = aligned16(q->start) && aligned16(q->end);
     const bool slack = q->slack != 0;
     const unsigned nb = (unsigned)cdiv(q->n, JN_TILE);
-    // resident blocks per SM the kernel is compiled for: 4 (62 registers, no spills; default) or 5 (48 registers);
-    // IV_JOIN_OCC is a tuning switch for measurements
-    static const int occ = getenv("IV_JOIN_OCC") ? atoi(getenv("IV_JOIN_OCC")) : 4;
-    static const int variant = getenv("IV_JOIN_VARIANT") ? atoi(getenv("IV_JOIN_VARIANT")) : 0;
+    static const int variant = getenv("IV_JOIN_VARIANT") ? atoi(getenv("IV_JOIN_VARIANT")) : 0;  // measurements only
     if (variant == 1) IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
-#define IV_JK(X, SL, OC)                                                                                                \
+#define IV_JK(X, SL, AN)                                                                                                \
     do {                                                                                                               \
         static bool attr_done[64] = {false};                                                                           \
         int dev = 0;                                                                                                   \
         IV_CUDA(cudaGetDevice(&dev));                                                                                  \
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                                 \
-            IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
+            IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, AN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
             if (dev >= 0 && dev < 64) attr_done[dev] = true;                                                           \
         }                                                                                                              \
-        k_join<X, SL, OC><<<nb, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state,  \
+        k_join<X, SL, AN><<<nb, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state,  \
                                                           ticket, n_tiles, out_total, variant);                        \
     } while (0)
-#define IV_JK2(X, SL) do { if (occ == 5) IV_JK(X, SL, 5); else if (occ == 6) IV_JK(X, SL, 6); else IV_JK(X, SL, 4); } while (0)
+#define IV_JK2(X, SL) do { if (any) IV_JK(X, SL, true); else IV_JK(X, SL, false); } while (0)
+    const bool any = mode == IV_MODE_ANY;
     if (narrow_span(lists)) {
         if (slack) IV_JK2(uint32_t, true); else IV_JK2(uint32_t, false);
     } else {

@@ -664,13 +664,21 @@ class OverlapFirstStep:
     """gr.overlap(other, how="first") on resident columns: the self rows with at least one hit, in row order
     (NCLS.has_overlaps, pyranges/methods/intersection.py:78).  Same asynchronous protocol as JoinStep."""
 
-    def __init__(self, s_iv, group_ranges, q_iv, seg_group):
+    def __init__(self, s_iv, group_ranges, q_iv, seg_group, path="auto"):
         self.s_iv, self.q_iv, self.group_ranges = s_iv, q_iv, group_ranges
         self.q = Queries(q_iv, seg_group)
         self.cap = 0
         self.totals = _Totals()
+        if path == "auto":
+            path = "fused" if ListIndex.supported(s_iv, group_ranges, _mean_len(q_iv)) else "twopass"
+        self.path = path
+        self.reach = _max_len(self.q)
 
     def _run(self, cap):
+        if self.path == "fused":
+            ix = ListIndex(self.s_iv, self.group_ranges, reach=self.reach)
+            rows = torch.empty(cap, dtype=torch.int64, device=self.q_iv.device)
+            return rows, ix.join_pairs(self.q, rows, None, cap, mode=IV_MODE_ANY)
         ix = SubjectIndex(self.s_iv, self.group_ranges)
         _, ws, total = ix.count(self.q, IV_MODE_ANY, want_counts=False)
         rows = torch.empty(cap, dtype=torch.int64, device=self.q_iv.device)
@@ -732,15 +740,16 @@ class ListIndex:
                                              _ptr(self.ws), self.ws.numel(), C.byref(self.c), _stream()), "iv_lists_build")
         return self
 
-    def join_pairs(self, q, out_q, out_s, capacity, s_label=None):
+    def join_pairs(self, q, out_q, out_s, capacity, s_label=None, mode=IV_MODE_ALL):
         """launch the fused join into caller buffers of `capacity` entries; -> total (device int64[1]); pairs beyond
-        the capacity are dropped: compare the total and repeat with larger buffers"""
+        the capacity are dropped: compare the total and repeat with larger buffers.  mode IV_MODE_ANY: one entry per
+        query with hits (out_q only)."""
         L = cabi.lib()
         dev = self.iv.device
         ws = _bytes(L.iv_join_workspace_bytes(q.iv.n), dev)
         total = torch.empty(1, dtype=torch.int64, device=dev)
-        cabi.check(L.iv_join_pairs(C.byref(self.c), C.byref(q.c), _ptr(out_q), _ptr(out_s), _ptr(s_label), int(capacity),
-                                   _ptr(ws), ws.numel(), _ptr(total), _stream()), "iv_join_pairs")
+        cabi.check(L.iv_join_pairs(C.byref(self.c), C.byref(q.c), mode, _ptr(out_q), _ptr(out_s), _ptr(s_label),
+                                   int(capacity), _ptr(ws), ws.numel(), _ptr(total), _stream()), "iv_join_pairs")
         return total
 
     def pairs(self, q, want_q=True, want_s=True, s_label=None, capacity=None):
