@@ -286,7 +286,7 @@ int iv_lists_build(const int64_t* starts, const int64_t* ends, int64_t n, const 
                    void* ws, size_t ws_bytes, iv_lists_t* out, void* stream);
 
 size_t iv_join_workspace_bytes(int64_t n_queries);
-/* All (query label | row, subject row | s_label[row]) pairs in query order, ONE kernel: every 512-row tile (a warp) counts its
+/* All (query label | row, subject row | s_label[row]) pairs in query order, ONE kernel: every 256-row tile (a warp) counts its
  * hits, stages its pairs in shared memory, obtains its output offset by a decoupled look-back over the tiles before
  * it and writes its pairs with coalesced stores.  out_capacity = entries the output buffers hold; pairs beyond it are
  * dropped (never written) and *out_total (device) receives the true total, so the caller can repeat the call with

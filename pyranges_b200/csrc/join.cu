@@ -2,14 +2,14 @@
 // index (lists.cu).  Replaces NCLS.all_overlaps_both (pyranges/methods/join.py:15,23) and, in its count-only form,
 // all_overlaps_both + value_counts / has_overlaps (pyranges/methods/coverage.py:26-40, intersection.py:78).
 //
-// A block takes a ticket for 4096 consecutive query rows (so a tile only ever waits for tiles that are already running),
-// a WARP is its own tile of 512 consecutive rows, a lane owns two rows per iteration:
+// A block takes a ticket for 2048 consecutive query rows (so a tile only ever waits for tiles that are already running),
+// a WARP is its own tile of 256 consecutive rows, a lane owns two rows per iteration:
 //   1. 16-byte streaming loads of Start / End, 32-bit clamp into the partner group's window of the flattened axis,
 //      ONE 256-bit gather of the record of the bin the query starts in (list offset, length, first three entries);
 //   2. count sweep: two 16-bit compares per entry (inline entries from registers; longer lists and the later bins of a
 //      query that reaches beyond its first bin are walked in global memory, L2-resident);
 //   3. shuffle scan of the counts -> the lane's position in the warp's STAGING area in shared memory; emit sweep: the
-//      same compares again, hits go to the staging area as (row in tile: 16 bit, subject row: 32 bit);
+//      same compares again, hits go to the staging area as (row in tile: 8 bit, subject row: 32 bit);
 //   4. the tile's pair total is published and its output offset obtained by a decoupled look-back over the preceding
 //      tiles (status word = 62-bit value + 2-bit flag, one relaxed 64-bit access each);
 //   5. every warp copies its staged pairs to out_q / out_s with fully coalesced 8-byte streaming stores.
@@ -24,11 +24,15 @@ namespace iv {
 
 constexpr int JN_THREADS = 256;
 constexpr int JN_WARPS = JN_THREADS / 32;
-constexpr int JN_ITERS = 8;                       // iterations of 64 rows per warp
-constexpr int JN_WROWS = 64 * JN_ITERS;           // 512 rows per warp
-constexpr int JN_TILE = JN_WROWS * JN_WARPS;      // 4096 rows per block
-constexpr int JN_WCAP = 1088;                     // staged pairs per warp (2.1 per row; the rest is repeated later)
-constexpr size_t JN_SMEM = (size_t)JN_WARPS * JN_WCAP * 6;  // dynamic shared memory of k_join: staging areas
+constexpr int JN_ITERS = 4;                       // iterations of 64 rows per warp
+constexpr int JN_WROWS = 64 * JN_ITERS;           // 256 rows per warp
+constexpr int JN_TILE = JN_WROWS * JN_WARPS;      // 2048 rows per block
+// Staged pairs per warp (2.25 per row; iterations that do not fit are repeated once the offset is known), 5 bytes each.
+// The staging areas are kept SMALL on purpose: shared memory comes out of the L1, and every random 32-byte gather in
+// flight holds a 128-byte L1 line -- with 212 KB of shared memory per SM (16 KB of L1) the same count sweep ran 1.6x
+// slower than with 100 KB (measured, profiles/README.md).
+constexpr int JN_WCAP = 576;
+constexpr size_t JN_SMEM = (size_t)JN_WARPS * JN_WCAP * 5;  // dynamic shared memory of k_join: staging areas
 
 constexpr int JM_COUNT = 2, JM_ANY = 3;
 
@@ -302,7 +306,7 @@ k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_
 }
 
 // ---- the fused join ---------------------------------------------------------------------------------------------------------------
-// Every WARP is its own tile of 512 rows (tile id = block ticket * 8 + warp: the warps of a block are co-resident and
+// Every WARP is its own tile of 256 rows (tile id = block ticket * 8 + warp: the warps of a block are co-resident and
 // blocks with smaller tickets started earlier, so a tile only waits for tiles that are running or done); no block-wide
 // barrier after the ticket.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
 // pair total, looks back for its output offset and copies the staged pairs out with coalesced stores; iterations that
@@ -322,7 +326,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     if (wtile >= n_wtiles) return;
     const int64_t wbase = wtile * JN_WROWS;
     uint32_t* __restrict__ st_s = reinterpret_cast<uint32_t*>(jn_smem) + warp * JN_WCAP;
-    uint16_t* __restrict__ st_q = reinterpret_cast<uint16_t*>(jn_smem + (size_t)JN_WARPS * JN_WCAP * 4) + warp * JN_WCAP;
+    uint8_t* __restrict__ st_q = jn_smem + (size_t)JN_WARPS * JN_WCAP * 4 + warp * JN_WCAP;
 
     // coalesced copy of `n` staged pairs to the outputs at offset o0; rows are relative to rbase
     auto copy_out = [&](uint32_t n, unsigned long long o0, int64_t rbase) {
@@ -342,7 +346,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     auto stage_rows = [&](const Rows2<X>& R, const QPlan (&p)[2], uint32_t pos, uint32_t qloc) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const uint16_t ql = (uint16_t)(qloc + k);
+            const uint8_t ql = (uint8_t)(qloc + k);
             if (ANY) {  // one entry per query with hits: the query row only
                 if (p[k].count()) st_q[pos++] = ql;
             } else {
@@ -543,10 +547,12 @@ extern "C" int iv_join_count(const iv_lists_t* lists, const iv_queries_t* q, int
     const bool vec = aligned16(q->start) && aligned16(q->end) && aligned16(out_count);
     const bool slack = q->slack != 0;
     const unsigned nb = (unsigned)cdiv(q->n, JN_TILE);
+    static const int xsmem = getenv("IV_COUNT_SMEM") ? atoi(getenv("IV_COUNT_SMEM")) : 0;  // measurements only
 #define IV_JC(X, M)                                                                                           \
     do {                                                                                                      \
+        if (xsmem > 0) cudaFuncSetAttribute(k_join_count<X, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xsmem); \
         if (slack) k_join_count<X, M, true><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_count);            \
-        else k_join_count<X, M, false><<<nb, JN_THREADS, 0, st>>>(*lists, *q, vec, out_count);                 \
+        else k_join_count<X, M, false><<<nb, JN_THREADS, xsmem, st>>>(*lists, *q, vec, out_count);             \
     } while (0)
     if (narrow_span(lists)) {
         if (mode == IV_MODE_ALL) IV_JC(uint32_t, JM_COUNT); else IV_JC(uint32_t, JM_ANY);

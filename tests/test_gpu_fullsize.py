@@ -203,3 +203,154 @@ def test_radix_sort_large_vs_torch(n, bits, vdtype):
     assert bool((kk == want_k).all())
     if v is not None:
         assert bool((v.long() == want_o).all())
+
+
+def test_c3_fused_join_equals_rank_join_100m_x_1m():
+    """The north-star size through BOTH index families: the list index + fused single-pass join must produce exactly
+    the pair set (and per-row counts) of the rank index + count / emit pair; counts against the oracle on sampled keys."""
+    import torch
+
+    from oracle import oracle as orc
+    from pyranges_b200 import engine as E
+    from pyranges_b200 import synthetic as S
+
+    reads, annot = S.reads_by_chrom(100_000_000, seed=1), S.annotations_by_chrom(1_000_000, seed=2)
+    sg = (np.arange(reads.n_keys) // 2).astype(np.int32)
+    q_iv = E.DeviceIntervals.from_numpy(reads.starts, reads.ends, reads.seg_off)
+    s_iv = E.DeviceIntervals.from_numpy(annot.starts, annot.ends, annot.seg_off)
+    groups = annot.chrom_ranges()
+    q = E.Queries(q_iv, sg)
+    lx = E.ListIndex(s_iv, groups, reach=E._max_len(q))
+    a, b = lx.pairs(q)
+    p = a.numel()
+    assert p > 100_000_000 and bool((a[1:] >= a[:-1]).all())
+    counts = lx.count(q)
+    assert int(counts.sum().item()) == p
+    assert bool((torch.bincount(a, minlength=reads.n) == counts).all())
+    key_fused = torch.sort(a * annot.n + b).values
+    del a, b
+    c2, a2, b2 = E.SubjectIndex(s_iv, groups).pairs(q, E.IV_MODE_ALL)
+    assert bool((c2 == counts).all())
+    key_rank = torch.sort(a2 * annot.n + b2).values
+    del a2, b2, c2
+    assert key_fused.numel() == key_rank.numel() and bool((key_fused == key_rank).all())
+    del key_fused, key_rank
+    rows = torch.empty(reads.n, dtype=torch.int64, device="cuda")
+    k = int(lx.join_pairs(q, rows, None, reads.n, mode=E.IV_MODE_ANY).item())
+    assert bool((rows[:k] == torch.nonzero(counts > 0).flatten()).all())
+    hc = counts.cpu().numpy()
+    for key in (46, 47, 40):  # chrY +, chrY -, chr21 +
+        g = key // 2
+        sa, sb = annot.seg_off[2 * g], annot.seg_off[2 * g + 2]
+        t = orc.NCLS(annot.starts[sa:sb], annot.ends[sa:sb], np.arange(sa, sb))
+        sl = slice(reads.seg_off[key], reads.seg_off[key + 1])
+        assert np.array_equal(hc[sl], t.count(reads.starts[sl], reads.ends[sl])), key
+
+
+def test_count_beyond_2_to_31_pairs():
+    """more than 2^31 overlap pairs in total (count-only: the pairs themselves would take 40 GB): int64 counts"""
+    import torch
+
+    from pyranges_b200 import engine as E
+
+    rng = np.random.default_rng(31)
+    ns, nq = 50, 60_000_000
+    ss = rng.integers(0, 1000, ns).astype(np.int64)
+    se = ss + 1_000_000
+    qs = rng.integers(2000, 900_000, nq).astype(np.int64)
+    qe = qs + 100
+    s_iv = E.DeviceIntervals.from_numpy(ss, se, np.asarray([0, ns]))
+    q = E.Queries(E.DeviceIntervals.from_numpy(qs, qe, np.asarray([0, nq])), np.zeros(1, np.int32))
+    for counts in (E.ListIndex(s_iv).count(q), E.SubjectIndex(s_iv).count(q, E.IV_MODE_ALL, for_emit=False)[0]):
+        assert bool((counts == ns).all())
+        assert int(counts.sum().item()) == ns * nq > 2 ** 31
+    _, ws, total = E.SubjectIndex(s_iv).count(q, E.IV_MODE_ALL, for_emit=True, want_counts=False)
+    assert int(total.item()) == ns * nq
+
+
+def _sample_keys():
+    return (46, 47, 40, 41)  # chrY +, chrY -, chr21 +, chr21 -
+
+
+def test_c4_nearest_cluster_merge_vs_oracle_sampled_keys():
+    """config 4 at full size, the oracle on sampled keys: nearest upstream / same strand must return the MINIMAL
+    distance (not just a consistent one), cluster ids and merged rows must equal sorted_nearest's restatement."""
+    import torch
+
+    from oracle import oracle as orc
+    from pyranges_b200 import engine as E
+    from pyranges_b200 import synthetic as S
+
+    iv, ann = S.reads_by_chrom(50_000_000, seed=3, min_len=50, max_len=500), S.annotations_by_chrom(1_000_000, seed=2)
+    q_iv = E.DeviceIntervals.from_numpy(iv.starts, iv.ends, iv.seg_off)
+    s_iv = E.DeviceIntervals.from_numpy(ann.starts, ann.ends, ann.seg_off)
+    sg = np.arange(iv.n_keys, dtype=np.int32)
+    modes = np.asarray([E.IV_NEAREST_PREVIOUS if k % 2 == 0 else E.IV_NEAREST_NEXT for k in range(iv.n_keys)], np.int32)
+    row, dist = E.SubjectIndex(s_iv, None, ends_perm=True).nearest(E.Queries(q_iv, sg, seg_mode=modes), overlap=True)
+    row, dist = row.cpu().numpy(), dist.cpu().numpy()
+    for k in _sample_keys():
+        a, b = iv.seg_off[k], iv.seg_off[k + 1]
+        sa, sb = ann.seg_off[k], ann.seg_off[k + 1]
+        s, e, S_, E_ = iv.starts[a:b], iv.ends[a:b], ann.starts[sa:sb], ann.ends[sa:sb]
+        t = orc.NCLS(S_, E_, np.arange(sb - sa, dtype=np.int64))
+        hit = t.count(s, e) > 0
+        want = np.full(b - a, -1, np.int64)
+        want[hit] = 0
+        rest = np.flatnonzero(~hit)
+        if k % 2 == 0:  # '+': upstream = previous
+            o_e = np.argsort(E_, kind="stable")
+            ls = np.argsort(s[rest], kind="stable")
+            _, d = orc.nearest_previous_nonoverlapping(s[rest][ls], E_[o_e] - 1, o_e)
+            want[rest[ls]] = d
+        else:  # '-': upstream = next
+            o_s = np.argsort(S_, kind="stable")
+            le = np.argsort(e[rest], kind="stable")
+            _, d = orc.nearest_next_nonoverlapping(e[rest][le] - 1, S_[o_s], o_s)
+            want[rest[le]] = d
+        assert np.array_equal(dist[a:b], want), k
+        # the returned subject realises the distance
+        got = row[a:b]
+        ok = got >= 0
+        assert np.array_equal(ok, want >= 0)
+        Sg, Eg = ann.starts[got[ok]], ann.ends[got[ok]]
+        gap = np.where(Eg <= s[ok], s[ok] - Eg + 1, np.where(Sg >= e[ok], Sg - e[ok] + 1, 0))
+        assert np.array_equal(gap, want[ok]), k
+    del row, dist
+    r, cid, nc = E.cluster(q_iv)
+    ms, me, mc, mg = (x.cpu().numpy() for x in E.merge(q_iv))
+    r, cid = r.cpu().numpy(), cid.cpu().numpy()
+    m_off = np.concatenate([[0], np.cumsum(np.bincount(mg, minlength=iv.n_keys))])
+    for k in _sample_keys():
+        a, b = iv.seg_off[k], iv.seg_off[k + 1]
+        s, e = iv.starts[a:b], iv.ends[a:b]
+        o = np.lexsort([np.arange(b - a), e, s])
+        want_id = orc.annotate_clusters(s[o], e[o], 0)
+        assert np.array_equal(r[a:b] - a, o), k  # rows come back sorted by (Start, End, row)
+        first = cid[a] - 1  # ids are global over keys: this key's ids start after the earlier keys' clusters
+        assert first == m_off[k]
+        assert np.array_equal(cid[a:b] - first, want_id), k
+        cs, ce, cn = orc.find_clusters(s[o], e[o], 0)
+        sl = slice(m_off[k], m_off[k + 1])
+        assert np.array_equal(ms[sl], cs) and np.array_equal(me[sl], ce) and np.array_equal(mc[sl], cn), k
+
+
+def test_c5_to_rle_200m_vs_oracle_sampled_keys():
+    """config 5: coverage RLE of 200 M reads; the runs / values of sampled keys against pyrle's restatement, global
+    invariants for all keys"""
+    from oracle import oracle as orc
+    from pyranges_b200 import engine as E
+    from pyranges_b200 import synthetic as S
+
+    iv = S.reads_by_chrom(200_000_000, seed=4)
+    r_iv = E.DeviceIntervals.from_numpy(iv.starts, iv.ends, iv.seg_off)
+    off, runs, vals = E.coverage_rle(r_iv)
+    hi = r_iv.hi
+    for k in range(iv.n_keys):
+        sl = slice(int(off[k]), int(off[k + 1]))
+        assert int(runs[sl].sum().item()) == int(hi[k])
+    assert float((runs.double() * vals).sum().item()) == float(100 * iv.n)  # covered bases = sum of lengths
+    for k in _sample_keys():
+        a, b = iv.seg_off[k], iv.seg_off[k + 1]
+        wr, wv = orc.coverage_rle(iv.starts[a:b], iv.ends[a:b])
+        sl = slice(int(off[k]), int(off[k + 1]))
+        assert np.array_equal(runs[sl].cpu().numpy(), wr) and np.array_equal(vals[sl].cpu().numpy(), wv), k
