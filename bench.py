@@ -236,6 +236,18 @@ def run_reference(args, rank, world):
     val = pairs / dt
     sample = ("first %.2f%% of the rows of every read key (%d queries/step) x all %d annotations (NCLS rebuilt per step), "
               "%d threads over chromosomes" % (100 * frac, queries // max(args.steps, 1), annot.n, threads))
+    # the reference's own Python layer (pandas glue included) over the restated native layer, where /root/reference exists
+    layer = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import reference_baseline as rb
+
+        if rb.available():
+            layer = rb.run(2_000_000, 40_000, min(cores, 16))
+            layer["note"] = ("UNMODIFIED /root/reference pyranges layer, builder-sized sample (2 M x 40 k rows): end-to-end "
+                             "gr.join / gr.count_overlaps at nb_cpu=1, per-key fork pool, index only")
+    except Exception as ex:  # never take the baseline line down
+        layer = {"error": repr(ex)}
     line = {
         "impl": "reference", "metric": "join overlap pairs/s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
@@ -244,6 +256,7 @@ def run_reference(args, rank, world):
         "count_overlaps_queries_per_s": queries / dt,
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pyranges_layer": layer,
     }
     print(json.dumps(line), flush=True)
 
