@@ -82,6 +82,12 @@ extern "C" {
 
 /* index flags */
 #define IV_INDEX_ENDS_PERM 1 /* also keep the row permutation of the end-sorted order (nearest) */
+#define IV_INDEX_GRAPH 2     /* opt in: the second build with identical arguments (pointers, sizes, stream) captures its
+                                launch sequence into a CUDA graph, later ones replay it (kernel arguments are by value,
+                                data is read at replay time: contents may change, addresses may not).  At most 8
+                                sequences are kept per process; never used on the legacy default stream; the environment
+                                variable IV_NO_GRAPH=1 disables it globally.  Without the flag every build is plain
+                                launches. */
 
 /* Row groups of a set of intervals.  Group g owns rows [row_off[g], row_off[g+1]).
  * lo[g] <= every start, hi[g] >= every end of the group.  base[] is the flattened-coordinate origin:

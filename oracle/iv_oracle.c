@@ -12,7 +12,7 @@
  * Their *published* algorithms are restated here in plain C, anchored on the
  * reference's own call sites (cited per function) and pinned by replaying the
  * reference's doctest / unit-test known answers through the unmodified
- * reference Python layer (oracle/make_golden.py, tests/test_oracle_golden.py).
+ * reference Python layer (oracle/make_golden.py, tests/test_oracle_known_answers.py).
  *
  *   ncls            nested containment list (Alekseyenko & Lee, Bioinformatics 2007):
  *                   sort by (start asc, end desc), peel contained intervals into

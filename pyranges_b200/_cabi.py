@@ -13,6 +13,7 @@ IV_OK = 0
 IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
+IV_INDEX_GRAPH = 2
 IV_ABI_VERSION = 7
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t

@@ -376,8 +376,10 @@ extern "C" int iv_index_build(const int64_t* starts, const int64_t* ends, int64_
                               int32_t flags, void* ws, size_t ws_bytes, iv_index_t* out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     IV_REQUIRE(groups && out && n >= 0, IV_ERR_INVALID, "iv_index_build: null argument");
-    static const bool use_graphs = getenv("IV_NO_GRAPH") == nullptr;
-    if (!use_graphs || n == 0 || st == nullptr) return index_build_direct(starts, ends, n, groups, flags, ws, ws_bytes, out, stream);
+    // replay of a captured launch sequence is OPT-IN (IV_INDEX_GRAPH); IV_NO_GRAPH in the environment overrides it
+    static const bool no_graphs = getenv("IV_NO_GRAPH") != nullptr;
+    if (!(flags & IV_INDEX_GRAPH) || no_graphs || n == 0 || st == nullptr)
+        return index_build_direct(starts, ends, n, groups, flags, ws, ws_bytes, out, stream);
     BuildKey key;
     memset(&key, 0, sizeof(key));
     key.starts = starts; key.ends = ends; key.ws = ws; key.row_off = groups->row_off; key.lo = groups->lo;

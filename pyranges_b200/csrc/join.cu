@@ -2,8 +2,8 @@
 // index (lists.cu).  Replaces NCLS.all_overlaps_both (pyranges/methods/join.py:15,23) and, in its count-only form,
 // all_overlaps_both + value_counts / has_overlaps (pyranges/methods/coverage.py:26-40, intersection.py:78).
 //
-// A block takes a ticket for 2048 consecutive query rows (so a tile only ever waits for tiles that are already running),
-// a WARP is its own tile of 256 consecutive rows, a lane owns two rows per iteration:
+// A WARP is its own tile of 256 consecutive query rows, taken from a ticket counter by the warps of a persistent grid
+// (so a tile only ever waits for tiles that are already running); a lane owns two rows per iteration:
 //   1. 16-byte streaming loads of Start / End, 32-bit clamp into the partner group's window of the flattened axis,
 //      ONE 256-bit gather of the record of the bin the query starts in (list offset, length, first three entries);
 //   2. count sweep: two 16-bit compares per entry (inline entries from registers; longer lists and the later bins of a
@@ -150,10 +150,14 @@ __device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, con
     if (m & 2u) f(r.w[4]);
     if (m & 4u) f(r.w[6]);
     m >>= 3;
-    while (m) {
-        const int t = __ffs(m) - 1;
-        m &= m - 1;
-        f(__ldg(ix.cand_row + r.w[0] + 3 + t));
+    if (m) {  // hits among entries 3 .. 10: their rows in ONE round trip (predicated loads, all in flight together)
+        const uint32_t* __restrict__ c = ix.cand_row + r.w[0] + 3u;
+        uint32_t row[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) row[t] = (m >> t) & 1u ? __ldg(c + t) : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            if ((m >> t) & 1u) f(row[t]);
     }
     if (p.extra) {
         const QGeom<X> g(ix, sc, ec, r);
@@ -306,9 +310,8 @@ k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_
 }
 
 // ---- the fused join ---------------------------------------------------------------------------------------------------------------
-// Every WARP is its own tile of 256 rows (tile id = block ticket * 8 + warp: the warps of a block are co-resident and
-// blocks with smaller tickets started earlier, so a tile only waits for tiles that are running or done); no block-wide
-// barrier after the ticket.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
+// Every WARP is its own tile of 256 rows (tile ids come from a ticket counter, so a tile only waits for tiles that are
+// running or done); no block-wide barrier anywhere.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
 // pair total, looks back for its output offset and copies the staged pairs out with coalesced stores; iterations that
 // did not fit are repeated afterwards -- the offset is known by then -- through the same staging area, one at a time.
 template <typename X, bool SLACK, bool ANY>
@@ -318,13 +321,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
        unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total, int variant) {
     extern __shared__ __align__(16) unsigned char jn_smem[];  // [JN_WARPS][JN_WCAP] subject rows, then query rows
     __shared__ uint32_t s_cnt[JN_WARPS][JN_ITERS];
-    __shared__ unsigned int s_tile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int64_t wtile = (int64_t)s_tile * JN_WARPS + warp;
-    if (wtile >= n_wtiles) return;
-    const int64_t wbase = wtile * JN_WROWS;
     uint32_t* __restrict__ st_s = reinterpret_cast<uint32_t*>(jn_smem) + warp * JN_WCAP;
     uint8_t* __restrict__ st_q = jn_smem + (size_t)JN_WARPS * JN_WCAP * 4 + warp * JN_WCAP;
 
@@ -362,6 +359,15 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         return ANY ? (p[0].count() ? 1u : 0u) + (p[1].count() ? 1u : 0u) : p[0].count() + p[1].count();
     };
 
+  // The grid is persistent (as many blocks as fit the device): every warp takes tile after tile from the ticket counter,
+  // so no warp slot idles while the slowest warp of its block finishes, and a tile only ever waits for tiles with
+  // smaller tickets -- all of them taken by running warps.
+  for (;;) {
+    unsigned int tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, 1u);
+    const int64_t wtile = (int64_t)__shfl_sync(FULL, tk, 0);
+    if (wtile >= n_wtiles) break;
+    const int64_t wbase = wtile * JN_WROWS;
     Geo<X> G(q, wbase);
     unsigned long long total = 0;
     uint32_t staged = 0;
@@ -448,6 +454,8 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         }
         o += itot;
     }
+    __syncwarp();  // the staging area is reused by the warp's next tile
+  }
 }
 
 // pairs per query segment of a pair list in query order (ascending query rows): lower bounds of the segment boundaries
@@ -509,7 +517,7 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     IV_CUDA(cudaMemsetAsync(ws, 0, (size_t)(n_tiles + 1) * sizeof(unsigned long long), st));
     const bool vec = aligned16(q->start) && aligned16(q->end);
     const bool slack = q->slack != 0;
-    const unsigned nb = (unsigned)cdiv(q->n, JN_TILE);
+    const int64_t nb = cdiv(q->n, JN_TILE);
     static const int variant = getenv("IV_JOIN_VARIANT") ? atoi(getenv("IV_JOIN_VARIANT")) : 0;  // measurements only
     if (variant == 1) IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
 #define IV_JK(X, SL, AN)                                                                                                \
@@ -517,12 +525,18 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
         static bool attr_done[64] = {false};                                                                           \
         int dev = 0;                                                                                                   \
         IV_CUDA(cudaGetDevice(&dev));                                                                                  \
+        static int resident[64] = {0};                                                                                 \
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                                 \
             IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, AN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
-            if (dev >= 0 && dev < 64) attr_done[dev] = true;                                                           \
+            int sms = 0, per_sm = 0;                                                                                   \
+            IV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev));                   \
+            IV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_join<X, SL, AN>, JN_THREADS, JN_SMEM));    \
+            if (dev >= 0 && dev < 64) { attr_done[dev] = true; resident[dev] = sms * per_sm; }                         \
         }                                                                                                              \
-        k_join<X, SL, AN><<<nb, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state,  \
-                                                          ticket, n_tiles, out_total, variant);                        \
+        const int64_t fit = (dev >= 0 && dev < 64 && resident[dev] > 0) ? resident[dev] : 148;                         \
+        const unsigned grid = (unsigned)(nb < fit ? nb : fit);                                                         \
+        k_join<X, SL, AN><<<grid, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, \
+                                                            ticket, n_tiles, out_total, variant);                      \
     } while (0)
 #define IV_JK2(X, SL) do { if (any) IV_JK(X, SL, true); else IV_JK(X, SL, false); } while (0)
     const bool any = mode == IV_MODE_ANY;

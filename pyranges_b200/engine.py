@@ -250,18 +250,20 @@ def _max_len(q):
 
 
 class SubjectIndex:
-    """Device index over the subject ("other") intervals of ALL groups -- the NCLS replacement
-    (pyranges/methods/join.py:12).  Built by iv_index_build: radix sort of flattened starts and of
-    flattened ends, block-max skip index, direct-address rank tables."""
+    """Device RANK index over the subject ("other") intervals of ALL groups -- the NCLS replacement
+    (pyranges/methods/join.py:12) behind nearest, coverage, subtract, containment and first / last overlap.  Built by
+    iv_index_build: radix sorts of the flattened starts and ends, 32-byte rank records per coordinate bin, per-bin
+    stabbing lists.  (join / count_overlaps / overlap use ListIndex.)"""
 
-    def __init__(self, iv, seg_ranges=None, ends_perm=False):
+    def __init__(self, iv, seg_ranges=None, ends_perm=False, graph=True):
+        """graph: let repeated builds over the same buffers replay a captured launch sequence (IV_INDEX_GRAPH)"""
         self.iv = iv
         if iv.has_zero_length:
             # the rank index counts with #{S < e} - #{E <= s}, which needs S < E; join / count_overlaps / overlap go
             # through ListIndex, which handles such rows exactly
             raise ValueError("zero-length intervals (Start == End) in `other` are not supported by this operation")
         self.groups = iv.groups(seg_ranges, gap=1)
-        self.flags = IV_INDEX_ENDS_PERM if ends_perm else 0
+        self.flags = (IV_INDEX_ENDS_PERM if ends_perm else 0) | (cabi.IV_INDEX_GRAPH if graph else 0)
         L = cabi.lib()
         nbytes = L.iv_index_workspace_bytes(iv.n, self.groups.total_span, self.groups.sumlen, self.flags)
         self.ws = _bytes(nbytes, iv.device)

@@ -515,3 +515,36 @@ def test_split_empty(eng):
     z = np.zeros(0, np.int64)
     goff, st, en = eng.split(_dev(eng, z, z, np.zeros(3, np.int64)))
     assert goff.tolist() == [0, 0, 0] and st.numel() == 0 and en.numel() == 0
+
+
+def test_index_build_graph_replay_with_changed_data(eng):
+    """IV_INDEX_GRAPH: builds 2, 3, ... over the same buffers on a non-default stream capture / replay one launch
+    sequence; the DATA at those addresses changes between builds (rows permuted inside their segments: same bounds,
+    same launch sequence) and every result must follow it (oracle check); the last build drops the flag: plain
+    launches on the same buffers."""
+    import torch
+
+    qs, qe, qoff = gen_segments(41, 2, 3000, 40000, 200)
+    sg = np.arange(2, dtype=np.int32)
+    st = torch.cuda.Stream()
+    s0, e0, soff = gen_segments(42, 2, 1000, 40000, 300)
+    ds = torch.from_numpy(s0).cuda()
+    de = torch.from_numpy(e0).cuda()
+    rng = np.random.default_rng(7)
+    with torch.cuda.stream(st):
+        q = eng.Queries(_dev(eng, qs, qe, qoff), sg)
+        iv = eng.DeviceIntervals(ds, de, soff)
+        ix = eng.SubjectIndex(iv, graph=True)
+        for rep in range(5):
+            perm = np.concatenate([soff[k] + rng.permutation(soff[k + 1] - soff[k]) for k in range(2)])
+            s, e = s0[perm], e0[perm]
+            ds.copy_(torch.from_numpy(s))
+            de.copy_(torch.from_numpy(e))
+            if rep == 4:
+                ix.flags &= ~eng.cabi.IV_INDEX_GRAPH
+            ix.build()
+            counts, a, b = ix.pairs(q, eng.IV_MODE_ALL)
+            st.synchronize()
+            wa, wb = canon_pairs(*oracle_pairs(qs, qe, qoff, sg, s, e, soff, "all"))
+            ga, gb = canon_pairs(a.cpu().numpy(), b.cpu().numpy())
+            assert np.array_equal(ga, wa) and np.array_equal(gb, wb), rep
