@@ -174,10 +174,13 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
 __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// called by one full warp; -> pairs of all tiles before `tile`
-__device__ __forceinline__ unsigned long long lookback(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
+// publish a tile's pair total (tile 0: it is its inclusive prefix as well)
+__device__ __forceinline__ void post_aggregate(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
+    if (lane_id() == 0) st_relaxed(state + tile, (aggregate << 2) | (tile == 0 ? 2ull : 1ull));
+}
+// called by one full warp after post_aggregate; -> pairs of all tiles before `tile`
+__device__ __forceinline__ unsigned long long resolve(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
     const int lane = lane_id();
-    if (lane == 0) st_relaxed(state + tile, (aggregate << 2) | (tile == 0 ? 2ull : 1ull));
     unsigned long long excl = 0;
     int64_t look = tile - 1;
     while (look >= 0) {
@@ -309,13 +312,85 @@ k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_
     }
 }
 
+// Iterations of a tile whose pairs did not fit the staging area: processed once more after the tile's output offset
+// is known -- through the staging area when one iteration fits it, straight to memory otherwise (rare).
+template <typename X, bool SLACK, bool ANY>
+__device__ __forceinline__ void late_iterations(const iv_lists_t& ix, const iv_queries_t& q, bool vec, int64_t wbase, int first_it,
+                                             const uint32_t* cnt, unsigned long long o, uint32_t* __restrict__ st_s,
+                                             uint8_t* __restrict__ st_q, int64_t* __restrict__ out_q,
+                                             int64_t* __restrict__ out_s, const int64_t* __restrict__ s_label, int64_t cap) {
+    const int lane = lane_id();
+    for (int it = first_it; it < JN_ITERS; it++) {
+        const uint32_t itot = cnt[it];
+        if (itot == 0) continue;
+        const int64_t ibase = wbase + it * 64;
+        __syncwarp();
+        Geo<X> G2(q, ibase);
+        Rows2<X> R;
+        flatten_rows<X, SLACK>(ix, q, ibase, load_raw(q, vec, ibase), G2, R);
+        QPlan p[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
+        const uint32_t c0 = ANY ? (p[0].count() ? 1u : 0u) : p[0].count(), c1 = ANY ? (p[1].count() ? 1u : 0u) : p[1].count();
+        const uint32_t mine = c0 + c1;
+        const uint32_t inc = warp_incl_sum(mine);
+        if (itot <= (uint32_t)JN_WCAP) {
+            uint32_t pos = inc - mine;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint8_t ql = (uint8_t)(2 * lane + k);
+                if (ANY) {
+                    if (p[k].count()) st_q[pos++] = ql;
+                } else {
+                    emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
+                        st_s[pos] = row;
+                        st_q[pos] = ql;
+                        pos++;
+                    });
+                }
+            }
+            __syncwarp();
+            for (uint32_t k = lane; k < itot; k += 32) {
+                const int64_t oo = (int64_t)(o + k);
+                if (oo < cap) {
+                    const int64_t row_q = ibase + st_q[k];
+                    if (out_q) out_q[oo] = q.label ? __ldg(q.label + row_q) : row_q;
+                    if (!ANY && out_s) out_s[oo] = s_label ? __ldg(s_label + st_s[k]) : (int64_t)st_s[k];
+                }
+            }
+        } else {
+            unsigned long long oo = o + inc - mine;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int64_t row_q = ibase + 2 * lane + k;
+                const int64_t ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
+                if (ANY) {
+                    if (p[k].count()) {
+                        if ((int64_t)oo < cap && out_q) out_q[oo] = ql;
+                        oo++;
+                    }
+                    continue;
+                }
+                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
+                    if ((int64_t)oo < cap) {
+                        if (out_q) out_q[oo] = ql;
+                        if (out_s) out_s[oo] = s_label ? __ldg(s_label + row) : (int64_t)row;
+                    }
+                    oo++;
+                });
+            }
+        }
+        o += itot;
+    }
+}
+
 // ---- the fused join ---------------------------------------------------------------------------------------------------------------
 // Every WARP is its own tile of 256 rows (tile ids come from a ticket counter, so a tile only waits for tiles that are
 // running or done); no block-wide barrier anywhere.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
 // pair total, looks back for its output offset and copies the staged pairs out with coalesced stores; iterations that
 // did not fit are repeated afterwards -- the offset is known by then -- through the same staging area, one at a time.
-template <typename X, bool SLACK, bool ANY>
-__global__ void __launch_bounds__(JN_THREADS, 4)
+template <typename X, bool SLACK, bool ANY, int OCC>
+__global__ void __launch_bounds__(JN_THREADS, OCC)
 k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
        const int64_t* __restrict__ s_label, int64_t cap, unsigned long long* __restrict__ state,
        unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total, int variant) {
@@ -361,24 +436,57 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
 
   // The grid is persistent (as many blocks as fit the device): every warp takes tile after tile from the ticket counter,
   // so no warp slot idles while the slowest warp of its block finishes, and a tile only ever waits for tiles with
-  // smaller tickets -- all of them taken by running warps.
-  for (;;) {
-    unsigned int tk = 0;
-    if (lane == 0) tk = atomicAdd(ticket, 1u);
-    const int64_t wtile = (int64_t)__shfl_sync(FULL, tk, 0);
-    if (wtile >= n_wtiles) break;
+  // smaller tickets -- all of them taken by running warps.  Between publishing a tile's total and looking back for its
+  // offset the warp already counts the FIRST iteration of its next tile (registers only): the time the predecessors
+  // need to publish theirs is spent on work.
+  auto take = [&]() -> int64_t {
+      unsigned int tk = 0;
+      if (lane == 0) tk = atomicAdd(ticket, 1u);
+      return (int64_t)__shfl_sync(FULL, tk, 0);
+  };
+  Rows2<X> R0;  // iteration 0 of the current tile, counted ahead
+  QPlan p0[2];
+  auto count_first = [&](int64_t tile) {
+      const int64_t base = tile * JN_WROWS;
+      Geo<X> G0(q, base);
+      flatten_rows<X, SLACK>(ix, q, base, load_raw(q, vec, base), G0, R0);
+#pragma unroll
+      for (int k = 0; k < 2; k++) p0[k] = plan_query<X>(ix, R0.sc[k], R0.ec[k], R0.r[k], R0.live[k]);
+  };
+  int64_t wtile = take();
+  if (wtile < n_wtiles) count_first(wtile);
+  while (wtile < n_wtiles) {
     const int64_t wbase = wtile * JN_WROWS;
-    Geo<X> G(q, wbase);
     unsigned long long total = 0;
     uint32_t staged = 0;
     int staged_iters = 0;
     bool open = true;
-    Raw2 next = load_raw(q, vec, wbase);
+    // scan of the iteration's counts, staging while it fits
+    auto finish_iter = [&](const Rows2<X>& R, const QPlan (&p)[2], int it) {
+        const uint32_t mine = pairs_of(p);
+        const uint32_t inc = warp_incl_sum(mine);
+        const uint32_t itot = __shfl_sync(FULL, inc, 31);
+        if (open && staged + itot <= (uint32_t)JN_WCAP) {
+            if (itot) stage_rows(R, p, staged + inc - mine, (uint32_t)(it * 64 + 2 * lane));
+            staged += itot;
+            staged_iters = it + 1;
+        } else {
+            open = false;
+        }
+        if (lane == 0) s_cnt[warp][it] = itot;
+        total += itot;
+    };
+    finish_iter(R0, p0, 0);
+    if (wbase + 64 < q.n) {
+        Geo<X> G(q, wbase + 64);
+        Raw2 next = load_raw(q, vec, wbase + 64);
 #pragma unroll 1
-    for (int it = 0; it < JN_ITERS; it++) {
-        const int64_t ibase = wbase + it * 64;
-        uint32_t itot = 0;
-        if (ibase < q.n) {
+        for (int it = 1; it < JN_ITERS; it++) {
+            const int64_t ibase = wbase + it * 64;
+            if (ibase >= q.n) {
+                if (lane == 0) s_cnt[warp][it] = 0;
+                continue;
+            }
             const Raw2 cur = next;
             if (it + 1 < JN_ITERS && ibase + 64 < q.n) next = load_raw(q, vec, ibase + 64);
             Rows2<X> R;
@@ -386,75 +494,30 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
             QPlan p[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
-            const uint32_t mine = pairs_of(p);
-            const uint32_t inc = warp_incl_sum(mine);
-            itot = __shfl_sync(FULL, inc, 31);
-            if (open && staged + itot <= (uint32_t)JN_WCAP) {
-                if (itot) stage_rows(R, p, staged + inc - mine, (uint32_t)(it * 64 + 2 * lane));
-                staged += itot;
-                staged_iters = it + 1;
-            } else {
-                open = false;
-            }
+            finish_iter(R, p, it);
         }
-        if (lane == 0) s_cnt[warp][it] = itot;
-        total += itot;
+    } else if (lane == 0) {
+        for (int it = 1; it < JN_ITERS; it++) s_cnt[warp][it] = 0;
     }
     __syncwarp();
     unsigned long long o;
     if (variant == 1) {  // EXPERIMENT: unordered output regions from an atomic cursor (no waiting)
         if (lane == 0) o = atomicAdd(reinterpret_cast<unsigned long long*>(out_total), total);
         o = __shfl_sync(FULL, o, 0);
-    } else {
-        o = lookback(state, wtile, total);
+    }
+    if (variant != 1) post_aggregate(state, wtile, total);
+    const int64_t ntile = take();
+    if (ntile < n_wtiles) count_first(ntile);
+    if (variant != 1) {
+        o = resolve(state, wtile, total);
         if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);
     }
     copy_out(staged, o, wbase);
     o += staged;
-    // iterations that did not fit: once more, through the staging area (or straight to memory when a single iteration
-    // exceeds it)
-    for (int it = staged_iters; it < JN_ITERS; it++) {
-        const uint32_t itot = s_cnt[warp][it];
-        if (itot == 0) continue;
-        const int64_t ibase = wbase + it * 64;
-        __syncwarp();
-        Geo<X> G2(q, ibase);
-        Rows2<X> R;
-        flatten_rows<X, SLACK>(ix, q, ibase, load_raw(q, vec, ibase), G2, R);
-        QPlan p[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
-        const uint32_t mine = pairs_of(p);
-        const uint32_t inc = warp_incl_sum(mine);
-        if (itot <= (uint32_t)JN_WCAP) {
-            stage_rows(R, p, inc - mine, (uint32_t)(2 * lane));
-            __syncwarp();
-            copy_out(itot, o, ibase);
-        } else {
-            unsigned long long oo = o + inc - mine;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int64_t row_q = ibase + 2 * lane + k;
-                const int64_t ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
-                if (ANY) {
-                    if (p[k].count()) {
-                        if ((int64_t)oo < cap && out_q) out_q[oo] = ql;
-                        oo++;
-                    }
-                    continue;
-                }
-                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
-                    if ((int64_t)oo < cap) {
-                        if (out_q) out_q[oo] = ql;
-                        if (out_s) out_s[oo] = s_label ? __ldg(s_label + row) : (int64_t)row;
-                    }
-                    oo++;
-                });
-            }
-        }
-        o += itot;
-    }
+    if (staged_iters < JN_ITERS)  // iterations that did not fit (rare): once more, now that the offset is known
+        late_iterations<X, SLACK, ANY>(ix, q, vec, wbase, staged_iters, s_cnt[warp], o, st_s, st_q, out_q, out_s, s_label, cap);
     __syncwarp();  // the staging area is reused by the warp's next tile
+    wtile = ntile;
   }
 }
 
@@ -519,26 +582,27 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     const bool slack = q->slack != 0;
     const int64_t nb = cdiv(q->n, JN_TILE);
     static const int variant = getenv("IV_JOIN_VARIANT") ? atoi(getenv("IV_JOIN_VARIANT")) : 0;  // measurements only
+    static const int occ = getenv("IV_JOIN_OCC") ? atoi(getenv("IV_JOIN_OCC")) : 4;             // measurements only
     if (variant == 1) IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
-#define IV_JK(X, SL, AN)                                                                                                \
+#define IV_JK(X, SL, AN, OC)                                                                                            \
     do {                                                                                                               \
         static bool attr_done[64] = {false};                                                                           \
         int dev = 0;                                                                                                   \
         IV_CUDA(cudaGetDevice(&dev));                                                                                  \
         static int resident[64] = {0};                                                                                 \
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                                 \
-            IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, AN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
+            IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, AN, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
             int sms = 0, per_sm = 0;                                                                                   \
             IV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev));                   \
-            IV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_join<X, SL, AN>, JN_THREADS, JN_SMEM));    \
+            IV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_join<X, SL, AN, OC>, JN_THREADS, JN_SMEM));    \
             if (dev >= 0 && dev < 64) { attr_done[dev] = true; resident[dev] = sms * per_sm; }                         \
         }                                                                                                              \
         const int64_t fit = (dev >= 0 && dev < 64 && resident[dev] > 0) ? resident[dev] : 148;                         \
         const unsigned grid = (unsigned)(nb < fit ? nb : fit);                                                         \
-        k_join<X, SL, AN><<<grid, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, \
+        k_join<X, SL, AN, OC><<<grid, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, \
                                                             ticket, n_tiles, out_total, variant);                      \
     } while (0)
-#define IV_JK2(X, SL) do { if (any) IV_JK(X, SL, true); else IV_JK(X, SL, false); } while (0)
+#define IV_JK2(X, SL) do { if (any) IV_JK(X, SL, true, 4); else if (occ == 3) IV_JK(X, SL, false, 3); else IV_JK(X, SL, false, 4); } while (0)
     const bool any = mode == IV_MODE_ANY;
     if (narrow_span(lists)) {
         if (slack) IV_JK2(uint32_t, true); else IV_JK2(uint32_t, false);

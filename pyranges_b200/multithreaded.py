@@ -102,6 +102,7 @@ class _Frames:
         f.__dict__.update(self.__dict__)
         f.keys = [k for k, _ in items]
         f.dfs = [d for _, d in items]
+        f.__dict__.pop("_merged", None)  # concatenated partner frames belong to the frame objects
         return f
 
 
@@ -215,8 +216,15 @@ class _Plan:
         f = self._frames[g]
         if f is None:
             a, b = self.group_ranges[g]
-            dfs = self.s.dfs[a:b]
-            f = dfs[0] if len(dfs) == 1 else merge_dfs(dfs[0], dfs[1])
+            # the concatenated partner frame of a chromosome lives with the (cached) device ingest of `other`: building
+            # it costs a pandas concat per chromosome and call otherwise.  Every key of the group is concatenated, in
+            # key order -- the row layout of the device index.
+            memo = self.s.__dict__.setdefault("_merged", {})
+            f = memo.get((a, b))
+            if f is None:
+                dfs = self.s.dfs[a:b]
+                f = dfs[0] if len(dfs) == 1 else pd.concat(dfs, sort=False).reset_index(drop=True)
+                memo[(a, b)] = f
             self._frames[g] = f
         return f
 
