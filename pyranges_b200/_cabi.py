@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpyranges_b200.so")
+LIB_PATH = os.environ.get("PYRANGES_B200_LIB") or os.path.join(_HERE, "libpyranges_b200.so")  # (override: kernel A/B builds)
 
 IV_OK = 0
 IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3

@@ -35,6 +35,9 @@ constexpr int JN_WCAP = 576;
 constexpr size_t JN_SMEM = (size_t)JN_WARPS * JN_WCAP * 5;  // dynamic shared memory of k_join: staging areas
 
 constexpr int JM_COUNT = 2, JM_ANY = 3;
+#ifndef JN_AHEAD
+#define JN_AHEAD 0  // 1: count the first iteration of the next tile while waiting for the look-back (measured: slower)
+#endif
 
 
 struct LRec { uint32_t w[8]; };  // w0 = co, w1 = n8, (w2, w3) (w4, w5) (w6, w7) = entries {row, so | eo << 16}
@@ -91,29 +94,63 @@ template <typename X> struct QGeom {
     }
 };
 
-// hits beyond the masked entries: f(subject row)
+// Sinks of the emit sweep: small value types (no captures by reference), so that the rare walks below can live out of
+// line without a stack frame.
+struct CountSink {
+    uint32_t n;
+    __device__ __forceinline__ void operator()(uint32_t) { n++; }
+};
+struct StageSink {  // a warp's staging area: subject row + row in tile
+    uint32_t* st_s;
+    uint8_t* st_q;
+    uint32_t pos;
+    uint8_t ql;
+    __device__ __forceinline__ void operator()(uint32_t row) {
+        st_s[pos] = row;
+        st_q[pos] = ql;
+        pos++;
+    }
+};
+struct DirectSink {  // straight to the outputs (an iteration larger than the staging area)
+    int64_t* out_q;
+    int64_t* out_s;
+    const int64_t* s_label;
+    int64_t cap, ql;
+    unsigned long long o;
+    __device__ __forceinline__ void operator()(uint32_t row) {
+        if ((int64_t)o < cap) {
+            if (out_q) out_q[o] = ql;
+            if (out_s) out_s[o] = s_label ? __ldg(s_label + row) : (int64_t)row;
+        }
+        o++;
+    }
+};
+
+// hits beyond the masked entries -- the rest of a long list (eight entries per round trip) and the starts inside the
+// later bins of a query that reaches beyond its first bin.  Rare: out of line, everything by value.
 template <typename X, typename F>
-__device__ __forceinline__ void walk_extra(const iv_lists_t& ix, X ec, const LRec& r, const QGeom<X>& g, F&& f) {
-    const int shift = ix.shift;
-    // the rest of a long list, eight entries per round trip
-    for (uint32_t j0 = JN_MASKED; j0 < g.n; j0 += 8) {
-        const uint32_t* __restrict__ c = ix.cand_se + r.w[0] + j0;
+__device__ __noinline__ F walk_extra(const uint32_t* __restrict__ cand_se, const uint32_t* __restrict__ cand_row,
+                                     const iv_lrec_t* __restrict__ rec, int shift, X ec, uint32_t co, uint32_t n, uint32_t qw,
+                                     X b, bool single, F f) {
+    for (uint32_t j0 = JN_MASKED; j0 < n; j0 += 8) {
+        const uint32_t* __restrict__ c = cand_se + co + j0;
         uint32_t w[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) w[t] = __ldg(c + t);  // (the arrays end in slack: reading past the list is safe)
 #pragma unroll
         for (int t = 0; t < 8; t++)
-            if (j0 + t < g.n && hit_bit(w[t], g.qw)) f(__ldg(ix.cand_row + r.w[0] + j0 + t));
+            if (j0 + t < n && hit_bit(w[t], qw)) f(__ldg(cand_row + co + j0 + t));
     }
-    if (!g.single) {
+    if (!single) {
         const uint64_t bl = (uint64_t)(ec - 1) >> shift;
-        for (uint64_t bb = (uint64_t)g.b + 1; bb <= bl; bb++) {
-            const uint32_t c0 = __ldg(&ix.rec[bb].co), c1 = __ldg(&ix.rec[bb + 1].co);
+        for (uint64_t bb = (uint64_t)b + 1; bb <= bl; bb++) {
+            const uint32_t c0 = __ldg(&rec[bb].co), c1 = __ldg(&rec[bb + 1].co);
             const uint32_t re = bb < bl ? (1u << shift) : (uint32_t)(ec - (X)(bl << shift));
             for (uint32_t j = c0; j < c1; j++)
-                if (later_hit(__ldg(ix.cand_se + j), re)) f(__ldg(ix.cand_row + j));
+                if (later_hit(__ldg(cand_se + j), re)) f(__ldg(cand_row + j));
         }
     }
+    return f;
 }
 
 template <typename X>
@@ -134,17 +171,15 @@ __device__ __forceinline__ QPlan plan_query(const iv_lists_t& ix, X sc, X ec, co
     m = __funnelshift_l(hit_bit(r.w[5], g.qw), m, 1);
     m = __funnelshift_l(hit_bit(r.w[3], g.qw), m, 1);
     p.mask = m & (g.n >= (uint32_t)JN_MASKED ? (1u << JN_MASKED) - 1u : (1u << g.n) - 1u);
-    if (g.n > (uint32_t)JN_MASKED || !g.single) {
-        uint32_t x = 0;
-        walk_extra<X>(ix, ec, r, g, [&](uint32_t) { x++; });
-        p.extra = x;
-    }
+    if (g.n > (uint32_t)JN_MASKED || !g.single)
+        p.extra = walk_extra<X, CountSink>(ix.cand_se, ix.cand_row, ix.rec, ix.shift, ec, r.w[0], g.n, g.qw, g.b, g.single,
+                                           CountSink{0u}).n;
     return p;
 }
 
 // every hit of a planned query, in list order: f(subject row)
 template <typename X, typename F>
-__device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, const QPlan& p, F&& f) {
+__device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, const QPlan& p, F& f) {
     uint32_t m = p.mask;
     if (m & 1u) f(r.w[2]);
     if (m & 2u) f(r.w[4]);
@@ -161,7 +196,7 @@ __device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, con
     }
     if (p.extra) {
         const QGeom<X> g(ix, sc, ec, r);
-        walk_extra<X>(ix, ec, r, g, f);
+        f = walk_extra<X, F>(ix.cand_se, ix.cand_row, ix.rec, ix.shift, ec, r.w[0], g.n, g.qw, g.b, g.single, f);
     }
 }
 
@@ -335,18 +370,14 @@ __device__ __forceinline__ void late_iterations(const iv_lists_t& ix, const iv_q
         const uint32_t mine = c0 + c1;
         const uint32_t inc = warp_incl_sum(mine);
         if (itot <= (uint32_t)JN_WCAP) {
-            uint32_t pos = inc - mine;
+            StageSink sink{st_s, st_q, inc - mine, 0};
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                const uint8_t ql = (uint8_t)(2 * lane + k);
+                sink.ql = (uint8_t)(2 * lane + k);
                 if (ANY) {
-                    if (p[k].count()) st_q[pos++] = ql;
+                    if (p[k].count()) st_q[sink.pos++] = sink.ql;
                 } else {
-                    emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
-                        st_s[pos] = row;
-                        st_q[pos] = ql;
-                        pos++;
-                    });
+                    emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], sink);
                 }
             }
             __syncwarp();
@@ -359,25 +390,19 @@ __device__ __forceinline__ void late_iterations(const iv_lists_t& ix, const iv_q
                 }
             }
         } else {
-            unsigned long long oo = o + inc - mine;
+            DirectSink sink{out_q, out_s, s_label, cap, 0, o + inc - mine};
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const int64_t row_q = ibase + 2 * lane + k;
-                const int64_t ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
+                sink.ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
                 if (ANY) {
                     if (p[k].count()) {
-                        if ((int64_t)oo < cap && out_q) out_q[oo] = ql;
-                        oo++;
+                        if ((int64_t)sink.o < cap && out_q) out_q[sink.o] = sink.ql;
+                        sink.o++;
                     }
                     continue;
                 }
-                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
-                    if ((int64_t)oo < cap) {
-                        if (out_q) out_q[oo] = ql;
-                        if (out_s) out_s[oo] = s_label ? __ldg(s_label + row) : (int64_t)row;
-                    }
-                    oo++;
-                });
+                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], sink);
             }
         }
         o += itot;
@@ -416,17 +441,14 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     };
     // emit sweep of one iteration into the staging area, the lane's first pair at `pos`
     auto stage_rows = [&](const Rows2<X>& R, const QPlan (&p)[2], uint32_t pos, uint32_t qloc) {
+        StageSink sink{st_s, st_q, pos, 0};
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const uint8_t ql = (uint8_t)(qloc + k);
+            sink.ql = (uint8_t)(qloc + k);
             if (ANY) {  // one entry per query with hits: the query row only
-                if (p[k].count()) st_q[pos++] = ql;
+                if (p[k].count()) st_q[sink.pos++] = sink.ql;
             } else {
-                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
-                    st_s[pos] = row;
-                    st_q[pos] = ql;
-                    pos++;
-                });
+                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], sink);
             }
         }
     };
@@ -454,8 +476,9 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
       for (int k = 0; k < 2; k++) p0[k] = plan_query<X>(ix, R0.sc[k], R0.ec[k], R0.r[k], R0.live[k]);
   };
   int64_t wtile = take();
-  if (wtile < n_wtiles) count_first(wtile);
+  if (JN_AHEAD && wtile < n_wtiles) count_first(wtile);
   while (wtile < n_wtiles) {
+    if (!JN_AHEAD) count_first(wtile);
     const int64_t wbase = wtile * JN_WROWS;
     unsigned long long total = 0;
     uint32_t staged = 0;
@@ -507,7 +530,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     }
     if (variant != 1) post_aggregate(state, wtile, total);
     const int64_t ntile = take();
-    if (ntile < n_wtiles) count_first(ntile);
+    if (JN_AHEAD && ntile < n_wtiles) count_first(ntile);
     if (variant != 1) {
         o = resolve(state, wtile, total);
         if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);

@@ -33,8 +33,11 @@ def _worker(rank, world, port, q):
     all_keys = natsorted(set(A.keys()))
     counts, off = sharding.gather_key_counts(all_keys, {k: len(v) for k, v in j.dfs.items()})
     ccounts, coff = sharding.gather_key_counts(all_keys, {k: int(v.Cluster.max() - v.Cluster.min() + 1) for k, v in c.dfs.items()})
+    # the rank's cluster ids made global with the gathered per-key cluster counts (pyranges_main.py:1210-1223)
+    first = {k: int(coff[i]) for i, k in enumerate(all_keys)}
+    gl = {k: (v.Cluster.values - int(v.Cluster.min()) + 1 + first[k]).tolist() for k, v in c.dfs.items()}
     q.put((rank, {k: len(v) for k, v in j.dfs.items()}, counts.tolist(), off.tolist(), ccounts.tolist(),
-           sorted(set(assign.values()))))
+           sorted(set(assign.values())), dict(j.dfs), gl))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,8 +67,10 @@ def test_two_rank_join_matches_single_rank(monkeypatch):
     want = [len(full.dfs[k]) if k in full.dfs else 0 for k in keys]
     cl = A.cluster()
     want_c = [int(cl.dfs[k].Cluster.max() - cl.dfs[k].Cluster.min() + 1) if k in cl.dfs else 0 for k in keys]
-    local = {}
-    for rank, lens, counts, off, ccounts, ranks_used in res:
+    from tests.golden_util import assert_frames_equal
+
+    local, frames, gids = {}, {}, {}
+    for rank, lens, counts, off, ccounts, ranks_used, jdfs, gl in res:
         assert counts == want  # every rank sees the global per-key counts
         assert off == np.concatenate([[0], np.cumsum(want)]).tolist()
         assert ccounts == want_c
@@ -73,7 +78,15 @@ def test_two_rank_join_matches_single_rank(monkeypatch):
         for k, n in lens.items():
             assert k not in local  # keys are disjoint across ranks
             local[k] = n
+        frames.update(jdfs)
+        gids.update(gl)
     assert local == {k: len(v) for k, v in full.dfs.items()}
+    # the shards' results ARE the single-rank result, frame by frame, and the offset cluster ids are the global ones
+    assert set(frames) == set(full.dfs)
+    for k, v in full.dfs.items():
+        assert_frames_equal(frames[k], v, str(k))
+    for k, v in cl.dfs.items():
+        assert gids[k] == v.Cluster.values.tolist(), k
 
 
 def test_lpt_balance():
