@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: launch the step eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
     r, s = WORKLOADS[a.workload]
     a.reads = a.reads or r
@@ -350,6 +351,12 @@ def run_b200(args, rank, world, local_rank):
     time.sleep(0.3)
     t0 = time.perf_counter()
     join.phase_events = []
+    graph = world > 1 and not args.no_graph
+    if graph:
+        # per-rank steps of a multi-GPU run are short (a few hundred microseconds): the whole step is replayed as one
+        # CUDA graph so that eight Python launch loops do not pace the GPUs; the per-phase times of the roofline entry
+        # are then taken from an eager loop of the same step right after the timed region
+        join.capture()
     if world > 1:
         # the only communication of the path: per-key pair counts (global offsets of the concatenated result, keys are
         # disjoint over ranks so the sum is the gather).  Every step leaves its counts in a row of a device table;
@@ -369,6 +376,15 @@ def run_b200(args, rank, world, local_rank):
         join_step = join.step
     join_ms, launches = timed(join_step, args.steps, args.warmup)
     join.check()  # every step's device-side total fitted its buffers (else the run is invalid: raises)
+    if graph:
+        launches += args.steps * join.graph_launches  # kernels inside the replayed graphs of the timed steps
+        eager = E.JoinStep(s_iv, groups, q_iv, seg_group, path=args.path)
+        eager.run_sync()
+        eager.phase_events = []
+        for _ in range(args.steps):
+            eager.step()
+        eager.check()
+        join.phase_events = eager.phase_events
     if world > 1:  # the exchanged per-key counts of the last step add up to the global pair count
         assert int(key_pairs[-1].sum().item()) == pairs_all, "per-key pair counts do not add up"
     t1 = time.perf_counter()
@@ -392,6 +408,8 @@ def run_b200(args, rank, world, local_rank):
                 "frac": alg[dom] / (dom_ms / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg[dom]),
                 "rank0_phase_ms": phases,
+                "phase_source": ("eager loop of the same step after the timed region (the timed steps replay one CUDA graph)"
+                                 if graph else "CUDA events inside the timed region"),
                 "rank0_phase_achieved_gbs": {k: alg[k] / (m / 1e3) / 1e9 for k, m in phases.items() if m > 0},
                 "pipeline": {"bytes_8d": int(pipe), "bytes_no_labels": int(pipe_req), "ms": step_ms_local,
                              "achieved_8d": pipe / (step_ms_local / 1e3) / 1e9, "frac_8d": pipe / (step_ms_local / 1e3) / 1e9 / peak,

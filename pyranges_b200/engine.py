@@ -572,6 +572,9 @@ class JoinStep:
         self.totals = _Totals()
         self.phase_events = None
         self.out = None
+        self._graph = None
+        self.graph_replays = 0
+        self.graph_launches = 0
 
     def _ev(self):
         e = torch.cuda.Event(enable_timing=True)
@@ -624,10 +627,38 @@ class JoinStep:
     def step(self):
         if not self.cap:
             return self.run_sync()
-        out_q, out_s, total = self._run(self.cap)
+        if self._graph is not None:
+            self._graph.replay()
+            self.graph_replays += 1
+            out_q, out_s, total = self.out
+        else:
+            out_q, out_s, total = self._run(self.cap)
         self.totals.push(total, self.cap)
         self.out = (out_q, out_s, total)
         return self.out
+
+    def capture(self):
+        """Capture the whole step (index build, fused join, per-key counts) into ONE CUDA graph; later step() calls
+        replay it: one launch per step instead of a dozen, no Python between the kernels.  The outputs then live in
+        fixed buffers that every replay overwrites.  Explicit opt-in (bench.py uses it for the short per-rank steps
+        of a multi-GPU run); needs run_sync() first (buffer sizes) and cannot record per-phase events."""
+        assert self.cap, "run_sync() first"
+        self.phase_events = None
+        L = cabi.lib()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # lazy one-time work (function attributes, descriptor uploads) before the capture
+            self._run(self.cap)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = L.iv_launch_count()
+        with torch.cuda.graph(g):
+            self.out = self._run(self.cap)
+        self.graph_launches = int(L.iv_launch_count() - n0)  # kernels per replay (the library counts at capture time)
+        self._graph = g
+        return self
 
     def check(self):
         return self.totals.check("JoinStep")
