@@ -39,7 +39,37 @@ class NCLSBatch:
         dev = E._use(device)
         self.device = dev
         self.iv = E.DeviceIntervals(_to_device(starts, dev), _to_device(ends, dev), seg_off, bounds=bounds)
-        self.index = E.SubjectIndex(self.iv, group_ranges, ends_perm=ends_perm)
+        self.group_ranges, self.ends_perm = group_ranges, ends_perm
+        self._rank = None   # rank index (first / last / containment / nearest ...): built on first use
+        self._lists = None  # list index of the join / count path, keyed by its reach hint
+
+    @property
+    def index(self):
+        if self._rank is None:
+            self._rank = E.SubjectIndex(self.iv, self.group_ranges, ends_perm=self.ends_perm)
+        return self._rank
+
+    def _pairs_index(self, hs, he):
+        """the index all_overlaps_both / count run on: the list index (fused join) when these subjects and queries
+        suit it -- its reach hint is the longest of a sample of the query rows (a hint only: longer queries stay exact)
+        -- else the rank index"""
+        n = hs.numel()
+        step = max(1, n // 65536)
+        ln = (he[::step] - hs[::step])
+        mean_len = float(ln.double().mean()) if n else 0.0
+        if not E.ListIndex.supported(self.iv, self.group_ranges, mean_len):
+            return self.index
+        reach = int(ln.max()) if n else 0
+        if self._lists is None or self._lists.reach < reach:
+            self._lists = E.ListIndex(self.iv, self.group_ranges, reach=reach)
+        return self._lists
+
+    @staticmethod
+    def _pairs(ix, q, capacity=None):
+        if isinstance(ix, E.ListIndex):
+            return ix.pairs(q, capacity=capacity)
+        _, a, b = ix.pairs(q, E.IV_MODE_ALL, capacity=capacity, want_counts=False)
+        return a, b
 
     def _queries(self, starts, ends, seg_off, seg_group, slack=0):
         q = E.DeviceIntervals(_to_device(starts, self.device), _to_device(ends, self.device), seg_off)
@@ -57,9 +87,10 @@ class NCLSBatch:
         seg_off = np.asarray(seg_off, dtype=np.int64)
         if chunks is None:
             chunks = 8 if (n >= (1 << 21) and hs.is_pinned() and he.is_pinned() and out is not None) else 1
+        ix = self._pairs_index(hs, he)
         if chunks <= 1:
             q = self._queries(hs, he, seg_off, seg_group, slack)
-            _, a, b = self.index.pairs(q, E.IV_MODE_ALL, want_counts=False)
+            a, b = self._pairs(ix, q)
             if out is not None:  # pinned staging buffers supplied by the caller
                 p = a.numel()
                 out[0][:p].copy_(a, non_blocking=True)
@@ -103,7 +134,7 @@ class NCLSBatch:
             # the chunk's own segment offsets (empty segments allowed)
             civ = E.DeviceIntervals(ds, de, offs[ci], seg_off_dev=packed_dev[ci * k1:(ci + 1) * k1])
             q = E.Queries(civ, sg32, slack=slack, desc_dev=sg_dev)
-            _, qa, qb = self.index.pairs(q, E.IV_MODE_ALL, capacity=hint, want_counts=False)
+            qa, qb = self._pairs(ix, q, capacity=hint)
             hint = int(qa.numel() * 1.25) + 4096
             if a:
                 qa.add_(a)
@@ -125,8 +156,10 @@ class NCLSBatch:
 
     def count(self, starts, ends, seg_off, seg_group, slack=0, out=None):
         """-> overlaps per query, host int64 array (the NumberOverlaps column, coverage.py:26-40)."""
-        q = self._queries(starts, ends, seg_off, seg_group, slack)
-        c, _, _ = self.index.count(q, E.IV_MODE_ALL, for_emit=False)
+        hs, he = _host_tensor(starts), _host_tensor(ends)
+        q = self._queries(hs, he, seg_off, seg_group, slack)
+        ix = self._pairs_index(hs, he)
+        c = ix.count(q, E.IV_MODE_ALL) if isinstance(ix, E.ListIndex) else ix.count(q, E.IV_MODE_ALL, for_emit=False)[0]
         if out is not None:
             out.copy_(c, non_blocking=True)
             torch.cuda.current_stream().synchronize()
