@@ -516,6 +516,424 @@ static bool bucket_path(int64_t n, int nbits) {
     return n >= BK_MIN_N && n <= BK_MAX_N && nbits > 8 && nbits - 8 <= BK_MAX_LOW_BITS;
 }
 
+// ---- large inputs: one-sweep partition passes on the TOP bits + one shared-memory pass per bucket ------------------
+// Above BK_MAX_N keys the sort is bound by bytes moved per pass, so the number of passes over global memory is what
+// counts.  (1) ONE read of the keys gives the global digit histograms of every partition pass (k_rs_ghist).
+// (2) P stable partition passes (LSD order) over the top T bits only, T ~ log2(n / 1024): each tile takes a ticket,
+// ranks its keys, publishes its 256 digit counts and obtains the counts of all earlier tiles by a decoupled look-back
+// over the status words (2 flag bits + 30 value bits in one 32-bit word, so no fence is needed) -- keys are read once
+// and written once per pass, no per-tile histogram pass.  (3) The 2^T buckets (~1000 keys each) are found by binary
+// search (k_hy_starts) and every bucket is finished by one block in ONE pass whatever the number of remaining bits
+// (k_hy_buckets): composite words "low bits | position in the bucket" are all distinct, so a counting pass on the 12
+// bits below the highest bit that differs inside the bucket (atomics, unordered inside a bin) followed by a
+// rank-by-counting inside every bin (bins hold ~1 key) IS the stable order.  42-bit keys of 50 M rows: 3 passes over
+// global memory instead of 6 x (histogram + scatter).  A tile never waits for a tile that is not running (tickets).
+constexpr int HY_CAP = 4096;       // keys a bucket block sorts in shared memory
+constexpr int HY_POS_BITS = 12;    // log2(HY_CAP)
+constexpr int HY_DIG_BITS = 12;    // counting digit of the bucket pass
+constexpr int HY_BINS = 1 << HY_DIG_BITS;
+constexpr int HY_THREADS = 256;
+constexpr int HY_ITEMS = HY_CAP / HY_THREADS;
+constexpr int HY_MAX_P = 4;
+constexpr int HY_MAX_T = 20;
+constexpr int64_t HY_MAX_N = ((int64_t)1 << 30) - 1;
+constexpr uint32_t SW_AGG = 1u << 30, SW_INC = 2u << 30, SW_VAL = (1u << 30) - 1u;
+constexpr int SW_ITEMS = 16;
+constexpr int SW_TILE = RS_THREADS * SW_ITEMS;
+
+struct HyPlan {
+    bool use;
+    int P;                 // partition passes
+    int T;                 // bits they cover: [end_bit - T, end_bit)
+    int low_bits;          // bits left to the bucket pass (0: the partition passes already sort everything)
+    int shift[HY_MAX_P];   // LSD order
+    uint32_t mask[HY_MAX_P];
+};
+static HyPlan hy_plan(int64_t n, int begin_bit, int end_bit) {
+    HyPlan p;
+    memset(&p, 0, sizeof(p));
+    const int nbits = end_bit - begin_bit;
+    if (n <= BK_MAX_N || n > HY_MAX_N || nbits <= 0) return p;
+    int T = 1;
+    while (T < HY_MAX_T && ((int64_t)1024 << T) < n) T++;
+    if (T >= nbits) T = nbits;
+    else if (nbits - T > 64 - HY_POS_BITS) T = nbits - (64 - HY_POS_BITS);
+    p.use = true;
+    p.T = T;
+    p.low_bits = nbits - T;
+    p.P = (T + 7) / 8;
+    int lo = end_bit - T;
+    for (int i = 0; i < p.P; i++) {  // balanced digit widths
+        const int w = (T - (lo - (end_bit - T)) + (p.P - i) - 1) / (p.P - i);
+        p.shift[i] = lo;
+        p.mask[i] = (1u << w) - 1u;
+        lo += w;
+    }
+    return p;
+}
+struct HyDigits {
+    int P;
+    int shift[HY_MAX_P];
+    uint32_t mask[HY_MAX_P];
+};
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_ghist(const uint64_t* __restrict__ keys, int64_t n, HyDigits D, uint32_t* __restrict__ ghist, bool vec) {
+    __shared__ uint32_t h[HY_MAX_P][RS_RADIX];
+    for (int i = threadIdx.x; i < HY_MAX_P * RS_RADIX; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; 2 * i < n; i += stride) {
+        uint64_t a, b = 0;
+        const bool two = 2 * i + 1 < n;
+        if (two && vec) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(keys) + i);
+            a = v.x;
+            b = v.y;
+        } else if (two) {
+            a = __ldg(keys + 2 * i);
+            b = __ldg(keys + 2 * i + 1);
+        } else {
+            a = __ldg(keys + 2 * i);
+        }
+#pragma unroll
+        for (int p = 0; p < HY_MAX_P; p++) {
+            if (p < D.P) {
+                atomicAdd(&h[p][(uint32_t)(a >> D.shift[p]) & D.mask[p]], 1u);
+                if (two) atomicAdd(&h[p][(uint32_t)(b >> D.shift[p]) & D.mask[p]], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D.P * RS_RADIX; i += RS_THREADS) {
+        const uint32_t v = (&h[0][0])[i];
+        if (v) atomicAdd(ghist + i, v);
+    }
+}
+
+// One stable partition pass on digit (key >> shift) & mask.  VB: payload bytes (0 / 4 / 8); iota: the payload of
+// input position i is i itself (first pass of an argsort: nothing is read).
+template <int VB> struct SwVal { typedef uint32_t T; };
+template <> struct SwVal<8> { typedef uint64_t T; };
+
+template <int VB>
+__global__ void __launch_bounds__(RS_THREADS, VB == 8 ? 2 : (VB ? 3 : 4))
+k_rs_sweep(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const void* __restrict__ vin,
+           void* __restrict__ vout, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ ghist,
+           uint32_t* status, uint32_t* ticket, int iota) {
+    typedef typename SwVal<VB>::T V;
+    __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
+    __shared__ uint32_t digit_base[RS_RADIX];
+    __shared__ uint32_t gbase[RS_RADIX];
+    __shared__ uint64_t sbuf[SW_TILE];
+    __shared__ uint8_t sdig[SW_TILE];
+    __shared__ uint32_t wsum[RS_WARPS + 1];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) ((uint32_t*)warp_cnt)[i] = 0;
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t tbase = tile * SW_TILE;
+    const int nvalid = (int)((n - tbase) < (int64_t)SW_TILE ? (n - tbase) : (int64_t)SW_TILE);
+
+    uint64_t key[SW_ITEMS];
+    V val[VB ? SW_ITEMS : 1];
+    uint32_t rank[SW_ITEMS];
+#pragma unroll
+    for (int it = 0; it < SW_ITEMS; it++) {
+        const int li = w * (SW_ITEMS * 32) + it * 32 + lane;
+        key[it] = li < nvalid ? __ldg(kin + tbase + li) : ~0ull;
+    }
+    if (VB) {  // the payloads travel in registers: every load of the tile is in flight before the ranking starts
+#pragma unroll
+        for (int it = 0; it < SW_ITEMS; it++) {
+            const int li = w * (SW_ITEMS * 32) + it * 32 + lane;
+            val[it] = iota ? (V)(tbase + li) : (li < nvalid ? __ldg((const V*)vin + tbase + li) : V(0));
+        }
+    }
+    // warp-level multi-split, eight keys at a time: the counter updates (shared-memory atomics by the leader of
+    // every group of equal digits) are issued back to back and their results are only needed afterwards
+#pragma unroll
+    for (int h = 0; h < SW_ITEMS; h += 8) {
+        unsigned mm[8];
+        uint32_t cc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t d = (uint32_t)(key[h + j] >> shift) & mask;
+            mm[j] = __match_any_sync(FULL, d);
+            cc[j] = 0;
+            if (lane == __ffs(mm[j]) - 1) cc[j] = atomicAdd(&warp_cnt[w][d], (uint32_t)__popc(mm[j]));
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            rank[h + j] = __shfl_sync(FULL, cc[j], __ffs(mm[j]) - 1) + (uint32_t)__popc(mm[j] & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    {
+        // thread tid owns digit tid.  (The padding keys of a ragged last tile count as digit `mask`: they are the
+        // last keys of the last tile, so they only inflate that one count, which nobody reads after this tile.)
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            const uint32_t c = warp_cnt[ww][tid];
+            warp_cnt[ww][tid] = run;
+            run += c;
+        }
+        volatile uint32_t* st = status;
+        st[tile * RS_RADIX + tid] = (tile == 0 ? SW_INC : SW_AGG) | run;
+        uint32_t tot;
+        const uint32_t ex = block_excl_sum<uint32_t, RS_THREADS>(run, wsum, tot);
+        digit_base[tid] = ex;
+        uint32_t tt;
+        const uint32_t dstart = block_excl_sum<uint32_t, RS_THREADS>(__ldg(ghist + tid), wsum, tt);
+        uint32_t excl = 0;
+        if (tile > 0) {
+            // decoupled look-back, eight predecessors per round trip
+            int64_t t = tile - 1;
+            unsigned ns = 20;
+            bool done = false;
+            while (!done) {
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = t - j >= 0 ? st[(t - j) * RS_RADIX + tid] : (2u << 30);
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (!done && used == j && (v[j] >> 30) != 0) {
+                        excl += v[j] & SW_VAL;
+                        used++;
+                        if (v[j] & SW_INC) done = true;
+                    }
+                }
+                t -= used;
+                if (used == 0) {
+                    __nanosleep(ns);
+                    if (ns < 200) ns += 20;
+                }
+            }
+            st[tile * RS_RADIX + tid] = SW_INC | (excl + run);
+        }
+        gbase[tid] = dstart + excl - ex;
+    }
+    __syncthreads();
+    uint32_t pos[SW_ITEMS];
+#pragma unroll
+    for (int it = 0; it < SW_ITEMS; it++) {
+        const uint32_t d = (uint32_t)(key[it] >> shift) & mask;
+        pos[it] = digit_base[d] + warp_cnt[w][d] + rank[it];
+        sbuf[pos[it]] = key[it];
+        sdig[pos[it]] = (uint8_t)d;
+    }
+    __syncthreads();
+    for (int k = tid; k < nvalid; k += RS_THREADS) kout[gbase[sdig[k]] + (uint32_t)k] = sbuf[k];
+    if (VB) {
+        __syncthreads();
+        V* sv = (V*)sbuf;
+#pragma unroll
+        for (int it = 0; it < SW_ITEMS; it++) sv[pos[it]] = val[it];
+        __syncthreads();
+        V* vo = (V*)vout;
+        for (int k = tid; k < nvalid; k += RS_THREADS) vo[gbase[sdig[k]] + (uint32_t)k] = sv[k];
+    }
+}
+
+// starts[b] = first position whose top-T field is >= b (b = 0 .. 2^T); the keys are sorted on that field
+__global__ void __launch_bounds__(256)
+k_hy_starts(const uint64_t* __restrict__ keys, int64_t n, int tshift, uint32_t tmask, uint32_t nb,
+            uint32_t* __restrict__ starts) {
+    const uint32_t b = blockIdx.x * 256u + threadIdx.x;
+    if (b > nb) return;
+    int64_t lo = 0, hi = n;  // first i in [0, n] with field(i) >= b
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (((uint32_t)(__ldg(keys + mid) >> tshift) & tmask) >= b) hi = mid; else lo = mid + 1;
+    }
+    starts[b] = (uint32_t)lo;
+}
+
+template <int VB>
+__global__ void __launch_bounds__(HY_THREADS, 4)
+k_hy_buckets(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit, int low_bits,
+             const uint32_t* __restrict__ starts) {
+    extern __shared__ __align__(16) unsigned char hy_smem[];
+    uint64_t* c2 = reinterpret_cast<uint64_t*>(hy_smem);                    // [HY_CAP] composites grouped by bin
+    uint32_t* cur = reinterpret_cast<uint32_t*>(c2 + HY_CAP);               // [HY_BINS] counts -> cursors -> bin ends
+    __shared__ unsigned long long s_diff;
+    __shared__ uint32_t wsum[HY_THREADS / 32 + 1];
+    const int tid = threadIdx.x;
+    const uint32_t b0 = __ldg(starts + blockIdx.x), m = __ldg(starts + blockIdx.x + 1) - b0;
+    if (m == 0) return;
+    if (m == 1) {
+        if (tid == 0) {
+            kout[b0] = kin[b0];
+            if (VB == 4) ((uint32_t*)vout)[b0] = ((const uint32_t*)vin)[b0];
+            if (VB == 8) ((uint64_t*)vout)[b0] = ((const uint64_t*)vin)[b0];
+        }
+        return;
+    }
+    if (m > (uint32_t)HY_CAP) {
+        // oversize bucket (a pile-up): stable LSD passes through global memory inside the bucket's range
+        uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(hy_smem);          // [BK_WARPS][256]
+        uint32_t* base = warp_cnt + BK_WARPS * RS_RADIX;                    // [256]
+        uint64_t *ka = kin + b0, *kb = kout + b0;
+        char* va = VB ? (char*)vin + (size_t)b0 * VB : nullptr;
+        char* vb = VB ? (char*)vout + (size_t)b0 * VB : nullptr;
+        for (int sh = 0; sh < low_bits; sh += 8) {
+            const int bits = low_bits - sh < 8 ? low_bits - sh : 8;
+            bk_pass<VB != 0>(ka, kb, m, begin_bit + sh, (1u << bits) - 1u, base, warp_cnt, va, vb, VB);
+            uint64_t* tk = ka; ka = kb; kb = tk;
+            char* tv = va; va = vb; vb = tv;
+        }
+        if (ka != kout + b0) {
+            for (uint32_t i = tid; i < m; i += HY_THREADS) {
+                kout[b0 + i] = ka[i];
+                if (VB == 4) ((uint32_t*)vout)[b0 + i] = ((const uint32_t*)va)[i];
+                else if (VB == 8) ((uint64_t*)vout)[b0 + i] = ((const uint64_t*)va)[i];
+            }
+        }
+        return;
+    }
+    const uint64_t low_mask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
+    uint64_t low[HY_ITEMS];
+    // as many bins as keys (a power of two, 256 .. 4096): clearing and scanning the bins is the fixed cost of a bucket
+    const int dbits = m <= 256 ? 8 : 32 - __clz(m - 1);
+    const uint32_t nbins = 1u << dbits, per = nbins / HY_THREADS;
+    if (tid == 0) s_diff = 0ull;
+    for (uint32_t i = tid; i < nbins; i += HY_THREADS) cur[i] = 0;
+    const uint64_t first = (kin[b0] >> begin_bit) & low_mask;
+    uint64_t diff = 0;
+#pragma unroll
+    for (int j = 0; j < HY_ITEMS; j++) {
+        const uint32_t i = tid + j * HY_THREADS;
+        low[j] = i < m ? ((kin[b0 + i] >> begin_bit) & low_mask) : first;
+        diff |= low[j] ^ first;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
+    __syncthreads();
+    if ((tid & 31) == 0 && diff) atomicOr(&s_diff, (unsigned long long)diff);
+    __syncthreads();
+    const unsigned long long dall = s_diff;
+    const int hb = dall ? 63 - __clzll((long long)dall) : -1;      // highest bit that differs inside the bucket
+    const int sh = hb + 1 > dbits ? hb + 1 - dbits : 0;
+#pragma unroll
+    for (int j = 0; j < HY_ITEMS; j++)
+        if (tid + j * HY_THREADS < m) atomicAdd(&cur[(uint32_t)(low[j] >> sh) & (nbins - 1)], 1u);
+    __syncthreads();
+    {   // exclusive scan of the bin counts: `per` consecutive bins per thread
+        uint32_t sum = 0;
+        for (uint32_t j = 0; j < per; j++) sum += cur[tid * per + j];
+        uint32_t tot;
+        uint32_t run = block_excl_sum<uint32_t, HY_THREADS>(sum, wsum, tot);
+        for (uint32_t j = 0; j < per; j++) {
+            const uint32_t v = cur[tid * per + j];
+            cur[tid * per + j] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < HY_ITEMS; j++) {
+        const uint32_t i = tid + j * HY_THREADS;
+        if (i < m) {
+            const uint32_t p = atomicAdd(&cur[(uint32_t)(low[j] >> sh) & (nbins - 1)], 1u);
+            c2[p] = (low[j] << HY_POS_BITS) | i;
+        }
+    }
+    __syncthreads();
+    // rank inside the bin (bins hold about one key), then the gathers of four keys at a time
+    for (uint32_t p0 = tid; p0 < m; p0 += 4 * HY_THREADS) {
+        uint32_t r[4], src[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t p = p0 + u * HY_THREADS;
+            r[u] = 0xffffffffu;
+            src[u] = b0;
+            if (p < m) {
+                const uint64_t c = c2[p];
+                const uint32_t d = (uint32_t)((c >> HY_POS_BITS) >> sh) & (nbins - 1);
+                const uint32_t bs = d ? cur[d - 1] : 0u, be = cur[d];
+                uint32_t rr = bs;
+                for (uint32_t q = bs; q < be; q++) rr += c2[q] < c ? 1u : 0u;
+                r[u] = b0 + rr;
+                src[u] = b0 + ((uint32_t)c & (HY_CAP - 1));
+            }
+        }
+        uint64_t kk[4];
+        typename SwVal<VB>::T vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            kk[u] = __ldg(kin + src[u]);
+            if (VB) vv[u] = __ldg((const typename SwVal<VB>::T*)vin + src[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (r[u] != 0xffffffffu) {
+                kout[r[u]] = kk[u];
+                if (VB) ((typename SwVal<VB>::T*)vout)[r[u]] = vv[u];
+            }
+        }
+    }
+}
+constexpr size_t HY_SMEM = (size_t)HY_CAP * 8 + (size_t)HY_BINS * 4;  // 48 KB (>= the 9 KB of the oversize path)
+
+struct HyTemp {
+    uint32_t *ghist, *ticket, *status, *starts;
+    size_t zero_bytes;  // ghist + ticket + status: cleared before every sort
+};
+static void hy_temp(int64_t n, Bump& b, HyTemp& t) {
+    const size_t ntiles = (size_t)cdiv(n > 0 ? n : 1, SW_TILE);
+    t.ghist = b.take<uint32_t>(HY_MAX_P * RS_RADIX);
+    t.ticket = b.take<uint32_t>(64);
+    t.status = b.take<uint32_t>(3 * ntiles * RS_RADIX);
+    t.zero_bytes = b.off;
+    size_t nb = 2;
+    while (nb < ((size_t)1 << HY_MAX_T) && nb * 1024 < (size_t)(n > 0 ? n : 1)) nb <<= 1;
+    t.starts = b.take<uint32_t>(nb + 64);
+}
+
+template <int VB>
+static int hy_launch(const HyPlan& pl, uint64_t* k[2], void* v[2], int64_t n, int begin_bit, int end_bit,
+                     const HyTemp& t, bool iota, cudaStream_t stream, int* result_buf) {
+    static bool attr_set[64] = {false};  // opt in to 48 KB of dynamic shared memory once per device
+    int dev = 0;
+    IV_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        IV_CUDA(cudaFuncSetAttribute(k_hy_buckets<VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HY_SMEM));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    IV_CUDA(cudaMemsetAsync(t.ghist, 0, t.zero_bytes, stream));
+    HyDigits D;
+    D.P = pl.P;
+    for (int i = 0; i < HY_MAX_P; i++) { D.shift[i] = pl.shift[i]; D.mask[i] = pl.mask[i]; }
+    const int64_t ntiles = cdiv(n, SW_TILE);
+    const unsigned hb = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+    k_rs_ghist<<<hb, RS_THREADS, 0, stream>>>(k[0], n, D, t.ghist, ((uintptr_t)k[0] & 15) == 0);
+    IV_LAUNCH_CHECK();
+    int cur = 0;
+    for (int p = 0; p < pl.P; p++) {
+        k_rs_sweep<VB><<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(
+            k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], n, pl.shift[p], pl.mask[p], t.ghist + p * RS_RADIX,
+            t.status + (size_t)p * ntiles * RS_RADIX, t.ticket + p, (iota && p == 0) ? 1 : 0);
+        IV_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    if (pl.low_bits > 0) {
+        const uint32_t nb = 1u << pl.T;
+        k_hy_starts<<<nb / 256 + 1, 256, 0, stream>>>(k[cur], n, end_bit - pl.T, nb - 1u, nb, t.starts);
+        IV_LAUNCH_CHECK();
+        k_hy_buckets<VB><<<nb, HY_THREADS, HY_SMEM, stream>>>(k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], begin_bit,
+                                                              pl.low_bits, t.starts);
+        IV_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    *result_buf = cur;
+    return IV_OK;
+}
+
 // ---- host driver ---------------------------------------------------------------------------------------------
 static int items_for(int64_t n) { return n <= ((int64_t)1 << 20) ? RS_ITEMS_SMALL : RS_ITEMS_BIG; }
 // (11-bit digits -- 3 passes instead of 4 for 32-bit keys -- were measured for small inputs: the 2048-entry
@@ -523,13 +941,22 @@ static int items_for(int64_t n) { return n <= ((int64_t)1 << 20) ? RS_ITEMS_SMAL
 // network for the buckets of the small-input path took 61 us, the shared-memory LSD passes above 31 us.)
 int radix_sort_passes(int64_t n, int nbits) {
     if (n <= 1 || nbits <= 0) return 0;
+    const HyPlan pl = hy_plan(n, 0, nbits);
+    if (pl.use) return pl.P + (pl.low_bits > 0 ? 1 : 0);
     return bucket_path(n, nbits) ? 2 : (nbits + 7) / 8;
 }
 
 size_t radix_sort_temp_bytes(int64_t n) {
     int64_t ntiles = cdiv(n > 0 ? n : 1, (int64_t)RS_THREADS * items_for(n));
     size_t hist = (size_t)ntiles * RS_RADIX * RS_MAX_JOBS;
-    return (hist + RS_RADIX * RS_MAX_JOBS + 128) * sizeof(uint32_t) + 512;
+    size_t bytes = (hist + RS_RADIX * RS_MAX_JOBS + 128) * sizeof(uint32_t) + 512;
+    if (n > BK_MAX_N && n <= HY_MAX_N) {
+        Bump b(nullptr, 0);
+        HyTemp t;
+        hy_temp(n, b, t);
+        if (b.off + 256 > bytes) bytes = b.off + 256;
+    }
+    return bytes;
 }
 
 template <int ITEMS>
@@ -599,6 +1026,19 @@ int radix_sort_multi(const SortJob* jobs, int njobs, int64_t n, int begin_bit, i
     for (int j = 0; j < njobs; j++)
         IV_REQUIRE(jobs[j].vb == 0 || jobs[j].vb == 4 || jobs[j].vb == 8, IV_ERR_INVALID, "radix sort: value_bytes");
     IV_REQUIRE(temp_bytes >= radix_sort_temp_bytes(n), IV_ERR_WORKSPACE, "radix sort: temp too small");
+    if (njobs == 1) {
+        const HyPlan pl = hy_plan(n, begin_bit, end_bit);
+        if (pl.use) {
+            Bump b(temp, temp_bytes);
+            HyTemp t;
+            hy_temp(n, b, t);
+            uint64_t* k[2] = {jobs[0].k0, jobs[0].k1};
+            void* v[2] = {jobs[0].v0, jobs[0].v1};
+            if (jobs[0].vb == 0) return hy_launch<0>(pl, k, v, n, begin_bit, end_bit, t, false, stream, result_buf);
+            if (jobs[0].vb == 4) return hy_launch<4>(pl, k, v, n, begin_bit, end_bit, t, false, stream, result_buf);
+            return hy_launch<8>(pl, k, v, n, begin_bit, end_bit, t, false, stream, result_buf);
+        }
+    }
     if (items_for(n) == RS_ITEMS_SMALL)
         return radix_sort_multi_t<RS_ITEMS_SMALL>(jobs, njobs, n, begin_bit, end_bit, temp, stream, result_buf);
     return radix_sort_multi_t<RS_ITEMS_BIG>(jobs, njobs, n, begin_bit, end_bit, temp, stream, result_buf);

@@ -94,6 +94,39 @@ def test_radix_sort_small_input_path(eng):
                 assert np.array_equal(vt.cpu().numpy(), o), (n, b0, b1, vdtype)
 
 
+def test_radix_sort_large_input_path(eng):
+    """n > 2^18 keys: one-sweep partition passes on the top bits + one shared-memory pass per bucket (sort.cu).
+    Uniform keys, keys with fewer bits than the partition covers (no bucket pass), 64-bit keys (the partition widens
+    so that the composite words fit), a pile-up beyond the bucket capacity (global fallback), few distinct keys
+    (stability; bins as large as the bucket), identical keys, a begin bit, a ragged last tile."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    cases = []
+    for n, bits in [(262145, 32), (300001, 64), (1 << 20, 42), (700003, 6), (1234567, 17), (3000000, 40)]:
+        cases.append((rng.integers(0, 2 ** min(bits, 63), n, dtype=np.int64) | (rng.integers(0, 2, n) << (bits - 1)), 0, bits))
+    skew = rng.integers(0, 2 ** 40, 900000, dtype=np.int64)
+    skew[100000:700000] = (5 << 36) | rng.integers(0, 2 ** 18, 600000)       # 600 k keys inside one bucket
+    cases.append((skew, 0, 40))
+    dup = rng.integers(0, 37, 500000, dtype=np.int64) << 13                   # 37 distinct keys
+    cases.append((dup, 0, 30))
+    two = (rng.integers(0, 2 ** 10, 400000, dtype=np.int64) << 24) | (rng.integers(0, 2, 400000) * 0xFFFFF)
+    cases.append((two, 0, 34))                                                # two values of the low bits per bucket
+    cases.append((np.full(300000, 99 << 5, dtype=np.int64), 0, 20))
+    cases.append(((rng.integers(0, 2 ** 33, 800000, dtype=np.int64) << 1) | rng.integers(0, 2, 800000), 1, 34))
+    for k, b0, b1 in cases:
+        n = len(k)
+        sk = (k.astype(np.uint64) >> np.uint64(b0)) & np.uint64((1 << (b1 - b0)) - 1 if b1 - b0 < 64 else 2 ** 64 - 1)
+        o = np.argsort(sk, kind="stable")
+        for vdtype in (None, torch.int32, torch.int64):
+            kt = torch.from_numpy(k.copy()).cuda()
+            vt = torch.arange(n, dtype=vdtype).cuda() if vdtype is not None else None
+            eng.radix_sort_u64(kt, vt, b0, b1)
+            assert np.array_equal(kt.cpu().numpy(), k[o]), (n, b0, b1, vdtype)
+            if vt is not None:
+                assert np.array_equal(vt.cpu().numpy(), o), (n, b0, b1, vdtype)
+
+
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("slack", [0, 7])
 def test_count_modes(eng, case, slack):

@@ -1,5 +1,5 @@
 """Radix sort of n 64-bit keys (+ 4-byte payload) on `bits` bits, for ncu captures and throughput numbers.
-Usage: python tools/prof_sort.py [n] [bits] [value_bytes]"""
+Usage: python tools/prof_sort.py [n] [bits] [value_bytes] [pile]   pile = fraction of the keys inside ONE bucket"""
 import sys
 
 import torch
@@ -12,6 +12,10 @@ bits = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 vb = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 g = torch.Generator(device="cuda").manual_seed(1)
 src = torch.randint(0, 2 ** min(bits, 62), (n,), dtype=torch.int64, device="cuda", generator=g)
+pile = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
+if pile > 0:  # a pile-up: the first pile * n keys share their top 22 bits
+    m = int(n * pile)
+    src[:m] = (src[:m] & ((1 << max(bits - 22, 1)) - 1)) | (5 << max(bits - 4, 1))
 val = None if vb == 0 else torch.arange(n, dtype=torch.int32 if vb == 4 else torch.int64, device="cuda")
 k = src.clone()
 for _ in range(2):
@@ -28,6 +32,6 @@ for _ in range(3):
     torch.cuda.synchronize()
     ms += a.elapsed_time(b) / 3
 passes = (bits + 7) // 8
-print("sort %d keys, %d bits (%d passes), %d-byte payload: %.3f ms = %.1f G keys/s per pass, %.0f GB/s of pass traffic"
-      % (n, bits, passes, vb, ms, n * passes / ms / 1e6, n * passes * (24 + 2 * vb) / ms / 1e6))
-assert bool((k[1:] >= k[:-1]).all()) if bits >= 62 else True
+print("sort %d keys, %d bits (%d LSD passes), pile %.3f, %d-byte payload: %.3f ms = %.1f G keys/s per pass, %.0f GB/s of pass traffic"
+      % (n, bits, passes, pile, vb, ms, n * passes / ms / 1e6, n * passes * (24 + 2 * vb) / ms / 1e6))
+assert bool((k[1:] >= k[:-1]).all())
