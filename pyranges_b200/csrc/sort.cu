@@ -616,41 +616,40 @@ k_rs_ghist(const uint64_t* __restrict__ keys, int64_t n, HyDigits D, uint32_t* _
 template <int VB> struct SwVal { typedef uint32_t T; };
 template <> struct SwVal<8> { typedef uint64_t T; };
 
-template <int VB>
-__global__ void __launch_bounds__(RS_THREADS, VB == 8 ? 2 : (VB ? 3 : 4))
-k_rs_sweep(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const void* __restrict__ vin,
-           void* __restrict__ vout, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ ghist,
-           uint32_t* status, uint32_t* ticket, int iota) {
+struct SwSmem {
+    uint32_t warp_cnt[RS_WARPS][RS_RADIX];
+    uint32_t digit_base[RS_RADIX];
+    uint32_t gbase[RS_RADIX];
+    uint64_t sbuf[SW_TILE];
+    uint8_t sdig[SW_TILE];
+    uint32_t wsum[RS_WARPS + 1];
+    uint32_t s_tile;
+};
+
+// The tile body shared by the partition pass and by the pile-up path of the bucket pass: SW_TILE keys starting at
+// kin + tbase are ranked by digit (warp-level multi-split), staged through shared memory in digit order and written
+// as coalesced runs to kout / vout at gbase[digit] + rank.  `global_base(run, ex)` is called by thread d for digit d
+// with the tile's count of that digit and the exclusive prefix of the counts inside the tile, and returns the
+// position of the tile's first key of that digit minus ex.  S.warp_cnt must be zero on entry.
+template <int VB, typename GB>
+__device__ __forceinline__ void sw_tile(SwSmem& S, const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
+                                        const void* __restrict__ vin, void* __restrict__ vout, int64_t tbase,
+                                        int nvalid, int shift, uint32_t mask, int iota, GB global_base) {
     typedef typename SwVal<VB>::T V;
-    __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
-    __shared__ uint32_t digit_base[RS_RADIX];
-    __shared__ uint32_t gbase[RS_RADIX];
-    __shared__ uint64_t sbuf[SW_TILE];
-    __shared__ uint8_t sdig[SW_TILE];
-    __shared__ uint32_t wsum[RS_WARPS + 1];
-    __shared__ uint32_t s_tile;
-
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) ((uint32_t*)warp_cnt)[i] = 0;
-    __syncthreads();
-    const int64_t tile = s_tile;
-    const int64_t tbase = tile * SW_TILE;
-    const int nvalid = (int)((n - tbase) < (int64_t)SW_TILE ? (n - tbase) : (int64_t)SW_TILE);
-
     uint64_t key[SW_ITEMS];
     V val[VB ? SW_ITEMS : 1];
     uint32_t rank[SW_ITEMS];
 #pragma unroll
     for (int it = 0; it < SW_ITEMS; it++) {
         const int li = w * (SW_ITEMS * 32) + it * 32 + lane;
-        key[it] = li < nvalid ? __ldg(kin + tbase + li) : ~0ull;
+        key[it] = li < nvalid ? kin[tbase + li] : ~0ull;
     }
     if (VB) {  // the payloads travel in registers: every load of the tile is in flight before the ranking starts
 #pragma unroll
         for (int it = 0; it < SW_ITEMS; it++) {
             const int li = w * (SW_ITEMS * 32) + it * 32 + lane;
-            val[it] = iota ? (V)(tbase + li) : (li < nvalid ? __ldg((const V*)vin + tbase + li) : V(0));
+            val[it] = iota ? (V)(tbase + li) : (li < nvalid ? ((const V*)vin)[tbase + li] : V(0));
         }
     }
     // warp-level multi-split, eight keys at a time: the counter updates (shared-memory atomics by the leader of
@@ -664,7 +663,7 @@ k_rs_sweep(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const 
             const uint32_t d = (uint32_t)(key[h + j] >> shift) & mask;
             mm[j] = __match_any_sync(FULL, d);
             cc[j] = 0;
-            if (lane == __ffs(mm[j]) - 1) cc[j] = atomicAdd(&warp_cnt[w][d], (uint32_t)__popc(mm[j]));
+            if (lane == __ffs(mm[j]) - 1) cc[j] = atomicAdd(&S.warp_cnt[w][d], (uint32_t)__popc(mm[j]));
             __syncwarp();
         }
 #pragma unroll
@@ -674,21 +673,59 @@ k_rs_sweep(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const 
     __syncthreads();
     {
         // thread tid owns digit tid.  (The padding keys of a ragged last tile count as digit `mask`: they are the
-        // last keys of the last tile, so they only inflate that one count, which nobody reads after this tile.)
+        // last keys of the tile, so they only inflate that one count behind every real key.)
         uint32_t run = 0;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) {
-            const uint32_t c = warp_cnt[ww][tid];
-            warp_cnt[ww][tid] = run;
+            const uint32_t c = S.warp_cnt[ww][tid];
+            S.warp_cnt[ww][tid] = run;
             run += c;
         }
+        uint32_t tot;
+        const uint32_t ex = block_excl_sum<uint32_t, RS_THREADS>(run, S.wsum, tot);
+        S.digit_base[tid] = ex;
+        S.gbase[tid] = global_base(run, ex);
+    }
+    __syncthreads();
+    uint32_t pos[SW_ITEMS];
+#pragma unroll
+    for (int it = 0; it < SW_ITEMS; it++) {
+        const uint32_t d = (uint32_t)(key[it] >> shift) & mask;
+        pos[it] = S.digit_base[d] + S.warp_cnt[w][d] + rank[it];
+        S.sbuf[pos[it]] = key[it];
+        S.sdig[pos[it]] = (uint8_t)d;
+    }
+    __syncthreads();
+    for (int k = tid; k < nvalid; k += RS_THREADS) kout[S.gbase[S.sdig[k]] + (uint32_t)k] = S.sbuf[k];
+    if (VB) {
+        __syncthreads();
+        V* sv = (V*)S.sbuf;
+#pragma unroll
+        for (int it = 0; it < SW_ITEMS; it++) sv[pos[it]] = val[it];
+        __syncthreads();
+        V* vo = (V*)vout;
+        for (int k = tid; k < nvalid; k += RS_THREADS) vo[S.gbase[S.sdig[k]] + (uint32_t)k] = sv[k];
+    }
+}
+
+template <int VB>
+__global__ void __launch_bounds__(RS_THREADS, VB == 8 ? 2 : (VB ? 3 : 4))
+k_rs_sweep(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const void* __restrict__ vin,
+           void* __restrict__ vout, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ ghist,
+           uint32_t* status, uint32_t* ticket, int iota) {
+    __shared__ SwSmem S;
+    const int tid = threadIdx.x;
+    if (tid == 0) S.s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t tile = S.s_tile;
+    const int64_t tbase = tile * SW_TILE;
+    const int nvalid = (int)((n - tbase) < (int64_t)SW_TILE ? (n - tbase) : (int64_t)SW_TILE);
+    sw_tile<VB>(S, kin, kout, vin, vout, tbase, nvalid, shift, mask, iota, [&](uint32_t run, uint32_t ex) {
         volatile uint32_t* st = status;
         st[tile * RS_RADIX + tid] = (tile == 0 ? SW_INC : SW_AGG) | run;
-        uint32_t tot;
-        const uint32_t ex = block_excl_sum<uint32_t, RS_THREADS>(run, wsum, tot);
-        digit_base[tid] = ex;
         uint32_t tt;
-        const uint32_t dstart = block_excl_sum<uint32_t, RS_THREADS>(__ldg(ghist + tid), wsum, tt);
+        const uint32_t dstart = block_excl_sum<uint32_t, RS_THREADS>(__ldg(ghist + tid), S.wsum, tt);
         uint32_t excl = 0;
         if (tile > 0) {
             // decoupled look-back, eight predecessors per round trip
@@ -716,28 +753,8 @@ k_rs_sweep(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const 
             }
             st[tile * RS_RADIX + tid] = SW_INC | (excl + run);
         }
-        gbase[tid] = dstart + excl - ex;
-    }
-    __syncthreads();
-    uint32_t pos[SW_ITEMS];
-#pragma unroll
-    for (int it = 0; it < SW_ITEMS; it++) {
-        const uint32_t d = (uint32_t)(key[it] >> shift) & mask;
-        pos[it] = digit_base[d] + warp_cnt[w][d] + rank[it];
-        sbuf[pos[it]] = key[it];
-        sdig[pos[it]] = (uint8_t)d;
-    }
-    __syncthreads();
-    for (int k = tid; k < nvalid; k += RS_THREADS) kout[gbase[sdig[k]] + (uint32_t)k] = sbuf[k];
-    if (VB) {
-        __syncthreads();
-        V* sv = (V*)sbuf;
-#pragma unroll
-        for (int it = 0; it < SW_ITEMS; it++) sv[pos[it]] = val[it];
-        __syncthreads();
-        V* vo = (V*)vout;
-        for (int k = tid; k < nvalid; k += RS_THREADS) vo[gbase[sdig[k]] + (uint32_t)k] = sv[k];
-    }
+        return dstart + excl - ex;
+    });
 }
 
 // starts[b] = first position whose top-T field is >= b (b = 0 .. 2^T); the keys are sorted on that field
@@ -752,6 +769,77 @@ k_hy_starts(const uint64_t* __restrict__ keys, int64_t n, int tshift, uint32_t t
         if (((uint32_t)(__ldg(keys + mid) >> tshift) & tmask) >= b) hi = mid; else lo = mid + 1;
     }
     starts[b] = (uint32_t)lo;
+}
+
+// Pile-up path of the bucket pass (a bucket beyond HY_CAP keys), kept out of line so that its registers do not
+// weigh on the common path.
+template <int VB>
+__device__ __noinline__ void hy_pileup(unsigned char* hy_smem, unsigned long long& s_diff, uint32_t* base, uint32_t* wsum,
+                                       uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit, int low_bits,
+                                       uint32_t b0, uint32_t m) {
+    // oversize bucket (a pile-up): stable LSD passes through global memory inside the bucket's range, on the bits
+    // that differ inside the bucket only; every pass = histogram + the tile body of the partition pass
+    SwSmem& S = *reinterpret_cast<SwSmem*>(hy_smem);
+    const int tid = threadIdx.x;
+    const uint64_t low_mask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
+    if (tid == 0) s_diff = 0ull;
+    __syncthreads();
+    {
+        const uint64_t first = kin[b0];
+        uint64_t diff = 0;
+        for (uint32_t i = tid; i < m; i += HY_THREADS) diff |= kin[b0 + i] ^ first;
+        diff = (diff >> begin_bit) & low_mask;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
+        if ((tid & 31) == 0 && diff) atomicOr(&s_diff, (unsigned long long)diff);
+    }
+    __syncthreads();
+    const unsigned long long dall = s_diff;
+    uint64_t *ka = kin + b0, *kb = kout + b0;
+    char* va = VB ? (char*)vin + (size_t)b0 * VB : nullptr;
+    char* vb = VB ? (char*)vout + (size_t)b0 * VB : nullptr;
+    if (dall) {
+        const int lo = __ffsll((long long)dall) - 1, hi = 64 - __clzll((long long)dall);  // bits [lo, hi) differ
+        const int npass = (hi - lo + 7) / 8;
+        int at = lo;
+        for (int p = 0; p < npass; p++) {
+            const int bits = (hi - at + (npass - p) - 1) / (npass - p);
+            const int shift = begin_bit + at;
+            const uint32_t dmask = (1u << bits) - 1u;
+            base[tid] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < m; i += HY_THREADS) atomicAdd(&base[(uint32_t)(ka[i] >> shift) & dmask], 1u);
+            __syncthreads();
+            {
+                uint32_t tot;
+                const uint32_t v = base[tid];
+                const uint32_t ex = block_excl_sum<uint32_t, HY_THREADS>(v, wsum, tot);
+                base[tid] = ex;
+            }
+            __syncthreads();
+            for (uint32_t c0 = 0; c0 < m; c0 += SW_TILE) {
+                for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+                __syncthreads();
+                const int nvalid = (int)(m - c0 < (uint32_t)SW_TILE ? m - c0 : (uint32_t)SW_TILE);
+                sw_tile<VB>(S, ka, kb, va, vb, (int64_t)c0, nvalid, shift, dmask, 0, [&](uint32_t run, uint32_t ex) {
+                    const uint32_t g = base[tid];
+                    base[tid] = g + run;
+                    return g - ex;
+                });
+                __syncthreads();
+            }
+            uint64_t* tk = ka; ka = kb; kb = tk;
+            char* tv = va; va = vb; vb = tv;
+            at += bits;
+        }
+    }
+    if (ka != kout + b0) {
+        for (uint32_t i = tid; i < m; i += HY_THREADS) {
+            kout[b0 + i] = ka[i];
+            if (VB == 4) ((uint32_t*)vout)[b0 + i] = ((const uint32_t*)va)[i];
+            else if (VB == 8) ((uint64_t*)vout)[b0 + i] = ((const uint64_t*)va)[i];
+        }
+    }
 }
 
 template <int VB>
@@ -775,25 +863,8 @@ k_hy_buckets(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit
         return;
     }
     if (m > (uint32_t)HY_CAP) {
-        // oversize bucket (a pile-up): stable LSD passes through global memory inside the bucket's range
-        uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(hy_smem);          // [BK_WARPS][256]
-        uint32_t* base = warp_cnt + BK_WARPS * RS_RADIX;                    // [256]
-        uint64_t *ka = kin + b0, *kb = kout + b0;
-        char* va = VB ? (char*)vin + (size_t)b0 * VB : nullptr;
-        char* vb = VB ? (char*)vout + (size_t)b0 * VB : nullptr;
-        for (int sh = 0; sh < low_bits; sh += 8) {
-            const int bits = low_bits - sh < 8 ? low_bits - sh : 8;
-            bk_pass<VB != 0>(ka, kb, m, begin_bit + sh, (1u << bits) - 1u, base, warp_cnt, va, vb, VB);
-            uint64_t* tk = ka; ka = kb; kb = tk;
-            char* tv = va; va = vb; vb = tv;
-        }
-        if (ka != kout + b0) {
-            for (uint32_t i = tid; i < m; i += HY_THREADS) {
-                kout[b0 + i] = ka[i];
-                if (VB == 4) ((uint32_t*)vout)[b0 + i] = ((const uint32_t*)va)[i];
-                else if (VB == 8) ((uint64_t*)vout)[b0 + i] = ((const uint64_t*)va)[i];
-            }
-        }
+        __shared__ uint32_t base[RS_RADIX];
+        hy_pileup<VB>(hy_smem, s_diff, base, wsum, kin, kout, vin, vout, begin_bit, low_bits, b0, m);
         return;
     }
     const uint64_t low_mask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
@@ -878,7 +949,8 @@ k_hy_buckets(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit
         }
     }
 }
-constexpr size_t HY_SMEM = (size_t)HY_CAP * 8 + (size_t)HY_BINS * 4;  // 48 KB (>= the 9 KB of the oversize path)
+constexpr size_t HY_SMEM = (size_t)HY_CAP * 8 + (size_t)HY_BINS * 4;  // 48 KB
+static_assert(sizeof(SwSmem) <= HY_SMEM, "the pile-up path reuses the bucket pass's shared memory");
 
 struct HyTemp {
     uint32_t *ghist, *ticket, *status, *starts;
