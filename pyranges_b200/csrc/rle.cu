@@ -18,6 +18,7 @@
 //           position of its group; the first piece of a group at p > 0 also emits the leading zero run.
 //   length  next run start of the same group (or the group's largest End) minus own start.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace iv {
 
@@ -341,6 +342,18 @@ static void plan_rle(int64_t n, int n_groups, Bump& b, RleLayout& L) {
     L.sort_temp = b.take<char>(radix_sort_temp_bytes((int64_t)m));
 }
 
+// the dense path (rle_dense.cu): whole-genome read sets
+size_t rle_dense_workspace_bytes(int64_t n, int n_groups);
+bool rle_dense_applies(int64_t n, int64_t total_span);
+int rle_dense_count(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, void* ws,
+                    size_t ws_bytes, int64_t* out_run_off, cudaStream_t st);
+int rle_dense_emit(int64_t n, const iv_groups_t* groups, const void* ws, int64_t* out_runs, double* out_values,
+                   cudaStream_t st);
+static bool use_dense(int64_t n, const iv_groups_t& G) {
+    static const bool off = getenv("IV_RLE_NO_DENSE") != nullptr;  // A/B timing and tests of the sort-based path
+    return !off && rle_dense_applies(n, G.total_span);
+}
+
 }  // namespace iv
 
 using namespace iv;
@@ -349,7 +362,8 @@ extern "C" size_t iv_rle_workspace_bytes(int64_t n, int32_t n_groups) {
     Bump b(nullptr, 0);
     RleLayout L;
     plan_rle(n, n_groups > 0 ? n_groups : 0, b, L);
-    return b.off + 256;
+    const size_t dense = rle_dense_workspace_bytes(n, n_groups > 0 ? n_groups : 0);
+    return (b.off > dense ? b.off : dense) + 256;
 }
 
 extern "C" int iv_rle_count(const int64_t* starts, const int64_t* ends, int64_t n, const iv_groups_t* groups, void* ws,
@@ -360,6 +374,7 @@ extern "C" int iv_rle_count(const int64_t* starts, const int64_t* ends, int64_t 
     const iv_groups_t& G = *groups;
     int bits = bits_for((uint64_t)(G.total_span > 0 ? G.total_span : 1));
     IV_REQUIRE(bits <= 62, IV_ERR_RANGE, "iv_rle_count: flattened span too large");
+    if (use_dense(n, G)) return rle_dense_count(starts, ends, n, groups, ws, ws_bytes, out_run_off, st);
     Bump b(ws, ws_bytes);
     RleLayout L;
     plan_rle(n, G.n_groups, b, L);
@@ -403,6 +418,7 @@ extern "C" int iv_rle_emit(int64_t n, const iv_groups_t* groups, const void* ws,
     IV_REQUIRE(ws && run_off && out_runs && out_values, IV_ERR_INVALID, "iv_rle_emit: null argument");
     IV_REQUIRE(n_runs <= 2 * n, IV_ERR_INVALID, "iv_rle_emit: n_runs > 2n");
     const iv_groups_t& G = *groups;
+    if (use_dense(n, G)) return rle_dense_emit(n, groups, ws, out_runs, out_values, st);
     Bump b((void*)ws, (size_t)-1);
     RleLayout L;
     plan_rle(n, G.n_groups, b, L);

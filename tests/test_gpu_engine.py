@@ -314,6 +314,52 @@ def test_coverage_rle(eng, seed, n_seg, n, maxpos, maxlen):
         assert np.array_equal(vals[sl], wv), k
 
 
+def test_coverage_rle_dense_path(eng):
+    """Read sets dense enough for the bucket path of to_rle (rle_dense.cu: >= 1 event per 64 coordinates, span >= 2^27):
+    every key against pyrle's restatement.  Keys: two large ones, one without rows, one whose coverage starts at
+    coordinate 0, one whose first Start is far from 0, zero-length intervals (at 0, in the middle, at the last End),
+    a pile-up of identical reads, a tiny key sharing its bucket with the neighbours' origins, reads touching
+    bucket boundaries (multiples of 8192)."""
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(17)
+    keys = []
+
+    def reads(n, span, lo=0, maxlen=300):
+        st = rng.integers(lo, span, n, dtype=np.int64)
+        return st, st + rng.integers(1, maxlen, n, dtype=np.int64)
+
+    keys.append(reads(900_000, 90_000_000))
+    keys.append((np.zeros(0, np.int64), np.zeros(0, np.int64)))                      # no rows
+    st, en = reads(700_000, 70_000_000)
+    st[:5] = 0                                                                        # coverage from coordinate 0
+    en[:5] = [1, 7, 7, 8192, 8193]
+    keys.append((st, en))
+    keys.append((np.array([0, 0, 5], np.int64), np.array([0, 0, 9], np.int64)))       # zero-length at coordinate 0
+    keys.append((np.array([4], np.int64), np.array([4], np.int64)))                   # only a zero-length interval
+    keys.append(reads(30_000, 3_000_000, lo=2_500_000))                               # first Start far from 0
+    st, en = reads(60_000, 200_000)
+    st[:40_000] = 81_920                                                               # pile-up on a bucket boundary
+    en[:40_000] = 81_920 + 100
+    st[40_000:40_010] = en[40_000:40_010] = 150_000                                    # zero-length in the middle
+    st[-3:] = en[-3:] = int(en.max()) + 17                                             # zero-length at the last End
+    keys.append((st, en))
+    keys.append((np.array([8192, 16384, 16383], np.int64), np.array([16384, 16385, 16384], np.int64)))
+    s = np.concatenate([k[0] for k in keys])
+    e = np.concatenate([k[1] for k in keys])
+    off = np.concatenate([[0], np.cumsum([len(k[0]) for k in keys])]).astype(np.int64)
+    iv = _dev(eng, s, e, off)
+    run_off, runs, vals = eng.coverage_rle(iv)
+    runs, vals = runs.cpu().numpy(), vals.cpu().numpy()
+    assert run_off[-1] == len(runs)
+    for k in range(len(keys)):
+        a, b = off[k], off[k + 1]
+        wr, wv = orc.coverage_rle(s[a:b], e[a:b]) if b > a else (np.zeros(0, np.int64), np.zeros(0))
+        sl = slice(run_off[k], run_off[k + 1])
+        assert np.array_equal(runs[sl], wr), (k, runs[sl][:8], wr[:8])
+        assert np.array_equal(vals[sl], wv), (k, vals[sl][:8], wv[:8])
+
+
 def test_large_staged_paths(eng):
     """sizes above the staged-kernel threshold (>= 64 tiles of 2048 rows), ragged tail, several key segments,
     a key without partner: counts / pairs must equal the oracle."""
