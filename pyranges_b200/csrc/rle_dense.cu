@@ -37,10 +37,10 @@ constexpr int RD_ITEMS = 16;
 constexpr int RD_TILE = RD_THREADS * RD_ITEMS;  // 4096 events per tile
 constexpr int RD_BINS = 128;
 constexpr int RD_WARPS = RD_THREADS / 32;
-constexpr uint32_t RD_AGG = 1u << 30, RD_INC = 2u << 30, RD_VAL = (1u << 30) - 1u;
 constexpr int RD_CHUNK = 32;             // consecutive buckets a block of the dense pass takes per ticket
 constexpr int RD_NG = 16;                // groups of a chunk kept in shared memory (more: global lookups)
 constexpr int RD_PF = 4;                 // events per thread of the NEXT bucket loaded ahead
+constexpr int RD_CSTRIDE = 32;           // uint32 words per claim cursor: one cursor per 128-byte line
 
 struct RdPlan {
     bool use;
@@ -65,7 +65,7 @@ struct RdLayout {
     uint32_t *wa, *wb;        // event words after pass A / pass B; pass C writes its 16-bit words over wa
     uint32_t *joint;          // [2^(w1+w2)] events per (d2, d1) segment -> exclusive starts (+1 entry)
     uint32_t *start2, *toff2; // [2^w2 + 1] first event / first pass-B tile of every d2 segment
-    uint32_t *statA, *statB;  // look-back status words
+    uint32_t *curA, *curB;    // claim cursors of pass A / pass B, one per 128-byte line
     uint32_t *tickets;        // [8]
     uint32_t *bstart;         // [2^T + 1] first event of every bucket
     int64_t *gF, *gZ;         // [n_groups] first Start / last End (flattened)
@@ -78,14 +78,13 @@ constexpr int RD_BSCAN = 2048;
 
 static void rd_layout(int64_t n, int n_groups, Bump& b, RdLayout& L) {
     const size_t m = (size_t)(n > 0 ? 2 * n : 2);
-    const size_t tiles = (size_t)cdiv((int64_t)m, RD_TILE) + 72;
     const size_t nbmax = ((size_t)1 << RD_MAX_T) + 64;
     L.wa = b.take<uint32_t>(m);
     L.wb = b.take<uint32_t>(m);
     L.zero_from = b.off;
     L.joint = b.take<uint32_t>((1u << (RD_W1 + 6)) + 64);
-    L.statA = b.take<uint32_t>(tiles * 64);
-    L.statB = b.take<uint32_t>(tiles * RD_BINS);
+    L.curA = b.take<uint32_t>(64 * RD_CSTRIDE);
+    L.curB = b.take<uint32_t>(((size_t)1 << (RD_W1 + 6)) * RD_CSTRIDE);
     L.tickets = b.take<uint32_t>(64);
     L.bcnt = b.take<int64_t>(nbmax);
     L.bsum = b.take<int64_t>(nbmax);
@@ -260,53 +259,23 @@ __device__ __forceinline__ void pt_tile(PtSmem& S, const uint32_t (&word)[RD_ITE
     for (int k = tid; k < nvalid; k += RD_THREADS) out[S.gbase[S.sdig[k]] + (uint32_t)k] = (OutT)S.sbuf[k];
 }
 
-// decoupled look-back over the status words of tiles [first_tile, tile): thread d < RD_BINS, digit d
-__device__ __forceinline__ uint32_t pt_lookback(volatile uint32_t* st, int64_t tile, int64_t first_tile, int nbins,
-                                                uint32_t run) {
-    const int tid = threadIdx.x;
-    if (tile == first_tile) {
-        st[tile * nbins + tid] = RD_INC | run;
-        return 0;
-    }
-    st[tile * nbins + tid] = RD_AGG | run;
-    uint32_t excl = 0;
-    int64_t t = tile - 1;
-    unsigned ns = 20;
-    bool done = false;
-    while (!done) {
-        uint32_t v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = t - j >= first_tile ? st[(t - j) * nbins + tid] : (2u << 30);
-        int used = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (!done && used == j && (v[j] >> 30) != 0) {
-                excl += v[j] & RD_VAL;
-                used++;
-                if (v[j] >> 31) done = true;
-            }
-        }
-        t -= used;
-        if (used == 0) {
-            __nanosleep(ns);
-            if (ns < 200) ns += 20;
-        }
-    }
-    st[tile * nbins + tid] = RD_INC | (excl + run);
-    return excl;
+// Output space of a tile: one atomic claim per (tile, digit) on a cursor that owns a 128-byte line (the claims of the
+// ~600 tiles in flight go to the same few digits; cursors sharing a line would serialise them).  The claims make the
+// order of the tiles inside a digit -- not the result -- depend on timing: events are summed, never ordered.
+__device__ __forceinline__ uint32_t pt_claim(uint32_t* cursors, uint32_t idx, uint32_t run) {
+    return run ? atomicAdd(cursors + (size_t)idx * RD_CSTRIDE, run) : 0u;
 }
 
 // pass A: events straight from the rows, partitioned by d2
 __global__ void __launch_bounds__(RD_THREADS, 4)
 k_rd_pass_a(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, iv_groups_t G, int w2,
-            const uint32_t* __restrict__ start2, uint32_t* status, uint32_t* ticket, uint32_t* __restrict__ out) {
+            const uint32_t* __restrict__ start2, uint32_t* cursors, uint32_t* __restrict__ out) {
     __shared__ PtSmem S;
     __shared__ int span[2];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    if (tid == 0) S.s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < RD_WARPS * (RD_BINS + 1); i += RD_THREADS) (&S.warp_cnt[0][0])[i] = 0;
     __syncthreads();
-    const int64_t tile = S.s_tile;
+    const int64_t tile = blockIdx.x;
     const int64_t m = 2 * n, tbase = tile * RD_TILE;
     const int nvalid = (int)(m - tbase < (int64_t)RD_TILE ? m - tbase : (int64_t)RD_TILE);
     const int64_t r0 = tbase >> 1, r1 = (tbase + nvalid - 1) >> 1;
@@ -335,46 +304,39 @@ k_rd_pass_a(const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_
     }
     pt_tile<uint32_t>(S, word, dig, nvalid, out, [&](uint32_t run, uint32_t ex) {
         uint32_t excl = 0;
-        if (tid < nb2) excl = pt_lookback(status, tile, 0, nb2, run) + __ldg(start2 + tid);
+        if (tid < nb2) excl = pt_claim(cursors, tid, run) + __ldg(start2 + tid);
         return excl - ex;
     });
 }
 
-// pass B: partition by d1 inside every d2 segment
+// pass B: partition by d1 inside every d2 segment (tiles aligned to the segments)
 __global__ void __launch_bounds__(RD_THREADS, 4)
 k_rd_pass_b(const uint32_t* __restrict__ in, int w2, const uint32_t* __restrict__ start2,
-            const uint32_t* __restrict__ toff2, const uint32_t* __restrict__ joint, uint32_t* status, uint32_t* ticket,
+            const uint32_t* __restrict__ toff2, const uint32_t* __restrict__ joint, uint32_t* cursors,
             uint32_t* __restrict__ out) {
     __shared__ PtSmem S;
-    __shared__ uint32_t s_seg[3];
+    __shared__ uint32_t s_seg;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const uint32_t t = blockIdx.x;
     if (tid == 0) {
-        const uint32_t t = atomicAdd(ticket, 1u);
-        S.s_tile = t;
         const int n2 = 1 << w2;
-        int d = 0;
+        s_seg = 0xffffffffu;
         if (t < __ldg(toff2 + n2)) {
-            int lo = 0, hi = n2;  // largest d with toff2[d] <= t
+            int lo = 0, hi = n2;  // largest d with toff2[d] <= t (segments without events share their offset with the next)
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (__ldg(toff2 + mid) <= t) lo = mid; else hi = mid;
             }
-            d = lo;
-            // segments without events share their tile offset with the next one: take the last of them
-            while (d + 1 < n2 && __ldg(toff2 + d + 1) <= t) d++;
-            s_seg[0] = (uint32_t)d;
-        } else {
-            s_seg[0] = 0xffffffffu;
+            s_seg = (uint32_t)lo;
         }
     }
     for (int i = tid; i < RD_WARPS * (RD_BINS + 1); i += RD_THREADS) (&S.warp_cnt[0][0])[i] = 0;
     __syncthreads();
-    if (s_seg[0] == 0xffffffffu) return;
-    const int64_t tile = S.s_tile;
-    const uint32_t d2 = s_seg[0];
-    const int64_t first_tile = __ldg(toff2 + d2);
+    if (s_seg == 0xffffffffu) return;
+    const uint32_t d2 = s_seg;
+    const uint32_t first_tile = __ldg(toff2 + d2);
     const uint32_t seg_lo = __ldg(start2 + d2), seg_hi = __ldg(start2 + d2 + 1);
-    const uint32_t tbase = seg_lo + (uint32_t)(tile - first_tile) * RD_TILE;
+    const uint32_t tbase = seg_lo + (t - first_tile) * RD_TILE;
     const int nvalid = (int)(seg_hi - tbase < (uint32_t)RD_TILE ? seg_hi - tbase : (uint32_t)RD_TILE);
     uint32_t word[RD_ITEMS], dig[RD_ITEMS];
 #pragma unroll
@@ -385,8 +347,8 @@ k_rd_pass_b(const uint32_t* __restrict__ in, int w2, const uint32_t* __restrict_
         dig[it] = li < nvalid ? (v >> (RD_LW + RD_W0)) : (uint32_t)RD_BINS;
     }
     pt_tile<uint32_t>(S, word, dig, nvalid, out, [&](uint32_t run, uint32_t ex) {
-        const uint32_t excl = pt_lookback(status, tile, first_tile, RD_BINS, run);
-        return __ldg(joint + ((d2 << RD_W1) | (uint32_t)tid)) + excl - ex;
+        const uint32_t seg = (d2 << RD_W1) | (uint32_t)tid;
+        return __ldg(joint + seg) + pt_claim(cursors, seg, run) - ex;
     });
 }
 
@@ -468,6 +430,7 @@ k_rd_dense(const uint16_t* __restrict__ ev, const uint32_t* __restrict__ bstart,
     __shared__ RdGroups SG;
     __shared__ uint32_t s_chunk;
     __shared__ uint8_t sflag[RD_CHUNK];  // bit 0: a group origin inside the bucket, bit 1: a group end inside it
+    __shared__ int64_t s_scan[EMIT ? 3 * RD_CHUNK : 1];  // the chunk's scanned bucket values: runs, level, last run start
     __shared__ int4 wred[RD_WARPS];
     __shared__ int st_len[EMIT ? RD_STAGE : 1];  // staged as 32-bit words (a longer run is stored directly)
     __shared__ int st_val[EMIT ? RD_STAGE : 1];
@@ -485,6 +448,11 @@ k_rd_dense(const uint16_t* __restrict__ ev, const uint32_t* __restrict__ bstart,
         if (chunk >= nchunks) return;
         const int64_t b_lo = chunk * RD_CHUNK, b_hi = b_lo + RD_CHUNK < nb ? b_lo + RD_CHUNK : nb;
         if (tid <= (int)(b_hi - b_lo)) sstart[tid] = __ldg(bstart + b_lo + tid);
+        if (EMIT && tid >= 64 && tid < 64 + (int)(b_hi - b_lo)) {
+            s_scan[tid - 64] = bcnt[b_lo + tid - 64];
+            s_scan[RD_CHUNK + tid - 64] = bsum[b_lo + tid - 64];
+            s_scan[2 * RD_CHUNK + tid - 64] = blast[b_lo + tid - 64];
+        }
         if (tid == 32) {
             const int64_t x0 = b_lo << RD_L, x1 = (b_hi << RD_L) - 1;
             const int glo = find_seg(G.base, G.n_groups, x0), ghi = find_seg(G.base, G.n_groups, x1);
@@ -666,33 +634,51 @@ k_rd_dense(const uint16_t* __restrict__ ev, const uint32_t* __restrict__ bstart,
                 // every marker closes the run before it (length = own coordinate - previous run start); a run start
                 // also opens the next one with the level behind it.  The bucket's runs are staged in shared memory
                 // and written as coalesced rows; the run before the bucket's first one is closed with a direct store.
-                const int64_t base_r = bcnt[b];              // scanned: runs before this bucket
+                const int64_t base_r = s_scan[bi];           // scanned: runs before this bucket
                 const bool staged = c_tot <= RD_STAGE;
-                uint32_t marks = emit_mask | term_mask;
-                if (marks) {
-                    int level = 0;
-                    const int64_t level0 = bsum[b] + s_ex;       // scanned: level before this bucket
-                    int64_t prev = l_ex >= 0 ? l_ex : blast[b];  // scanned: last run start before this bucket
-                    int k = (int)c_ex;                           // runs of this bucket before the marker
-                    if (!bplain && !plain) load_group(xr0);
+                if (bplain && staged) {
+                    // the common case in 32-bit arithmetic relative to the bucket: every marker is a run start, its
+                    // predecessor lies in the same group, and only the bucket's first run start looks outside the bucket
+                    uint32_t marks = emit_mask;
+                    int level = (int)s_scan[RD_CHUNK + bi] + s_ex32, prevr = l_ex32, k = c_ex32;
                     while (marks) {
                         const int j = __ffs(marks) - 1;
                         marks &= marks - 1;
                         const int xr = xr0 + j;
-                        if (!bplain && xr >= gnext) load_group(xr);
                         level += dmine[j];
-                        const int64_t x = x0 + xr;
-                        if (bplain || prev >= gb64) {
-                            const int64_t len = x - prev;
-                            if (staged && k > 0) st_len[k - 1] = len < INT32_MAX ? (int)len : -1;
-                            if (!staged || k == 0 || len >= INT32_MAX) out_runs[base_r + k - 1] = len;
-                        }
-                        if (emit_mask >> j & 1u) {
-                            const int64_t v = (!bplain && xr == gb && lead) ? 0 : level0 + level;
-                            if (staged) st_val[k] = (int)v;
-                            else out_values[base_r + k] = (double)v;
-                            prev = x;
-                            k++;
+                        if (k > 0) st_len[k - 1] = xr - prevr;
+                        else out_runs[base_r - 1] = (x0 + xr) - s_scan[2 * RD_CHUNK + bi];
+                        st_val[k] = level;
+                        prevr = xr;
+                        k++;
+                    }
+                } else {
+                    uint32_t marks = emit_mask | term_mask;
+                    if (marks) {
+                        int level = 0;
+                        const int64_t level0 = s_scan[RD_CHUNK + bi] + s_ex;           // scanned: level before this bucket
+                        int64_t prev = l_ex >= 0 ? l_ex : s_scan[2 * RD_CHUNK + bi];  // scanned: last run start before it
+                        int k = (int)c_ex;                                             // runs of this bucket before the marker
+                        if (!bplain && !plain) load_group(xr0);
+                        while (marks) {
+                            const int j = __ffs(marks) - 1;
+                            marks &= marks - 1;
+                            const int xr = xr0 + j;
+                            if (!bplain && xr >= gnext) load_group(xr);
+                            level += dmine[j];
+                            const int64_t x = x0 + xr;
+                            if (bplain || prev >= gb64) {
+                                const int64_t len = x - prev;
+                                if (staged && k > 0) st_len[k - 1] = len < INT32_MAX ? (int)len : -1;
+                                if (!staged || k == 0 || len >= INT32_MAX) out_runs[base_r + k - 1] = len;
+                            }
+                            if (emit_mask >> j & 1u) {
+                                const int64_t v = (!bplain && xr == gb && lead) ? 0 : level0 + level;
+                                if (staged) st_val[k] = (int)v;
+                                else out_values[base_r + k] = (double)v;
+                                prev = x;
+                                k++;
+                            }
                         }
                     }
                 }
@@ -865,10 +851,10 @@ int rle_dense_count(const int64_t* starts, const int64_t* ends, int64_t n, const
     k_rd_scan<<<1, 1024, 0, st>>>(L.joint, nseg, RD_W1, L.start2, L.toff2, L.bstart + ((size_t)1 << pl.T));
     IV_LAUNCH_CHECK();
     const unsigned tiles_a = (unsigned)cdiv(m, RD_TILE);
-    k_rd_pass_a<<<tiles_a, RD_THREADS, 0, st>>>(starts, ends, n, G, pl.w2, L.start2, L.statA, L.tickets, L.wa);
+    k_rd_pass_a<<<tiles_a, RD_THREADS, 0, st>>>(starts, ends, n, G, pl.w2, L.start2, L.curA, L.wa);
     IV_LAUNCH_CHECK();
     const unsigned tiles_b = tiles_a + (1u << pl.w2);  // >= the exact count in toff2[2^w2]; surplus blocks leave at once
-    k_rd_pass_b<<<tiles_b, RD_THREADS, 0, st>>>(L.wa, pl.w2, L.start2, L.toff2, L.joint, L.statB, L.tickets + 1, L.wb);
+    k_rd_pass_b<<<tiles_b, RD_THREADS, 0, st>>>(L.wa, pl.w2, L.start2, L.toff2, L.joint, L.curB, L.wb);
     IV_LAUNCH_CHECK();
     k_rd_pass_c<<<(unsigned)nseg, RD_THREADS, 0, st>>>(L.wb, L.joint, L.bstart, reinterpret_cast<uint16_t*>(L.wa));
     IV_LAUNCH_CHECK();
