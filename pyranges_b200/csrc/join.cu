@@ -2,8 +2,8 @@
 // index (lists.cu).  Replaces NCLS.all_overlaps_both (pyranges/methods/join.py:15,23) and, in its count-only form,
 // all_overlaps_both + value_counts / has_overlaps (pyranges/methods/coverage.py:26-40, intersection.py:78).
 //
-// A WARP is its own tile of 256 consecutive query rows, taken from a ticket counter by the warps of a persistent grid
-// (so a tile only ever waits for tiles that are already running); a lane owns two rows per iteration:
+// A block takes a ticket for 2048 consecutive query rows (so a tile only ever waits for tiles that are already running),
+// a WARP is its own tile of 256 consecutive rows, a lane owns two rows per iteration:
 //   1. 16-byte streaming loads of Start / End, 32-bit clamp into the partner group's window of the flattened axis,
 //      ONE 256-bit gather of the record of the bin the query starts in (list offset, length, first three entries);
 //   2. count sweep: two 16-bit compares per entry (inline entries from registers; longer lists and the later bins of a
@@ -35,9 +35,6 @@ constexpr int JN_WCAP = 576;
 constexpr size_t JN_SMEM = (size_t)JN_WARPS * JN_WCAP * 5;  // dynamic shared memory of k_join: staging areas
 
 constexpr int JM_COUNT = 2, JM_ANY = 3;
-#ifndef JN_AHEAD
-#define JN_AHEAD 0  // 1: count the first iteration of the next tile while waiting for the look-back (measured: slower)
-#endif
 
 
 struct LRec { uint32_t w[8]; };  // w0 = co, w1 = n8, (w2, w3) (w4, w5) (w6, w7) = entries {row, so | eo << 16}
@@ -94,63 +91,29 @@ template <typename X> struct QGeom {
     }
 };
 
-// Sinks of the emit sweep: small value types (no captures by reference), so that the rare walks below can live out of
-// line without a stack frame.
-struct CountSink {
-    uint32_t n;
-    __device__ __forceinline__ void operator()(uint32_t) { n++; }
-};
-struct StageSink {  // a warp's staging area: subject row + row in tile
-    uint32_t* st_s;
-    uint8_t* st_q;
-    uint32_t pos;
-    uint8_t ql;
-    __device__ __forceinline__ void operator()(uint32_t row) {
-        st_s[pos] = row;
-        st_q[pos] = ql;
-        pos++;
-    }
-};
-struct DirectSink {  // straight to the outputs (an iteration larger than the staging area)
-    int64_t* out_q;
-    int64_t* out_s;
-    const int64_t* s_label;
-    int64_t cap, ql;
-    unsigned long long o;
-    __device__ __forceinline__ void operator()(uint32_t row) {
-        if ((int64_t)o < cap) {
-            if (out_q) out_q[o] = ql;
-            if (out_s) out_s[o] = s_label ? __ldg(s_label + row) : (int64_t)row;
-        }
-        o++;
-    }
-};
-
-// hits beyond the masked entries -- the rest of a long list (eight entries per round trip) and the starts inside the
-// later bins of a query that reaches beyond its first bin.  Rare: out of line, everything by value.
+// hits beyond the masked entries: f(subject row)
 template <typename X, typename F>
-__device__ __noinline__ F walk_extra(const uint32_t* __restrict__ cand_se, const uint32_t* __restrict__ cand_row,
-                                     const iv_lrec_t* __restrict__ rec, int shift, X ec, uint32_t co, uint32_t n, uint32_t qw,
-                                     X b, bool single, F f) {
-    for (uint32_t j0 = JN_MASKED; j0 < n; j0 += 8) {
-        const uint32_t* __restrict__ c = cand_se + co + j0;
+__device__ __forceinline__ void walk_extra(const iv_lists_t& ix, X ec, const LRec& r, const QGeom<X>& g, F&& f) {
+    const int shift = ix.shift;
+    // the rest of a long list, eight entries per round trip
+    for (uint32_t j0 = JN_MASKED; j0 < g.n; j0 += 8) {
+        const uint32_t* __restrict__ c = ix.cand_se + r.w[0] + j0;
         uint32_t w[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) w[t] = __ldg(c + t);  // (the arrays end in slack: reading past the list is safe)
 #pragma unroll
         for (int t = 0; t < 8; t++)
-            if (j0 + t < n && hit_bit(w[t], qw)) f(__ldg(cand_row + co + j0 + t));
+            if (j0 + t < g.n && hit_bit(w[t], g.qw)) f(__ldg(ix.cand_row + r.w[0] + j0 + t));
     }
-    if (!single) {
+    if (!g.single) {
         const uint64_t bl = (uint64_t)(ec - 1) >> shift;
-        for (uint64_t bb = (uint64_t)b + 1; bb <= bl; bb++) {
-            const uint32_t c0 = __ldg(&rec[bb].co), c1 = __ldg(&rec[bb + 1].co);
+        for (uint64_t bb = (uint64_t)g.b + 1; bb <= bl; bb++) {
+            const uint32_t c0 = __ldg(&ix.rec[bb].co), c1 = __ldg(&ix.rec[bb + 1].co);
             const uint32_t re = bb < bl ? (1u << shift) : (uint32_t)(ec - (X)(bl << shift));
             for (uint32_t j = c0; j < c1; j++)
-                if (later_hit(__ldg(cand_se + j), re)) f(__ldg(cand_row + j));
+                if (later_hit(__ldg(ix.cand_se + j), re)) f(__ldg(ix.cand_row + j));
         }
     }
-    return f;
 }
 
 template <typename X>
@@ -171,15 +134,17 @@ __device__ __forceinline__ QPlan plan_query(const iv_lists_t& ix, X sc, X ec, co
     m = __funnelshift_l(hit_bit(r.w[5], g.qw), m, 1);
     m = __funnelshift_l(hit_bit(r.w[3], g.qw), m, 1);
     p.mask = m & (g.n >= (uint32_t)JN_MASKED ? (1u << JN_MASKED) - 1u : (1u << g.n) - 1u);
-    if (g.n > (uint32_t)JN_MASKED || !g.single)
-        p.extra = walk_extra<X, CountSink>(ix.cand_se, ix.cand_row, ix.rec, ix.shift, ec, r.w[0], g.n, g.qw, g.b, g.single,
-                                           CountSink{0u}).n;
+    if (g.n > (uint32_t)JN_MASKED || !g.single) {
+        uint32_t x = 0;
+        walk_extra<X>(ix, ec, r, g, [&](uint32_t) { x++; });
+        p.extra = x;
+    }
     return p;
 }
 
 // every hit of a planned query, in list order: f(subject row)
 template <typename X, typename F>
-__device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, const QPlan& p, F& f) {
+__device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, const LRec& r, const QPlan& p, F&& f) {
     uint32_t m = p.mask;
     if (m & 1u) f(r.w[2]);
     if (m & 2u) f(r.w[4]);
@@ -196,7 +161,7 @@ __device__ __forceinline__ void emit_query(const iv_lists_t& ix, X sc, X ec, con
     }
     if (p.extra) {
         const QGeom<X> g(ix, sc, ec, r);
-        f = walk_extra<X, F>(ix.cand_se, ix.cand_row, ix.rec, ix.shift, ec, r.w[0], g.n, g.qw, g.b, g.single, f);
+        walk_extra<X>(ix, ec, r, g, f);
     }
 }
 
@@ -209,13 +174,10 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
 __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// publish a tile's pair total (tile 0: it is its inclusive prefix as well)
-__device__ __forceinline__ void post_aggregate(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
-    if (lane_id() == 0) st_relaxed(state + tile, (aggregate << 2) | (tile == 0 ? 2ull : 1ull));
-}
-// called by one full warp after post_aggregate; -> pairs of all tiles before `tile`
-__device__ __forceinline__ unsigned long long resolve(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
+// called by one full warp; -> pairs of all tiles before `tile`
+__device__ __forceinline__ unsigned long long lookback(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
     const int lane = lane_id();
+    if (lane == 0) st_relaxed(state + tile, (aggregate << 2) | (tile == 0 ? 2ull : 1ull));
     unsigned long long excl = 0;
     int64_t look = tile - 1;
     while (look >= 0) {
@@ -347,81 +309,26 @@ k_join_count(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_
     }
 }
 
-// Iterations of a tile whose pairs did not fit the staging area: processed once more after the tile's output offset
-// is known -- through the staging area when one iteration fits it, straight to memory otherwise (rare).
-template <typename X, bool SLACK, bool ANY>
-__device__ __forceinline__ void late_iterations(const iv_lists_t& ix, const iv_queries_t& q, bool vec, int64_t wbase, int first_it,
-                                             const uint32_t* cnt, unsigned long long o, uint32_t* __restrict__ st_s,
-                                             uint8_t* __restrict__ st_q, int64_t* __restrict__ out_q,
-                                             int64_t* __restrict__ out_s, const int64_t* __restrict__ s_label, int64_t cap) {
-    const int lane = lane_id();
-    for (int it = first_it; it < JN_ITERS; it++) {
-        const uint32_t itot = cnt[it];
-        if (itot == 0) continue;
-        const int64_t ibase = wbase + it * 64;
-        __syncwarp();
-        Geo<X> G2(q, ibase);
-        Rows2<X> R;
-        flatten_rows<X, SLACK>(ix, q, ibase, load_raw(q, vec, ibase), G2, R);
-        QPlan p[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
-        const uint32_t c0 = ANY ? (p[0].count() ? 1u : 0u) : p[0].count(), c1 = ANY ? (p[1].count() ? 1u : 0u) : p[1].count();
-        const uint32_t mine = c0 + c1;
-        const uint32_t inc = warp_incl_sum(mine);
-        if (itot <= (uint32_t)JN_WCAP) {
-            StageSink sink{st_s, st_q, inc - mine, 0};
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                sink.ql = (uint8_t)(2 * lane + k);
-                if (ANY) {
-                    if (p[k].count()) st_q[sink.pos++] = sink.ql;
-                } else {
-                    emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], sink);
-                }
-            }
-            __syncwarp();
-            for (uint32_t k = lane; k < itot; k += 32) {
-                const int64_t oo = (int64_t)(o + k);
-                if (oo < cap) {
-                    const int64_t row_q = ibase + st_q[k];
-                    if (out_q) out_q[oo] = q.label ? __ldg(q.label + row_q) : row_q;
-                    if (!ANY && out_s) out_s[oo] = s_label ? __ldg(s_label + st_s[k]) : (int64_t)st_s[k];
-                }
-            }
-        } else {
-            DirectSink sink{out_q, out_s, s_label, cap, 0, o + inc - mine};
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int64_t row_q = ibase + 2 * lane + k;
-                sink.ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
-                if (ANY) {
-                    if (p[k].count()) {
-                        if ((int64_t)sink.o < cap && out_q) out_q[sink.o] = sink.ql;
-                        sink.o++;
-                    }
-                    continue;
-                }
-                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], sink);
-            }
-        }
-        o += itot;
-    }
-}
-
 // ---- the fused join ---------------------------------------------------------------------------------------------------------------
-// Every WARP is its own tile of 256 rows (tile ids come from a ticket counter, so a tile only waits for tiles that are
-// running or done); no block-wide barrier anywhere.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
+// Every WARP is its own tile of 256 rows (tile id = block ticket * 8 + warp: the warps of a block are co-resident and
+// blocks with smaller tickets started earlier, so a tile only waits for tiles that are running or done); no block-wide
+// barrier after the ticket.  The warp stages the pairs of its iterations in shared memory while they fit, publishes its
 // pair total, looks back for its output offset and copies the staged pairs out with coalesced stores; iterations that
 // did not fit are repeated afterwards -- the offset is known by then -- through the same staging area, one at a time.
-template <typename X, bool SLACK, bool ANY, int OCC>
-__global__ void __launch_bounds__(JN_THREADS, OCC)
+template <typename X, bool SLACK, bool ANY>
+__global__ void __launch_bounds__(JN_THREADS, 4)
 k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
        const int64_t* __restrict__ s_label, int64_t cap, unsigned long long* __restrict__ state,
        unsigned int* __restrict__ ticket, int64_t n_wtiles, int64_t* __restrict__ out_total, int variant) {
     extern __shared__ __align__(16) unsigned char jn_smem[];  // [JN_WARPS][JN_WCAP] subject rows, then query rows
     __shared__ uint32_t s_cnt[JN_WARPS][JN_ITERS];
+    __shared__ unsigned int s_tile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t wtile = (int64_t)s_tile * JN_WARPS + warp;
+    if (wtile >= n_wtiles) return;
+    const int64_t wbase = wtile * JN_WROWS;
     uint32_t* __restrict__ st_s = reinterpret_cast<uint32_t*>(jn_smem) + warp * JN_WCAP;
     uint8_t* __restrict__ st_q = jn_smem + (size_t)JN_WARPS * JN_WCAP * 4 + warp * JN_WCAP;
 
@@ -441,14 +348,17 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
     };
     // emit sweep of one iteration into the staging area, the lane's first pair at `pos`
     auto stage_rows = [&](const Rows2<X>& R, const QPlan (&p)[2], uint32_t pos, uint32_t qloc) {
-        StageSink sink{st_s, st_q, pos, 0};
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            sink.ql = (uint8_t)(qloc + k);
+            const uint8_t ql = (uint8_t)(qloc + k);
             if (ANY) {  // one entry per query with hits: the query row only
-                if (p[k].count()) st_q[sink.pos++] = sink.ql;
+                if (p[k].count()) st_q[pos++] = ql;
             } else {
-                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], sink);
+                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
+                    st_s[pos] = row;
+                    st_q[pos] = ql;
+                    pos++;
+                });
             }
         }
     };
@@ -456,60 +366,17 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         return ANY ? (p[0].count() ? 1u : 0u) + (p[1].count() ? 1u : 0u) : p[0].count() + p[1].count();
     };
 
-  // The grid is persistent (as many blocks as fit the device): every warp takes tile after tile from the ticket counter,
-  // so no warp slot idles while the slowest warp of its block finishes, and a tile only ever waits for tiles with
-  // smaller tickets -- all of them taken by running warps.  Between publishing a tile's total and looking back for its
-  // offset the warp already counts the FIRST iteration of its next tile (registers only): the time the predecessors
-  // need to publish theirs is spent on work.
-  auto take = [&]() -> int64_t {
-      unsigned int tk = 0;
-      if (lane == 0) tk = atomicAdd(ticket, 1u);
-      return (int64_t)__shfl_sync(FULL, tk, 0);
-  };
-  Rows2<X> R0;  // iteration 0 of the current tile, counted ahead
-  QPlan p0[2];
-  auto count_first = [&](int64_t tile) {
-      const int64_t base = tile * JN_WROWS;
-      Geo<X> G0(q, base);
-      flatten_rows<X, SLACK>(ix, q, base, load_raw(q, vec, base), G0, R0);
-#pragma unroll
-      for (int k = 0; k < 2; k++) p0[k] = plan_query<X>(ix, R0.sc[k], R0.ec[k], R0.r[k], R0.live[k]);
-  };
-  int64_t wtile = take();
-  if (JN_AHEAD && wtile < n_wtiles) count_first(wtile);
-  while (wtile < n_wtiles) {
-    if (!JN_AHEAD) count_first(wtile);
-    const int64_t wbase = wtile * JN_WROWS;
+    Geo<X> G(q, wbase);
     unsigned long long total = 0;
     uint32_t staged = 0;
     int staged_iters = 0;
     bool open = true;
-    // scan of the iteration's counts, staging while it fits
-    auto finish_iter = [&](const Rows2<X>& R, const QPlan (&p)[2], int it) {
-        const uint32_t mine = pairs_of(p);
-        const uint32_t inc = warp_incl_sum(mine);
-        const uint32_t itot = __shfl_sync(FULL, inc, 31);
-        if (open && staged + itot <= (uint32_t)JN_WCAP) {
-            if (itot) stage_rows(R, p, staged + inc - mine, (uint32_t)(it * 64 + 2 * lane));
-            staged += itot;
-            staged_iters = it + 1;
-        } else {
-            open = false;
-        }
-        if (lane == 0) s_cnt[warp][it] = itot;
-        total += itot;
-    };
-    finish_iter(R0, p0, 0);
-    if (wbase + 64 < q.n) {
-        Geo<X> G(q, wbase + 64);
-        Raw2 next = load_raw(q, vec, wbase + 64);
+    Raw2 next = load_raw(q, vec, wbase);
 #pragma unroll 1
-        for (int it = 1; it < JN_ITERS; it++) {
-            const int64_t ibase = wbase + it * 64;
-            if (ibase >= q.n) {
-                if (lane == 0) s_cnt[warp][it] = 0;
-                continue;
-            }
+    for (int it = 0; it < JN_ITERS; it++) {
+        const int64_t ibase = wbase + it * 64;
+        uint32_t itot = 0;
+        if (ibase < q.n) {
             const Raw2 cur = next;
             if (it + 1 < JN_ITERS && ibase + 64 < q.n) next = load_raw(q, vec, ibase + 64);
             Rows2<X> R;
@@ -517,31 +384,74 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
             QPlan p[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
-            finish_iter(R, p, it);
+            const uint32_t mine = pairs_of(p);
+            const uint32_t inc = warp_incl_sum(mine);
+            itot = __shfl_sync(FULL, inc, 31);
+            if (open && staged + itot <= (uint32_t)JN_WCAP) {
+                if (itot) stage_rows(R, p, staged + inc - mine, (uint32_t)(it * 64 + 2 * lane));
+                staged += itot;
+                staged_iters = it + 1;
+            } else {
+                open = false;
+            }
         }
-    } else if (lane == 0) {
-        for (int it = 1; it < JN_ITERS; it++) s_cnt[warp][it] = 0;
+        if (lane == 0) s_cnt[warp][it] = itot;
+        total += itot;
     }
     __syncwarp();
     unsigned long long o;
     if (variant == 1) {  // EXPERIMENT: unordered output regions from an atomic cursor (no waiting)
         if (lane == 0) o = atomicAdd(reinterpret_cast<unsigned long long*>(out_total), total);
         o = __shfl_sync(FULL, o, 0);
-    }
-    if (variant != 1) post_aggregate(state, wtile, total);
-    const int64_t ntile = take();
-    if (JN_AHEAD && ntile < n_wtiles) count_first(ntile);
-    if (variant != 1) {
-        o = resolve(state, wtile, total);
+    } else {
+        o = lookback(state, wtile, total);
         if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);
     }
     copy_out(staged, o, wbase);
     o += staged;
-    if (staged_iters < JN_ITERS)  // iterations that did not fit (rare): once more, now that the offset is known
-        late_iterations<X, SLACK, ANY>(ix, q, vec, wbase, staged_iters, s_cnt[warp], o, st_s, st_q, out_q, out_s, s_label, cap);
-    __syncwarp();  // the staging area is reused by the warp's next tile
-    wtile = ntile;
-  }
+    // iterations that did not fit: once more, through the staging area (or straight to memory when a single iteration
+    // exceeds it)
+    for (int it = staged_iters; it < JN_ITERS; it++) {
+        const uint32_t itot = s_cnt[warp][it];
+        if (itot == 0) continue;
+        const int64_t ibase = wbase + it * 64;
+        __syncwarp();
+        Geo<X> G2(q, ibase);
+        Rows2<X> R;
+        flatten_rows<X, SLACK>(ix, q, ibase, load_raw(q, vec, ibase), G2, R);
+        QPlan p[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) p[k] = plan_query<X>(ix, R.sc[k], R.ec[k], R.r[k], R.live[k]);
+        const uint32_t mine = pairs_of(p);
+        const uint32_t inc = warp_incl_sum(mine);
+        if (itot <= (uint32_t)JN_WCAP) {
+            stage_rows(R, p, inc - mine, (uint32_t)(2 * lane));
+            __syncwarp();
+            copy_out(itot, o, ibase);
+        } else {
+            unsigned long long oo = o + inc - mine;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int64_t row_q = ibase + 2 * lane + k;
+                const int64_t ql = (q.label && row_q < q.n) ? __ldg(q.label + row_q) : row_q;
+                if (ANY) {
+                    if (p[k].count()) {
+                        if ((int64_t)oo < cap && out_q) out_q[oo] = ql;
+                        oo++;
+                    }
+                    continue;
+                }
+                emit_query<X>(ix, R.sc[k], R.ec[k], R.r[k], p[k], [&](uint32_t row) {
+                    if ((int64_t)oo < cap) {
+                        if (out_q) out_q[oo] = ql;
+                        if (out_s) out_s[oo] = s_label ? __ldg(s_label + row) : (int64_t)row;
+                    }
+                    oo++;
+                });
+            }
+        }
+        o += itot;
+    }
 }
 
 // pairs per query segment of a pair list in query order (ascending query rows): lower bounds of the segment boundaries
@@ -603,29 +513,22 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     IV_CUDA(cudaMemsetAsync(ws, 0, (size_t)(n_tiles + 1) * sizeof(unsigned long long), st));
     const bool vec = aligned16(q->start) && aligned16(q->end);
     const bool slack = q->slack != 0;
-    const int64_t nb = cdiv(q->n, JN_TILE);
+    const unsigned nb = (unsigned)cdiv(q->n, JN_TILE);
     static const int variant = getenv("IV_JOIN_VARIANT") ? atoi(getenv("IV_JOIN_VARIANT")) : 0;  // measurements only
-    static const int occ = getenv("IV_JOIN_OCC") ? atoi(getenv("IV_JOIN_OCC")) : 4;             // measurements only
     if (variant == 1) IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
-#define IV_JK(X, SL, AN, OC)                                                                                            \
+#define IV_JK(X, SL, AN)                                                                                                \
     do {                                                                                                               \
         static bool attr_done[64] = {false};                                                                           \
         int dev = 0;                                                                                                   \
         IV_CUDA(cudaGetDevice(&dev));                                                                                  \
-        static int resident[64] = {0};                                                                                 \
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                                 \
-            IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, AN, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
-            int sms = 0, per_sm = 0;                                                                                   \
-            IV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev));                   \
-            IV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_join<X, SL, AN, OC>, JN_THREADS, JN_SMEM));    \
-            if (dev >= 0 && dev < 64) { attr_done[dev] = true; resident[dev] = sms * per_sm; }                         \
+            IV_CUDA(cudaFuncSetAttribute(k_join<X, SL, AN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JN_SMEM)); \
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;                                                           \
         }                                                                                                              \
-        const int64_t fit = (dev >= 0 && dev < 64 && resident[dev] > 0) ? resident[dev] : 148;                         \
-        const unsigned grid = (unsigned)(nb < fit ? nb : fit);                                                         \
-        k_join<X, SL, AN, OC><<<grid, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state, \
-                                                            ticket, n_tiles, out_total, variant);                      \
+        k_join<X, SL, AN><<<nb, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state,  \
+                                                          ticket, n_tiles, out_total, variant);                        \
     } while (0)
-#define IV_JK2(X, SL) do { if (any) IV_JK(X, SL, true, 4); else if (occ == 3) IV_JK(X, SL, false, 3); else IV_JK(X, SL, false, 4); } while (0)
+#define IV_JK2(X, SL) do { if (any) IV_JK(X, SL, true); else IV_JK(X, SL, false); } while (0)
     const bool any = mode == IV_MODE_ANY;
     if (narrow_span(lists)) {
         if (slack) IV_JK2(uint32_t, true); else IV_JK2(uint32_t, false);
