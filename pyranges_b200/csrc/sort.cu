@@ -528,9 +528,12 @@ static bool bucket_path(int64_t n, int nbits) {
 // bits below the highest bit that differs inside the bucket (atomics, unordered inside a bin) followed by a
 // rank-by-counting inside every bin (bins hold ~1 key) IS the stable order.  42-bit keys of 50 M rows: 3 passes over
 // global memory instead of 6 x (histogram + scatter).  A tile never waits for a tile that is not running (tickets).
-constexpr int HY_CAP = 4096;       // keys a bucket block sorts in shared memory
-constexpr int HY_POS_BITS = 12;    // log2(HY_CAP)
-constexpr int HY_DIG_BITS = 12;    // counting digit of the bucket pass
+#ifndef HY_CAP_LOG
+#define HY_CAP_LOG 12
+#endif
+constexpr int HY_CAP = 1 << HY_CAP_LOG;   // keys a bucket block sorts in shared memory
+constexpr int HY_POS_BITS = HY_CAP_LOG;
+constexpr int HY_DIG_BITS = HY_CAP_LOG;   // counting digit of the bucket pass
 constexpr int HY_BINS = 1 << HY_DIG_BITS;
 constexpr int HY_THREADS = 256;
 constexpr int HY_ITEMS = HY_CAP / HY_THREADS;
@@ -555,7 +558,7 @@ static HyPlan hy_plan(int64_t n, int begin_bit, int end_bit) {
     const int nbits = end_bit - begin_bit;
     if (n <= BK_MAX_N || n > HY_MAX_N || nbits <= 0) return p;
     int T = 1;
-    while (T < HY_MAX_T && ((int64_t)1024 << T) < n) T++;
+    while (T < HY_MAX_T && ((int64_t)(HY_CAP / 4) << T) < n) T++;  // <= CAP / 4 keys per bucket if all were used
     if (T >= nbits) T = nbits;
     else if (nbits - T > 64 - HY_POS_BITS) T = nbits - (64 - HY_POS_BITS);
     p.use = true;
@@ -843,9 +846,9 @@ __device__ __noinline__ void hy_pileup(unsigned char* hy_smem, unsigned long lon
 }
 
 template <int VB>
-__global__ void __launch_bounds__(HY_THREADS, 4)
+__global__ void __launch_bounds__(HY_THREADS, HY_CAP_LOG >= 12 ? 4 : 6)
 k_hy_buckets(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit, int low_bits,
-             const uint32_t* __restrict__ starts) {
+             const uint32_t* __restrict__ starts, uint32_t* __restrict__ pile_count, uint32_t* __restrict__ pile_list) {
     extern __shared__ __align__(16) unsigned char hy_smem[];
     uint64_t* c2 = reinterpret_cast<uint64_t*>(hy_smem);                    // [HY_CAP] composites grouped by bin
     uint32_t* cur = reinterpret_cast<uint32_t*>(c2 + HY_CAP);               // [HY_BINS] counts -> cursors -> bin ends
@@ -862,9 +865,8 @@ k_hy_buckets(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit
         }
         return;
     }
-    if (m > (uint32_t)HY_CAP) {
-        __shared__ uint32_t base[RS_RADIX];
-        hy_pileup<VB>(hy_smem, s_diff, base, wsum, kin, kout, vin, vout, begin_bit, low_bits, b0, m);
+    if (m > (uint32_t)HY_CAP) {  // a pile-up: left to k_hy_pileups
+        if (tid == 0) pile_list[atomicAdd(pile_count, 1u)] = blockIdx.x;
         return;
     }
     const uint64_t low_mask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
@@ -950,10 +952,28 @@ k_hy_buckets(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit
     }
 }
 constexpr size_t HY_SMEM = (size_t)HY_CAP * 8 + (size_t)HY_BINS * 4;  // 48 KB
-static_assert(sizeof(SwSmem) <= HY_SMEM, "the pile-up path reuses the bucket pass's shared memory");
+
+// the buckets beyond HY_CAP keys, one block each (a persistent grid over the list the bucket pass left)
+template <int VB>
+__global__ void __launch_bounds__(HY_THREADS)
+k_hy_pileups(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit, int low_bits,
+             const uint32_t* __restrict__ starts, const uint32_t* __restrict__ pile_count,
+             const uint32_t* __restrict__ pile_list) {
+    __shared__ __align__(16) unsigned char smem[sizeof(SwSmem)];
+    __shared__ unsigned long long s_diff;
+    __shared__ uint32_t wsum[HY_THREADS / 32 + 1];
+    __shared__ uint32_t base[RS_RADIX];
+    const uint32_t np = *pile_count;
+    for (uint32_t i = blockIdx.x; i < np; i += gridDim.x) {
+        const uint32_t b = pile_list[i];
+        const uint32_t b0 = __ldg(starts + b), m = __ldg(starts + b + 1) - b0;
+        __syncthreads();
+        hy_pileup<VB>(smem, s_diff, base, wsum, kin, kout, vin, vout, begin_bit, low_bits, b0, m);
+    }
+}
 
 struct HyTemp {
-    uint32_t *ghist, *ticket, *status, *starts;
+    uint32_t *ghist, *ticket, *status, *starts, *pile_list;  // ticket[8] = number of pile-up buckets
     size_t zero_bytes;  // ghist + ticket + status: cleared before every sort
 };
 static void hy_temp(int64_t n, Bump& b, HyTemp& t) {
@@ -963,8 +983,9 @@ static void hy_temp(int64_t n, Bump& b, HyTemp& t) {
     t.status = b.take<uint32_t>(3 * ntiles * RS_RADIX);
     t.zero_bytes = b.off;
     size_t nb = 2;
-    while (nb < ((size_t)1 << HY_MAX_T) && nb * 1024 < (size_t)(n > 0 ? n : 1)) nb <<= 1;
+    while (nb < ((size_t)1 << HY_MAX_T) && nb * (HY_CAP / 4) < (size_t)(n > 0 ? n : 1)) nb <<= 1;
     t.starts = b.take<uint32_t>(nb + 64);
+    t.pile_list = b.take<uint32_t>(nb + 64);
 }
 
 template <int VB>
@@ -998,7 +1019,10 @@ static int hy_launch(const HyPlan& pl, uint64_t* k[2], void* v[2], int64_t n, in
         k_hy_starts<<<nb / 256 + 1, 256, 0, stream>>>(k[cur], n, end_bit - pl.T, nb - 1u, nb, t.starts);
         IV_LAUNCH_CHECK();
         k_hy_buckets<VB><<<nb, HY_THREADS, HY_SMEM, stream>>>(k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], begin_bit,
-                                                              pl.low_bits, t.starts);
+                                                              pl.low_bits, t.starts, t.ticket + 8, t.pile_list);
+        IV_LAUNCH_CHECK();
+        k_hy_pileups<VB><<<148 * 2, HY_THREADS, 0, stream>>>(k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], begin_bit, pl.low_bits,
+                                                             t.starts, t.ticket + 8, t.pile_list);
         IV_LAUNCH_CHECK();
         cur ^= 1;
     }
