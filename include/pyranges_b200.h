@@ -23,6 +23,8 @@
  *   iv_nearest                <- first_overlap_both + nearest_previous_nonoverlapping +
  *                                nearest_next_nonoverlapping + nearest_nonoverlapping
  *                                                                        pyranges/methods/nearest.py:29-53,59,69,113
+ *   iv_k_nearest_count/_emit  <- k_nearest_previous_nonoverlapping + k_nearest_next_nonoverlapping
+ *                                                                        pyranges/methods/k_nearest.py:6-48
  *   iv_cluster                <- sort_values("Start") + annotate_clusters pyranges/methods/cluster.py:11-15,
  *                                + global id offsets                      pyranges/pyranges_main.py:1210-1223
  *   iv_merge_count/_emit      <- sort_values("Start") + find_clusters     pyranges/methods/merge.py:12-14
@@ -61,7 +63,7 @@
 extern "C" {
 #endif
 
-#define IV_ABI_VERSION 7
+#define IV_ABI_VERSION 8
 
 #define IV_OK 0
 #define IV_ERR_INVALID (-1)   /* bad argument */
@@ -73,7 +75,7 @@ extern "C" {
 #define IV_MODE_ALL 0     /* every overlapping (query, subject) pair            all_overlaps_both      */
 #define IV_MODE_ANY 1     /* one entry per query with >= 1 hit                   has_overlaps / first   */
 #define IV_MODE_CONTAIN 2 /* pairs with subject.start <= q.start && q.end <= subject.end             */
-#define IV_MODE_LAST 3    /* like ANY, the subject is the LAST hit of the nested-list traversal   last_overlap_both */
+#define IV_MODE_LAST 3    /* like ANY, the subject is the hit that ENDS LAST (ties: smallest start, row)  last_overlap_both */
 
 /* nearest direction per query segment (pyranges/methods/nearest.py:85-90) */
 #define IV_NEAREST_BOTH 0
@@ -232,6 +234,23 @@ int iv_subtract_emit(const iv_index_t* index, const iv_queries_t* q, const int64
 /* out_row[i] = subject row of the nearest interval or -1, out_dist[i] = 0 (overlap), gap+1, or -1 */
 int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_t overlap, int64_t* out_row,
                int64_t* out_dist, void* stream);
+
+/* k-nearest candidates (pyranges/methods/k_nearest.py:6-48): for every query the non-overlapping subjects before it
+ * (End <= query Start), nearest first, then those behind it (Start >= query End), nearest first; the direction(s) follow
+ * q->seg_mode like iv_nearest.  k[i] = how many to keep for query row i, per direction; ties: */
+#define IV_TIES_NONE 0      /* the k nearest subjects                                                       */
+#define IV_TIES_FIRST 1     /* one subject per distinct distance (the first met), k distinct distances      */
+#define IV_TIES_LAST 2      /* ... the last met                                                             */
+#define IV_TIES_DIFFERENT 3 /* every subject of the k nearest distinct distances                            */
+/* Subjects at equal distance are met in descending row order before the query, ascending row order behind it.  Phase 1
+ * leaves the exclusive entry offsets in out_offsets[nq] and the number of entries in *out_total (device); phase 2
+ * writes (query label, subject row, distance = gap + 1 >= 1) per entry, query order.  The index needs
+ * IV_INDEX_ENDS_PERM.  Overlapping subjects are not reported (the caller joins them in, pyranges_main.py:2737-2746). */
+size_t iv_k_nearest_workspace_bytes(int64_t n_queries);
+int iv_k_nearest_count(const iv_index_t* index, const iv_queries_t* q, const int64_t* k, int32_t ties,
+                       int64_t* out_offsets, void* ws, size_t ws_bytes, int64_t* out_total, void* stream);
+int iv_k_nearest_emit(const iv_index_t* index, const iv_queries_t* q, const int64_t* k, int32_t ties,
+                      const int64_t* offsets, int64_t* out_q, int64_t* out_s, int64_t* out_dist, void* stream);
 
 /* ---- list index + fused join: the join / count_overlaps / overlap fast path ------------------------------------ */
 /* Every coordinate bin (bin = flattened coordinate >> shift, shift <= 14) owns its TOUCH LIST: the subjects that

@@ -141,7 +141,14 @@ static void hit_contain(void *c, i64 pos) {
     if (x->t->start[pos] <= x->qs && x->qe <= x->t->end[pos]) { vpush(x->q, x->qid); vpush(x->s, x->t->id[pos]); }
 }
 static void hit_count(void *c, i64 pos) { qctx *x = (qctx *)c; (void)pos; x->cnt++; }
-static void hit_firstlast(void *c, i64 pos) { qctx *x = (qctx *)c; if (x->cnt++ == 0) x->first = pos; x->last = pos; }
+/* first: the first hit of the traversal.  last: the hit that ends last (the first such hit met) -- ncls keeps the hit with
+ * the largest end; pinned by the reference's tests/unit/k_nearest.py:163-211 (last overlap of [15,20) among [11,16) and
+ * [11,20) is [11,20)); "the last hit of the traversal" would give [11,16) there. */
+static void hit_firstlast(void *c, i64 pos) {
+    qctx *x = (qctx *)c;
+    if (x->cnt++ == 0) { x->first = pos; x->last = pos; }
+    else if (x->t->end[pos] > x->t->end[x->last]) x->last = pos;
+}
 static void hit_cov(void *c, i64 pos) {
     qctx *x = (qctx *)c;
     i64 lo = x->t->start[pos] > x->qs ? x->t->start[pos] : x->qs;

@@ -219,6 +219,46 @@ def known_answers():
     gr1 = pr.from_dict({"Chromosome": ["chr1", "chr1", "chr1"], "Start": [3, 8, 5], "End": [6, 9, 7]})
     gr2 = pr.from_dict({"Chromosome": ["chr1", "chr1"], "Start": [1, 6], "End": [2, 7]})
     assert gr1.join(gr2, how="left", preserve_order=True).df.Start.tolist() == [3, 8, 5]
+    # k_nearest doctests pyranges_main.py:2560-2700
+    kf1 = pr.from_dict({"Chromosome": ["chr1"] * 3, "Start": [3, 8, 5], "End": [6, 9, 7], "Strand": ["+", "+", "-"]})
+    kf2 = pr.from_dict({"Chromosome": ["chr1"] * 2, "Start": [1, 6], "End": [2, 7], "Strand": ["+", "-"]})
+    cols = ["Start", "End", "Start_b", "End_b", "Distance"]
+    assert kf1.k_nearest(kf2, k=2).df[cols].values.tolist() == [
+        [3, 6, 6, 7, 1], [3, 6, 1, 2, -2], [8, 9, 6, 7, -2], [8, 9, 1, 2, -7], [5, 7, 6, 7, 0], [5, 7, 1, 2, 4]]
+    assert kf1.k_nearest(kf2, how="upstream", k=2).df[cols].values.tolist() == [
+        [3, 6, 1, 2, -2], [8, 9, 6, 7, -2], [8, 9, 1, 2, -7], [5, 7, 6, 7, 0]]
+    assert kf1.k_nearest(kf2, k=[1, 2, 1]).df[cols].values.tolist() == [
+        [3, 6, 6, 7, 1], [8, 9, 6, 7, -2], [8, 9, 1, 2, -7], [5, 7, 6, 7, 0]]
+    kg = pr.from_dict({"Chromosome": [1], "Start": [5], "End": [6]})
+    kg2 = pr.from_dict({"Chromosome": 1, "Start": [1] * 2 + [5] * 2 + [9] * 2, "End": [3] * 2 + [7] * 2 + [11] * 2,
+                        "ID": range(6)})
+    idd = lambda r: r.df[["ID", "Distance"]].values.tolist()  # noqa: E731
+    assert idd(kg.k_nearest(kg2, k=2)) == [[2, 0], [3, 0]]
+    assert idd(kg.k_nearest(kg2, k=2, ties="different")) == [[2, 0], [3, 0], [1, -3], [0, -3]]
+    assert idd(kg.k_nearest(kg2, k=3, ties="first")) == [[2, 0], [1, -3], [4, 4]]
+    assert idd(kg.k_nearest(kg2, k=1, overlap=False)) == [[1, -3]]
+    # tests/unit/k_nearest.py:35-200 (the frames of the fixtures, column by column)
+    ug = pr.PyRanges(chromosomes="chr1", starts=[1, 15, 200], ends=[10, 20, 2000])
+    ug2 = pr.PyRanges(chromosomes="chr1", starts=[11, 11, 20, 20, 50], ends=[16, 20, 21, 22, 100])
+    assert ug.k_nearest(ug2, ties="different", k=[3, 2, 1]).df[cols].values.tolist() == [
+        [1, 10, 11, 16, 2], [1, 10, 11, 20, 2], [1, 10, 20, 21, 11], [1, 10, 20, 22, 11], [1, 10, 50, 100, 41],
+        [15, 20, 11, 20, 0], [15, 20, 11, 16, 0], [15, 20, 20, 21, 1], [15, 20, 20, 22, 1], [200, 2000, 50, 100, -101]]
+    # (rows of one interval follow an unstable sort_values("__IX__") when k varies over the rows: compared as a set)
+    assert sorted(ug2.k_nearest(ug, ties="different", k=[1, 2, 3, 4, 2]).df[cols].values.tolist()) == sorted([
+        [11, 16, 15, 20, 0], [11, 20, 15, 20, 0], [11, 20, 1, 10, -2], [20, 21, 15, 20, 1], [20, 21, 1, 10, -11],
+        [20, 21, 200, 2000, 180], [20, 22, 15, 20, 1], [20, 22, 1, 10, -11], [20, 22, 200, 2000, 179],
+        [50, 100, 15, 20, -31], [50, 100, 1, 10, -41]])
+    assert ug.k_nearest(ug2, ties="first", k=[3, 2, 1]).df[cols].values.tolist() == [
+        [1, 10, 11, 16, 2], [1, 10, 20, 21, 11], [1, 10, 50, 100, 41], [15, 20, 11, 20, 0], [15, 20, 20, 21, 1],
+        [200, 2000, 50, 100, -101]]
+    first2 = [[11, 16, 15, 20, 0], [11, 20, 15, 20, 0], [11, 20, 1, 10, -2], [20, 21, 15, 20, 1], [20, 21, 1, 10, -11],
+              [20, 21, 200, 2000, 180], [20, 22, 15, 20, 1], [20, 22, 1, 10, -11], [20, 22, 200, 2000, 179],
+              [50, 100, 15, 20, -31], [50, 100, 1, 10, -41], [50, 100, 200, 2000, 101]]
+    assert ug2.k_nearest(ug, ties="first", k=list(range(1, 6))).df[cols].values.tolist() == first2
+    assert ug.k_nearest(ug2, ties="last", k=[3, 2, 1]).df[cols].values.tolist() == [
+        [1, 10, 11, 20, 2], [1, 10, 20, 22, 11], [1, 10, 50, 100, 41], [15, 20, 11, 20, 0], [15, 20, 20, 22, 1],
+        [200, 2000, 50, 100, -101]]
+    assert ug2.k_nearest(ug, ties="last", k=list(range(1, 6))).df[cols].values.tolist() == first2
     print("known answers of the reference doctests/unit tests: all reproduced by reference+oracle")
 
 
@@ -232,7 +272,8 @@ def run_case(name, op, kwargs, sdf, odf=None, note=""):
     s = mk(sdf)
     o = mk(odf) if odf is not None else None
     kw = dict(kwargs)
-    if op in ("join", "overlap", "count_overlaps", "coverage", "nearest", "intersect", "set_intersect", "set_union", "subtract"):
+    if op in ("join", "overlap", "count_overlaps", "coverage", "nearest", "k_nearest", "intersect", "set_intersect", "set_union",
+              "subtract"):
         try:
             res = getattr(s, op)(o, **kw)
         except AssertionError as exc:
@@ -360,6 +401,29 @@ def main():
                     run_case("nearest_%s_%s_%s" % (how, tag, sn), "nearest", {"how": how, "strandedness": st}, s, o)
                 run_case("nearest_%s_nooverlap_%s" % (how, tag), "nearest",
                          {"how": how, "strandedness": "same", "overlap": False}, s, o)
+
+    # k_nearest (small sets: the oracle's k-nearest walks are plain Python)
+    Ks = ("Ks", synth(21, 400, chroms[:2], maxpos=4000, maxlen=120, nested=True))
+    Ko = ("Ko", synth(22, 250, chroms[:3], maxpos=4000, maxlen=120, nested=True))
+    Ksu = ("Ksu", synth(23, 300, chroms[:2], stranded=False, maxpos=4000, maxlen=120, nested=True))
+    Kou = ("Kou", synth(24, 200, chroms[:2], stranded=False, maxpos=4000, maxlen=120, nested=True))
+    for tag, (s, o) in {"f1f2": (f1, f2), "ksyn": (Ks, Ko), "ksyn_uu": (Ksu, Kou), "ksyn_us": (Ksu, Ko),
+                        "pile": (pileq, pile)}.items():
+        both_stranded = "Strand" in s[1].columns and "Strand" in o[1].columns
+        per_row = [int(i % 4) + 1 for i in range(len(s[1]))]
+        for ties in (None, "first", "last", "different"):
+            tn = ties or "none"
+            run_case("knear_k1_%s_%s" % (tn, tag), "k_nearest", {"k": 1, "ties": ties}, s, o)
+            run_case("knear_k3_%s_%s" % (tn, tag), "k_nearest", {"k": 3, "ties": ties}, s, o)
+            run_case("knear_rowk_%s_%s" % (tn, tag), "k_nearest", {"k": per_row, "ties": ties}, s, o)
+            run_case("knear_k2_nooverlap_%s_%s" % (tn, tag), "k_nearest", {"k": 2, "ties": ties, "overlap": False}, s, o)
+        if both_stranded:
+            for st in ("same", "opposite"):
+                run_case("knear_k2_%s_%s" % (st, tag), "k_nearest", {"k": 2, "strandedness": st}, s, o)
+            for how in ("upstream", "downstream"):
+                run_case("knear_k2_%s_%s" % (how, tag), "k_nearest", {"k": 2, "how": how, "ties": "different"}, s, o)
+                run_case("knear_k2_%s_same_%s" % (how, tag), "k_nearest",
+                         {"k": 2, "how": how, "strandedness": "same", "overlap": False}, s, o)
 
     unary_sets = {"f1": f1, "chipseq": cs, "synth": A, "synth_u": Au, "pile": pile}
     for tag, s in unary_sets.items():

@@ -230,3 +230,115 @@ def brute_pairs(S, E, sid, qs, qe, qid):
     a, b = _a64(qid)[qi], _a64(sid)[sj]
     o = np.lexsort([b, a])
     return a[o], b[o]
+
+
+# ---- k-nearest (sorted_nearest 0.0.39: k_nearest_*_nonoverlapping, get_all_ties, get_different_ties) ----------------
+# The package is not vendored in the reference and not installable here; these are restatements of its published
+# behaviour as the reference uses it (pyranges/methods/k_nearest.py:6-48, pyranges/pyranges_main.py:2726-2800), pinned by
+# the reference's doctests (pyranges_main.py:2560-2700) and unit tests (tests/unit/k_nearest.py) through
+# oracle/make_golden.py.  What those answers do not pin is said where it applies.  Plain Python loops: small cases only.
+def _k_walk(values, positions, k, ties):
+    """positions in walking order (nearest first), values = distance key at each; -> kept positions.
+    ties None: the k nearest; "first" / "last": one entry (the first / last met) per distinct value, k distinct values;
+    "different": every entry of the k nearest distinct values."""
+    out = []
+    if k <= 0:
+        return out
+    if ties is None or ties is False:
+        return list(positions[:k])
+    distinct, last_v, pend = 0, None, None
+    for p, v in zip(positions, values):
+        if last_v is None or v != last_v:
+            if ties == "last" and pend is not None:
+                out.append(pend)
+            if distinct == k:
+                pend = None
+                break
+            distinct += 1
+            last_v = v
+            if ties == "first":
+                out.append(p)
+        if ties == "different":
+            out.append(p)
+        pend = p
+    if ties == "last" and pend is not None:
+        out.append(pend)
+    return out
+
+
+def _k_of(k, labels, i):
+    """k of the i-th query of the sorted / filtered arrays: the reference passes d1.__k__.values (frame order) next to
+    arrays in sorted order (k_nearest.py:23,46); its per-key frames carry a range index, so the row label finds the
+    row's own k.  (Positional vs. label lookup is not pinned by the reference's tests -- both agree there; a too large k
+    here is harmless because pyranges_main.py:2745-2790 trims with the row's own k again.)"""
+    k = np.asarray(k)
+    if k.ndim == 0:
+        return int(k)
+    lab = int(labels[i])
+    return int(k[lab]) if 0 <= lab < len(k) else int(k[min(i, len(k) - 1)])
+
+
+def k_nearest_previous_nonoverlapping(l_s, r_e, l_idx, ix, k, ties=None):
+    """l_s: sorted query starts, r_e: sorted subject ends, ix[i]: position of the last end <= l_s[i].
+    -> (query labels, positions into r_e, l_s - r_e) walking leftwards from ix[i]."""
+    l_s, r_e, l_idx, ix = _a64(l_s), _a64(r_e), np.asarray(l_idx), _a64(ix)
+    lo, ro, do = [], [], []
+    for i in range(len(l_s)):
+        pos = list(range(int(ix[i]), -1, -1))
+        keep = _k_walk([int(r_e[p]) for p in pos], pos, _k_of(k, l_idx, i), ties)
+        for p in keep:
+            lo.append(l_idx[i])
+            ro.append(p)
+            do.append(int(l_s[i] - r_e[p]))
+    return np.asarray(lo, dtype=np.int64), np.asarray(ro, dtype=np.int64), np.asarray(do, dtype=np.int64)
+
+
+def k_nearest_next_nonoverlapping(l_e, r_s, l_idx, ix, k, ties=None):
+    """l_e: sorted query ends, r_s: sorted subject starts, ix[i]: position of the first start >= l_e[i].
+    -> (query labels, positions into r_s, r_s - l_e) walking rightwards from ix[i]."""
+    l_e, r_s, l_idx, ix = _a64(l_e), _a64(r_s), np.asarray(l_idx), _a64(ix)
+    lo, ro, do = [], [], []
+    for i in range(len(l_e)):
+        pos = list(range(int(ix[i]), len(r_s)))
+        keep = _k_walk([int(r_s[p]) for p in pos], pos, _k_of(k, l_idx, i), ties)
+        for p in keep:
+            lo.append(l_idx[i])
+            ro.append(p)
+            do.append(int(r_s[p] - l_e[i]))
+    return np.asarray(lo, dtype=np.int64), np.asarray(ro, dtype=np.int64), np.asarray(do, dtype=np.int64)
+
+
+def get_all_ties(index, ix, dist, k):
+    """rows (labels `index`, sorted by (ix, dist)) of every query ix up to its k-th row plus the rows tied with it."""
+    index, ix, dist = np.asarray(index), _a64(ix), _a64(dist)
+    out, i, n = [], 0, len(ix)
+    while i < n:
+        j = i
+        while j < n and ix[j] == ix[i]:
+            j += 1
+        m = j - i
+        if k > 0:
+            cut = dist[i + min(k, m) - 1]
+            out.extend(index[t] for t in range(i, j) if dist[t] <= cut)
+        i = j
+    return np.asarray(out, dtype=index.dtype if len(out) else np.int64)
+
+
+def get_different_ties(index, ix, dist, k):
+    """rows of every query ix whose distance is among its k smallest distinct distances."""
+    index, ix, dist = np.asarray(index), _a64(ix), _a64(dist)
+    out, i, n = [], 0, len(ix)
+    while i < n:
+        j = i
+        while j < n and ix[j] == ix[i]:
+            j += 1
+        distinct, last = 0, None
+        for t in range(i, j):
+            if last is None or dist[t] != last:
+                distinct += 1
+                last = dist[t]
+            if distinct > k:
+                break
+            out.append(index[t])
+        i = j
+    return np.asarray(out, dtype=index.dtype if len(out) else np.int64)

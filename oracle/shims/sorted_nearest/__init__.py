@@ -6,6 +6,10 @@ from oracle.oracle import (  # noqa: F401
     annotate_clusters,
     cluster_by,
     find_clusters,
+    get_all_ties,
+    get_different_ties,
+    k_nearest_next_nonoverlapping,
+    k_nearest_previous_nonoverlapping,
     merge_by,
     nearest_next_nonoverlapping,
     nearest_nonoverlapping,
@@ -21,8 +25,5 @@ def _out_of_scope(name):
     return f
 
 
-for _n in (
-    "k_nearest_next_nonoverlapping k_nearest_previous_nonoverlapping "
-    "max_disjoint maketiles makewindows get_all_ties get_different_ties"
-).split():
+for _n in "max_disjoint maketiles makewindows".split():
     globals()[_n] = _out_of_scope(_n)

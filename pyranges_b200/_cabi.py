@@ -14,7 +14,7 @@ IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
 IV_INDEX_GRAPH = 2
-IV_ABI_VERSION = 7
+IV_ABI_VERSION = 8
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
 
@@ -70,6 +70,9 @@ PROTOTYPES = {
     "iv_subtract_count": (C.c_int, [_PI, _PQ, _vp, _vp, _sz, _vp, _vp]),
     "iv_subtract_emit": (C.c_int, [_PI, _PQ, _vp, _vp, _vp, _vp, _vp]),
     "iv_nearest": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _vp]),
+    "iv_k_nearest_workspace_bytes": (_sz, [_i64]),
+    "iv_k_nearest_count": (C.c_int, [_PI, _PQ, _vp, _i32, _vp, _vp, _sz, _vp, _vp]),
+    "iv_k_nearest_emit": (C.c_int, [_PI, _PQ, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "iv_cluster_workspace_bytes": (_sz, [_i64]),
     "iv_cluster": (C.c_int, [_vp, _vp, _i64, _PG, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "iv_merge_count": (C.c_int, [_vp, _vp, _i64, _PG, _i64, _i32, _vp, _vp, _sz, _vp]),

@@ -238,55 +238,23 @@ __device__ __forceinline__ uint32_t first_hit_rec(const iv_index_t& ix, X sc, X 
     return __ldg(ix.row_s + best);
 }
 
-// The LAST hit of the same traversal order: largest start, then smallest end, then largest row -- the mirror image:
-// starts inside the query come last, then the bin's earlier starts, then the stabbing list.
+// NCLS.last_overlap_both: the hit that ENDS LAST (ties: smallest start, then smallest row).  ncls keeps the hit with the
+// largest end while it walks the nested lists; the reference's own known answer pins it (tests/unit/k_nearest.py:163-211:
+// the "last" overlap of [15, 20) among [11, 16) and [11, 20) is [11, 20)).  Every hit is visited: `last` is not a hot mode.
 template <typename X>
 __device__ __forceinline__ uint32_t last_hit_rec(const iv_index_t& ix, X sc, X ec, const Rec& r) {
-    const uint64_t b = sc >> ix.shift;
-    const uint32_t rel = rel_of(ix, sc);
-    const uint32_t pS = rec_rank_s(ix, r, b, rel);
-    const uint32_t pE = (ec >> ix.shift) == b ? rec_rank_s(ix, r, b, rel_of(ix, ec)) : rank_s_lt<X>(ix, ec);
-    uint32_t hi = 0xffffffffu, lo = 0;  // the winner is position hi; candidates of its class reach down to lo
-    if (pE > pS) {  // class A: every position is a hit
-        hi = pE - 1;
-        lo = pS;
-    } else {
-        uint32_t pL = r.w[0];
-        if (pS - pL > 8 && ix.groups.max_len > 0 && (int64_t)rel >= ix.groups.max_len)
-            pL = rank_in(ix.soff, pL, pS, (uint32_t)((int64_t)rel - ix.groups.max_len + 1));
-        for (uint32_t p = pS; p > pL; p--)  // class B, started in this bin: the latest start still open
-            if (__ldg(ix.seoff + p - 1) > rel) { hi = p - 1; lo = pL; break; }
-        if (hi == 0xffffffffu) {  // class B, open at the bin origin: the latest start of the stabbing list
-            const uint32_t nc = (r.w[3] >> 16) & 0xffu;
-            const uint32_t c0 = r.w[2], c1 = nc < 255 ? c0 + nc : __ldg(&ix.bins[b + 1].co);
-            uint32_t best = 0;
-            bool any = false;
-            for (uint32_t j = c0; j < c1; j++) {
-                const uint2 en = __ldg(reinterpret_cast<const uint2*>(ix.cross) + j);
-                if (en.y > rel) {
-                    const uint32_t p = __ldg(ix.cross_p + j);
-                    best = (!any || p > best) ? p : best;
-                    any = true;
-                }
-            }
-            hi = best;
-            lo = 0;
+    uint64_t be = 0, bs = 0;
+    uint32_t brow = 0xffffffffu;
+    for_each_hit_rec<X, true>(ix, sc, ec, r, [&](uint32_t p) {
+        const uint64_t e = __ldg(ix.end_s + p), st = __ldg(ix.key_s + p);
+        const uint32_t row = __ldg(ix.row_s + p);
+        if (brow == 0xffffffffu || e > be || (e == be && (st < bs || (st == bs && row < brow)))) {
+            be = e;
+            bs = st;
+            brow = row;
         }
-    }
-    // ties: the run of starts equal to key_s[hi] reaching down from hi; every member that is a hit competes on
-    // (smallest end, largest position)
-    uint32_t best = hi;
-    if (hi > lo) {
-        const uint64_t s0 = __ldg(ix.key_s + hi);
-        if (__ldg(ix.key_s + hi - 1) == s0) {
-            uint64_t be = __ldg(ix.end_s + hi);
-            for (uint32_t p = hi; p > lo && __ldg(ix.key_s + p - 1) == s0; p--) {
-                const uint64_t e = __ldg(ix.end_s + p - 1);
-                if (e > (uint64_t)sc && e < be) { be = e; best = p - 1; }
-            }
-        }
-    }
-    return __ldg(ix.row_s + best);
+    });
+    return brow;
 }
 
 __device__ __forceinline__ void load_items(const int64_t* __restrict__ p, int64_t i0, int64_t n, bool vec, int64_t (&v)[OV_ITEMS]) {
@@ -409,7 +377,7 @@ k_tile_sums(const int64_t* __restrict__ gran_sums, int64_t n, int64_t ntiles, in
 // bin with more than four starts / ends) go to a per-warp queue in shared memory and are counted 32 at a time by
 // the full warp, so the long path never runs with one or two active lanes.
 constexpr int LN_THREADS = 256;
-constexpr int LN_TILES = 4;                        // consecutive 1024-row tiles per block
+constexpr int LN_TILES = 4;                        // consecutive 1024-row tiles per block (ws_grans() rounds to it)
 constexpr int LN_QCAP = 64;                        // slow queue entries per warp
 
 __device__ __forceinline__ bool rec_fast(const Rec& r) {
@@ -807,6 +775,92 @@ k_nearest(iv_index_t ix, iv_queries_t q, int overlap, int64_t* __restrict__ out_
     out_dist[i] = dist;
 }
 
+// ---- k-nearest ------------------------------------------------------------------------------------------------------
+// sorted_nearest.k_nearest_previous_nonoverlapping / k_nearest_next_nonoverlapping as pyranges calls them
+// (pyranges/methods/k_nearest.py:6-48): for every query the subjects that end at or before its Start, walked from the
+// nearest one leftwards through the end order, then those that start at or after its End, walked rightwards through the
+// start order.  ties: 0 = the k nearest of each direction, 1 / 2 = one subject (the first / last met) per distinct
+// distance, k distinct distances, 3 = every subject of the k nearest distinct distances.  Equal ends / starts are met
+// in descending / ascending row order (both orders are stable sorts of the rows).  EMIT = false counts the entries of
+// a query (previous + next), EMIT = true writes (query label, subject row, distance = gap + 1) at offsets[i]: previous
+// entries first, nearest first in both directions.
+template <bool EMIT, typename V, typename E>
+__device__ __forceinline__ int64_t knear_walk(int64_t p, const int64_t end, const int step, int64_t k, int ties, V value,
+                                              E emit) {
+    int64_t n = 0;
+    if (k <= 0) return 0;
+    if (ties == 0) {
+        for (; p != end && n < k; p += step, n++)
+            if (EMIT) emit(p);
+        return n;
+    }
+    int64_t distinct = 0, pend = -1;
+    uint64_t last = 0;
+    bool have = false;
+    for (; p != end; p += step) {
+        const uint64_t v = value(p);
+        if (!have || v != last) {
+            if (ties == 2 && pend >= 0) { if (EMIT) emit(pend); n++; }
+            if (distinct == k) { pend = -1; break; }
+            distinct++;
+            last = v;
+            have = true;
+            if (ties == 1) { if (EMIT) emit(p); n++; }
+        }
+        if (ties == 3) { if (EMIT) emit(p); n++; }
+        pend = p;
+    }
+    if (ties == 2 && pend >= 0) { if (EMIT) emit(pend); n++; }
+    return n;
+}
+
+template <typename X, bool EMIT>
+__global__ void __launch_bounds__(OV_THREADS, 4)
+k_knear(iv_index_t ix, iv_queries_t q, const int64_t* __restrict__ kq, int ties, int64_t* __restrict__ counts,
+        const int64_t* __restrict__ offsets, int64_t* __restrict__ out_q, int64_t* __restrict__ out_s,
+        int64_t* __restrict__ out_d) {
+    __shared__ int span[2];
+    const int64_t tbase = (int64_t)blockIdx.x * OV_THREADS;
+    const int64_t last = tbase + OV_THREADS - 1 < q.n - 1 ? tbase + OV_THREADS - 1 : q.n - 1;
+    const FlatCache<X> fc(ix, q, block_seg_span(q.seg_off, q.n_seg, tbase, last, span));
+    const int64_t i = tbase + threadIdx.x;
+    if (i >= q.n) return;
+    int seg;
+    const Flat<X> f = fc.of(ix, q, i, &seg);
+    const int64_t s = __ldg(q.start + i), e = __ldg(q.end + i);
+    const int64_t k = __ldg(kq + i);
+    int64_t n = 0, o = EMIT ? __ldg(offsets + i) : 0;
+    const int64_t ql = (EMIT && q.label) ? __ldg(q.label + i) : i;
+    if (f.g >= 0 && k > 0) {
+        const int mode = q.seg_mode ? __ldg(q.seg_mode + seg) : IV_NEAREST_BOTH;
+        const X sc = f.at(s), ec = f.at(e);
+        const int64_t g_first = __ldg(ix.groups.row_off + f.g), g_end = __ldg(ix.groups.row_off + f.g + 1);
+        if (mode != IV_NEAREST_NEXT && s >= f.lo) {
+            const int64_t r = rank_e_lt<X>(ix, (X)(sc + 1));  // subject ends <= s
+            n += knear_walk<EMIT>(r - 1, g_first - 1, -1, k, ties,
+                                  [&](int64_t p) { return (uint64_t)__ldg(ix.key_e + p); },
+                                  [&](int64_t p) {
+                                      out_q[o] = ql;
+                                      out_s[o] = __ldg(ix.row_e + p);
+                                      out_d[o] = s - f.raw(__ldg(ix.key_e + p)) + 1;
+                                      o++;
+                                  });
+        }
+        if (mode != IV_NEAREST_PREVIOUS && !(e > f.lo && (uint64_t)(e - f.lo) > f.width)) {
+            const int64_t j = rank_s_lt<X>(ix, ec);  // subject starts < e
+            n += knear_walk<EMIT>(j > g_first ? j : g_first, g_end, 1, k, ties,
+                                  [&](int64_t p) { return (uint64_t)__ldg(ix.key_s + p); },
+                                  [&](int64_t p) {
+                                      out_q[o] = ql;
+                                      out_s[o] = __ldg(ix.row_s + p);
+                                      out_d[o] = f.raw(__ldg(ix.key_s + p)) - e + 1;
+                                      o++;
+                                  });
+        }
+    }
+    if (!EMIT) counts[i] = n;
+}
+
 // ---- subtract -------------------------------------------------------------------------------------------------------
 // NCLS.set_difference_helper (pyranges/methods/subtraction.py:63-65): the parts of every query not covered by the
 // subjects.  The subjects are the MERGED other intervals (pyranges/pyranges_main.py:4868), i.e. disjoint: the hits
@@ -903,7 +957,10 @@ static int check_query(const iv_index_t* ix, const iv_queries_t* q, const char* 
 //   [hits per granule, uint32 (n/64 + 2)] [scan scratch]
 //   [hit list: one 16-byte (32-bit index) or 32-byte (64-bit index) slot per query row]
 static size_t ws_tiles(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_TILE) + 2; }
-static size_t ws_grans(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, OV_GRAN) + 2; }
+// granules of the queries rounded up to a whole block of the lean count kernel (4 x 1024 rows): its ragged last block
+// writes the granule slots of every started half-tile
+static_assert(LN_TILES == 4, "ws_grans() sizes the granule arrays for blocks of LN_TILES tiles");
+static size_t ws_grans(int64_t n) { return (size_t)cdiv(n > 0 ? n : 1, 4 * OV_TILE) * (4 * OV_TILE / OV_GRAN) + 2; }
 struct OverlapWs {
     int64_t* tile_sums;
     int64_t* gran_sums;
@@ -1120,6 +1177,44 @@ extern "C" int iv_nearest(const iv_index_t* index, const iv_queries_t* q, int32_
     unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
     if (narrow(index)) k_nearest<uint32_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, overlap, out_row, out_dist);
     else k_nearest<uint64_t><<<nb, OV_THREADS, 0, st>>>(*index, *q, overlap, out_row, out_dist);
+    IV_LAUNCH_CHECK();
+    return IV_OK;
+}
+
+extern "C" size_t iv_k_nearest_workspace_bytes(int64_t n_queries) { return iv_subtract_workspace_bytes(n_queries); }
+
+extern "C" int iv_k_nearest_count(const iv_index_t* index, const iv_queries_t* q, const int64_t* k, int32_t ties,
+                                  int64_t* out_offsets, void* ws, size_t ws_bytes, int64_t* out_total, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_query(index, q, "iv_k_nearest_count");
+    if (rc != IV_OK) return rc;
+    IV_REQUIRE(ties >= 0 && ties <= 3, IV_ERR_INVALID, "iv_k_nearest_count: ties must be 0 .. 3");
+    IV_REQUIRE(out_total && ws && ws_bytes >= iv_k_nearest_workspace_bytes(q->n), IV_ERR_WORKSPACE, "iv_k_nearest_count: workspace");
+    if (q->n == 0) {
+        IV_CUDA(cudaMemsetAsync(out_total, 0, 8, st));
+        return IV_OK;
+    }
+    IV_REQUIRE(out_offsets && k, IV_ERR_INVALID, "iv_k_nearest_count: null argument");
+    IV_REQUIRE(index->n == 0 || index->row_e, IV_ERR_INVALID, "iv_k_nearest_count: index built without IV_INDEX_ENDS_PERM");
+    unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
+    if (narrow(index)) k_knear<uint32_t, false><<<nb, OV_THREADS, 0, st>>>(*index, *q, k, ties, out_offsets, nullptr, nullptr, nullptr, nullptr);
+    else k_knear<uint64_t, false><<<nb, OV_THREADS, 0, st>>>(*index, *q, k, ties, out_offsets, nullptr, nullptr, nullptr, nullptr);
+    IV_LAUNCH_CHECK();
+    return scan_exclusive_i64_large(out_offsets, q->n, (int64_t*)ws, out_total, st);
+}
+
+extern "C" int iv_k_nearest_emit(const iv_index_t* index, const iv_queries_t* q, const int64_t* k, int32_t ties,
+                                 const int64_t* offsets, int64_t* out_q, int64_t* out_s, int64_t* out_dist, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_query(index, q, "iv_k_nearest_emit");
+    if (rc != IV_OK) return rc;
+    if (q->n == 0) return IV_OK;
+    IV_REQUIRE(ties >= 0 && ties <= 3, IV_ERR_INVALID, "iv_k_nearest_emit: ties must be 0 .. 3");
+    IV_REQUIRE(k && offsets && out_q && out_s && out_dist, IV_ERR_INVALID, "iv_k_nearest_emit: null argument");
+    IV_REQUIRE(index->n == 0 || index->row_e, IV_ERR_INVALID, "iv_k_nearest_emit: index built without IV_INDEX_ENDS_PERM");
+    unsigned nb = (unsigned)cdiv(q->n, OV_THREADS);
+    if (narrow(index)) k_knear<uint32_t, true><<<nb, OV_THREADS, 0, st>>>(*index, *q, k, ties, nullptr, offsets, out_q, out_s, out_dist);
+    else k_knear<uint64_t, true><<<nb, OV_THREADS, 0, st>>>(*index, *q, k, ties, nullptr, offsets, out_q, out_s, out_dist);
     IV_LAUNCH_CHECK();
     return IV_OK;
 }

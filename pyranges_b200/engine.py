@@ -372,6 +372,35 @@ class SubjectIndex:
                                          _stream()), "iv_nearest")
         return row, dist
 
+    def k_nearest(self, q, k, ties=None):
+        """k_nearest_previous_nonoverlapping + k_nearest_next_nonoverlapping (pyranges/methods/k_nearest.py:6-48) for
+        all keys: k = int64 device tensor, one entry per query row; ties in (None, "first", "last", "different").
+        -> (query row, subject row, distance >= 1) per candidate, query order, previous candidates before next ones."""
+        assert self.flags & IV_INDEX_ENDS_PERM, "build the index with ends_perm=True for k_nearest"
+        L = cabi.lib()
+        dev = self.iv.device
+        code = {None: 0, False: 0, "first": 1, "last": 2, "different": 3}[ties]
+        assert k.dtype == torch.int64 and k.numel() == q.iv.n and k.is_cuda
+        k = k.contiguous()
+        off = torch.empty(max(q.iv.n, 1), dtype=torch.int64, device=dev)
+        ws = _bytes(L.iv_k_nearest_workspace_bytes(q.iv.n), dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        cabi.check(L.iv_k_nearest_count(C.byref(self.c), C.byref(q.c), _ptr(k), code, _ptr(off), _ptr(ws), ws.numel(),
+                                        _ptr(total), _stream()), "iv_k_nearest_count")
+        m = int(total.item())
+        oq = torch.empty(m, dtype=torch.int64, device=dev)
+        os_ = torch.empty(m, dtype=torch.int64, device=dev)
+        od = torch.empty(m, dtype=torch.int64, device=dev)
+        if m:
+            cabi.check(L.iv_k_nearest_emit(C.byref(self.c), C.byref(q.c), _ptr(k), code, _ptr(off), _ptr(oq), _ptr(os_),
+                                           _ptr(od), _stream()), "iv_k_nearest_emit")
+        return oq, os_, od
+
+
+def to_device_i64(a, device):
+    """int64 host array -> device tensor (per-row parameters of an operation, e.g. the k of k_nearest)."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(_use(device))
+
 
 # ---- unary operations -------------------------------------------------------------------------------
 def _cluster_groups(iv, seg_ranges, slack):

@@ -608,7 +608,46 @@ def _b_nearest(plan, kwargs):
     return results
 
 
+def _b_k_nearest(plan, kwargs):
+    """The per-key candidate frames of k_nearest (pyranges/methods/k_nearest.py:51-168) for all keys: rows of self
+    (they carry the `__k__` column PyRanges.k_nearest adds) next to their non-overlapping neighbours in other, previous
+    ones before next ones at equal distance, sorted by (self row, Distance); Distance = gap + 1, still unsigned."""
+    how, suffix, ties = kwargs.get("how"), kwargs.get("suffix", "_b"), kwargs.get("ties")
+    stranded = kwargs.get("stranded", False)
+    modes = []
+    for k, key in enumerate(plan.q.keys):
+        h = None
+        if how in ("upstream", "downstream"):
+            if stranded:
+                strand = key[1] if isinstance(key, tuple) else plan.q.dfs[k].Strand.iloc[0]
+                h = ({"+": "previous", "-": "next"} if how == "upstream" else {"+": "next", "-": "previous"})[strand]
+            else:
+                h = "previous" if how == "upstream" else "next"
+        modes.append({"previous": E.IV_NEAREST_PREVIOUS, "next": E.IV_NEAREST_NEXT}.get(h, E.IV_NEAREST_BOTH))
+    if not plan.q.iv.n:
+        return [None] * len(plan.q.dfs)
+    ks = np.concatenate([np.asarray(df["__k__"].values, dtype=np.int64) for df in plan.q.dfs])
+    kdev = E.to_device_i64(ks, getattr(plan.q.iv, "device", None))
+    q, r, d = plan.index(ends_perm=True).k_nearest(plan.queries(seg_mode=np.asarray(modes, np.int32)), kdev, ties)
+    q, r, d = q.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+    cut = np.searchsorted(q, np.asarray(plan.q.seg_off))  # candidates come in query order
+    results = []
+    for k, scdf in enumerate(plan.q.dfs):
+        ocdf = plan.partner(k)
+        a, b = cut[k], cut[k + 1]
+        if scdf.empty or ocdf.empty or a == b:
+            results.append(None)
+            continue
+        lq = q[a:b] - plan.q.seg_off[k]
+        ls = r[a:b] - plan.group_row_off[plan.seg_group[k]]
+        dd = d[a:b]
+        o = np.lexsort((dd, lq))  # stable: previous before next at equal distance (k_nearest.py:79)
+        results.append(_assemble(scdf, ocdf, lq[o], ls[o], suffix, extra={"Distance": dd[o]}))
+    return results
+
+
 _BINARY = {
+    "_k_nearest": _b_k_nearest,
     "_write_both": _b_write_both,
     "_number_overlapping": _b_number_overlapping,
     "_overlap": _b_overlap,
@@ -627,6 +666,8 @@ def pyrange_apply(function, self, other, **kwargs):
     PyRanges-like objects exposing ``.dfs``.  ``nb_cpu`` is accepted and ignored: all keys run in one
     batched launch sequence on the current CUDA device."""
     name = _name(function)
+    if name == "_nearest" and getattr(function, "__module__", "").endswith("k_nearest"):
+        name = "_k_nearest"  # pyranges.methods.k_nearest._nearest shares its name with pyranges.methods.nearest._nearest
     if name not in _BINARY:
         raise NotImplementedError(
             "pyranges_b200.pyrange_apply: %r is not on the B200 hot path (supported: %s); no CPU fallback"

@@ -128,7 +128,9 @@ class PyRanges:
                     ok = ok and ("Strand" in d) and key[1] in ("+", "-") and \
                         _all_equal(d["Chromosome"], str(key[0])) and _all_equal(d["Strand"], key[1])
                 else:
-                    ok = ok and _all_equal(d["Chromosome"], str(key))
+                    # a frame that carries a Strand column belongs under a (chromosome, strand) key: the reference
+                    # regroups such dicts (pyranges/methods/init.py:112-150), e.g. the result of unstranded.join(stranded)
+                    ok = ok and "Strand" not in d and _all_equal(d["Chromosome"], str(key))
             if not ok:
                 alldf = pd.concat(dfs.values()).reset_index(drop=True)
                 stranded = _check_strandedness(alldf)
@@ -424,6 +426,74 @@ class PyRanges:
                       file=sys.stderr)
             elif apply_strand_suffix:
                 gr.columns = gr.columns.str.replace("Strand", "Strand" + kwargs["suffix"])
+        return gr
+
+    def k_nearest(self, other, k=1, ties=None, strandedness=None, overlap=True, how=None, suffix="_b", nb_cpu=1,
+                  apply_strand_suffix=None):
+        """pyranges/pyranges_main.py:2480-2834.  k: int or one int per row; ties in (None, "first", "last",
+        "different").  Rows of one interval come out by increasing |Distance| (overlaps, then previous before next at
+        equal distance); the reference leaves that order to an unstable sort when k varies over the rows."""
+        kwargs = fill_kwargs({"strandedness": strandedness, "how": how, "overlap": overlap, "nb_cpu": nb_cpu, "k": k,
+                              "ties": ties, "suffix": suffix})
+        kwargs["stranded"] = self.stranded and other.stranded
+        if ties not in (None, False, "first", "last", "different"):
+            raise ValueError("ties must be None, 'first', 'last' or 'different'")
+        ties = ties or None
+        kwargs["ties"] = ties
+        if not len(self):
+            return PyRanges()
+        me = self.copy()
+        if isinstance(k, pd.Series):
+            k = k.values
+        me.__k__ = k if np.ndim(k) else int(k)   # how many to find, per row
+        me.__IX__ = np.arange(len(me))            # row identity across the overlap / neighbour frames
+        # (the validating constructor: frames of an unstranded self that picked up other's Strand column are regrouped by
+        # (chromosome, strand) as in the reference -- the k nearest are then chosen per strand of the neighbour)
+        near = PyRanges(pyrange_apply("_k_nearest", me, other, **kwargs))
+        if overlap:
+            hits = me.join(other, strandedness=strandedness, how={"first": "first", "last": "last"}.get(ties),
+                           suffix=suffix, nb_cpu=nb_cpu, apply_strand_suffix=apply_strand_suffix)
+            hits = PyRanges(hits.dfs)
+            if len(hits):
+                hits.Distance = 0
+            result = concat([hits, near])
+        else:
+            result = near
+        if not len(result):
+            return PyRanges()
+        out = {}
+        for key, df in result.items():
+            # by row, then distance; the stable sort keeps overlaps / previous / next in that order at equal distance
+            ix, dist, kk = df["__IX__"].values, df["Distance"].values.astype(np.int64), df["__k__"].values.astype(np.int64)
+            order = np.lexsort((dist, ix))
+            ix, dist, kk = ix[order], dist[order], kk[order]
+            first = np.r_[True, ix[1:] != ix[:-1]]
+            start = np.maximum.accumulate(np.where(first, np.arange(len(ix)), 0))
+            if ties == "different":   # every row of the k smallest distinct distances (get_different_ties)
+                new_d = first | np.r_[True, dist[1:] != dist[:-1]]
+                rank = np.cumsum(new_d)
+                keep = rank - rank[start] < kk
+            else:                     # the k first rows (get_all_ties + head(k); head(k) for first / last)
+                keep = np.arange(len(ix)) - start < kk
+            df = df.take(order[keep]).drop(["__IX__", "__k__"], axis=1)
+            if not len(df):
+                continue
+            # neighbours in front of the interval (behind it on the - strand) get a negative distance (:2802-2813)
+            strand = df.Strand.iloc[0] if "Strand" in df else "+"
+            neg = (df["End" + suffix].values < df.Start.values)
+            if strand != "+":
+                neg = ~neg
+            d = df["Distance"].values.astype(np.int64)
+            df = df.assign(Distance=np.where(neg, -d, d)).reset_index(drop=True)
+            out[key] = df
+        gr = PyRanges._wrap(out)
+        if not self.stranded and other.stranded:
+            if apply_strand_suffix is None:
+                print("join: Strand data from other will be added as strand data to self.\nIf this is undesired use the "
+                      "flag apply_strand_suffix=False.\nTo turn off the warning set apply_strand_suffix to True or False.",
+                      file=sys.stderr)
+            elif apply_strand_suffix:
+                gr.columns = gr.columns.str.replace("Strand", "Strand" + suffix)
         return gr
 
     def cluster(self, strand=None, by=None, slack=0, count=False, nb_cpu=1):

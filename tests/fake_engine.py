@@ -128,6 +128,38 @@ class SubjectIndex:
             dist[a + rest] = rd
         return _t(row), _t(dist)
 
+    def k_nearest(self, q, k, ties=None):
+        k = np.asarray(k.cpu().numpy() if hasattr(k, "cpu") else k, dtype=np.int64)
+        Q, R, D = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)], [np.zeros(0, np.int64)]
+        for kk, a, b, sa, sb, s, e, t in self._per_key(q):
+            S, En = self.iv.s[sa:sb], self.iv.e[sa:sb]
+            mode = IV_NEAREST_BOTH if q.seg_mode is None else q.seg_mode[kk]
+            o_e, o_s = np.argsort(En, kind="stable"), np.argsort(S, kind="stable")
+            lab = np.arange(b - a, dtype=np.int64)
+            kq = k[a:b]
+            parts = []
+            if mode != IV_NEAREST_NEXT:
+                ix = np.searchsorted(En[o_e], s, side="right") - 1
+                v = ix >= 0
+                li, rp, dd = orc.k_nearest_previous_nonoverlapping(s[v], En[o_e], lab[v], ix[v], kq, ties)
+                parts.append((li, o_e[rp], dd + 1, np.zeros(len(li), np.int64)))
+            if mode != IV_NEAREST_PREVIOUS:
+                ix = np.searchsorted(S[o_s], e, side="left")
+                v = ix < len(S)
+                li, rp, dd = orc.k_nearest_next_nonoverlapping(e[v], S[o_s], lab[v], ix[v], kq, ties)
+                parts.append((li, o_s[rp], dd + 1, np.ones(len(li), np.int64)))
+            li = np.concatenate([p[0] for p in parts])
+            rr = np.concatenate([p[1] for p in parts])
+            dd = np.concatenate([p[2] for p in parts])
+            pn = np.concatenate([p[3] for p in parts])
+            o = np.lexsort((np.arange(len(li)), pn, li))  # query order, previous before next, walking order inside
+            Q.append(li[o] + a), R.append(rr[o] + sa), D.append(dd[o])
+        return _t(np.concatenate(Q)), _t(np.concatenate(R)), _t(np.concatenate(D))
+
+
+def to_device_i64(a, device):
+    return _t(np.ascontiguousarray(a, dtype=np.int64))
+
 
 def _ranges(iv, seg_ranges):
     if seg_ranges is None:

@@ -49,8 +49,8 @@ def load_case(name):
     return meta, res
 
 
-BINARY_OPS = ("join", "overlap", "count_overlaps", "coverage", "nearest", "intersect", "set_intersect", "set_union",
-              "subtract")
+BINARY_OPS = ("join", "overlap", "count_overlaps", "coverage", "nearest", "k_nearest", "intersect", "set_intersect",
+              "set_union", "subtract")
 
 
 def run_case(meta, PyRanges):
@@ -129,6 +129,34 @@ def check_case(name, PyRanges):
         gap = np.where(Eb <= S, S - Eb + 1, np.where(Sb >= E, Sb - E + 1, 0))
         assert np.array_equal(gap, D), name
         # where the distance pins the partner coordinate, it must match the reference's
+        return
+    if op == "k_nearest":
+        assert list(gdf.columns) == list(want.columns), (name, list(gdf.columns), list(want.columns))
+        # every row: the partner sits at |Distance| in front of / behind the interval, the sign follows
+        # pyranges_main.py:2802-2813 (negative in front of the interval, mirrored on the - strand)
+        S, E, Sb, Eb, D = (gdf[c].values.astype(np.int64) for c in ("Start", "End", "Start_b", "End_b", "Distance"))
+        gap = np.where(Eb <= S, S - Eb + 1, np.where(Sb >= E, Sb - E + 1, 0))
+        assert np.array_equal(gap, np.abs(D)), name
+        minus = (gdf["Strand"].values.astype(str) == "-") if "Strand" in gdf.columns else np.zeros(len(gdf), bool)
+        assert np.array_equal(D < 0, ((Eb < S) != minus) & (D != 0)), name
+        if meta["kwargs"].get("ties") == "different":
+            assert_frames_equal(gdf, want, name)  # every subject of the k nearest distinct distances: a set
+            return
+        # ties None / first / last keep ONE of several equally near subjects (the k-th row; one per distance): which one
+        # follows the traversal order of ncls / an unstable sort upstream.  The interval's own columns
+        # and the distances are pinned.
+        own = [c for c in want.columns if c in s.columns or c == "Distance"]
+        if "Strand" in o.columns and "Strand" not in s.columns:
+            # an unstranded self picks up other's Strand and the reference then chooses the k nearest PER STRAND OF THE
+            # NEIGHBOUR (PyRanges(dict) regroups the frames): which of two equally near neighbours is met first decides
+            # the group a row lands in, i.e. even the number of rows.  Pinned here: the intervals that get neighbours and
+            # the distance of each one's nearest neighbour.
+            base = [c for c in own if c != "Distance"]
+            g = gdf.assign(D=np.abs(gdf["Distance"].values)).groupby(base, sort=True).D.min().reset_index()
+            w = want.assign(D=np.abs(want["Distance"].values)).groupby(base, sort=True).D.min().reset_index()
+            assert_frames_equal(g, w, name)
+            return
+        assert_frames_equal(gdf[own], want[own], name)
         return
     if op == "cluster":
         # row order inside a key follows an unstable sort upstream; ids are pinned

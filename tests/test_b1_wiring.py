@@ -73,9 +73,12 @@ def _mk(pr, tag):
     return pr.PyRanges({k: v for k, v in gr.dfs.items() if not v.empty})
 
 
-_OPS = ("join", "overlap", "count_overlaps", "coverage", "intersect", "subtract", "cluster", "merge")
+_OPS = ("join", "overlap", "count_overlaps", "coverage", "intersect", "subtract", "cluster", "merge", "k_nearest")
 _CASES = [n for n in case_names() if n.split("_")[0] in ("join", "overlap", "count", "coverage", "intersect", "subtract",
                                                           "cluster", "merge")][::4]
+# k_nearest reaches the dispatcher with pyranges.methods.k_nearest._nearest (same __name__ as nearest's callable); the
+# cases whose answer is a set (ties="different")
+_CASES += [n for n in case_names() if n.startswith("knear_") and "_different_" in n][::3]
 
 
 @pytest.mark.parametrize("name", _CASES)

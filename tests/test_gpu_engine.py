@@ -262,6 +262,30 @@ def test_nearest(eng, case, overlap):
         assert np.array_equal(gap, d[ok])
 
 
+@pytest.mark.parametrize("case", CASES[:3] + [(9, 2, 400, 2, 300, 300, 40)])  # the last one: many equal ends / starts
+@pytest.mark.parametrize("ties", [None, "first", "last", "different"])
+def test_k_nearest_candidates(eng, case, ties):
+    """iv_k_nearest_count / _emit against the restatement of sorted_nearest.k_nearest_previous_nonoverlapping /
+    k_nearest_next_nonoverlapping (oracle.py) driven the way pyranges/methods/k_nearest.py:6-48 drives them: the same
+    (query row, subject row, distance) triples in the same order -- previous candidates (equal ends: descending row)
+    before next ones (equal starts: ascending row); BOTH / PREVIOUS / NEXT per key, one k per row (0 .. 4)."""
+    import torch
+
+    from tests import fake_engine as fe
+
+    qs, qe, qoff, ss, se, soff, sg = _setup(eng, case)
+    kq = len(qoff) - 1
+    modes = np.asarray([k % 3 for k in range(kq)], np.int32)
+    kk = (np.arange(len(qs)) * 7 % 5).astype(np.int64)
+    q = eng.Queries(_dev(eng, qs, qe, qoff), sg, seg_mode=modes)
+    ix = eng.SubjectIndex(_dev(eng, ss, se, soff), ends_perm=True)
+    a, b, d = (t.cpu().numpy() for t in ix.k_nearest(q, torch.from_numpy(kk).cuda(), ties))
+    fq = fe.Queries(fe.DeviceIntervals(qs, qe, qoff), sg, seg_mode=modes)
+    wa, wb, wd = (t.numpy() for t in fe.SubjectIndex(fe.DeviceIntervals(ss, se, soff), ends_perm=True).k_nearest(fq, kk, ties))
+    assert len(a) == len(wa) and len(a) > 0
+    assert np.array_equal(a, wa) and np.array_equal(b, wb) and np.array_equal(d, wd)
+
+
 @pytest.mark.parametrize("seed,n_seg,n,maxpos,maxlen", [(1, 1, 40, 300, 40), (2, 5, 3000, 50000, 300),
                                                          (3, 7, 20000, 3000000, 2000), (4, 2, 5000, 400, 100)])
 @pytest.mark.parametrize("slack", [0, 10, -5])
