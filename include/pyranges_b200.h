@@ -31,6 +31,7 @@
  *   iv_rle_count/_emit        <- pyrle.methods.coverage                   pyranges/methods/to_rle.py:18
  *   iv_split_count/_emit      <- concat(Start, End).sort_values().drop_duplicates() + consecutive pairs
  *                                                                        pyranges/methods/split.py:4-24
+ *   iv_text_* / iv_bed_parse  <- pandas.read_csv(f, sep="\t") of read_bed      pyranges/readers.py:63-153
  *   iv_materialize_pairs      <- scdf.reindex / ocdf.reindex + "Overlap"  pyranges/methods/join.py:95-123,147-151
  *                                and the clip of intersect                pyranges/methods/intersection.py:39-48
  *   iv_gather                 <- the same reindex for a payload column    pyranges/methods/join.py:95-123
@@ -391,6 +392,28 @@ int iv_materialize_pairs(const int64_t* q_start, const int64_t* q_end, const int
  * *fill (host pointer to one element, NULL = zero bytes). */
 int iv_gather(const void* column, int32_t elem_bytes, const int64_t* rows, int64_t n, void* out, const void* fill,
               void* stream);
+
+/* ---- ingest: BED text -> device columns (pyranges/readers.py:63-153) ----------------------------------------------
+ * The file's bytes live on the device (buf, nbytes; readable up to the next multiple of 16).
+ *   iv_text_count_lines: *out_newlines (device) = number of '\n'; per-tile offsets stay in ws for iv_text_line_starts.
+ *     n_lines = newlines + 1 if the text does not end in '\n' (the caller looks at the last byte).
+ *   iv_text_line_starts: out_line_start[n_lines + 1]; line i = bytes [line_start[i], line_start[i + 1] - 1).
+ *   iv_bed_parse: rows = lines [first_line, first_line + n_rows) (first_line = 1 skips a header).  Start / End / Score
+ *     (fields 1, 2, 4) as int64, FNV-1a hash of field 0, field 5 as one byte (0: absent), number of fields, and the
+ *     spans of the first 12 fields as [12][n_rows] arrays (a trailing '\r' is not part of the last field).
+ *     out_bad[3] (device): rows whose Start / End are not integers, Score fields that are not, Strand fields longer than
+ *     one character -- the caller decides what to do with such a file.
+ *   iv_text_gather: the bytes of n spans packed back to back + their offsets (call with out_bytes = NULL first: the
+ *     total lands in out_off[n]). */
+size_t iv_text_workspace_bytes(int64_t nbytes);
+int iv_text_count_lines(const uint8_t* buf, int64_t nbytes, void* ws, size_t ws_bytes, int64_t* out_newlines, void* stream);
+int iv_text_line_starts(const uint8_t* buf, int64_t nbytes, const void* ws, int64_t n_lines, int64_t* out_line_start,
+                        void* stream);
+int iv_bed_parse(const uint8_t* buf, const int64_t* line_start, int64_t first_line, int64_t n_rows, int64_t* out_start,
+                 int64_t* out_end, int64_t* out_score, uint64_t* out_chrom_hash, uint8_t* out_strand,
+                 uint8_t* out_n_fields, int64_t* out_field_off, int32_t* out_field_len, int32_t* out_bad, void* stream);
+int iv_text_gather(const uint8_t* buf, const int64_t* off, const int32_t* len, int64_t n, int64_t* out_off,
+                   uint8_t* out_bytes, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,11 @@ PROTOTYPES = {
     "iv_subtract_count": (C.c_int, [_PI, _PQ, _vp, _vp, _sz, _vp, _vp]),
     "iv_subtract_emit": (C.c_int, [_PI, _PQ, _vp, _vp, _vp, _vp, _vp]),
     "iv_nearest": (C.c_int, [_PI, _PQ, _i32, _vp, _vp, _vp]),
+    "iv_text_workspace_bytes": (_sz, [_i64]),
+    "iv_text_count_lines": (C.c_int, [_vp, _i64, _vp, _sz, _vp, _vp]),
+    "iv_text_line_starts": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "iv_bed_parse": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "iv_text_gather": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "iv_k_nearest_workspace_bytes": (_sz, [_i64]),
     "iv_k_nearest_count": (C.c_int, [_PI, _PQ, _vp, _i32, _vp, _vp, _sz, _vp, _vp]),
     "iv_k_nearest_emit": (C.c_int, [_PI, _PQ, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -169,6 +169,24 @@ def _frames_of(gr, device):
     return f
 
 
+def seed_frame_cache(gr, device, frames):
+    """A device ingest made elsewhere (pyranges_b200.readers: columns parsed on the device) becomes the cached one of
+    `gr`; False when the frames do not qualify (non-int64 coordinate columns)."""
+    items = natsorted(gr.dfs.items())
+    sig, held = [str(device), id(E)], []
+    for k, d in items:
+        ps, vs = _col_ptr(d, "Start")
+        pe, ve = _col_ptr(d, "End")
+        if ps is None or pe is None:
+            return False
+        sig.append((k, len(d), ps, pe, vs.strides[0], ve.strides[0]))
+        held.append((vs, ve))
+    if len(_FRAME_CACHE) >= _FRAME_CACHE_MAX:
+        _FRAME_CACHE.pop(next(iter(_FRAME_CACHE)))
+    _FRAME_CACHE[tuple(sig)] = (frames, held)
+    return True
+
+
 def clear_device_cache():
     """drop every cached device copy of coordinate columns"""
     _FRAME_CACHE.clear()

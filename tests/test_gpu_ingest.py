@@ -1,0 +1,104 @@
+"""GPU: read_bed with the parse on the device (pyranges_b200/readers.py, csrc/ingest.cu) against pandas.read_csv --
+what the reference's read_bed calls (pyranges/readers.py:133-139) -- on generated BED files: BED3 / BED6 / BED12, with
+and without header, with and without a final newline, CRLF line ends, nrows, gzip; and the seeded device columns
+against the frames of the PyRanges."""
+import gzip
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+COLS = ("Chromosome Start End Name Score Strand ThickStart ThickEnd ItemRGB BlockCount BlockSizes BlockStarts").split()
+
+
+def _bed(tmp_path, n, ncols, header=False, final_newline=True, crlf=False, gz=False, seed=0, float_score=False):
+    rng = np.random.default_rng(seed)
+    chroms = rng.choice(["chr1", "chr2", "chr10", "chrX", "chrUn_gl000220"], n)
+    st = rng.integers(0, 5_000_000, n)
+    en = st + rng.integers(1, 4000, n)
+    rows = []
+    for i in range(n):
+        f = [chroms[i], str(st[i]), str(en[i]), "name_%d" % (i % 97), ("%.2f" % (i / 7)) if float_score else str(i % 1000),
+             "+-"[i % 2], str(st[i] + 1), str(en[i] - 1), "255,0,%d" % (i % 255), str(2), "10,20,", "0,%d," % (i % 50)]
+        rows.append("\t".join(f[:ncols]))
+    nl = "\r\n" if crlf else "\n"
+    text = nl.join(rows) + (nl if final_newline else "")
+    if header:
+        text = "\t".join(COLS[:ncols]) + nl + text
+    p = os.path.join(str(tmp_path), "t%d_%d.bed%s" % (n, ncols, ".gz" if gz else ""))
+    with (gzip.open(p, "wt", newline="") if gz else open(p, "w", newline="")) as fh:
+        fh.write(text)
+    return p
+
+
+def _want(path, header, nrows=None):
+    df = pd.read_csv(path, dtype={"Chromosome": "category", "Strand": "category"}, nrows=nrows,
+                     header=0 if header else None, sep="\t")
+    df.columns = COLS[:df.shape[1]]
+    return df
+
+
+def _same(got, want):
+    assert list(got.columns) == list(want.columns)
+    assert len(got) == len(want)
+    for c in want.columns:
+        a, b = got[c], want[c]
+        if str(b.dtype) == "category" or b.dtype == object or str(b.dtype) in ("str", "string"):
+            assert (a.astype(str).values == b.astype(str).values).all(), c
+        else:
+            assert a.dtype == b.dtype, (c, a.dtype, b.dtype)
+            assert np.array_equal(a.values, b.values), c
+
+
+@pytest.mark.parametrize("n,ncols,kw", [
+    (1, 3, {}), (1000, 3, {}), (70000, 6, {}), (70000, 6, {"header": True}), (5000, 6, {"final_newline": False}),
+    (5000, 6, {"crlf": True}), (3000, 12, {}), (4000, 6, {"gz": True}), (2000, 5, {"float_score": True}),
+    (300000, 6, {"seed": 5}),
+])
+def test_read_bed_frame(tmp_path, n, ncols, kw):
+    from pyranges_b200.readers import read_bed
+
+    path = _bed(tmp_path, n, ncols, **kw)
+    header = kw.get("header", False)
+    _same(read_bed(path, as_df=True), _want(path, header))
+    _same(read_bed(path, as_df=True, nrows=7), _want(path, header, nrows=7))
+
+
+def test_read_bed_pyranges_and_device_columns(tmp_path):
+    """the PyRanges equals the one built from the pandas frame; its device columns are the cached ingest (no upload on
+    the first operation) and hold exactly the rows of its frames, key by key"""
+    from pyranges_b200 import multithreaded as M
+    from pyranges_b200.pyranges_main import PyRanges
+    from pyranges_b200.readers import read_bed
+
+    path = _bed(tmp_path, 50000, 6, seed=3)
+    M.clear_device_cache()
+    gr = read_bed(path)
+    want = PyRanges(_want(path, False))
+    assert gr.keys() == want.keys()
+    for k in gr.keys():
+        _same(gr.dfs[k].reset_index(drop=True), want.dfs[k].reset_index(drop=True))
+    assert len(M._FRAME_CACHE) == 1
+    f = M._frames_of(gr, next(iter(M._FRAME_CACHE.values()))[0].iv.device)
+    assert f is next(iter(M._FRAME_CACHE.values()))[0]  # served from the cache: nothing was uploaded
+    s, e = f.iv.start.cpu().numpy(), f.iv.end.cpu().numpy()
+    for i, (k, d) in enumerate(zip(f.keys, f.dfs)):
+        a, b = f.seg_off[i], f.seg_off[i + 1]
+        assert np.array_equal(s[a:b], d.Start.values) and np.array_equal(e[a:b], d.End.values), k
+    # and an operation on it agrees with the same operation on the pandas-built object
+    got, ref = gr.cluster().df, want.cluster().df
+    assert np.array_equal(np.sort(got.Cluster.values), np.sort(ref.Cluster.values))
+    assert len(gr.join(want)) == len(want.join(want))
+
+
+def test_read_bed_rejects_bad_rows(tmp_path):
+    from pyranges_b200.readers import read_bed
+
+    p = os.path.join(str(tmp_path), "bad.bed")
+    with open(p, "w") as fh:
+        fh.write("chr1\t10\t20\nchr1\t30\tforty\n")
+    with pytest.raises(ValueError):
+        read_bed(p)
