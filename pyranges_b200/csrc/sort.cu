@@ -9,6 +9,7 @@
 // (blockIdx.y).  Small inputs use 1024-key tiles so that they still spread over the 148 SMs.
 // No inter-block dependencies (no spin waits), so it cannot hang.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace iv {
 
@@ -539,6 +540,7 @@ constexpr int HY_THREADS = 256;
 constexpr int HY_ITEMS = HY_CAP / HY_THREADS;
 constexpr int HY_MAX_P = 4;
 constexpr int HY_MAX_T = 20;
+constexpr uint32_t HY_HUGE = 1u << 16;  // keys: a pile-up beyond this is sorted by all blocks together (k_hy_huge)
 constexpr int64_t HY_MAX_N = ((int64_t)1 << 30) - 1;
 constexpr uint32_t SW_AGG = 1u << 30, SW_INC = 2u << 30, SW_VAL = (1u << 30) - 1u;
 constexpr int SW_ITEMS = 16;
@@ -865,8 +867,11 @@ k_hy_buckets(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit
         }
         return;
     }
-    if (m > (uint32_t)HY_CAP) {  // a pile-up: left to k_hy_pileups
-        if (tid == 0) pile_list[atomicAdd(pile_count, 1u)] = blockIdx.x;
+    if (m > (uint32_t)HY_CAP) {  // a pile-up: left to k_hy_pileups (one block) or, beyond HY_HUGE keys, to the whole grid
+        if (tid == 0) {
+            if (m > HY_HUGE) pile_list[(gridDim.x + 32) + atomicAdd(pile_count + 1, 1u)] = blockIdx.x;
+            else pile_list[atomicAdd(pile_count, 1u)] = blockIdx.x;
+        }
         return;
     }
     const uint64_t low_mask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
@@ -972,6 +977,115 @@ k_hy_pileups(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit
     }
 }
 
+// A pile-up of more than HY_HUGE keys: stable LSD passes over the bits that differ inside the bucket, every pass by ALL
+// blocks of a cooperative launch -- per-tile digit histograms, a prefix along the tiles of every digit row, the tile
+// body of the partition pass with the offsets from the table -- with a grid barrier between the phases.  The grid is
+// as large as the device holds (the launch is cooperative); without such buckets it leaves at once.
+template <int VB>
+__global__ void __launch_bounds__(HY_THREADS)
+k_hy_huge(uint64_t* kin, uint64_t* kout, void* vin, void* vout, int begin_bit, int low_bits,
+          const uint32_t* __restrict__ starts, const uint32_t* __restrict__ pile_count,
+          const uint32_t* __restrict__ pile_list, uint32_t list_off, uint32_t* table /* [256][tiles] + [256] + 2 */,
+          uint32_t table_tiles) {
+    namespace cg = cooperative_groups;
+    const uint32_t np = pile_count[1];
+    if (np == 0) return;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ SwSmem S;
+    __shared__ uint32_t h[RS_RADIX];
+    const int tid = threadIdx.x;
+    uint32_t* totals = table + (size_t)RS_RADIX * table_tiles;
+    unsigned long long* gdiff = reinterpret_cast<unsigned long long*>(totals + RS_RADIX);
+    const uint64_t low_mask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
+    for (uint32_t pi = 0; pi < np; pi++) {
+        const uint32_t b = pile_list[list_off + pi];
+        const uint32_t b0 = __ldg(starts + b), m = __ldg(starts + b + 1) - b0;
+        const uint32_t ntiles = (m + SW_TILE - 1) / SW_TILE;
+        if (ntiles > table_tiles) continue;  // (cannot happen: the table is sized for all keys)
+        if (blockIdx.x == 0 && tid == 0) *gdiff = 0ull;
+        grid.sync();
+        {   // bits that differ inside the bucket
+            const uint64_t first = kin[b0];
+            uint64_t diff = 0;
+            for (uint64_t i = (uint64_t)blockIdx.x * HY_THREADS + tid; i < m; i += (uint64_t)gridDim.x * HY_THREADS)
+                diff |= kin[b0 + i] ^ first;
+            diff = (diff >> begin_bit) & low_mask;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
+            if ((tid & 31) == 0 && diff) atomicOr(gdiff, (unsigned long long)diff);
+        }
+        grid.sync();
+        const unsigned long long dall = *gdiff;
+        uint64_t *ka = kin + b0, *kb = kout + b0;
+        char* va = VB ? (char*)vin + (size_t)b0 * VB : nullptr;
+        char* vb = VB ? (char*)vout + (size_t)b0 * VB : nullptr;
+        if (dall) {
+            const int lo = __ffsll((long long)dall) - 1, hi = 64 - __clzll((long long)dall);
+            const int npass = (hi - lo + 7) / 8;
+            int at = lo;
+            for (int p = 0; p < npass; p++) {
+                const int bits = (hi - at + (npass - p) - 1) / (npass - p);
+                const int shift = begin_bit + at;
+                const uint32_t dmask = (1u << bits) - 1u;
+                // per-tile digit histograms, digit-major
+                for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                    h[tid] = 0;
+                    __syncthreads();
+                    const uint32_t t0 = t * SW_TILE, t1 = t0 + SW_TILE < m ? t0 + SW_TILE : m;
+                    for (uint32_t i = t0 + tid; i < t1; i += HY_THREADS) atomicAdd(&h[(uint32_t)(ka[i] >> shift) & dmask], 1u);
+                    __syncthreads();
+                    table[(size_t)tid * table_tiles + t] = h[tid];
+                    __syncthreads();
+                }
+                grid.sync();
+                // exclusive prefix along the tiles of every digit row + the row total
+                for (uint32_t d = blockIdx.x; d < RS_RADIX; d += gridDim.x) {
+                    uint32_t* row = table + (size_t)d * table_tiles;
+                    const uint32_t per = (ntiles + HY_THREADS - 1) / HY_THREADS;
+                    const uint32_t a = tid * per, e = a + per < ntiles ? a + per : ntiles;
+                    uint32_t sum = 0;
+                    for (uint32_t t = a; t < e; t++) sum += row[t];
+                    uint32_t tot;
+                    uint32_t run = block_excl_sum<uint32_t, HY_THREADS>(sum, S.wsum, tot);
+                    for (uint32_t t = a; t < e; t++) {
+                        const uint32_t v = row[t];
+                        row[t] = run;
+                        run += v;
+                    }
+                    if (tid == 0) totals[d] = tot;
+                    __syncthreads();
+                }
+                grid.sync();
+                // scatter
+                for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+                    __syncthreads();
+                    const uint32_t t0 = t * SW_TILE;
+                    const int nvalid = (int)(m - t0 < (uint32_t)SW_TILE ? m - t0 : (uint32_t)SW_TILE);
+                    sw_tile<VB>(S, ka, kb, va, vb, (int64_t)t0, nvalid, shift, dmask, 0, [&](uint32_t run, uint32_t ex) {
+                        uint32_t tt;
+                        const uint32_t dstart = block_excl_sum<uint32_t, RS_THREADS>(totals[tid], S.wsum, tt);
+                        return dstart + table[(size_t)tid * table_tiles + t] - ex;
+                    });
+                    __syncthreads();
+                }
+                grid.sync();
+                uint64_t* tk = ka; ka = kb; kb = tk;
+                char* tv = va; va = vb; vb = tv;
+                at += bits;
+            }
+        }
+        if (ka != kout + b0) {
+            for (uint64_t i = (uint64_t)blockIdx.x * HY_THREADS + tid; i < m; i += (uint64_t)gridDim.x * HY_THREADS) {
+                kout[b0 + i] = ka[i];
+                if (VB == 4) ((uint32_t*)vout)[b0 + i] = ((const uint32_t*)va)[i];
+                else if (VB == 8) ((uint64_t*)vout)[b0 + i] = ((const uint64_t*)va)[i];
+            }
+        }
+        grid.sync();
+    }
+}
+
 struct HyTemp {
     uint32_t *ghist, *ticket, *status, *starts, *pile_list;  // ticket[8] = number of pile-up buckets
     size_t zero_bytes;  // ghist + ticket + status: cleared before every sort
@@ -984,8 +1098,9 @@ static void hy_temp(int64_t n, Bump& b, HyTemp& t) {
     t.zero_bytes = b.off;
     size_t nb = 2;
     while (nb < ((size_t)1 << HY_MAX_T) && nb * (HY_CAP / 4) < (size_t)(n > 0 ? n : 1)) nb <<= 1;
+    if (nb < ((size_t)1 << HY_POS_BITS)) nb = (size_t)1 << HY_POS_BITS;  // wide keys: the plan partitions on nbits - 52 <= 12 bits
     t.starts = b.take<uint32_t>(nb + 64);
-    t.pile_list = b.take<uint32_t>(nb + 64);
+    t.pile_list = b.take<uint32_t>(2 * (nb + 64));  // [one-block pile-ups][nb + 32 entries later: the huge ones]
 }
 
 template <int VB>
@@ -1024,6 +1139,29 @@ static int hy_launch(const HyPlan& pl, uint64_t* k[2], void* v[2], int64_t n, in
         k_hy_pileups<VB><<<148 * 2, HY_THREADS, 0, stream>>>(k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], begin_bit, pl.low_bits,
                                                              t.starts, t.ticket + 8, t.pile_list);
         IV_LAUNCH_CHECK();
+        {   // the huge ones: one cooperative launch (it needs every block resident: sized by the occupancy query)
+            static int coop_blocks[64] = {0};
+            if (dev < 0 || dev >= 64 || coop_blocks[dev] == 0) {
+                int sms = 0, per_sm = 0, ok = 0;
+                IV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev));
+                IV_CUDA(cudaDeviceGetAttribute(&ok, cudaDevAttrCooperativeLaunch, dev < 0 ? 0 : dev));
+                IV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hy_huge<VB>, HY_THREADS, 0));
+                IV_REQUIRE(ok && sms * per_sm > 0, IV_ERR_CUDA, "radix sort: the device does not support cooperative launches");
+                if (dev >= 0 && dev < 64) coop_blocks[dev] = sms * per_sm;
+            }
+            const int blocks = (dev >= 0 && dev < 64) ? coop_blocks[dev] : 148;
+            uint64_t *a0 = k[cur], *a1 = k[cur ^ 1];
+            void *a2 = v[cur], *a3 = v[cur ^ 1];
+            int a4 = begin_bit, a5 = pl.low_bits;
+            const uint32_t *a6 = t.starts, *a7 = t.ticket + 8, *a8 = t.pile_list;
+            uint32_t a9 = nb + 32;  // the second list starts gridDim.x (of k_hy_buckets) + 32 entries in
+            uint32_t* a10 = t.status;
+            uint32_t a11 = (uint32_t)ntiles;
+            void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11};
+            IV_CUDA(cudaLaunchCooperativeKernel((const void*)k_hy_huge<VB>, dim3((unsigned)blocks), dim3(HY_THREADS), args, 0,
+                                                stream));
+            __atomic_fetch_add(&iv::g_launches, 1ull, __ATOMIC_RELAXED);
+        }
         cur ^= 1;
     }
     *result_buf = cur;
