@@ -174,10 +174,13 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
 __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// called by one full warp; -> pairs of all tiles before `tile`
+// called by one full warp: the tile's own total becomes visible to its successors
+__device__ __forceinline__ void publish_total(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
+    if (lane_id() == 0) st_relaxed(state + tile, (aggregate << 2) | (tile == 0 ? 2ull : 1ull));
+}
+// called by one full warp after publish_total; -> pairs of all tiles before `tile`
 __device__ __forceinline__ unsigned long long lookback(unsigned long long* state, int64_t tile, unsigned long long aggregate) {
     const int lane = lane_id();
-    if (lane == 0) st_relaxed(state + tile, (aggregate << 2) | (tile == 0 ? 2ull : 1ull));
     unsigned long long excl = 0;
     int64_t look = tile - 1;
     while (look >= 0) {
@@ -404,6 +407,7 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         if (lane == 0) o = atomicAdd(reinterpret_cast<unsigned long long*>(out_total), total);
         o = __shfl_sync(FULL, o, 0);
     } else {
+        publish_total(state, wtile, total);
         o = lookback(state, wtile, total);
         if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);
     }
@@ -452,6 +456,85 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
         }
         o += itot;
     }
+}
+
+// ---- overlap(how="first"): the rows with at least one hit -----------------------------------------------------------
+// The same tiles and the same look-back as k_join, but a row contributes at most one entry -- its own number -- so
+// nothing is staged: the hit flags of a tile's 256 rows live in registers (two ballots per iteration) and the positions
+// inside the tile come from population counts.  That makes the ordering wait avoidable: a warp takes JA_DEPTH tiles, one
+// ticket each, and writes a tile only after it has counted and published the next one -- the tile's predecessors had
+// a whole tile's time to publish theirs.
+constexpr int JA_DEPTH = 4;
+
+template <typename X, bool SLACK>
+__global__ void __launch_bounds__(JN_THREADS, 4)
+k_join_any(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int64_t cap,
+           unsigned long long* __restrict__ state, unsigned int* __restrict__ ticket, int64_t n_wtiles,
+           int64_t* __restrict__ out_total) {
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    unsigned p0[JN_ITERS], p1[JN_ITERS];  // hit flags of the tile waiting for its offset
+    uint32_t ptotal = 0;
+    int64_t ptile = -1;
+
+    auto write_tile = [&](int64_t wtile, const unsigned (&b0)[JN_ITERS], const unsigned (&b1)[JN_ITERS], uint32_t total) {
+        unsigned long long o = lookback(state, wtile, total);
+        if (wtile == n_wtiles - 1 && lane == 0) *out_total = (int64_t)(o + total);
+        if (!out_q) return;
+        const int64_t wbase = wtile * JN_WROWS;
+#pragma unroll
+        for (int it = 0; it < JN_ITERS; it++) {
+            // rows of the iteration in order: (lane 0: k = 0, 1), (lane 1: k = 0, 1) ...
+            const uint32_t before = __popc(b0[it] & below) + __popc(b1[it] & below);
+            const int64_t row = wbase + it * 64 + 2 * lane;
+            if (b0[it] >> lane & 1u) {
+                const int64_t at = (int64_t)o + before;
+                if (at < cap) __stcs(out_q + at, q.label ? __ldg(q.label + row) : row);
+            }
+            if (b1[it] >> lane & 1u) {
+                const int64_t at = (int64_t)o + before + (b0[it] >> lane & 1u);
+                if (at < cap) __stcs(out_q + at, q.label ? __ldg(q.label + row + 1) : row + 1);
+            }
+            o += __popc(b0[it]) + __popc(b1[it]);
+        }
+    };
+
+#pragma unroll 1
+    for (int j = 0; j < JA_DEPTH; j++) {
+        // one ticket per tile: a tile only ever waits for tiles taken earlier, all of them by running warps
+        unsigned int tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1u);
+        const int64_t wtile = (int64_t)__shfl_sync(FULL, tk, 0);
+        if (wtile >= n_wtiles) break;
+        const int64_t wbase = wtile * JN_WROWS;
+        Geo<X> G(q, wbase);
+        unsigned b0[JN_ITERS], b1[JN_ITERS];
+        uint32_t total = 0;
+        Raw2 next = load_raw(q, vec, wbase);
+#pragma unroll
+        for (int it = 0; it < JN_ITERS; it++) {
+            const int64_t ibase = wbase + it * 64;
+            bool h0 = false, h1 = false;
+            if (ibase < q.n) {
+                const Raw2 cur = next;
+                if (it + 1 < JN_ITERS && ibase + 64 < q.n) next = load_raw(q, vec, ibase + 64);
+                Rows2<X> R;
+                flatten_rows<X, SLACK>(ix, q, ibase, cur, G, R);
+                h0 = plan_query<X>(ix, R.sc[0], R.ec[0], R.r[0], R.live[0]).count() != 0;
+                h1 = plan_query<X>(ix, R.sc[1], R.ec[1], R.r[1], R.live[1]).count() != 0;
+            }
+            b0[it] = __ballot_sync(FULL, h0);
+            b1[it] = __ballot_sync(FULL, h1);
+            total += __popc(b0[it]) + __popc(b1[it]);
+        }
+        publish_total(state, wtile, total);
+        if (ptile >= 0) write_tile(ptile, p0, p1, ptotal);
+#pragma unroll
+        for (int it = 0; it < JN_ITERS; it++) { p0[it] = b0[it]; p1[it] = b1[it]; }
+        ptotal = total;
+        ptile = wtile;
+    }
+    if (ptile >= 0) write_tile(ptile, p0, p1, ptotal);
 }
 
 // pairs per query segment of a pair list in query order (ascending query rows): lower bounds of the segment boundaries
@@ -528,7 +611,14 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
         k_join<X, SL, AN><<<nb, JN_THREADS, JN_SMEM, st>>>(*lists, *q, vec, out_q, out_s, s_label, out_capacity, state,  \
                                                           ticket, n_tiles, out_total, variant);                        \
     } while (0)
-#define IV_JK2(X, SL) do { if (any) IV_JK(X, SL, true); else IV_JK(X, SL, false); } while (0)
+#define IV_JK2(X, SL)                                                                                                  \
+    do {                                                                                                               \
+        if (any && variant != 3)                                                                                       \
+            k_join_any<X, SL><<<(unsigned)cdiv(n_tiles, JN_WARPS * JA_DEPTH), JN_THREADS, 0, st>>>(                     \
+                *lists, *q, vec, out_q, out_capacity, state, ticket, n_tiles, out_total);                              \
+        else if (any) IV_JK(X, SL, true);                                                                              \
+        else IV_JK(X, SL, false);                                                                                      \
+    } while (0)
     const bool any = mode == IV_MODE_ANY;
     if (narrow_span(lists)) {
         if (slack) IV_JK2(uint32_t, true); else IV_JK2(uint32_t, false);
