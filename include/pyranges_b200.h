@@ -319,6 +319,11 @@ size_t iv_join_workspace_bytes(int64_t n_queries);
  * larger buffers.  ws: iv_join_workspace_bytes(q->n) bytes, 256-byte aligned.
  * mode IV_MODE_ANY: one entry per query WITH hits -- out_q only (has_overlaps / overlap(how="first"),
  * pyranges/methods/intersection.py:78), out_s is not written. */
+/* mode flag of iv_join_pairs (IV_MODE_ALL | IV_JOIN_HINT_ORDERED): the query rows come in position order (a BAM-sorted
+ * read set): rows with many hits then sit next to each other, whole tiles outgrow the staging areas, and the kernel
+ * with one larger staging area per warp (k_join) serves them better than the pipelined one (k_join_pipe).  A hint:
+ * results do not depend on it. */
+#define IV_JOIN_HINT_ORDERED 0x100
 int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int32_t mode, int64_t* out_q, int64_t* out_s,
                   const int64_t* s_label, int64_t out_capacity, void* ws, size_t ws_bytes, int64_t* out_total,
                   void* stream);

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("PYRANGES_B200_LIB") or os.path.join(_HERE, "libpyrang
 
 IV_OK = 0
 IV_MODE_ALL, IV_MODE_ANY, IV_MODE_CONTAIN, IV_MODE_LAST = 0, 1, 2, 3
+IV_JOIN_HINT_ORDERED = 0x100
 IV_NEAREST_BOTH, IV_NEAREST_PREVIOUS, IV_NEAREST_NEXT = 0, 1, 2
 IV_INDEX_ENDS_PERM = 1
 IV_INDEX_GRAPH = 2

@@ -140,6 +140,21 @@ class DeviceIntervals:
         return self.bounds[2]
 
     @property
+    def position_ordered(self):
+        """True when the rows come (mostly) in Start order inside their segments, e.g. a BAM-sorted read set: judged
+        once per upload from a strided sample of adjacent row pairs (ingest-time metadata, like the bounds)."""
+        v = self.__dict__.get("_ordered")
+        if v is None:
+            v = False
+            if self.n >= 4096:
+                step = max(1, (self.n - 1) // (1 << 20))
+                a = self.start[0:self.n - 1:step]
+                b = self.start[1:self.n:step]
+                v = bool(float((b >= a).float().mean()) >= 0.9)
+            self.__dict__["_ordered"] = v
+        return v
+
+    @property
     def sumlen(self):
         return self.bounds[3]
 
@@ -810,6 +825,8 @@ class ListIndex:
         dev = self.iv.device
         ws = _bytes(L.iv_join_workspace_bytes(q.iv.n), dev)
         total = torch.empty(1, dtype=torch.int64, device=dev)
+        if mode == IV_MODE_ALL and q.iv.position_ordered:
+            mode |= cabi.IV_JOIN_HINT_ORDERED
         cabi.check(L.iv_join_pairs(C.byref(self.c), C.byref(q.c), mode, _ptr(out_q), _ptr(out_s), _ptr(s_label),
                                    int(capacity), _ptr(ws), ws.numel(), _ptr(total), _stream()), "iv_join_pairs")
         return total
