@@ -27,11 +27,13 @@ constexpr int JN_WARPS = JN_THREADS / 32;
 constexpr int JN_ITERS = 4;                       // iterations of 64 rows per warp
 constexpr int JN_WROWS = 64 * JN_ITERS;           // 256 rows per warp
 constexpr int JN_TILE = JN_WROWS * JN_WARPS;      // 2048 rows per block
-// Staged pairs per warp (2.25 per row; iterations that do not fit are repeated once the offset is known), 5 bytes each.
-// The staging areas are kept SMALL on purpose: shared memory comes out of the L1, and every random 32-byte gather in
-// flight holds a 128-byte L1 line -- with 212 KB of shared memory per SM (16 KB of L1) the same count sweep ran 1.6x
-// slower than with 100 KB (measured, profiles/README.md).
-constexpr int JN_WCAP = 576;
+// Staged pairs per warp of k_join, 5 bytes each (iterations that do not fit are counted again once the offset is known).
+// k_join serves position-ordered read sets (IV_JOIN_HINT_ORDERED): rows with many hits sit next to each other there,
+// so the area is large -- measured on the sorted C3 reads: 576 pairs 3.12 ms, 896: 2.55, 1152: 2.39, 1536: 2.74 --
+// while their record gathers coalesce and do not miss the L1 the shared memory takes away.  (For reads in random
+// order it is the other way round: with 212 KB of shared memory per SM the count sweep ran 1.6x slower than with
+// 100 KB; k_join_pipe keeps two areas of 640 pairs at three blocks per SM.)
+constexpr int JN_WCAP = 1152;
 constexpr size_t JN_SMEM = (size_t)JN_WARPS * JN_WCAP * 5;  // dynamic shared memory of k_join: staging areas
 
 constexpr int JM_COUNT = 2, JM_ANY = 3;
