@@ -709,7 +709,8 @@ class JoinStep:
 
     def kernel_of(self, phase):
         names = {"index_build": "iv_lists_build" if self.path == "fused" else "iv_index_build",
-                 "join": "k_join", "count": "k_count_lean", "emit": "k_emit"}
+                 "join": "k_join" if self.q.iv.position_ordered else "k_join_pipe", "count": "k_count_lean",
+                 "emit": "k_emit"}
         return names.get(phase, phase)
 
     def phase_summary(self, last_n):

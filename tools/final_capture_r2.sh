@@ -9,7 +9,9 @@ $A > gpurun_out/${T}_plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --c
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --ops cluster,merge,rle,nearest --ops-steps 2"
 $B > gpurun_out/${T}_plain2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches_ops.csv $B > gpurun_out/${T}_ncu2.log 2>&1
 C="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --ops none"
-$C > gpurun_out/${T}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_join" -s 3 -c 1 -o gpurun_out/${T}_join $C > gpurun_out/${T}_ncu3.log 2>&1
-D="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --ops cluster,rle --ops-steps 2"
-ncu --set full --clock-control none --import-source on -k regex:"k_rd_dense|k_rd_pass_a|k_rs_sweep|k_hy_buckets" -s 4 -c 8 -o gpurun_out/${T}_unary $D > gpurun_out/${T}_ncu4.log 2>&1
+$C > gpurun_out/${T}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_join_pipe" -s 3 -c 1 -o gpurun_out/${T}_join $C > gpurun_out/${T}_ncu3.log 2>&1
+D="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --ops cluster --ops-steps 2"
+ncu --set full --clock-control none --import-source on -k regex:"k_rs_sweep|k_hy_buckets" -s 4 -c 4 -o gpurun_out/${T}_unary $D > gpurun_out/${T}_ncu4.log 2>&1
+E2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --ops rle,overlap --ops-steps 2"
+ncu --set full --clock-control none --import-source on -k regex:"k_rd_dense|k_rd_pass_a|k_join_any" -s 3 -c 4 -o gpurun_out/${T}_rle $E2 > gpurun_out/${T}_ncu5.log 2>&1
 python tools/time_api.py 2000000 > gpurun_out/${T}_api.log 2>&1
