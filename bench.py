@@ -399,7 +399,8 @@ def run_b200(args, rank, world, local_rank):
     alg = {"index_build": 24 * ns, "join": 16 * nq + 16 * p_local, "count": 16 * nq, "emit": 16 * p_local}
     dom = max(phases, key=lambda k: phases[k])
     dom_ms = phases[dom]
-    traffic, traffic_src = ncu_traffic(join.kernel_of(dom), args.workload)
+    # (the committed capture is of the single-GPU launch: no figure for the smaller per-rank launches of N > 1)
+    traffic, traffic_src = ncu_traffic(join.kernel_of(dom), args.workload) if world == 1 else (None, None)
     pipe = 24 * nq + 24 * ns + 16 * p_local  # the join's algorithmic bytes (labels included)
     pipe_req = 16 * nq + 16 * ns + 16 * p_local  # what this implementation has to move (labels = row numbers)
     step_ms_local = join_ms / args.steps
