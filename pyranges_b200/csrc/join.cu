@@ -467,9 +467,8 @@ k_join(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q, int
 // other area -- the predecessors of tile j had a whole tile's time to publish.  One ticket per tile.  Measured at C3
 // (100 M x 1 M): 2.31 ms against 2.60 ms for k_join; the staging capacity matters more than anything else (an iteration
 // that does not fit is counted again after the look-back): 320 pairs 6.2 ms, 384: 4.4, 512: 2.8, 640 / 704 / 768 at three
-// blocks per SM: 2.31 / 2.35 / 2.34, 896: 2.62; two tiles per warp 2.93, four 2.31, eight 2.29 (but 0.249 instead of
-// 0.209 ms at 10 M rows: fewer blocks).
-constexpr int JP_DEPTH = 4;      // tiles per warp
+// blocks per SM: 2.31 / 2.35 / 2.34, 896: 2.62; two tiles per warp 2.93, four 2.31, eight 2.29.  The grid is persistent
+// (as many blocks as the device holds, tiles handed out one by one): no partly filled last wave at small sizes.
 constexpr int JP_WCAP = 640;     // pairs per staging area
 constexpr int JP_MINB = 3;       // blocks per SM: 2 x 8 x 640 x 5 bytes = 51 KB each
 constexpr size_t JP_SMEM = (size_t)2 * JN_WARPS * JP_WCAP * 5;
@@ -562,7 +561,7 @@ k_join_pipe(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q
     };
 
 #pragma unroll 1
-    for (int j = 0; j < JP_DEPTH; j++) {
+    for (int j = 0;; j++) {  // persistent: the grid is as large as the device holds, a warp takes tiles until none is left
         unsigned int tk = 0;
         if (lane == 0) tk = atomicAdd(ticket, 1u);
         const int64_t wtile = (int64_t)__shfl_sync(FULL, tk, 0);
@@ -618,10 +617,9 @@ k_join_pipe(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q
 // ---- overlap(how="first"): the rows with at least one hit -----------------------------------------------------------
 // The same tiles and the same look-back as k_join, but a row contributes at most one entry -- its own number -- so
 // nothing is staged: the hit flags of a tile's 256 rows live in registers (two ballots per iteration) and the positions
-// inside the tile come from population counts.  That makes the ordering wait avoidable: a warp takes JA_DEPTH tiles, one
+// inside the tile come from population counts.  That makes the ordering wait avoidable: a warp of the persistent grid takes tile after tile, one
 // ticket each, and writes a tile only after it has counted and published the next one -- the tile's predecessors had
 // a whole tile's time to publish theirs.
-constexpr int JA_DEPTH = 4;
 
 template <typename X, bool SLACK>
 __global__ void __launch_bounds__(JN_THREADS, 4)
@@ -657,7 +655,7 @@ k_join_any(iv_lists_t ix, iv_queries_t q, bool vec, int64_t* __restrict__ out_q,
     };
 
 #pragma unroll 1
-    for (int j = 0; j < JA_DEPTH; j++) {
+    for (;;) {  // persistent: a warp takes tiles until none is left
         // one ticket per tile: a tile only ever waits for tiles taken earlier, all of them by running warps
         unsigned int tk = 0;
         if (lane == 0) tk = atomicAdd(ticket, 1u);
@@ -772,19 +770,33 @@ extern "C" int iv_join_pairs(const iv_lists_t* lists, const iv_queries_t* q, int
     } while (0)
 #define IV_JK2(X, SL)                                                                                                  \
     do {                                                                                                               \
-        if (any && variant != 3)                                                                                       \
-            k_join_any<X, SL><<<(unsigned)cdiv(n_tiles, JN_WARPS * JA_DEPTH), JN_THREADS, 0, st>>>(                     \
-                *lists, *q, vec, out_q, out_capacity, state, ticket, n_tiles, out_total);                              \
-        else if (any) IV_JK(X, SL, true);                                                                              \
-        else if (variant != 2 && !ordered) {  /* variant 2: the unpipelined k_join for any input (measurements) */                                                                                       \
-            static bool attr4[64] = {false};                                                                           \
+        if (any && variant != 3) {                                                                                     \
+            static int fit_any[64] = {0};                                                                              \
             int dev = 0;                                                                                               \
             IV_CUDA(cudaGetDevice(&dev));                                                                              \
-            if (dev < 0 || dev >= 64 || !attr4[dev]) {                                                                 \
-                IV_CUDA(cudaFuncSetAttribute(k_join_pipe<X, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JP_SMEM)); \
-                if (dev >= 0 && dev < 64) attr4[dev] = true;                                                           \
+            if (dev < 0 || dev >= 64 || !fit_any[dev]) {                                                               \
+                int sms = 0, per_sm = 0;                                                                               \
+                IV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev));               \
+                IV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_join_any<X, SL>, JN_THREADS, 0));      \
+                if (dev >= 0 && dev < 64) fit_any[dev] = sms * per_sm > 0 ? sms * per_sm : 148;                        \
             }                                                                                                          \
-            k_join_pipe<X, SL><<<(unsigned)cdiv(n_tiles, JN_WARPS * JP_DEPTH), JN_THREADS, JP_SMEM, st>>>(               \
+            const int64_t fit = (dev >= 0 && dev < 64) ? fit_any[dev] : 148, need = cdiv(n_tiles, JN_WARPS);           \
+            k_join_any<X, SL><<<(unsigned)(need < fit ? need : fit), JN_THREADS, 0, st>>>(                              \
+                *lists, *q, vec, out_q, out_capacity, state, ticket, n_tiles, out_total);                              \
+        } else if (any) IV_JK(X, SL, true);                                                                            \
+        else if (variant != 2 && !ordered) {  /* variant 2: the unpipelined k_join for any input (measurements) */                                                                                       \
+            static int fit_pipe[64] = {0};                                                                             \
+            int dev = 0;                                                                                               \
+            IV_CUDA(cudaGetDevice(&dev));                                                                              \
+            if (dev < 0 || dev >= 64 || !fit_pipe[dev]) {                                                              \
+                IV_CUDA(cudaFuncSetAttribute(k_join_pipe<X, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JP_SMEM)); \
+                int sms = 0, per_sm = 0;                                                                               \
+                IV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev));               \
+                IV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_join_pipe<X, SL>, JN_THREADS, JP_SMEM)); \
+                if (dev >= 0 && dev < 64) fit_pipe[dev] = sms * per_sm > 0 ? sms * per_sm : 148;                       \
+            }                                                                                                          \
+            const int64_t fit = (dev >= 0 && dev < 64) ? fit_pipe[dev] : 148, need = cdiv(n_tiles, JN_WARPS);          \
+            k_join_pipe<X, SL><<<(unsigned)(need < fit ? need : fit), JN_THREADS, JP_SMEM, st>>>(                       \
                 *lists, *q, vec, out_q, out_s, s_label, out_capacity, state, ticket, n_tiles, out_total);              \
         } else IV_JK(X, SL, false);                                                                                    \
     } while (0)
