@@ -126,12 +126,29 @@ def _col_array(df, col):
         return df[col].values
 
 
+_COLUMN_INDEX = {}  # column names -> pd.Index (the same few tuples come back for every key of every call)
+
+
 def _new_frame(data, n):
-    """DataFrame over ready column arrays with a RangeIndex (3x cheaper than the dict constructor, which re-validates
-    every column; pandas-internal constructor with the public one as fallback)"""
+    """DataFrame over ready column arrays with a RangeIndex: no re-validation of the columns, no consolidation of
+    equal-typed columns into one block (a copy of every column), the Index of the column names built once per set of
+    names -- pandas-internal constructors with the public one as fallback."""
+    names = tuple(data.keys())
+    cols = _COLUMN_INDEX.get(names)
+    if cols is None:
+        if len(_COLUMN_INDEX) > 256:
+            _COLUMN_INDEX.clear()
+        cols = _COLUMN_INDEX[names] = pd.Index(list(names))
+    arrays = list(data.values())
     try:
-        return pd.DataFrame._from_arrays(list(data.values()), pd.Index(list(data.keys())), pd.RangeIndex(n),
-                                         verify_integrity=False)
+        from pandas.core.internals.construction import arrays_to_mgr
+
+        mgr = arrays_to_mgr(arrays, cols, pd.RangeIndex(n), verify_integrity=False, consolidate=False)
+        return pd.DataFrame._from_mgr(mgr, axes=mgr.axes)
+    except Exception:
+        pass
+    try:
+        return pd.DataFrame._from_arrays(arrays, cols, pd.RangeIndex(n), verify_integrity=False)
     except Exception:
         return pd.DataFrame(data, copy=False)
 
