@@ -488,7 +488,8 @@ def _b_overlap(plan, kwargs):
     results = []
     for k, scdf in enumerate(plan.q.dfs):
         ocdf = plan.partner(k)
-        scdf, ocdf = _sparse(kwargs, scdf, ocdf)
+        # (only the self frame is used below: the sparse copy of the partner frame, intersection.py:63, is skipped)
+        scdf, _ = _sparse(kwargs, scdf, None)
         if scdf.empty or ocdf.empty:
             results.append(None)
             continue
@@ -519,7 +520,7 @@ def _b_intersection(plan, kwargs):
     results = []
     for k, scdf in enumerate(plan.q.dfs):
         ocdf = plan.partner(k)
-        scdf, ocdf = _sparse(kwargs, scdf, ocdf)
+        scdf, _ = _sparse(kwargs, scdf, None)  # (of the partner frame only emptiness and the Start dtype are used)
         a, b = first[k], first[k + 1]
         if scdf.empty or ocdf.empty or a == b:
             results.append(None)
