@@ -66,15 +66,73 @@ def _strings(buf, off, length, device):
     return [b[o[i]:o[i + 1]].decode() for i in range(n)]
 
 
-def _infer(values):
-    """dtype inference of one text column as pandas.read_csv would do it: int64, else float64, else object"""
-    s = pd.Series(values, dtype=object)
-    for conv in (lambda x: x.astype(np.int64), lambda x: x.astype(np.float64)):
+def _infer_bytes(arr):
+    """dtype inference of a fixed-width bytes column the way pandas.read_csv would decide: int64, else float64, else
+    None (text)"""
+    for dt in (np.int64, np.float64):
         try:
-            return conv(s).values
-        except (ValueError, TypeError):
+            return arr.astype(dt)
+        except ValueError:
             pass
-    return s.values
+    return None
+
+
+def _to_str_objects(arr):
+    """fixed-width bytes array -> object array of str"""
+    try:
+        return arr.astype("U").astype(object)
+    except UnicodeDecodeError:  # non-ASCII names: decode element-wise
+        return np.asarray([x.decode("utf-8", errors="replace") for x in arr.tolist()], dtype=object)
+
+
+_TEXT_CHUNK = 1 << 21
+
+
+def _as_text(vals, inv=None):
+    """object array of str (optionally a dictionary `vals` with row codes `inv`) -> the column pandas.read_csv would
+    hold: the "str" extension dtype where pandas infers it (pandas >= 3), else the object array"""
+    if getattr(pd.options.future, "infer_string", False):
+        arr = pd.array(vals, dtype="str")
+        return arr.take(inv) if inv is not None else arr
+    return vals[inv] if inv is not None else vals
+
+
+def _text_column(buf, nbytes, off, length, dev):
+    """One text column (spans off / length into the file bytes) -> int64 / float64 / text column, without a Python
+    loop over the rows: the fields are laid out as fixed-width, zero-padded records on the device; fields of up to 8
+    bytes with few distinct values are dictionary-encoded there (one 64-bit word per field, torch.unique) so that only
+    the dictionary is decoded; everything else crosses as an "S<width>" array that numpy converts."""
+    n = int(off.numel())
+    if n == 0:
+        return np.empty(0, dtype=object)
+    maxlen = int(length.max().item())
+    if maxlen > 64:  # long list fields (BlockSizes ...): spans packed on the device, sliced on the host
+        return _as_text(np.asarray(_strings(buf, off, length, dev), dtype=object))
+    W = max(8, (maxlen + 7) // 8 * 8)
+    lane = torch.arange(W, device=dev)
+    parts = []
+    for a in range(0, n, _TEXT_CHUNK):
+        o, l = off[a:a + _TEXT_CHUNK], length[a:a + _TEXT_CHUNK]
+        idx = (o[:, None] + lane[None, :]).clamp_(max=max(nbytes - 1, 0))
+        rec = torch.where(lane[None, :] < l[:, None], buf[idx], torch.zeros((), dtype=torch.uint8, device=dev))
+        parts.append(rec)
+    rec = parts[0] if len(parts) == 1 else torch.cat(parts)
+    if W == 8:
+        uniq, inv = torch.unique(rec.view(torch.int64).reshape(-1), return_inverse=True)
+        if uniq.numel() <= max(n // 4, 1):
+            table = uniq.cpu().numpy().view("S8")
+            vals = _infer_bytes(table)
+            if vals is None:
+                return _as_text(_to_str_objects(table), inv.cpu().numpy())
+            return vals[inv.cpu().numpy()]
+    host = rec.cpu().numpy().view("S%d" % W).reshape(-1)
+    vals = _infer_bytes(host)
+    if vals is not None:
+        return vals
+    return _as_text(np.concatenate([_to_str_objects(host[a:a + _TEXT_CHUNK]) for a in range(0, n, _TEXT_CHUNK)]))
+
+
+_STRAND_DTYPE = pd.CategoricalDtype([".", "-", "+"], ordered=True)  # pyranges/methods/init.py:28-30
 
 
 def read_bed(f, as_df=False, nrows=None, device=None):
@@ -144,58 +202,66 @@ def read_bed(f, as_df=False, nrows=None, device=None):
     # mismatch inside a hash class would give it away
     if len(set(names)) != len(names) or not bool((l0 == l0[rep][inv]).all()):
         raise ValueError("read_bed: chromosome-name hash collision")
-    data = {"Chromosome": pd.Categorical.from_codes(inv.cpu().numpy(), categories=names),
-            "Start": start.cpu().numpy(), "End": end.cpu().numpy()}
+    # categories in sorted order, as astype("category") leaves them (pyranges/methods/init.py:24)
+    lex = sorted(range(len(names)), key=lambda i: names[i])
+    rank = np.empty(len(names), np.int64)
+    rank[lex] = np.arange(len(names))
+    names = [names[i] for i in lex]
+    chrom_code = torch.from_numpy(rank).to(dev)[inv]
+    strand_chars = None
+    if ncols >= 6 and not bad_h[2]:
+        strand_chars = sorted(torch.unique(strand).cpu().numpy().tolist())
+
+    # the PyRanges is assembled directly in its key order when the Strand column (if any) holds nothing but the
+    # characters the reference's dtype knows; otherwise through the constructor
+    direct = not as_df and (ncols < 6 or (strand_chars is not None and set(strand_chars) <= {43, 45, 46}))
+    order = seg = keys = None
+    if direct:
+        stranded = ncols >= 6 and set(strand_chars) <= {43, 45}
+        key = chrom_code * 256 + strand.to(torch.int64) if stranded else chrom_code
+        ukeys, kinv = torch.unique(key, return_inverse=True)
+        labels = [((names[k >> 8], chr(k & 255)) if stranded else names[k]) for k in ukeys.cpu().numpy().tolist()]
+        keys = natsorted(labels)
+        where = {lab: p for p, lab in enumerate(keys)}
+        pos = torch.from_numpy(np.asarray([where[lab] for lab in labels], np.int64)).to(dev)[kinv]
+        seg = np.zeros(len(keys) + 1, np.int64)
+        np.cumsum(torch.bincount(pos, minlength=len(keys)).cpu().numpy(), out=seg[1:])
+        rows = torch.arange(n_rows, dtype=torch.int32, device=dev)
+        E.radix_sort_u64(pos, rows, 0, max(1, int(len(keys)).bit_length()))  # stable: file order inside a key
+        order = rows.to(torch.int64)
+    take = (lambda t: t[order].contiguous()) if order is not None else (lambda t: t)  # noqa: E731
+
+    start_d, end_d = take(start), take(end)
+    data = {"Chromosome": pd.Categorical.from_codes(take(chrom_code).cpu().numpy(), categories=names),
+            "Start": start_d.cpu().numpy(), "End": end_d.cpu().numpy()}
     for c in range(3, ncols):
         name = BED_COLUMNS[c]
         if c == 4 and not bad_h[1]:
-            data[name] = score.cpu().numpy()
-        elif c == 5 and not bad_h[2]:
-            sv = strand.cpu().numpy()
-            cats = sorted(set(sv.tolist()))
-            lut = np.zeros(256, np.int64)
-            lut[cats] = np.arange(len(cats))
-            data[name] = pd.Categorical.from_codes(lut[sv], categories=[chr(x) for x in cats])
+            data[name] = take(score).cpu().numpy()
+        elif c == 5 and strand_chars is not None:
+            sv = take(strand).cpu().numpy()
+            lut = np.zeros(256, np.int8)
+            if direct:
+                lut[[46, 45, 43]] = [0, 1, 2]
+                data[name] = pd.Categorical.from_codes(lut[sv], dtype=_STRAND_DTYPE)
+            else:
+                lut[strand_chars] = np.arange(len(strand_chars))
+                data[name] = pd.Categorical.from_codes(lut[sv], categories=[chr(x) for x in strand_chars])
         else:
             o, l = col(c)
-            vals = _infer(_strings(buf, o, l, dev))
+            vals = _text_column(buf, nbytes, take(o), take(l), dev)
             data[name] = pd.Categorical(vals) if c == 5 else vals
-    df = pd.DataFrame(data)
-    if as_df:
-        return df
-    gr = PyRanges(df)
-    _seed_device_columns(gr, start, end, inv, strand if ("Strand" in df.columns and gr.stranded) else None, names, dev)
+    if not direct:
+        df = pd.DataFrame(data)
+        return df if as_df else PyRanges(df)
+    # frames of the keys: row ranges of one frame in key order whose index holds the rows' positions in the file,
+    # which is what the groupby of the constructor leaves (pyranges/methods/init.py:140-150)
+    big = M._new_frame(data, n_rows)
+    big.index = pd.Index(order.cpu().numpy())
+    gr = PyRanges._wrap({k: big.iloc[int(seg[i]):int(seg[i + 1])] for i, k in enumerate(keys)})
+    fr = M._Frames(natsorted(gr.dfs.items()), dev, upload=False)
+    if fr.keys == keys:
+        fr.starts, fr.ends = data["Start"], data["End"]
+        fr.iv = E.DeviceIntervals(start_d, end_d, fr.seg_off)
+        M.seed_frame_cache(gr, dev, fr)
     return gr
-
-
-def _seed_device_columns(gr, start, end, chrom_code, strand, names, dev):
-    """The parsed Start / End, brought into the key order of `gr` on the device (stable: rows keep their file order
-    inside a key, like the groupby of the constructor), become the cached device ingest of the object."""
-    from . import multithreaded as M
-
-    items = natsorted(gr.dfs.items())
-    if not items:
-        return
-    n = start.numel()
-    # key id of every row -> position of the key in natsorted order
-    nkeys = len(names) * (256 if strand is not None else 1)
-    pos_of = np.full(nkeys, len(items), dtype=np.int64)
-    code_of = {nm: i for i, nm in enumerate(names)}
-    for p, (k, _) in enumerate(items):
-        if isinstance(k, tuple):
-            pos_of[code_of[str(k[0])] * 256 + ord(k[1])] = p
-        else:
-            pos_of[code_of[str(k)]] = p
-    key = chrom_code * 256 + strand.to(torch.int64) if strand is not None else chrom_code
-    pos = torch.from_numpy(pos_of).to(dev)[key]
-    if int(pos.max().item()) >= len(items):
-        return  # rows the constructor regrouped differently: leave the upload to the first operation
-    rows = torch.arange(n, dtype=torch.int32, device=dev)
-    E.radix_sort_u64(pos, rows, 0, max(1, int(len(items)).bit_length()))
-    order = rows.to(torch.int64)
-    s_dev, e_dev = start[order].contiguous(), end[order].contiguous()
-    f = M._Frames(items, dev, upload=False)
-    f.starts = np.concatenate([np.asarray(d["Start"].values, dtype=np.int64) for d in f.dfs])
-    f.ends = np.concatenate([np.asarray(d["End"].values, dtype=np.int64) for d in f.dfs])
-    f.iv = E.DeviceIntervals(s_dev, e_dev, f.seg_off)
-    M.seed_frame_cache(gr, dev, f)

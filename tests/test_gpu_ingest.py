@@ -35,10 +35,11 @@ def _bed(tmp_path, n, ncols, header=False, final_newline=True, crlf=False, gz=Fa
 
 
 def _want(path, header, nrows=None):
-    df = pd.read_csv(path, dtype={"Chromosome": "category", "Strand": "category"}, nrows=nrows,
-                     header=0 if header else None, sep="\t")
-    df.columns = COLS[:df.shape[1]]
-    return df
+    """what the reference's read_bed hands to PyRanges (pyranges/readers.py:118-139)"""
+    with (gzip.open(path, "rt") if path.endswith(".gz") else open(path)) as fh:
+        ncols = len(fh.readline().rstrip("\r\n").split("\t"))
+    return pd.read_csv(path, dtype={"Chromosome": "category", "Strand": "category"}, nrows=nrows,
+                       header=0 if header else None, names=COLS[:ncols], sep="\t")
 
 
 def _same(got, want):
@@ -47,7 +48,9 @@ def _same(got, want):
     for c in want.columns:
         a, b = got[c], want[c]
         if str(b.dtype) == "category" or b.dtype == object or str(b.dtype) in ("str", "string"):
-            assert (a.astype(str).values == b.astype(str).values).all(), c
+            assert str(a.dtype) == str(b.dtype), (c, a.dtype, b.dtype)
+            txt = lambda x: np.asarray(x.astype(object).where(x.notna(), "<missing>"), dtype=str)  # noqa: E731
+            assert (txt(a) == txt(b)).all(), c
         else:
             assert a.dtype == b.dtype, (c, a.dtype, b.dtype)
             assert np.array_equal(a.values, b.values), c
@@ -81,6 +84,11 @@ def test_read_bed_pyranges_and_device_columns(tmp_path):
     assert gr.keys() == want.keys()
     for k in gr.keys():
         _same(gr.dfs[k].reset_index(drop=True), want.dfs[k].reset_index(drop=True))
+        # the frames are the constructor's: same dtypes (ordered Strand categories included), and the index holds the
+        # rows' positions in the file
+        assert gr.dfs[k].dtypes.equals(want.dfs[k].dtypes), (k, gr.dfs[k].dtypes, want.dfs[k].dtypes)
+        assert np.array_equal(gr.dfs[k].index.values, want.dfs[k].index.values), k
+    _same(gr.df, want.df)
     assert len(M._FRAME_CACHE) == 1
     f = M._frames_of(gr, next(iter(M._FRAME_CACHE.values()))[0].iv.device)
     assert f is next(iter(M._FRAME_CACHE.values()))[0]  # served from the cache: nothing was uploaded
@@ -102,3 +110,45 @@ def test_read_bed_rejects_bad_rows(tmp_path):
         fh.write("chr1\t10\t20\nchr1\t30\tforty\n")
     with pytest.raises(ValueError):
         read_bed(p)
+
+
+@pytest.mark.parametrize("strands,stranded", [("+-", True), ("+-.", False), ("+-x", False)])
+def test_read_bed_strand_values(tmp_path, strands, stranded):
+    """'.' strands leave an unstranded PyRanges keyed by chromosome; characters outside the reference's Strand dtype go
+    through the constructor -- either way the object equals PyRanges(pandas frame)"""
+    from pyranges_b200.pyranges_main import PyRanges
+    from pyranges_b200.readers import read_bed
+
+    rng = np.random.default_rng(11)
+    n = 20000
+    st = rng.integers(0, 1_000_000, n)
+    p = os.path.join(str(tmp_path), "s.bed")
+    with open(p, "w") as fh:
+        for i in range(n):
+            fh.write("chr%d\t%d\t%d\tn%d\t%d\t%s\n" % (rng.integers(1, 30), st[i], st[i] + 50, i, i % 9,
+                                                        strands[i % len(strands)]))
+    gr, want = read_bed(p), PyRanges(_want(p, False))
+    assert gr.stranded == stranded == want.stranded
+    assert gr.keys() == want.keys()
+    for k in gr.keys():
+        _same(gr.dfs[k].reset_index(drop=True), want.dfs[k].reset_index(drop=True))
+        assert np.array_equal(gr.dfs[k].index.values, want.dfs[k].index.values), k
+    assert len(gr.join(want)) == len(want.join(want))
+
+
+def test_read_bed_text_columns(tmp_path):
+    """text columns of every shape the host assembly treats differently: short with few distinct values (dictionary on
+    the device), short and all distinct, wider than 8 bytes, longer than 64 bytes, numeric text in a late column"""
+    from pyranges_b200.readers import read_bed
+
+    rng = np.random.default_rng(12)
+    n = 30000
+    st = rng.integers(0, 1_000_000, n)
+    p = os.path.join(str(tmp_path), "t.bed")
+    with open(p, "w") as fh:
+        for i in range(n):
+            f = ["chr%d" % (i % 3), str(st[i]), str(st[i] + 9), "g%d" % (i % 50), str(i % 7), "+-"[i % 2],
+                 "u%06d" % i, "%d" % (i * 3), "a_rather_long_identifier_%d" % i, "2", "7," * (1 + i % 40), "0.5"]
+            fh.write("\t".join(f) + "\n")
+    _same(read_bed(p, as_df=True), _want(p, False))
+    _same(read_bed(p).df, _want(p, False).sort_values(["Chromosome", "Strand"], kind="stable").reset_index(drop=True))
