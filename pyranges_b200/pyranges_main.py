@@ -36,26 +36,105 @@ def fill_kwargs(kwargs):
     return defaults
 
 
-def _set_dtypes(df):
-    """pyranges/methods/init.py:10-32: Start/End int64, Chromosome category, Strand ordered category."""
+def _codes_of(col):
+    """(codes, names): the column as small-integer codes into the str() of its distinct values, without stringifying
+    row by row; None when str() would merge values or a missing value would become the text 'nan' (the callers then
+    take the row-by-row route)."""
+    if isinstance(col.dtype, pd.CategoricalDtype):
+        codes, values = col.cat.codes.to_numpy(), list(col.cat.categories)
+    else:
+        if col.dtype.kind in "iufb":
+            return None
+        codes, values = pd.factorize(col)
+        values = list(values)
+    if len(codes) and codes.min() < 0:
+        return None
+    names = [str(v) for v in values]
+    if len(set(names)) != len(names):
+        return None
+    return codes, names
+
+
+def _strand_dtype():
     from pandas.api.types import CategoricalDtype
 
-    for column in ("Chromosome", "Strand"):
-        if column in df:
-            df[column] = df[column].astype(str)
+    return CategoricalDtype([".", "-", "+"], ordered=True)
+
+
+def _set_dtypes(df, coded=None):
+    """pyranges/methods/init.py:10-32: Start/End int64, Chromosome category, Strand ordered category.  `coded` holds
+    the (codes, names) of Chromosome / Strand where _codes_of could produce them: the categoricals are then built
+    from the codes (same result as astype(str).astype(dtype), which walks every row twice)."""
+    coded = coded or {}
     df["Start"] = df["Start"].astype(np.int64)
     df["End"] = df["End"].astype(np.int64)
-    df["Chromosome"] = df["Chromosome"].astype("category")
+    c = coded.get("Chromosome")
+    if c is not None:
+        codes, names = c
+        used = np.zeros(len(names), bool)
+        used[codes] = True
+        cats = sorted(n for n, u in zip(names, used) if u)
+        where = {n: i for i, n in enumerate(cats)}
+        lut = np.asarray([where.get(n, -1) for n in names] + [-1], dtype=np.int64)
+        df["Chromosome"] = pd.Categorical.from_codes(lut[codes], categories=cats)
+    else:
+        df["Chromosome"] = df["Chromosome"].astype(str).astype("category")
     if "Strand" in df:
-        df["Strand"] = df["Strand"].astype(CategoricalDtype([".", "-", "+"], ordered=True))
+        c = coded.get("Strand")
+        if c is not None:
+            codes, names = c
+            where = {".": 0, "-": 1, "+": 2}
+            lut = np.asarray([where.get(n, -1) for n in names] + [-1], dtype=np.int64)
+            df["Strand"] = pd.Categorical.from_codes(lut[codes], dtype=_strand_dtype())
+        else:
+            df["Strand"] = df["Strand"].astype(str).astype(_strand_dtype())
     return df
 
 
-def _check_strandedness(df):
+def _check_strandedness(df, coded=None):
     """pyranges/methods/init.py:73-102: stranded iff a Strand column holds only '+' / '-'."""
     if "Strand" not in df:
         return False
+    c = (coded or {}).get("Strand")
+    if c is not None:
+        codes, names = c
+        used = np.zeros(len(names), bool)
+        used[codes] = True
+        return all(n in ("+", "-") for n, u in zip(names, used) if u)
     return bool(df["Strand"].astype(str).isin(["+", "-"]).all())
+
+
+def _group_frames(df, stranded):
+    """{key: frame} of df.groupby(Chromosome[, Strand], observed=True) (pyranges/methods/init.py:140-150) for the
+    categorical columns _set_dtypes leaves: one stable sort of the combined category codes, one gather per column, and
+    the groups as row ranges of the gathered frame -- same keys in the same order, same rows with the same index."""
+    ch = df["Chromosome"]
+    st = df["Strand"] if stranded else None
+    ok = isinstance(ch.dtype, pd.CategoricalDtype) and (st is None or isinstance(st.dtype, pd.CategoricalDtype))
+    if ok:
+        code = ch.cat.codes.to_numpy().astype(np.int64)
+        ok = not len(code) or code.min() >= 0
+        if ok and st is not None:
+            sc = st.cat.codes.to_numpy().astype(np.int64)
+            ok = sc.min() >= 0
+            code = code * len(st.cat.categories) + sc
+    if not ok:
+        by = ["Chromosome", "Strand"] if stranded else "Chromosome"
+        return {k: v for k, v in df.groupby(by, observed=True)}
+    top = int(code.max()) + 1
+    small = code.astype(np.int16) if top < (1 << 15) else code  # 16-bit keys: numpy's stable sort is a radix sort
+    order = np.argsort(small, kind="stable")
+    counts = np.bincount(code, minlength=top)
+    big = df.take(order)
+    chrom_cats = list(ch.cat.categories)
+    strand_cats = list(st.cat.categories) if st is not None else None
+    out, a = {}, 0
+    for c in np.flatnonzero(counts).tolist():
+        b = a + int(counts[c])
+        key = (chrom_cats[c // len(strand_cats)], strand_cats[c % len(strand_cats)]) if st is not None else chrom_cats[c]
+        out[key] = big.iloc[a:b]
+        a = b
+    return out
 
 
 def _all_equal(col, value):
@@ -112,12 +191,12 @@ class PyRanges:
                 "The dataframe does not have all the columns Chromosome, Start and End."
             df = df.copy() if copy_df else df
             df = df.reset_index(drop=True)
-            stranded = _check_strandedness(df)
+            coded = {c: _codes_of(df[c]) for c in ("Chromosome", "Strand") if c in df}
+            stranded = _check_strandedness(df, coded)
             if len(df):
-                df = _set_dtypes(df)
-                by = ["Chromosome", "Strand"] if stranded else "Chromosome"
-                # observed=True: pandas >= 3 would otherwise create empty (chrom, '.') groups
-                dfs = {k: v for k, v in df.groupby(by, observed=True)}
+                df = _set_dtypes(df, coded)
+                # observed groups only: pandas >= 3 would otherwise create empty (chrom, '.') groups
+                dfs = _group_frames(df, stranded)
             else:
                 dfs = {}
         else:
@@ -134,8 +213,7 @@ class PyRanges:
             if not ok:
                 alldf = pd.concat(dfs.values()).reset_index(drop=True)
                 stranded = _check_strandedness(alldf)
-                by = ["Chromosome", "Strand"] if stranded else "Chromosome"
-                dfs = {k: v for k, v in alldf.groupby(by, observed=True)}
+                dfs = _group_frames(alldf, stranded)
         self.__dict__["dfs"] = dfs
 
     @classmethod
