@@ -66,26 +66,45 @@ def _strings(buf, off, length, device):
     return [b[o[i]:o[i + 1]].decode() for i in range(n)]
 
 
-def _infer_bytes(arr):
-    """dtype inference of a fixed-width bytes column the way pandas.read_csv would decide: int64, else float64, else
-    None (text)"""
-    for dt in (np.int64, np.float64):
-        try:
-            return arr.astype(dt)
-        except ValueError:
-            pass
-    return None
+_TEXT_CHUNK = 1 << 21
+
+# the spellings pandas.read_csv reads as a missing value (pandas/_libs/parsers.pyx STR_NA_VALUES)
+_NA_BYTES = np.asarray([b"", b"#N/A", b"#N/A N/A", b"#NA", b"-1.#IND", b"-1.#QNAN", b"-NaN", b"-nan", b"1.#IND",
+                        b"1.#QNAN", b"<NA>", b"N/A", b"NA", b"NULL", b"NaN", b"None", b"n/a", b"nan", b"null"])
+
+
+def _convert_bytes(arr):
+    """A fixed-width bytes column the way pandas.read_csv would type it: int64, else float64 (missing values as NaN),
+    else text -> (values, None) for numbers, (object array of str with NaN for missing values, True) for text."""
+    missing = np.isin(arr, _NA_BYTES)
+    if not missing.any():
+        for dt in (np.int64, np.float64):
+            try:
+                return arr.astype(dt), None
+            except ValueError:
+                pass
+        return _to_str_objects(arr), True
+    out = np.full(len(arr), np.nan)
+    try:
+        out[~missing] = arr[~missing].astype(np.float64)
+        return out, None
+    except ValueError:
+        pass
+    txt = _to_str_objects(arr)
+    txt[missing] = np.nan
+    return txt, True
 
 
 def _to_str_objects(arr):
     """fixed-width bytes array -> object array of str"""
-    try:
-        return arr.astype("U").astype(object)
-    except UnicodeDecodeError:  # non-ASCII names: decode element-wise
-        return np.asarray([x.decode("utf-8", errors="replace") for x in arr.tolist()], dtype=object)
-
-
-_TEXT_CHUNK = 1 << 21
+    out = np.empty(len(arr), dtype=object)
+    for a in range(0, len(arr), _TEXT_CHUNK):  # in pieces: the "U" intermediate is four times as wide
+        part = arr[a:a + _TEXT_CHUNK]
+        try:
+            out[a:a + _TEXT_CHUNK] = part.astype("U").astype(object)
+        except UnicodeDecodeError:  # non-ASCII names: decode element-wise
+            out[a:a + _TEXT_CHUNK] = [x.decode("utf-8", errors="replace") for x in part.tolist()]
+    return out
 
 
 def _as_text(vals, inv=None):
@@ -120,16 +139,11 @@ def _text_column(buf, nbytes, off, length, dev):
     if W == 8:
         uniq, inv = torch.unique(rec.view(torch.int64).reshape(-1), return_inverse=True)
         if uniq.numel() <= max(n // 4, 1):
-            table = uniq.cpu().numpy().view("S8")
-            vals = _infer_bytes(table)
-            if vals is None:
-                return _as_text(_to_str_objects(table), inv.cpu().numpy())
-            return vals[inv.cpu().numpy()]
+            vals, text = _convert_bytes(uniq.cpu().numpy().view("S8"))
+            return _as_text(vals, inv.cpu().numpy()) if text else vals[inv.cpu().numpy()]
     host = rec.cpu().numpy().view("S%d" % W).reshape(-1)
-    vals = _infer_bytes(host)
-    if vals is not None:
-        return vals
-    return _as_text(np.concatenate([_to_str_objects(host[a:a + _TEXT_CHUNK]) for a in range(0, n, _TEXT_CHUNK)]))
+    vals, text = _convert_bytes(host)
+    return _as_text(vals) if text else vals
 
 
 _STRAND_DTYPE = pd.CategoricalDtype([".", "-", "+"], ordered=True)  # pyranges/methods/init.py:28-30
