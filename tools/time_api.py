@@ -27,5 +27,7 @@ for name, fn in [("count_overlaps", lambda: gr.count_overlaps(an)), ("join", lam
                  ("cluster", lambda: gr.cluster()), ("merge", lambda: gr.merge()), ("to_rle", lambda: gr.to_rle()),
                  ("coverage", lambda: gr.coverage(an))]:
     fn()
-    t = time.time(); r = fn(); dt = time.time() - t
+    dt = 1e9
+    for _ in range(3):  # best of three: a call now and then pays for a fresh device allocation
+        t = time.time(); r = fn(); dt = min(dt, time.time() - t)
     print("%-16s %.3f s   (%d rows out)" % (name, dt, len(r) if not hasattr(r, "rles") else sum(len(v) for v in r.rles.values())), flush=True)
