@@ -89,6 +89,89 @@ def test_two_rank_join_matches_single_rank(monkeypatch):
         assert gids[k] == v.Cluster.values.tolist(), k
 
 
+OPS = {
+    "count_overlaps": lambda a, b: a.count_overlaps(b),
+    "overlap": lambda a, b: a.overlap(b),
+    "nearest": lambda a, b: a.nearest(b),
+    "k_nearest": lambda a, b: a.k_nearest(b, k=2, ties="different"),
+    "merge": lambda a, b: a.merge(),
+    "subtract": lambda a, b: a.subtract(b),
+    "coverage": lambda a, b: a.coverage(b),
+}
+
+
+def _ops_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from pyranges_b200 import multithreaded, sharding
+    from pyranges_b200.pyranges_main import PyRanges
+    from tests import fake_engine
+    from tests.golden_util import load_input
+
+    multithreaded.E = fake_engine
+    multithreaded._device_of = lambda kwargs: "cpu"
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    A, B = PyRanges(load_input("A")), PyRanges(load_input("B"))
+    keys = A.keys()
+    assign = sharding.shard_keys(keys, [len(A.dfs[k]) for k in keys], world)
+    la, lb = sharding.local_part(A, assign, rank), sharding.local_part(B, assign, rank)
+    out = {name: dict(f(la, lb).dfs) for name, f in OPS.items()}
+    rle = la.to_rle()
+    out["to_rle"] = {k: (np.asarray(v.runs).tolist(), np.asarray(v.values).tolist()) for k, v in rle.rles.items()}
+    # per-key row counts of every operation, summed over the ranks: the offsets of the concatenated results
+    all_keys = sorted(set(map(str, A.keys())))
+    n_rows = {name: sharding.gather_key_counts(all_keys, {str(k): len(v) for k, v in d.items()} if name != "to_rle"
+                                               else {str(k): len(v[0]) for k, v in d.items()})[0].tolist()
+              for name, d in out.items()}
+    q.put((rank, out, n_rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_other_operations_match_single_rank(monkeypatch):
+    """count_overlaps / overlap / nearest / k_nearest / merge / subtract / coverage / to_rle on two ranks: every key's
+    frame (or run list) is the single-rank one, and the gathered per-key row counts are the global ones on both ranks"""
+    from pyranges_b200 import multithreaded
+    from pyranges_b200.pyranges_main import PyRanges
+    from tests import fake_engine
+    from tests.golden_util import assert_frames_equal, load_input
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ops_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    monkeypatch.setattr(multithreaded, "E", fake_engine)
+    monkeypatch.setattr(multithreaded, "_device_of", lambda kwargs: "cpu")
+    A, B = PyRanges(load_input("A")), PyRanges(load_input("B"))
+    all_keys = sorted(set(map(str, A.keys())))
+    for name, f in OPS.items():
+        full = f(A, B).dfs
+        got = {}
+        for _, out, _ in res:
+            assert not (set(out[name]) & set(got)), name  # keys are disjoint across ranks
+            got.update(out[name])
+        assert set(got) == set(full), name
+        for k, v in full.items():
+            assert_frames_equal(got[k], v, "%s %s" % (name, k))
+        want_rows = [sum(len(v) for k, v in full.items() if str(k) == ks) for ks in all_keys]
+        for _, _, n_rows in res:
+            assert n_rows[name] == want_rows, name
+    full = A.to_rle().rles
+    got = {}
+    for _, out, _ in res:
+        got.update(out["to_rle"])
+    assert set(got) == set(full)
+    for k, v in full.items():
+        assert got[k] == (np.asarray(v.runs).tolist(), np.asarray(v.values).tolist()), k
+
+
 def test_lpt_balance():
     from pyranges_b200 import sharding
     from pyranges_b200.synthetic import HG38
