@@ -193,16 +193,36 @@ k_cl_ids(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ends_op
         cnt += f[j];
     }
     int64_t tot;
-    int64_t id = block_excl_sum<int64_t, CL_THREADS>((int64_t)cnt, sm, tot) + __ldg(tile_off + blockIdx.x);
+    const int64_t toff = __ldg(tile_off + blockIdx.x);
+    int64_t id = block_excl_sum<int64_t, CL_THREADS>((int64_t)cnt, sm, tot) + toff;
+    if (!MERGE) {
+        // the ids leave through shared memory (12 bits each, relative to the tile's first id) so that every store
+        // instruction of a warp writes 256 consecutive bytes; the rows are a widening copy in the same order
+        __shared__ uint16_t rel[CL_TILE];
+        uint32_t r = (uint32_t)(id - toff);
+#pragma unroll
+        for (int j = 0; j < CL_ITEMS; j++) {
+            r += f[j];
+            rel[threadIdx.x * CL_ITEMS + j] = (uint16_t)r;
+        }
+        __syncthreads();
+        const int64_t tb = (int64_t)blockIdx.x * CL_TILE;
+#pragma unroll
+        for (int k = 0; k < CL_ITEMS; k++) {
+            const int64_t p = tb + k * CL_THREADS + threadIdx.x;
+            if (p < n) {
+                __stcs(out_id + p, toff + (int64_t)rel[k * CL_THREADS + threadIdx.x]);
+                __stcs(out_row + p, (int64_t)__ldg(rows + p));
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < CL_ITEMS; j++) {
         const int64_t p = p0 + j;
         if (p >= n) break;
         id += f[j];
-        if (!MERGE) {
-            out_id[p] = id;
-            out_row[p] = (int64_t)__ldg(rows + p);
-        } else {
+        {
             uint64_t k = __ldg(keys + p);
             int64_t S = (int64_t)(k >> lbits);
             int64_t E = ends_opt ? (int64_t)__ldg(ends_opt + p) : S + (int64_t)(k & lmask);
