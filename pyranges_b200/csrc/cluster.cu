@@ -217,25 +217,33 @@ k_cl_ids(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ends_op
         }
         return;
     }
+    // the max end of a cluster: one atomic per run of rows of the same cluster inside the thread's eight rows (a
+    // cluster holds nine rows on average at C4), not one per row
+    int64_t run_id = 0, run_max = INT64_MIN;
 #pragma unroll
     for (int j = 0; j < CL_ITEMS; j++) {
         const int64_t p = p0 + j;
         if (p >= n) break;
         id += f[j];
-        {
-            uint64_t k = __ldg(keys + p);
-            int64_t S = (int64_t)(k >> lbits);
-            int64_t E = ends_opt ? (int64_t)__ldg(ends_opt + p) : S + (int64_t)(k & lmask);
-            if (f[j]) {
-                // group of a flattened coordinate: largest g with base[g] <= S
-                int g = find_seg(G.base, G.n_groups, S);
-                c_start[id - 1] = S - __ldg(G.base + g) + __ldg(G.lo + g);
-                c_group[id - 1] = g;
-                c_first[id - 1] = p;
-            }
-            atomicMax((long long*)c_end + (id - 1), (long long)E);
+        uint64_t k = __ldg(keys + p);
+        int64_t S = (int64_t)(k >> lbits);
+        int64_t E = ends_opt ? (int64_t)__ldg(ends_opt + p) : S + (int64_t)(k & lmask);
+        if (f[j]) {
+            // group of a flattened coordinate: largest g with base[g] <= S
+            int g = find_seg(G.base, G.n_groups, S);
+            c_start[id - 1] = S - __ldg(G.base + g) + __ldg(G.lo + g);
+            c_group[id - 1] = g;
+            c_first[id - 1] = p;
+        }
+        if (id != run_id) {
+            if (run_id > 0) atomicMax((long long*)c_end + (run_id - 1), (long long)run_max);
+            run_id = id;
+            run_max = E;
+        } else {
+            run_max = E > run_max ? E : run_max;
         }
     }
+    if (run_id > 0) atomicMax((long long*)c_end + (run_id - 1), (long long)run_max);
 }
 
 __global__ void k_merge_finish(int64_t n, int64_t nc, iv_groups_t G,
